@@ -1,0 +1,268 @@
+// K5: overlap-aware stitching of per-patch logits into the downscaled whole-slide map.
+//
+// Reference path replaced:
+//   examples/predict_full_patched.py:40-63  ImagePredictorPatched.process
+//     prediction[y//d:(y+ps)//d, x//d:(x+ps)//d, :] += logits_i   (sampler order)   then argmax(axis=2)
+//
+// dh_stitch_dense is a GATHER formulation for the dense enumeration of full_samplers.py:374-404:
+// every output cell sums the logits of the patches that cover it, visited in the reference's order
+// (main grid row-major, last column, last row, corner, padding copies of the corner), with plain
+// fp32 adds, so the sum map is bit-identical to the numpy loop and needs no atomics.
+// Rows that are covered by the same set of patch rows have identical values: a block computes one
+// column tile once per such row class into shared memory and streams it out for every row of the
+// class, so the kernel is a pure coalesced store stream (16-byte vectors) -> HBM write roofline.
+#include "dh_common.cuh"
+
+namespace dh {
+
+struct StitchGrid {
+    int64_t H, W;
+    int ps, stride, d, n;
+    int64_t ny, nx, N, pads;  // pads = number of padding copies of the corner patch
+    int64_t dh, dw;
+    int64_t lastrow_cell, lastcol_cell;  // (H-ps)//d, (W-ps)//d
+};
+
+struct Cover {
+    int64_t lo, hi;  // main-grid index range (inclusive), empty if lo > hi
+    bool last;       // covered by the last row / column patch
+};
+
+__host__ __device__ __forceinline__ Cover cover_1d(int64_t i, int64_t cnt, int ps, int stride, int d, int64_t last_cell) {
+    Cover c;
+    int64_t e = (i + 1) * (int64_t)d;  // patch covers cell i  <=>  e - ps <= y <= e - 1
+    c.hi = (e - 1) / stride;
+    if (c.hi > cnt - 1) c.hi = cnt - 1;
+    int64_t t = e - ps;
+    c.lo = t <= 0 ? 0 : (t + stride - 1) / stride;
+    c.last = i >= last_cell;
+    return c;
+}
+
+constexpr int kStitchThreads = 256;
+
+// smem: 4 copies of the tile values, copy s stored at float offset s (so that a row whose global
+// float offset is == s mod 4 can be streamed out with aligned 16-byte loads and stores).
+template <bool WITH_SUM, bool WITH_ARGMAX, bool WITH_COUNT>
+__global__ void __launch_bounds__(kStitchThreads) stitch_dense_kernel(const float* __restrict__ logits, StitchGrid g,
+                                                                      float* __restrict__ sum_map,
+                                                                      uint32_t* __restrict__ count_map,
+                                                                      uint8_t* __restrict__ argmax_map,
+                                                                      int64_t row_begin, int64_t row_end, int tj_max,
+                                                                      int rows_per_block) {
+    extern __shared__ __align__(16) float smem[];
+    const int n = g.n;
+    const int copy_stride = tj_max * n + 4;             // floats per shifted copy (multiple of 4: tj_max % 4 == 0)
+    float* vals = smem;                                  // [4][copy_stride]
+    uint32_t* cnts = reinterpret_cast<uint32_t*>(smem + 4 * copy_stride);  // [tj_max]
+    uint8_t* amax = reinterpret_cast<uint8_t*>(cnts + tj_max);             // [tj_max]
+
+    const int64_t j0 = (int64_t)blockIdx.x * tj_max;
+    const int tj = (int)((g.dw - j0) < tj_max ? (g.dw - j0) : tj_max);
+    const int64_t i0 = row_begin + (int64_t)blockIdx.y * rows_per_block;
+    const int64_t i1 = (i0 + rows_per_block) < row_end ? (i0 + rows_per_block) : row_end;
+
+    int64_t sig_lo = -2, sig_hi = -2;
+    int sig_last = -1;
+    for (int64_t i = i0; i < i1; ++i) {
+        Cover cy = cover_1d(i, g.ny, g.ps, g.stride, g.d, g.lastrow_cell);
+        if (cy.lo != sig_lo || cy.hi != sig_hi || (int)cy.last != sig_last) {
+            sig_lo = cy.lo; sig_hi = cy.hi; sig_last = (int)cy.last;
+            __syncthreads();  // previous row's readers are done with vals
+            for (int t = threadIdx.x; t < tj; t += blockDim.x) {
+                const int64_t j = j0 + t;
+                Cover cx = cover_1d(j, g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+                const int64_t main_n = g.ny * g.nx;
+                uint32_t cnt = 0;
+                float best = 0.f;
+                int best_c = 0;
+                for (int c = 0; c < n; ++c) {
+                    float acc = 0.f;
+                    for (int64_t gy = cy.lo; gy <= cy.hi; ++gy)
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, __ldg(logits + (gy * g.nx + gx) * n + c));
+                    if (cx.last)
+                        for (int64_t gy = cy.lo; gy <= cy.hi; ++gy) acc = __fadd_rn(acc, __ldg(logits + (main_n + gy) * n + c));
+                    if (cy.last)
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, __ldg(logits + (main_n + g.ny + gx) * n + c));
+                    if (cx.last && cy.last)
+                        for (int64_t k = 0; k <= g.pads; ++k) acc = __fadd_rn(acc, __ldg(logits + (g.N - 1 + k) * n + c));
+                    if (WITH_SUM) {
+#pragma unroll
+                        for (int s = 0; s < 4; ++s) vals[s * copy_stride + s + t * n + c] = acc;
+                    }
+                    if (WITH_ARGMAX) {
+                        // np.argmax: first maximum; a NaN is a maximum
+                        if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; best_c = c; }
+                    }
+                }
+                if (WITH_COUNT) {
+                    int64_t ry = cy.hi >= cy.lo ? cy.hi - cy.lo + 1 : 0;
+                    int64_t rx = cx.hi >= cx.lo ? cx.hi - cx.lo + 1 : 0;
+                    cnt = (uint32_t)(ry * rx + (cx.last ? ry : 0) + (cy.last ? rx : 0) + ((cx.last && cy.last) ? 1 + g.pads : 0));
+                    cnts[t] = cnt;
+                }
+                if (WITH_ARGMAX) amax[t] = (uint8_t)best_c;
+            }
+            __syncthreads();
+        }
+        const int64_t lrow = i - row_begin;  // output pointers start at row_begin
+        if (WITH_SUM) {
+            const int64_t base = (lrow * g.dw + j0) * n;  // float offset of the segment
+            const int len = tj * n;
+            const int s = (int)(base & 3);
+            const float* v = vals + s * copy_stride + s;  // v[f] = value f of the tile, (v + f) 16B-aligned iff (base+f)%4==0
+            int head = (4 - s) & 3;
+            if (head > len) head = len;
+            const int nvec = (len - head) >> 2;
+            float* out = sum_map + base;
+            if ((int)threadIdx.x < head) __stcs(out + threadIdx.x, v[threadIdx.x]);
+            for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
+                const int f = head + 4 * q;
+                float4 val = *reinterpret_cast<const float4*>(v + f);
+                __stcs(reinterpret_cast<float4*>(out + f), val);
+            }
+            const int tail0 = head + 4 * nvec;
+            if ((int)threadIdx.x < len - tail0) __stcs(out + tail0 + threadIdx.x, v[tail0 + threadIdx.x]);
+        }
+        if (WITH_COUNT) {
+            for (int t = threadIdx.x; t < tj; t += blockDim.x) count_map[lrow * g.dw + j0 + t] = cnts[t];
+        }
+        if (WITH_ARGMAX) {
+            for (int t = threadIdx.x; t < tj; t += blockDim.x) argmax_map[lrow * g.dw + j0 + t] = amax[t];
+        }
+    }
+}
+
+// ---- scatter (arbitrary coordinates) ------------------------------------------------------------
+__global__ void __launch_bounds__(256) stitch_scatter_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords,
+                                                             int64_t P, int ps, int d, int n, float* __restrict__ sum_map,
+                                                             uint32_t* __restrict__ count_map, int64_t rows, int64_t dw,
+                                                             int64_t row_offset) {
+    for (int64_t patch = blockIdx.x; patch < P; patch += gridDim.x) {
+        const int y = __ldg(coords + 2 * patch), x = __ldg(coords + 2 * patch + 1);
+        // numpy slice semantics: start/stop clipped to [0, size]
+        int64_t r0 = y / d, r1 = ((int64_t)y + ps) / d, c0 = x / d, c1 = ((int64_t)x + ps) / d;
+        if (y < 0) r0 = 0;  // callers never pass negative origins; keep the footprint inside the map
+        if (x < 0) c0 = 0;
+        if (c1 > dw) c1 = dw;
+        int64_t lo = r0 > row_offset ? r0 : row_offset;
+        int64_t hi = r1 < row_offset + rows ? r1 : row_offset + rows;
+        if (hi <= lo || c1 <= c0) continue;
+        const int fw = (int)(c1 - c0);
+        const int64_t cells = (hi - lo) * fw;
+        const int64_t total = cells * n;
+        const float* lg = logits + patch * n;
+        for (int64_t f = threadIdx.x; f < total; f += blockDim.x) {
+            int64_t cell = f / n;
+            int c = (int)(f - cell * n);
+            int64_t rr = cell / fw;
+            int cc = (int)(cell - rr * fw);
+            int64_t idx = (lo - row_offset + rr) * dw + c0 + cc;
+            if (sum_map) atomicAdd(sum_map + idx * n + c, __ldg(lg + c));
+            if (count_map && c == 0) atomicAdd(count_map + idx, 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) stitch_finalize_kernel(const float* __restrict__ sum_map, const uint32_t* __restrict__ count_map,
+                                                              int64_t cells, int n, float* __restrict__ norm_map,
+                                                              uint8_t* __restrict__ argmax_map) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+        float cntf = 1.f;
+        if (count_map) { uint32_t c = count_map[i]; cntf = c ? (float)c : 1.f; }
+        float best = 0.f;
+        int best_c = 0;
+        for (int c = 0; c < n; ++c) {
+            float v = sum_map[i * n + c];
+            if (norm_map) norm_map[i * n + c] = __fdiv_rn(v, cntf);
+            if (c == 0 || v > best || (v != v && best == best)) { best = v; best_c = c; }
+        }
+        if (argmax_map) argmax_map[i] = (uint8_t)best_c;
+    }
+}
+
+static int make_stitch_grid(int64_t H, int64_t W, int ps, int stride, int d, int n, int batch_size, StitchGrid* g) {
+    DH_REQUIRE(ps > 0 && stride > 0 && d > 0, "stitch: ps, stride and downscale must be positive");
+    DH_REQUIRE(n > 0 && n <= 64, "stitch: n classes %d outside 1..64", n);
+    DH_REQUIRE(H >= ps && W >= ps, "stitch: slide smaller than a patch");
+    g->H = H; g->W = W; g->ps = ps; g->stride = stride; g->d = d; g->n = n;
+    g->ny = (H - ps) <= 0 ? 0 : (H - ps + stride - 1) / stride;
+    g->nx = (W - ps) <= 0 ? 0 : (W - ps + stride - 1) / stride;
+    g->N = g->ny * g->nx + g->ny + g->nx + 1;
+    int64_t npad = batch_size > 0 ? (g->N + batch_size - 1) / batch_size * batch_size : g->N;
+    g->pads = npad - g->N;
+    g->dh = H / d; g->dw = W / d;
+    g->lastrow_cell = (H - ps) / d;
+    g->lastcol_cell = (W - ps) / d;
+    return DH_OK;
+}
+
+}  // namespace dh
+
+using namespace dh;
+
+extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t W, int ps, int stride, int d, int n,
+                                  int batch_size, float* sum_map, uint32_t* count_map, uint8_t* argmax_u8,
+                                  int64_t row_begin, int64_t row_end, void* stream) {
+    StitchGrid g;
+    int rc = make_stitch_grid(H, W, ps, stride, d, n, batch_size, &g);
+    if (rc != DH_OK) return rc;
+    DH_REQUIRE(logits, "dh_stitch_dense: null logits");
+    DH_REQUIRE(sum_map || argmax_u8 || count_map, "dh_stitch_dense: no output requested");
+    DH_REQUIRE(row_begin >= 0 && row_begin <= row_end && row_end <= g.dh, "dh_stitch_dense: rows [%lld,%lld) outside map of %lld rows",
+               (long long)row_begin, (long long)row_end, (long long)g.dh);
+    DH_REQUIRE(!sum_map || reinterpret_cast<uintptr_t>(sum_map) % 16 == 0, "dh_stitch_dense: sum_map must be 16-byte aligned");
+    DH_REQUIRE(!argmax_u8 || n <= 256, "dh_stitch_dense: argmax_u8 needs n <= 256");
+    if (row_end == row_begin || g.dw == 0) return DH_OK;
+    int tj = 2048 / n;
+    tj = tj / 32 * 32;
+    if (tj > 256) tj = 256;
+    if (tj < 32) tj = 32;
+    const int64_t rows = row_end - row_begin;
+    const int64_t col_tiles = (g.dw + tj - 1) / tj;
+    // enough row groups to fill the machine a few times over, but long enough to reuse a row class
+    int rpb = 32;
+    while (rpb > 4 && col_tiles * ((rows + rpb - 1) / rpb) < (int64_t)kNumSMs * 8) rpb >>= 1;
+    const int64_t row_groups = (rows + rpb - 1) / rpb;
+    DH_REQUIRE(row_groups <= 65535, "dh_stitch_dense: too many row groups (%lld); stitch in bands", (long long)row_groups);
+    dim3 grid((unsigned)col_tiles, (unsigned)row_groups);
+    size_t smem = (size_t)(4 * (tj * n + 4)) * sizeof(float) + (size_t)tj * sizeof(uint32_t) + (size_t)tj;
+    cudaStream_t st = as_stream(stream);
+#define DH_ST(S, A, C) stitch_dense_kernel<S, A, C><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, rpb)
+    const bool s = sum_map != nullptr, a = argmax_u8 != nullptr, c = count_map != nullptr;
+    if (s) { if (a) { if (c) DH_ST(true, true, true); else DH_ST(true, true, false); } else { if (c) DH_ST(true, false, true); else DH_ST(true, false, false); } }
+    else   { if (a) { if (c) DH_ST(false, true, true); else DH_ST(false, true, false); } else { DH_ST(false, false, true); } }
+#undef DH_ST
+    DH_CHECK_LAUNCH("stitch_dense_kernel");
+    return DH_OK;
+}
+
+extern "C" DH_API int dh_stitch_dense(const float* logits, int64_t H, int64_t W, int ps, int stride, int d, int n, int batch_size,
+                               float* sum_map, uint32_t* count_map, int64_t row_begin, int64_t row_end, void* stream) {
+    return dh_stitch_dense_ex(logits, H, W, ps, stride, d, n, batch_size, sum_map, count_map, nullptr, row_begin, row_end, stream);
+}
+
+extern "C" DH_API int dh_stitch_scatter(const float* logits, const int32_t* coords, int64_t P, int ps, int d, int n, float* sum_map,
+                                 uint32_t* count_map, int64_t rows, int64_t dw, int64_t row_offset, void* stream) {
+    DH_REQUIRE(logits && coords, "dh_stitch_scatter: null input");
+    DH_REQUIRE(sum_map || count_map, "dh_stitch_scatter: no output requested");
+    DH_REQUIRE(ps > 0 && d > 0 && n > 0 && rows >= 0 && dw >= 0 && P >= 0 && row_offset >= 0, "dh_stitch_scatter: bad sizes");
+    if (P == 0 || rows == 0 || dw == 0) return DH_OK;
+    int grid = (int)(P < (int64_t)kNumSMs * 8 ? P : (int64_t)kNumSMs * 8);
+    stitch_scatter_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, coords, P, ps, d, n, sum_map, count_map, rows, dw, row_offset);
+    DH_CHECK_LAUNCH("stitch_scatter_kernel");
+    return DH_OK;
+}
+
+extern "C" DH_API int dh_stitch_finalize(const float* sum_map, const uint32_t* count_map, int64_t cells, int n, float* norm_map,
+                                  uint8_t* argmax_u8, void* stream) {
+    DH_REQUIRE(sum_map, "dh_stitch_finalize: null sum map");
+    DH_REQUIRE(norm_map || argmax_u8, "dh_stitch_finalize: no output requested");
+    DH_REQUIRE(cells >= 0 && n > 0 && n <= 256, "dh_stitch_finalize: bad sizes");
+    if (cells == 0) return DH_OK;
+    int64_t blocks = (cells + 255) / 256;
+    int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
+    stitch_finalize_kernel<<<grid, 256, 0, as_stream(stream)>>>(sum_map, count_map, cells, n, norm_map, argmax_u8);
+    DH_CHECK_LAUNCH("stitch_finalize_kernel");
+    return DH_OK;
+}

@@ -1,0 +1,284 @@
+"""Torch-tensor level wrappers over the C-ABI (device memory and streams come from torch; all
+arithmetic happens in the hand-written sm_100a kernels of libdeephisto_b200.so)."""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DH_BF16, DH_F32, DH_NCHW, DH_NHWC, DH_U8, check
+
+_DTYPES = {torch.float32: DH_F32, torch.bfloat16: DH_BF16, torch.uint8: DH_U8}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=None) -> None:
+    if not t.is_cuda:
+        raise _lib.DeepHistoError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+class DeviceSlide:
+    """uint8 RGB slide layer resident in HBM: rows of `pitch` bytes (pitch % 16 == 0), 3*W used."""
+
+    def __init__(self, storage: torch.Tensor, H: int, W: int, pitch: int):
+        _need_cuda(storage, "slide storage", torch.uint8)
+        if storage.numel() < H * pitch:
+            raise ValueError("slide storage smaller than H * pitch")
+        self.storage, self.H, self.W, self.pitch = storage, int(H), int(W), int(pitch)
+
+    @staticmethod
+    def pitch_for(W: int) -> int:
+        return (3 * W + 15) // 16 * 16
+
+    @classmethod
+    def empty(cls, H: int, W: int, device="cuda") -> "DeviceSlide":
+        pitch = cls.pitch_for(W)
+        return cls(torch.empty(H * pitch, dtype=torch.uint8, device=device), H, W, pitch)
+
+    @classmethod
+    def from_numpy(cls, arr: np.ndarray, device="cuda") -> "DeviceSlide":
+        if arr.ndim != 3 or arr.shape[2] != 3 or arr.dtype != np.uint8:
+            raise ValueError("slide must be uint8 [H, W, 3]")
+        H, W, _ = arr.shape
+        s = cls.empty(H, W, device)
+        src = torch.from_numpy(np.ascontiguousarray(arr)).view(H, 3 * W)
+        s.storage.view(H, s.pitch)[:, : 3 * W].copy_(src, non_blocking=False)
+        return s
+
+    @classmethod
+    def synthetic(cls, H: int, W: int, seed: int = 0, device="cuda") -> "DeviceSlide":
+        """Counter-hash slide generated on the device (oracle/synth.py restates the bytes)."""
+        lib = _lib.require_device()
+        s = cls.empty(H, W, device)
+        with torch.cuda.device(s.storage.device):
+            check(lib.dh_synth_slide(s.storage.data_ptr(), H, W, s.pitch, seed, _stream()), "dh_synth_slide")
+        return s
+
+    def to_numpy(self) -> np.ndarray:
+        return self.storage.view(self.H, self.pitch)[:, : 3 * self.W].cpu().numpy().reshape(self.H, self.W, 3)
+
+    @property
+    def device(self):
+        return self.storage.device
+
+
+def dense_count(H: int, W: int, ps: int, stride: int, batch_size: int) -> tuple[int, int]:
+    """(N, N padded to a multiple of batch_size) of full_samplers.py:374-404."""
+    lib = _lib.load()
+    npad = C.c_int64(0)
+    n = lib.dh_dense_count(H, W, ps, stride, batch_size, C.byref(npad))
+    if n < 0:
+        raise ValueError(f"dh_dense_count: {_lib.last_error()}")
+    return int(n), int(npad.value)
+
+
+def dense_coords(H: int, W: int, ps: int, stride: int, batch_size: int, first: int = 0, count: Optional[int] = None,
+                 device="cuda") -> torch.Tensor:
+    """int32 [count, 2] (y, x) of the padded dense enumeration, generated on the device."""
+    lib = _lib.require_device()
+    n, npad = dense_count(H, W, ps, stride, batch_size)
+    if count is None:
+        count = npad - first
+    out = torch.empty((count, 2), dtype=torch.int32, device=device)
+    with torch.cuda.device(out.device):
+        check(lib.dh_dense_coords(H, W, ps, stride, batch_size, first, count, out.data_ptr(), _stream()), "dh_dense_coords")
+    return out
+
+
+def gather_normalize(slide: DeviceSlide, coords: torch.Tensor, ps: int, *, dtype=torch.float32, layout: str = "NHWC",
+                     scale255: bool = True, mean: Optional[Sequence[float]] = None, std: Optional[Sequence[float]] = None,
+                     flip: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                     out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Patches at int32 `coords` [B,2] (y,x) -> [B,ps,ps,3] (NHWC) or [B,3,ps,ps] (NCHW)."""
+    lib = _lib.require_device()
+    _need_cuda(coords, "coords", torch.int32)
+    if coords.ndim != 2 or coords.shape[1] != 2:
+        raise ValueError("coords must be [B, 2]")
+    B = coords.shape[0]
+    lay = {"NHWC": DH_NHWC, "NCHW": DH_NCHW}[layout]
+    shape = (B, ps, ps, 3) if lay == DH_NHWC else (B, 3, ps, ps)
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=coords.device)
+    else:
+        _need_cuda(out, "out", dtype)
+        if out_index is None and tuple(out.shape) != shape:
+            raise ValueError(f"out must have shape {shape}")
+    if flip is not None:
+        _need_cuda(flip, "flip", torch.uint8)
+    if out_index is not None:
+        _need_cuda(out_index, "out_index", torch.int32)
+    m = s = None
+    if mean is not None or std is not None:
+        m = (C.c_float * 3)(*(mean if mean is not None else (0.0, 0.0, 0.0)))
+        s = (C.c_float * 3)(*(std if std is not None else (1.0, 1.0, 1.0)))
+    with torch.cuda.device(coords.device):
+        check(
+            lib.dh_gather_normalize(slide.storage.data_ptr(), slide.H, slide.W, slide.pitch, coords.data_ptr(), _ptr(out_index), B,
+                                    ps, out.data_ptr(), _DTYPES[dtype], lay, int(bool(scale255)), m, s, _ptr(flip), _stream()),
+            "dh_gather_normalize",
+        )
+    return out
+
+
+def stitch_dense(logits: torch.Tensor, H: int, W: int, ps: int, stride: int, d: int, batch_size: int, *, row_begin: int = 0,
+                 row_end: Optional[int] = None, want_sum: bool = True, want_count: bool = False, want_argmax: bool = False):
+    """Deterministic stitch of dense-sampler logits [Npad, n] -> (sum [rows,dw,n] f32, count u32, argmax u8)."""
+    lib = _lib.require_device()
+    _need_cuda(logits, "logits", torch.float32)
+    n = logits.shape[1]
+    dh, dw = H // d, W // d
+    if row_end is None:
+        row_end = dh
+    rows = row_end - row_begin
+    N, npad = dense_count(H, W, ps, stride, batch_size)
+    if logits.shape[0] < npad:
+        raise ValueError(f"logits has {logits.shape[0]} rows, the padded enumeration needs {npad}")
+    dev = logits.device
+    sum_map = torch.empty((rows, dw, n), dtype=torch.float32, device=dev) if want_sum else None
+    cnt = torch.empty((rows, dw), dtype=torch.int32, device=dev) if want_count else None
+    amax = torch.empty((rows, dw), dtype=torch.uint8, device=dev) if want_argmax else None
+    with torch.cuda.device(dev):
+        check(
+            lib.dh_stitch_dense_ex(logits.data_ptr(), H, W, ps, stride, d, n, batch_size, _ptr(sum_map), _ptr(cnt), _ptr(amax), row_begin,
+                                   row_end, _stream()),
+            "dh_stitch_dense_ex",
+        )
+    return sum_map, cnt, amax
+
+
+def stitch_scatter(logits: torch.Tensor, coords: torch.Tensor, ps: int, d: int, sum_map: Optional[torch.Tensor],
+                   count_map: Optional[torch.Tensor], row_offset: int = 0) -> None:
+    """Accumulate logits [P,n] of patches at int32 coords [P,2] into sum_map [rows,dw,n] / count_map [rows,dw] (atomics)."""
+    lib = _lib.require_device()
+    _need_cuda(logits, "logits", torch.float32)
+    _need_cuda(coords, "coords", torch.int32)
+    ref = sum_map if sum_map is not None else count_map
+    if sum_map is not None:
+        _need_cuda(sum_map, "sum_map", torch.float32)
+    if count_map is not None:
+        _need_cuda(count_map, "count_map", torch.int32)
+    rows, dw = ref.shape[0], ref.shape[1]
+    with torch.cuda.device(logits.device):
+        check(
+            lib.dh_stitch_scatter(logits.data_ptr(), coords.data_ptr(), logits.shape[0], ps, d, logits.shape[1], _ptr(sum_map),
+                                  _ptr(count_map), rows, dw, row_offset, _stream()),
+            "dh_stitch_scatter",
+        )
+
+
+def stitch_finalize(sum_map: torch.Tensor, count_map: Optional[torch.Tensor] = None, *, want_norm: bool = False,
+                    want_argmax: bool = True):
+    lib = _lib.require_device()
+    _need_cuda(sum_map, "sum_map", torch.float32)
+    n = sum_map.shape[-1]
+    cells = sum_map.numel() // n
+    norm = torch.empty_like(sum_map) if want_norm else None
+    amax = torch.empty(sum_map.shape[:-1], dtype=torch.uint8, device=sum_map.device) if want_argmax else None
+    with torch.cuda.device(sum_map.device):
+        check(lib.dh_stitch_finalize(sum_map.data_ptr(), _ptr(count_map), cells, n, _ptr(norm), _ptr(amax), _stream()),
+              "dh_stitch_finalize")
+    return norm, amax
+
+
+class CoverState:
+    """Device state of the coverage-driven random sampler (accumulator + scratch)."""
+
+    def __init__(self, H: int, W: int, ps: int, speedup: int, dense_level: int, batch_size: int, seed: int, device="cuda"):
+        lib = _lib.require_device()
+        self.H, self.W, self.ps, self.speedup, self.dense_level, self.B, self.seed = H, W, ps, speedup, dense_level, batch_size, seed
+        self.dh, self.dw = H // speedup, W // speedup
+        self.accum = torch.zeros((self.dh, self.dw), dtype=torch.int32, device=device)
+        self.scratch = torch.empty(int(lib.dh_cover_scratch_words(self.dh, self.dw)), dtype=torch.int32, device=device)
+        self.nonzero = torch.zeros(1, dtype=torch.int32, device=device)
+        self.batch_index = 0
+
+    def next_coords(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """One batch: int32 coords [B,2] and the device counter of non-zero accumulator cells."""
+        lib = _lib.require_device()
+        coords = torch.empty((self.B, 2), dtype=torch.int32, device=self.accum.device)
+        with torch.cuda.device(self.accum.device):
+            check(
+                lib.dh_cover_sample(self.accum.data_ptr(), self.dh, self.dw, self.H, self.W, self.ps, self.speedup, self.dense_level, self.B,
+                                    self.seed, self.batch_index, coords.data_ptr(), self.nonzero.data_ptr(), self.scratch.data_ptr(),
+                                    _stream()),
+                "dh_cover_sample",
+            )
+        self.batch_index += 1
+        return coords, self.nonzero
+
+
+def region_accept_dense(edges: torch.Tensor, edge_begin: int, edge_end: int, y0: int, x0: int, ny: int, nx: int, stride: int,
+                        ps: int, threshold: float, want_area: bool = False):
+    """Acceptance mask u8 [ny*nx] (+ float64 clip areas) for the candidate grid of one region."""
+    lib = _lib.require_device()
+    _need_cuda(edges, "edges", torch.float64)
+    mask = torch.empty(max(ny * nx, 0), dtype=torch.uint8, device=edges.device)
+    area = torch.empty(max(ny * nx, 0), dtype=torch.float64, device=edges.device) if want_area else None
+    with torch.cuda.device(edges.device):
+        check(lib.dh_region_accept_dense(edges.data_ptr(), edge_begin, edge_end, y0, x0, ny, nx, stride, ps, float(threshold),
+                                         mask.data_ptr(), _ptr(area), _stream()), "dh_region_accept_dense")
+    return mask, area
+
+
+def compact_coords(mask: torch.Tensor, y0: int, x0: int, ny: int, nx: int, stride: int) -> torch.Tensor:
+    """Accepted candidates in row-major order as int32 [n,2] (one small D2H sync for n)."""
+    lib = _lib.require_device()
+    _need_cuda(mask, "mask", torch.uint8)
+    coords = torch.empty((max(ny * nx, 1), 2), dtype=torch.int32, device=mask.device)
+    n_out = torch.zeros(1, dtype=torch.int32, device=mask.device)
+    if ny * nx == 0:
+        return coords[:0]
+    with torch.cuda.device(mask.device):
+        check(lib.dh_compact_coords(mask.data_ptr(), y0, x0, ny, nx, stride, coords.data_ptr(), n_out.data_ptr(), _stream()),
+              "dh_compact_coords")
+    return coords[: int(n_out.item())]
+
+
+def region_sample(tables: "_lib.RegionTables", n_slots: int, k: int, ps: int, threshold: float, *, miss_limit: int = 500,
+                  max_redraw: int = 64, fixed_class: int = -1, slots_per_table_draw: int = 1, seed: int = 0, slot_offset: int = 0,
+                  device="cuda", out=None):
+    """Random region sampling: (coords int32 [S,2], labels int64 [S], images int32 [S], status u8 [S])."""
+    lib = _lib.require_device()
+    if out is None:
+        coords = torch.empty((n_slots, 2), dtype=torch.int32, device=device)
+        labels = torch.empty(n_slots, dtype=torch.int64, device=device)
+        images = torch.empty(n_slots, dtype=torch.int32, device=device)
+        status = torch.empty(n_slots, dtype=torch.uint8, device=device)
+    else:
+        coords, labels, images, status = out
+    with torch.cuda.device(coords.device):
+        check(
+            lib.dh_region_sample(C.byref(tables), n_slots, k, ps, float(threshold), miss_limit, max_redraw, fixed_class,
+                                 slots_per_table_draw, seed, slot_offset, coords.data_ptr(), labels.data_ptr(), images.data_ptr(),
+                                 status.data_ptr(), _stream()),
+            "dh_region_sample",
+        )
+    return coords, labels, images, status
+
+
+def rasterize_polygons(edges: torch.Tensor, edge_off: torch.Tensor, reg_bbox: torch.Tensor, scale: float, mh: int, mw: int) -> torch.Tensor:
+    """int32 [mh, mw] label map: 1 + index of the last polygon containing the pixel centre, 0 = background."""
+    lib = _lib.require_device()
+    _need_cuda(edges, "edges", torch.float64)
+    _need_cuda(edge_off, "edge_off", torch.int32)
+    _need_cuda(reg_bbox, "reg_bbox", torch.float64)
+    out = torch.empty((mh, mw), dtype=torch.int32, device=edges.device)
+    with torch.cuda.device(edges.device):
+        check(lib.dh_rasterize_polygons(edges.data_ptr(), edge_off.data_ptr(), reg_bbox.data_ptr(), edge_off.numel() - 1, float(scale),
+                                        out.data_ptr(), mh, mw, _stream()), "dh_rasterize_polygons")
+    return out

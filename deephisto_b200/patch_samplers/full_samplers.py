@@ -1,0 +1,178 @@
+"""Whole-slide samplers -- drop-in for the reference's `patch_samplers/full_samplers.py`.
+
+Same class names, constructor arguments, iterator protocol and yielded shapes as the reference
+(FullImageRndSampler full_samplers.py:21-299, FullImageDenseSampler :302-452); the work is done by the
+sm_100a kernels of libdeephisto_b200.so on a slide that is uploaded to HBM once:
+  coordinates   dh_dense_coords (:374-404) / dh_cover_sample (:81-162)
+  pixels        dh_gather_normalize (:187-202, :353-369, :437-452)
+`generator_torch()` yields CUDA tensors (the reference yields CPU tensors that the caller moves to the
+device, predict_full_patched.py:70, train.py:166). `generator()` / `__iter__` still yield `list[Patch]`
+with numpy uint8 data, materialised lazily with one device->host copy per batch.
+Both `SamplerExecutionMode`s run the same HBM-resident path; the reference's ProcessPool / shared-memory
+machinery (:57-60,229-261,406-423) has no equivalent here and no worker processes are created."""
+
+from __future__ import annotations
+
+from enum import Enum
+from pathlib import Path
+from typing import Iterable, Iterator
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..slide import Patch, layer_to_device, open_slide
+
+
+class SamplerExecutionMode(Enum):
+    INMEMORY_SINGLEPROC = 1
+    ONDISK_MULTIPROC = 2
+
+
+def _patches_from_device(slide, coords_dev: torch.Tensor, layer: int, ps: int) -> list[Patch]:
+    """list[Patch] with uint8 [ps,ps,3] numpy data for int32 device coords (one D2H copy)."""
+    raw = ops.gather_normalize(slide, coords_dev, ps, dtype=torch.uint8, layout="NHWC")
+    data = raw.cpu().numpy()
+    yx = coords_dev.cpu().numpy()
+    return [Patch(layer=layer, pos_x=int(x), pos_y=int(y), patch_size=ps, data=data[i]) for i, (y, x) in enumerate(yx.tolist())]
+
+
+class FullImageRndSampler:
+    """Coverage-driven random sampling until every coarse (1/speedup) cell is covered (full_samplers.py:21-299).
+
+    Extra keyword-only arguments (not in the reference): `seed` (Philox key; the reference uses the unseeded
+    global numpy RNG), `device`."""
+
+    def __init__(self, psimage_path: Path, layer: int, patch_size: int, batch_size: int, mode: SamplerExecutionMode,
+                 dense_level: int = 2, speedup: int = 16, *, seed: int = 0, device="cuda"):
+        self.mode = mode
+        self._psim_path = psimage_path
+        src = open_slide(psimage_path)
+        with src as psim:
+            self.layer = layer
+            psim._assert_layer(layer)
+            self.h, self.w = psim.layer_size(self.layer)
+            self._slide = layer_to_device(psim, layer, device)
+        self.dh = self.h // speedup
+        self.dw = self.w // speedup
+        print(f"Image {self.h} x {self.w} at {speedup}x -> {self.dh} x {self.dw}")
+        self.patch_size = patch_size
+        self.batch_size = batch_size
+        self._downscale = speedup
+        self.dense_level = dense_level
+        self._filled_ratio: list[float] = []
+        self._seed = seed
+        self._device = device
+        self._state: ops.CoverState | None = None
+
+    # -- device-side iteration ------------------------------------------------------------------------
+    def coords_generator(self) -> Iterator[tuple[torch.Tensor, float]]:
+        """(int32 device coords [B,2], filled_ratio) per batch until filled_ratio >= 1 (:263-274)."""
+        self._state = ops.CoverState(self.h, self.w, self.patch_size, self._downscale, self.dense_level, self.batch_size,
+                                     self._seed, self._device)
+        cells = self.dh * self.dw
+        filled_ratio = 0.0
+        while filled_ratio < 1:
+            coords, nonzero = self._state.next_coords()
+            filled_ratio = int(nonzero.item()) / cells
+            self._filled_ratio.append(filled_ratio)
+            yield coords, filled_ratio
+
+    def generator(self) -> Iterator[tuple[list[Patch], float]]:
+        for coords, filled_ratio in self.coords_generator():
+            yield _patches_from_device(self._slide, coords, self.layer, self.patch_size), filled_ratio
+
+    def __iter__(self) -> Iterator[tuple[list[Patch], float]]:
+        return self.generator()
+
+    def generator_torch(self, normalize: bool = False, dtype=torch.float32,
+                        layout: str = "NHWC") -> Iterator[tuple[torch.Tensor, torch.Tensor, float]]:
+        """features [B,ps,ps,3] float32 with values 0..255 -- the reference does NOT divide by 255 here
+        (:286); pass normalize=True for [0,1]. coords float32 [B,2] (y, x)."""
+        for coords, filled_ratio in self.coords_generator():
+            features = ops.gather_normalize(self._slide, coords, self.patch_size, dtype=dtype, layout=layout, scale255=normalize)
+            yield features, coords.to(torch.float32), filled_ratio
+
+    # -- reporting helpers of the reference -------------------------------------------------------------
+    @property
+    def _accum(self):
+        return None if self._state is None else self._state.accum.cpu().numpy().astype(np.float32)
+
+    def plot_empty_area_history(self, filename: str):
+        try:
+            import matplotlib.pyplot as plt
+        except ImportError as e:
+            raise RuntimeError("plot_empty_area_history needs matplotlib") from e
+        plt.plot(self._filled_ratio)
+        plt.title("Empty area")
+        plt.xlabel("iteration")
+        plt.ylabel("empty area percentage")
+        plt.savefig(filename, format="jpg", dpi=300)
+
+    def visualize_heatmap(self, name: str):
+        from PIL import Image
+
+        acc = self._accum
+        if acc is not None:
+            a = (acc / np.max(acc) * 255).astype(np.uint8)
+            Image.fromarray(a).save(name)
+            a = np.where(a > 0, 255, 0).astype(np.uint8)
+            Image.fromarray(a).save("_" + name, quality=98)
+
+
+class FullImageDenseSampler:
+    """Dense grid + last column / row / corner, batched, last batch padded with the corner (:302-452).
+
+    `stride=None` means stride = patch_size (the reference would raise a TypeError in `range`)."""
+
+    def __init__(self, psimage_path: Path, layer: int, patch_size: int, batch_size: int, mode: SamplerExecutionMode,
+                 stride: int = None, *, device="cuda"):
+        self._psim_path = psimage_path
+        self.mode = mode
+        src = open_slide(psimage_path)
+        with src as psim:
+            self.layer = layer
+            psim._assert_layer(layer)
+            self.h, self.w = psim.layer_size(self.layer)
+            self._slide = layer_to_device(psim, layer, device)
+        self.patch_size = patch_size
+        self.batch_size = batch_size
+        self.stride = patch_size if stride is None else stride
+        self._device = device
+        print(f"Image {self.h} x {self.w}")
+        self.n_patches, self.n_padded = ops.dense_count(self.h, self.w, self.patch_size, self.stride, self.batch_size)
+
+    def __len__(self) -> int:
+        return self.n_padded // self.batch_size
+
+    def coords_device(self) -> torch.Tensor:
+        """int32 [n_padded, 2] device tensor of all (y, x) in reference order, padding included."""
+        return ops.dense_coords(self.h, self.w, self.patch_size, self.stride, self.batch_size, device=self._device)
+
+    def _create_batched_coords(self) -> list[list[tuple[int, int]]]:
+        """Same return value as the reference's method (:374-404), produced by the device enumeration."""
+        c = self.coords_device().cpu().numpy().tolist()
+        b = self.batch_size
+        return [[(y, x) for y, x in c[i : i + b]] for i in range(0, len(c), b)]
+
+    def coords_generator(self) -> Iterator[tuple[torch.Tensor, float]]:
+        coords = self.coords_device()
+        n_batches = len(self)
+        for i in range(n_batches):
+            yield coords[i * self.batch_size : (i + 1) * self.batch_size], i / n_batches
+
+    def generator(self) -> Iterable[tuple[list[Patch], float]]:
+        for coords, progress in self.coords_generator():
+            yield _patches_from_device(self._slide, coords, self.layer, self.patch_size), progress
+
+    def __iter__(self) -> Iterable[tuple[list[Patch], float]]:
+        return self.generator()
+
+    def generator_torch(self, dtype=torch.float32, layout: str = "NHWC", mean=None,
+                        std=None) -> Iterator[tuple[torch.Tensor, torch.Tensor, float]]:
+        """features [B,ps,ps,3] float32 in [0,1] (bit-identical to `.astype(float32) / 255`, :441-443),
+        coords float32 [B,2] (y, x), progress i / n_batches (never reaches 1.0, like the reference)."""
+        for coords, progress in self.coords_generator():
+            features = ops.gather_normalize(self._slide, coords, self.patch_size, dtype=dtype, layout=layout, scale255=True,
+                                            mean=mean, std=std)
+            yield features, coords.to(torch.float32), progress

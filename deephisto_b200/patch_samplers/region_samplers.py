@@ -1,0 +1,384 @@
+"""Annotation-driven samplers -- drop-in for the reference's `patch_samplers/region_samplers.py`.
+
+Same classes and call signatures as the reference (RegionAnnotation :18-191, AnnoRegionRndSampler :252-796,
+AnnoRegionDenseSampler :799-871, extract_and_save_subset :874-909). Differences, all deliberate:
+  * polygons are packed once into device tables (deephisto_b200/geometry.py); candidate generation,
+    the exact clip-area acceptance test and the patch gather run in sm_100a kernels;
+  * randomness is Philox4x32-10 keyed by `seed` (keyword argument, default 0) with documented counters, not the
+    unseeded global numpy RNG; `max_workers` / `batches_per_worker` are accepted, and no worker process is ever
+    spawned (the reference's mp.set_start_method("spawn", force=True), :314-323, is dropped -- SURVEY Q12);
+  * `torch_generator` yields CUDA tensors;
+  * random origins are clamped so that patches never overhang the slide; `cls_idx=0` means class 0,
+    not "any class" (Q5); `torch_iterable_dataset` yields (y, x), not (y, y) (Q6);
+  * invalid (self-intersecting) polygons are skipped and counted as failed regions: shapely's buffer(0) repair
+    (:69-71) needs GEOS."""
+
+from __future__ import annotations
+
+import json
+from collections import defaultdict
+from pathlib import Path
+from typing import Iterator
+
+import numpy as np
+import torch
+from torch.utils.data import IterableDataset
+
+from .. import geometry, ops
+from ..slide import Patch, layer_to_device, open_slide
+
+
+class RegionAnnotation:
+    """One annotated polygon (reference :18-191). `polygon` is replaced by `vertices_scaled` + an edge table."""
+
+    def __init__(self, img_path: Path, region_idx: int, class_: str, vertices: np.ndarray, layer: int,
+                 layer_size: tuple[int, int], *, image_index: int = 0, seed: int = 0, device="cuda"):
+        self.file_path = img_path
+        self.region_idx = region_idx
+        self.class_ = class_
+        self.vertices = vertices
+        self._layer = layer
+        self._layer_size = layer_size
+        self._region = geometry.make_region(image_index, region_idx, class_, vertices, layer)  # raises like :64-67
+        self.area = self._region.area
+        self.bounds = self._region.bounds
+        self._seed, self._device, self._calls = seed, device, 0
+        self._edges_dev = None
+        self._tables = None
+
+    def __str__(self) -> str:
+        stem = Path(self.file_path).stem if isinstance(self.file_path, (str, Path)) else type(self.file_path).__name__
+        return f"Region [{stem}, {self.region_idx}, {self.class_}, {self.vertices.shape}, {round(self.area, 0)}]"
+
+    def _edges(self) -> torch.Tensor:
+        if self._edges_dev is None:
+            self._edges_dev = torch.from_numpy(self._region.edges.reshape(-1)).to(self._device)
+        return self._edges_dev
+
+    def _extract_patch_coords_rnd(self, patch_size: int, n_patches: int, region_intersection: float = 0.75,
+                                  miss_limit: int = 500) -> list[tuple[int, int]]:
+        """Reference :82-143. Raises RuntimeError("Region is too small.") / ("Miss limit reached...") alike."""
+        ps = patch_size
+        thr = ps * ps * region_intersection
+        if self.area < thr:
+            raise RuntimeError("Region is too small.")
+        if self._tables is None:
+            reg = self._region
+            one = geometry.Region(0, reg.region_idx, reg.class_, reg.vertices, reg.area, reg.bounds, reg.edges)
+            self._tables = geometry.RegionTables([one], [reg.class_], [tuple(self._layer_size)], [{reg.class_: [0]}], np.ones(1), 0.0,
+                                                 device=self._device)
+        offset = self._calls * (1 << 20)
+        self._calls += 1
+        coords, _, _, status = ops.region_sample(self._tables.struct, n_patches, 1, ps, thr, miss_limit=miss_limit, max_redraw=1,
+                                                 seed=self._seed ^ (self.region_idx << 32), slot_offset=offset, device=self._device)
+        st = status.cpu().numpy()
+        if (st != 0).any():
+            raise RuntimeError("Miss limit reached. Probably region is too small.")
+        return [(int(y), int(x)) for y, x in coords.cpu().numpy().tolist()]
+
+    def _dense_grid(self, patch_size: int, stride: int):
+        """Candidate grid of reference :171-179 (Python round = banker's rounding; upper clamps only)."""
+        h, w = self._layer_size
+        x0, y0, x1, y1 = self.bounds
+        x0, y0, x1, y1 = round(x0), round(y0), round(x1), round(y1)
+        x1 = min(x1, w - patch_size)
+        y1 = min(y1, h - patch_size)
+        return y0, x0, len(range(y0, y1, stride)), len(range(x0, x1, stride))
+
+    def _extract_patch_coords_dense_device(self, patch_size: int, stride: int, region_intersection: float = 0.75) -> torch.Tensor:
+        y0, x0, ny, nx = self._dense_grid(patch_size, stride)
+        if ny == 0 or nx == 0:
+            return torch.zeros((0, 2), dtype=torch.int32, device=self._device)
+        e = self._edges()
+        mask, _ = ops.region_accept_dense(e, 0, len(self._region.edges), y0, x0, ny, nx, stride, patch_size,
+                                          patch_size * patch_size * region_intersection)
+        return ops.compact_coords(mask, y0, x0, ny, nx, stride)
+
+    def _extract_patch_coords_dense(self, patch_size: int, stride: int, region_intersection: float = 0.75) -> list[tuple[int, int]]:
+        """Reference :145-191: accepted (y, x) in row-major order."""
+        c = self._extract_patch_coords_dense_device(patch_size, stride, region_intersection)
+        return [(int(y), int(x)) for y, x in c.cpu().numpy().tolist()]
+
+
+def _load_annotation(anno) -> list[dict]:
+    if isinstance(anno, (str, Path)):
+        with open(anno) as f:
+            return json.load(f)
+    return list(anno)
+
+
+def _parse_annotations(img_anno_paths, layer: int, classes: list[str] = None, *, seed: int = 0, device="cuda", verbose: bool = True):
+    """Reference :194-249. Returns (regions_all, regions_per_image, layer sizes, opened slide sources)."""
+    regions_all = defaultdict(list)
+    regions_per_image = [defaultdict(list) for _ in img_anno_paths]
+    sizes, sources = [], []
+    regions_failed = 0
+    for j, (psim_path, anno_path) in enumerate(img_anno_paths):
+        src = open_slide(psim_path)
+        sources.append(src)
+        with src as psim:
+            size = tuple(psim.layer_size(layer))
+            sizes.append(size)
+            for i, a in enumerate(_load_annotation(anno_path)):
+                cls = a["class"]
+                if classes is not None and cls not in classes:
+                    continue
+                try:
+                    reg = RegionAnnotation(img_path=psim_path, region_idx=i, class_=cls, vertices=np.array(a["vertices"], dtype=np.float64),
+                                           layer=layer, layer_size=size, image_index=j, seed=seed, device=device)
+                    regions_per_image[j][cls].append(reg)
+                    regions_all[cls].append(reg)
+                except Exception:
+                    regions_failed += 1
+    if verbose:
+        if regions_failed > 0:
+            print(f"Failed to parse {regions_failed} regions.")
+        print(f"regions all: { {cls: len(r) for cls, r in regions_all.items()} }")
+        print("regions per image:")
+        for i, rpi in enumerate(regions_per_image):
+            print(f"\timage {i}: { {cls: len(r) for cls, r in rpi.items()} }")
+    return regions_all, regions_per_image, sizes, sources
+
+
+def build_tables(images, layer: int, area_influence: float, classes, one_image_for_batch: bool, device="cuda"):
+    """(RegionTables, flat region list, sorted class names) from [(layer_hw, [ {"class","vertices"} ...]) ...].
+    Table layout: struct dh_region_tables; weights: reference _calc_weights :395-482."""
+    regions: list[geometry.Region] = []
+    per_image: list[dict[str, list[int]]] = [dict() for _ in images]
+    everything: dict[str, list[int]] = {}
+    for j, (hw, annos) in enumerate(images):
+        for i, a in enumerate(annos):
+            cls = a["class"]
+            if classes is not None and cls not in classes:
+                continue
+            try:
+                reg = geometry.make_region(j, i, cls, np.array(a["vertices"], dtype=np.float64), layer)
+            except Exception:
+                continue
+            per_image[j].setdefault(cls, []).append(len(regions))
+            everything.setdefault(cls, []).append(len(regions))
+            regions.append(reg)
+    names = sorted(everything.keys())
+    if one_image_for_batch:
+        img_areas = [sum(sum(regions[r].area for r in regs) for regs in t.values()) for t in per_image]
+        weights = geometry.area_weights(img_areas, area_influence)                                  # :469-475
+        tables = geometry.RegionTables(regions, names, [tuple(hw) for hw, _ in images], per_image, weights, area_influence, device)
+    else:
+        tables = geometry.RegionTables(regions, names, [tuple(hw) for hw, _ in images], [everything], np.ones(1), area_influence, device,
+                                       sorted_classes_per_table=True)
+    return tables, regions, names
+
+
+class AnnoRegionRndSampler:
+    """Random patches inside annotated regions (reference :252-796).
+
+    Keyword-only extras: seed, device, out_dtype, out_layout ("NHWC" like the reference, or "NCHW"), flips (fused
+    random H/V flip per BATCH, train.py:71-81), mean / std."""
+
+    def __init__(self, img_anno_paths, layer: int, patch_size: int, region_intersection: float = 0.75,
+                 patches_from_one_region: int = 4, region_area_influence: float = 0.5, classes: list[str] = None,
+                 one_image_for_batch: bool = False, *, seed: int = 0, device="cuda", out_dtype=torch.float32, out_layout: str = "NHWC",
+                 flips: bool = False, mean=None, std=None, verbose: bool = True):
+        self.img_anno_paths = img_anno_paths
+        self.layer = layer
+        self.patch_size = patch_size
+        self.region_intersection = region_intersection
+        self.patches_from_one_region = patches_from_one_region
+        self.region_area_influence = region_area_influence
+        self.one_image_for_batch = one_image_for_batch
+        self._seed, self._device = seed, device
+        self._out_dtype, self._out_layout, self._flips, self._mean, self._std = out_dtype, out_layout, flips, mean, std
+        self.regions, self.regions_per_image, self._sizes, self._sources = _parse_annotations(
+            img_anno_paths, layer=layer, classes=classes, seed=seed, device=device, verbose=verbose)
+        self.classes = sorted(list(self.regions.keys()))
+        annos = [[{"class": r.class_, "vertices": r.vertices} for rs in rpi.values() for r in rs] for rpi in self.regions_per_image]
+        # keep the per-image dict order of the reference (class first-appearance order, then file order)
+        images = []
+        for j, rpi in enumerate(self.regions_per_image):
+            ordered = sorted((r for rs in rpi.values() for r in rs), key=lambda r: r.region_idx)
+            images.append((self._sizes[j], [{"class": r.class_, "vertices": r.vertices} for r in ordered]))
+        del annos
+        self._tables, self._flat_regions, names = build_tables(images, layer, region_area_influence, None, one_image_for_batch, device)
+        assert names == self.classes
+        self._slides = [None] * len(img_anno_paths)
+        self._slot_cursor = 0
+        self._fail = torch.zeros(1, dtype=torch.uint8, device=device) if torch.device(device).type == "cuda" else None
+        if verbose:
+            self._print_anno_stats(self.regions)
+
+    # -- bookkeeping identical to the reference -------------------------------------------------------
+    def _print_anno_stats(self, regions):
+        areas = {cls: sum(i.area for i in regs) for cls, regs in regions.items()}
+        print("Total area per class:")
+        for cls in areas:
+            print(f"\t{cls}: {round(areas[cls] / 1e9, 2)} Gpx ({round(areas[cls] / sum(areas.values()) * 100, 2)}%)")
+        print(f"Approximate number of patches in dataset: {len(self)}")
+
+    def _calc_area_weights(self, areas: list[float], area_influence: float) -> np.ndarray:
+        return geometry.area_weights(areas, area_influence)
+
+    def __len__(self):
+        ps = self.patch_size * self.layer                                                          # :788-796
+        return int(sum(sum(r.area for r in lst) for lst in self.regions.values()) / (ps * ps))
+
+    def _split_chunks(self, n, k):
+        q = [k] * (n // k)
+        if n % k > 0:
+            q.append(n % k)
+        return q
+
+    # -- device pipeline --------------------------------------------------------------------------------
+    def _slide(self, j: int):
+        if self._slides[j] is None:
+            with self._sources[j] as psim:
+                self._slides[j] = layer_to_device(psim, self.layer, self._device)
+        return self._slides[j]
+
+    def _check_failures(self):
+        if self._fail is not None and int(self._fail.item()) != 0:
+            raise RuntimeError("region sampling failed for some slots after max_redraw redraws "
+                               "(regions too small for the patch size / intersection, or miss limit reached)")
+
+    def sample_coords(self, n_slots: int, slots_per_image_draw: int, cls_idx: int = None, slot_offset: int = None):
+        """(coords int32 [n,2], labels int64 [n], images int32 [n]) on the device for one worker-sized chunk (:525-591)."""
+        if cls_idx is not None and not (0 <= cls_idx < len(self.classes)):
+            raise ValueError(f"cls_idx {cls_idx} out of range")
+        if slot_offset is None:
+            slot_offset = self._slot_cursor
+            self._slot_cursor += n_slots
+        ps = self.patch_size
+        coords, labels, images, status = ops.region_sample(
+            self._tables.struct, n_slots, self.patches_from_one_region, ps, ps * ps * self.region_intersection, miss_limit=500,
+            max_redraw=64, fixed_class=-1 if cls_idx is None else cls_idx, slots_per_table_draw=max(slots_per_image_draw, 1),
+            seed=self._seed, slot_offset=slot_offset, device=self._device)
+        torch.maximum(self._fail, status.max().reshape(1), out=self._fail)
+        return coords, labels, images
+
+    def _gather(self, coords, images, dtype, layout, flip=None, scale255=True):
+        ps = self.patch_size
+        if len(self._slides) == 1:
+            return ops.gather_normalize(self._slide(0), coords, ps, dtype=dtype, layout=layout, scale255=scale255, mean=self._mean,
+                                        std=self._std, flip=flip)
+        shape = (len(coords), ps, ps, 3) if layout == "NHWC" else (len(coords), 3, ps, ps)
+        out = torch.empty(shape, dtype=dtype, device=coords.device)
+        for j in torch.unique(images).tolist():                                                  # one gather per source slide
+            idx = torch.nonzero(images == j).reshape(-1).to(torch.int32)
+            ops.gather_normalize(self._slide(j), coords[idx.long()].contiguous(), ps, dtype=dtype, layout=layout, scale255=scale255,
+                                 mean=self._mean, std=self._std, flip=None if flip is None else flip[idx.long()].contiguous(), out=out,
+                                 out_index=idx)
+        return out
+
+    def _batch_flip(self, batch_global_index: int, B: int):
+        """One H and one V coin per batch (torchvision flips the whole [B,3,H,W] tensor, train.py:71-81)."""
+        if not self._flips:
+            return None
+        g = torch.Generator().manual_seed((self._seed << 20) ^ batch_global_index)
+        bits = int(torch.randint(0, 4, (1,), generator=g).item())
+        return torch.full((B,), bits, dtype=torch.uint8, device=self._device)
+
+    def torch_generator(self, batch_size: int, n_batches: int, batches_per_worker: int = 2, transforms: callable = None,
+                        max_workers: int = None, cls_idx: int = None) -> Iterator[tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+        """Reference :685-738: yields (features [B,ps,ps,3] float32 in [0,1], labels int64 [B], coords float32 [B,2] (y,x))."""
+        batch_no = 0
+        for nb in self._split_chunks(n_batches, batches_per_worker):
+            first_slot = self._slot_cursor
+            coords, labels, images = self.sample_coords(batch_size * nb, batch_size * batches_per_worker, cls_idx)
+            for i in range(nb):
+                sl = slice(i * batch_size, (i + 1) * batch_size)
+                flip = self._batch_flip(first_slot // max(batch_size, 1) + i, batch_size)
+                features = self._gather(coords[sl], images[sl], self._out_dtype, self._out_layout, flip)
+                if transforms is not None:
+                    features = transforms(features)
+                batch_no += 1
+                if batch_no % 64 == 0:
+                    self._check_failures()
+                yield features, labels[sl], coords[sl].to(torch.float32)
+        self._check_failures()
+
+    def structs_generator(self, batch_size: int, n_batches: int, batches_per_worker: int = 2, max_workers: int = None,
+                          cls_idx: int = None) -> Iterator[list[tuple[Patch, int]]]:
+        """Reference :641-683: yields list[(Patch, class_index)] per batch, Patch.data uint8 numpy [ps,ps,3]."""
+        for nb in self._split_chunks(n_batches, batches_per_worker):
+            coords, labels, images = self.sample_coords(batch_size * nb, batch_size * batches_per_worker, cls_idx)
+            self._check_failures()
+            raw = self._gather(coords, images, torch.uint8, "NHWC").cpu().numpy()
+            yx, lab = coords.cpu().numpy().tolist(), labels.cpu().numpy().tolist()
+            lst = [(Patch(self.layer, pos_x=x, pos_y=y, patch_size=self.patch_size, data=raw[i]), int(lab[i])) for i, (y, x) in enumerate(yx)]
+            for i in range(0, len(lst), batch_size):
+                yield lst[i : i + batch_size]
+
+    def torch_iterable_dataset(self) -> IterableDataset:
+        """Reference :740-786: infinite per-sample stream (features [ps,ps,3], label, coords (y, x))."""
+        outer = self
+
+        class CustomIterableDataset(IterableDataset):
+            def __iter__(self):
+                while True:
+                    for f, l, c in outer.torch_generator(batch_size=64, n_batches=2, batches_per_worker=2):
+                        for i in range(f.shape[0]):
+                            yield f[i], l[i], c[i]
+
+        return CustomIterableDataset()
+
+
+class AnnoRegionDenseSampler:
+    """Dense grid inside every annotated region (reference :799-871)."""
+
+    def __init__(self, img_anno_paths, layer: int, patch_size: int, stride: int, region_intersection: float = 0.75,
+                 classes: list[str] = None, *, device="cuda", verbose: bool = True):
+        self.img_anno_paths = img_anno_paths
+        self.layer = layer
+        self.patch_size = patch_size
+        self.stride = stride
+        self.region_intersection = region_intersection
+        self._device = device
+        self.regions, _, self._sizes, self._sources = _parse_annotations(img_anno_paths, layer=layer, classes=classes, device=device,
+                                                                       verbose=verbose)
+        self.classes = sorted(list(self.regions.keys()))
+        self._slides = [None] * len(img_anno_paths)
+
+    def _slide(self, j: int):
+        if self._slides[j] is None:
+            with self._sources[j] as psim:
+                self._slides[j] = layer_to_device(psim, self.layer, self._device)
+        return self._slides[j]
+
+    def region_batches(self, dtype=torch.float32, layout: str = "NHWC"):
+        """Device-side iteration: (features of ALL accepted patches of one region, int32 coords, class index)."""
+        for cls_idx, cls in enumerate(self.classes):
+            for region in self.regions[cls]:
+                coords = region._extract_patch_coords_dense_device(self.patch_size, self.stride, self.region_intersection)
+                if len(coords) == 0:
+                    continue
+                feats = ops.gather_normalize(self._slide(region._region.image), coords, self.patch_size, dtype=dtype, layout=layout)
+                yield feats, coords, cls_idx
+
+    def _patches_one_region(self, region: RegionAnnotation) -> list[Patch]:
+        coords = region._extract_patch_coords_dense_device(self.patch_size, self.stride, self.region_intersection)
+        if len(coords) == 0:
+            return []
+        raw = ops.gather_normalize(self._slide(region._region.image), coords, self.patch_size, dtype=torch.uint8).cpu().numpy()
+        return [Patch(self.layer, pos_x=x, pos_y=y, patch_size=self.patch_size, data=raw[i]) for i, (y, x) in enumerate(coords.cpu().numpy().tolist())]
+
+    def structs_generator(self) -> Iterator[tuple[Patch, int]]:
+        for cls_idx, cls in enumerate(self.classes):
+            for region in self.regions[cls]:
+                for p in self._patches_one_region(region):
+                    yield p, cls_idx
+
+
+def extract_and_save_subset(img_anno_paths, out_folder: Path, patch_size: int, layer: int, patches_per_class: int, intersection=0.95):
+    """Reference :874-909 (JPEG dump of test patches; IO-bound tooling around the path)."""
+    from PIL import Image
+
+    sampler = AnnoRegionRndSampler(img_anno_paths=img_anno_paths, layer=layer, patch_size=patch_size, region_intersection=intersection,
+                                   region_area_influence=0, patches_from_one_region=1)
+    batch_size = 4
+    for cls_idx, cls in enumerate(sampler.classes):
+        (out_folder / str(cls_idx)).mkdir(parents=True, exist_ok=True)
+        g = sampler.structs_generator(batch_size=batch_size, n_batches=patches_per_class // batch_size, cls_idx=cls_idx)
+        count = 0
+        for batch in g:
+            for patch, _ in batch:
+                Image.fromarray(patch.data).save(out_folder / str(cls_idx) / f"{count}.jpg")
+                count += 1

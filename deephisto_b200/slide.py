@@ -1,0 +1,180 @@
+"""Slide source seam.
+
+The reference talks to `psimage.PSImage` (full_samplers.py:35-38,55,176-180; region_samplers.py:216,229,
+501,513-520; predict_full_patched.py:37-38,103-105): context manager, `_assert_layer`, `layer_size`,
+`get_region_from_layer(layer, (y0,x0), (y1,x1))`, `get_region`, `height`, `width`, `close`. psimage is not
+part of the reference tree, so every sampler here accepts, wherever the reference takes a `.psi` path:
+  * a `DeviceSlide` (already resident in HBM), a `SyntheticSlide`, a uint8 numpy array [H,W,3],
+  * a path to a `.npy` file holding such an array,
+  * any object with the PSImage duck type above (including a real psimage.PSImage if it is installed),
+  * a `.psi` path when the `psimage` package is importable.
+The chosen layer is uploaded ONCE to HBM (row pitch padded to 16 B) and all patch extraction runs there.
+`layer` is a downscale factor (1, 2, 4, ...), as in the reference (region_samplers.py:68,792)."""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+
+from .ops import DeviceSlide
+
+
+@dataclass
+class Patch:
+    """Field-compatible stand-in for psimage.core.patches.Patch (fields used by the reference:
+    predict_full_patched.py:51-52, full_samplers.py:87-88,286-288)."""
+
+    layer: int
+    pos_x: int
+    pos_y: int
+    patch_size: int
+    data: Any = None
+
+
+class ArraySlide:
+    """numpy-backed object with the PSImage duck type (layer n = every n-th pixel of layer 1)."""
+
+    def __init__(self, array: np.ndarray):
+        if array.ndim != 3 or array.shape[2] != 3 or array.dtype != np.uint8:
+            raise ValueError("ArraySlide needs a uint8 [H, W, 3] array")
+        self._a = array
+        self.height, self.width = array.shape[:2]
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def close(self):
+        pass
+
+    def _assert_layer(self, layer: int):
+        if layer < 1 or int(layer) != layer:
+            raise ValueError(f"invalid layer {layer}")
+
+    def layer_size(self, layer: int):
+        return self.height // layer, self.width // layer
+
+    def get_region_from_layer(self, layer: int, p0, p1) -> np.ndarray:
+        (y0, x0), (y1, x1) = p0, p1
+        a = self._a if layer == 1 else self._a[::layer, ::layer][: self.height // layer, : self.width // layer]
+        return a[y0:y1, x0:x1, :]
+
+    def get_region(self, p0, p1, target_hw=None) -> np.ndarray:
+        r = self.get_region_from_layer(1, p0, p1)
+        if target_hw is None:
+            return r
+        th, tw = target_hw
+        ys = (np.arange(th) * (r.shape[0] / th)).astype(np.int64)
+        xs = (np.arange(tw) * (r.shape[1] / tw)).astype(np.int64)
+        return r[ys][:, xs]
+
+
+class SyntheticSlide:
+    """Seeded synthetic slide generated directly in HBM by dh_synth_slide; layer must be 1."""
+
+    def __init__(self, H: int, W: int, seed: int = 0):
+        self.height, self.width, self.seed = int(H), int(W), int(seed)
+        self._dev: dict[str, DeviceSlide] = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def close(self):
+        pass
+
+    def _assert_layer(self, layer: int):
+        if layer != 1:
+            raise ValueError("SyntheticSlide only has layer 1")
+
+    def layer_size(self, layer: int):
+        self._assert_layer(layer)
+        return self.height, self.width
+
+    def device_slide(self, device="cuda") -> DeviceSlide:
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = DeviceSlide.synthetic(self.height, self.width, self.seed, device)
+        return self._dev[key]
+
+    def get_region_from_layer(self, layer: int, p0, p1) -> np.ndarray:
+        self._assert_layer(layer)
+        (y0, x0), (y1, x1) = p0, p1
+        s = self.device_slide()
+        return s.storage.view(s.H, s.pitch)[y0:y1, 3 * x0 : 3 * x1].cpu().numpy().reshape(y1 - y0, x1 - x0, 3)
+
+
+def open_slide(source):
+    """Return a PSImage-duck-typed object for `source` (see module docstring)."""
+    if isinstance(source, (ArraySlide, SyntheticSlide, DeviceSlideSource)):
+        return source
+    if isinstance(source, DeviceSlide):
+        return DeviceSlideSource(source)
+    if isinstance(source, np.ndarray):
+        return ArraySlide(source)
+    if isinstance(source, (str, Path)):
+        p = Path(source)
+        if p.suffix == ".npy":
+            return ArraySlide(np.load(p, mmap_mode="r"))
+        try:
+            from psimage.core.image import PSImage  # type: ignore
+        except ImportError as e:
+            raise RuntimeError(
+                f"cannot open {p}: the `psimage` package is not installed; pass a .npy file, a numpy array, "
+                "a DeviceSlide or any object with the PSImage interface"
+            ) from e
+        return PSImage(p)
+    if all(hasattr(source, a) for a in ("layer_size", "get_region_from_layer")):
+        return source
+    raise TypeError(f"unsupported slide source {type(source)!r}")
+
+
+class DeviceSlideSource:
+    """PSImage duck type over a slide that already lives in HBM (layer 1 only)."""
+
+    def __init__(self, dev: DeviceSlide):
+        self.dev = dev
+        self.height, self.width = dev.H, dev.W
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def close(self):
+        pass
+
+    def _assert_layer(self, layer: int):
+        if layer != 1:
+            raise ValueError("a DeviceSlide holds exactly one layer; pass layer=1")
+
+    def layer_size(self, layer: int):
+        self._assert_layer(layer)
+        return self.dev.H, self.dev.W
+
+    def get_region_from_layer(self, layer: int, p0, p1) -> np.ndarray:
+        self._assert_layer(layer)
+        (y0, x0), (y1, x1) = p0, p1
+        s = self.dev
+        return s.storage.view(s.H, s.pitch)[y0:y1, 3 * x0 : 3 * x1].cpu().numpy().reshape(y1 - y0, x1 - x0, 3)
+
+
+def layer_to_device(src, layer: int, device="cuda") -> DeviceSlide:
+    """Upload layer `layer` of an opened slide to HBM once (the analogue of full_samplers.py:53-55)."""
+    if isinstance(src, DeviceSlideSource):
+        src._assert_layer(layer)
+        return src.dev
+    if isinstance(src, SyntheticSlide):
+        src._assert_layer(layer)
+        return src.device_slide(device)
+    h, w = src.layer_size(layer)
+    arr = np.asarray(src.get_region_from_layer(layer, (0, 0), (h, w)))
+    return DeviceSlide.from_numpy(arr, device)

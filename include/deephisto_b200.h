@@ -1,0 +1,222 @@
+/*
+ * deephisto_b200.h -- C-ABI of libdeephisto_b200.so
+ *
+ * B200 (sm_100a) implementation of the DeepHisto patch-sampling / patched-prediction hot path.
+ * Every entry point replaces one piece of the reference's Python/numpy/GEOS host path; the
+ * reference location is cited as path:line relative to the xubiker/deephisto tree.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every call only enqueues work: no allocation, no synchronisation, no global state
+ *     (a per-thread error string and a per-process tensor-map cache are the only statics);
+ *   - return value: 0 (DH_OK) or a negative dh_status; dh_last_error() gives the text;
+ *   - coordinates are int32 pairs (y, x) of the patch's top-left corner, like the reference's
+ *     `(y, x)` tuples (full_samplers.py:380-397, region_samplers.py:135,190);
+ *   - the slide is uint8 [H][W][3] RGB with a row pitch in bytes (pitch >= 3*W).
+ */
+#ifndef DEEPHISTO_B200_H
+#define DEEPHISTO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DH_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define DH_API __attribute__((visibility("default")))
+#else
+#define DH_API
+#endif
+
+typedef enum dh_status {
+    DH_OK = 0,
+    DH_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, misaligned buffer) */
+    DH_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+    DH_ERR_UNSUPPORTED = -3, /* combination not implemented */
+    DH_ERR_NO_DEVICE = -4    /* no sm_100 device / kernel image cannot run here */
+} dh_status;
+
+typedef enum dh_dtype { DH_F32 = 0, DH_BF16 = 1, DH_U8 = 2 } dh_dtype;
+typedef enum dh_layout { DH_NHWC = 0, DH_NCHW = 1 } dh_layout;
+
+/* flip bits for dh_gather_normalize (train.py:71-81 RandomHorizontalFlip / RandomVerticalFlip) */
+#define DH_FLIP_H 1u
+#define DH_FLIP_V 2u
+
+/* per-slot status written by the region samplers */
+#define DH_SLOT_OK 0u
+#define DH_SLOT_MISS_LIMIT 1u  /* region_samplers.py:139-142 "Miss limit reached" */
+#define DH_SLOT_EMPTY_RANGE 2u /* np.random.randint(low >= high) would raise, region_samplers.py:123-124 */
+
+DH_API int dh_version(void);
+DH_API const char* dh_last_error(void);
+/* 0 if the current device can run the sm_100a kernels, DH_ERR_NO_DEVICE otherwise. */
+DH_API int dh_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic slide: byte k of the logical [H][W*3] array is
+ *   (mix32(seed_lo ^ (k>>2)) ^ seed_hi-fold) >> (8*(k&3)) & 255,  see oracle/synth.py.
+ * Replaces: psimage get_region_from_layer of the whole layer (full_samplers.py:53-55,328-330)
+ * for benchmark inputs (no 30 GB host->device copy for the 100k x 100k case).
+ * ------------------------------------------------------------------------------------------ */
+DH_API int dh_synth_slide(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, uint64_t seed, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A1  FullImageDenseSampler._create_batched_coords (full_samplers.py:374-404)
+ * Enumeration: main grid (y outer, x inner), last column, last row, corner, then the last batch
+ * is padded with copies of the corner.
+ * dh_dense_count: host-only arithmetic; returns N (unpadded) and writes N rounded up to a
+ * multiple of batch_size to *n_padded_host (may be NULL). Returns <0 on invalid arguments.
+ * dh_dense_coords: writes coords[i] for i in [first, first+count) of the PADDED enumeration.
+ * ------------------------------------------------------------------------------------------ */
+DH_API int64_t dh_dense_count(int64_t H, int64_t W, int ps, int stride, int batch_size, int64_t* n_padded_host);
+DH_API int dh_dense_coords(int64_t H, int64_t W, int ps, int stride, int batch_size, int64_t first, int64_t count,
+                    int32_t* coords_out /* [count][2] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * A2/A3/H  gather + normalise
+ *   FullImageDenseSampler._generate_batch_memory + generator_torch (full_samplers.py:353-369,437-452)
+ *   FullImageRndSampler._extract_patches_np + generator_torch     (full_samplers.py:187-202,282-290)
+ *   batch_predictor's stack / 255 / permute                        (examples/predict_full_patched.py:66-71)
+ *   _gen_single_proc_torch's tensor(data)/255                      (region_samplers.py:616)
+ * out[b] = patch at coords[b]; value = scale255 ? float(u8)/255 (IEEE fp32 division) : float(u8);
+ * then, if mean3_host/std3_host are given, (value - mean[c]) / std[c] in IEEE fp32.
+ * out_dtype DH_F32 | DH_BF16 (round-to-nearest-even of the fp32 value) | DH_U8 (raw copy; scale,
+ * mean, std ignored). out_layout DH_NHWC [B][ps][ps][3] or DH_NCHW [B][3][ps][ps].
+ * out_index (optional): patch b is written to slot out_index[b] instead of b.
+ * flip (optional): per-patch DH_FLIP_H / DH_FLIP_V bits applied to the written patch.
+ * Pixels outside the slide are read as 0.
+ * ------------------------------------------------------------------------------------------ */
+DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, const int32_t* coords,
+                        const int32_t* out_index, int64_t B, int ps, void* out, int out_dtype, int out_layout,
+                        int scale255, const float* mean3_host, const float* std3_host, const uint8_t* flip,
+                        void* stream);
+
+/* Variant selector for profiling: 0 = auto, 1 = direct (LDG/STG) kernel, 2 = TMA-staged kernel. */
+DH_API int dh_gather_set_variant(int variant);
+
+/* ------------------------------------------------------------------------------------------
+ * A4  ImagePredictorPatched.process (examples/predict_full_patched.py:40-63)
+ *   prediction[y//d:(y+ps)//d, x//d:(x+ps)//d, :] += logits[i]   in sampler order, then argmax.
+ * dh_stitch_dense: gather formulation for the dense enumeration of A1 -- every output cell sums the
+ *   patches that cover it in reference order (fp32 adds, no FMA) => bit-exact sum map. logits is
+ *   [n_padded][n]; the (n_padded - N) padding duplicates of the corner are added again, as the
+ *   reference does, unless batch_size <= 0 (no padding).
+ *   Only map rows [row_begin, row_end) are produced; sum_map / count_map point at row `row_begin`.
+ * dh_stitch_scatter: arbitrary coordinates (random sampler); fp32 atomics, order not preserved.
+ *   The map passed holds rows [row_offset, row_offset+rows) of the full [dh][dw] map.
+ * dh_stitch_finalize: count normalisation (sum / max(count,1)) and argmax (first maximum, like
+ *   np.argmax) over the n classes; any of norm_map / argmax_u8 / count_map may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+DH_API int dh_stitch_dense(const float* logits, int64_t H, int64_t W, int ps, int stride, int d, int n,
+                    int batch_size, float* sum_map, uint32_t* count_map, int64_t row_begin, int64_t row_end,
+                    void* stream);
+/* same, with the argmax fused into the store epilogue; sum_map and/or count_map may be NULL
+ * (argmax-only mode writes dh*dw bytes instead of dh*dw*n*4). */
+DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t W, int ps, int stride, int d, int n,
+                       int batch_size, float* sum_map, uint32_t* count_map, uint8_t* argmax_u8,
+                       int64_t row_begin, int64_t row_end, void* stream);
+DH_API int dh_stitch_scatter(const float* logits, const int32_t* coords, int64_t P, int ps, int d, int n,
+                      float* sum_map, uint32_t* count_map, int64_t rows, int64_t dw, int64_t row_offset,
+                      void* stream);
+DH_API int dh_stitch_finalize(const float* sum_map, const uint32_t* count_map, int64_t cells, int n,
+                       float* norm_map, uint8_t* argmax_u8, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * B1-B3  FullImageRndSampler (full_samplers.py:81-94,105-114,125-162,263-274)
+ * Coverage-driven random sampling on the 1/speedup coarse accumulator.
+ * One call = one batch: eligible cells (accum < dense_level) are compacted in index order, topped
+ * up with random non-eligible cells when fewer than B, B distinct cells are drawn (partial
+ * Fisher-Yates, Philox4x32-10 keyed by seed, counters documented in oracle/cover.py), jittered,
+ * clamped, written to coords_out, and the accumulator footprint of every patch is incremented.
+ * scratch: uint32 [dh_cover_scratch_words(dh, dw)]; nonzero_out: device uint32 count of non-zero
+ * accumulator cells after the update (filled_ratio = nonzero / (dh*dw)). B <= 2048.
+ * ------------------------------------------------------------------------------------------ */
+DH_API int64_t dh_cover_scratch_words(int64_t dh, int64_t dw);
+DH_API int dh_cover_sample(uint32_t* accum, int64_t dh, int64_t dw, int64_t H, int64_t W, int ps, int speedup,
+                    int dense_level, int B, uint64_t seed, uint64_t batch_index, int32_t* coords_out,
+                    uint32_t* nonzero_out, uint32_t* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * C/D  RegionAnnotation._extract_patch_coords_dense / _rnd (region_samplers.py:82-191)
+ * Acceptance = float64 area(polygon ∩ [x,x+ps]x[y,y+ps]) > threshold (strict), threshold =
+ * ps*ps*region_intersection computed by the caller exactly as the reference does (:134,189).
+ * The area is the boundary integral of the clamped polygon edges (every op separately rounded;
+ * oracle/region.py restates the same operation order; shapely/GEOS is absent from the reference
+ * tree). Polygons are passed as an EDGE TABLE built once on the host (deephisto_b200/geometry.py):
+ *   edges [E][8] float64 = xA, yA, xB, yB (yA < yB), m = (xB-xA)/(yB-yA), r = (yB-yA)/(xB-xA)
+ *                          (0 for vertical edges), sgn (+1 if the polygon edge ran A->B, else -1), 0
+ *   horizontal edges are dropped; region i owns edges [edge_off[i], edge_off[i+1]).
+ *
+ * dh_region_accept_dense: candidates (y0 + iy*stride, x0 + ix*stride), iy < ny, ix < nx, row-major;
+ *   writes mask_u8[ny*nx] (1 = accepted) and, if area_out != NULL, the clip area per candidate.
+ * dh_compact_coords: ordered compaction of the accepted candidates into coords_out, count to *n_out
+ *   (device int32); single-block ordered scan, candidates < 2^31.
+ * ------------------------------------------------------------------------------------------ */
+DH_API int dh_region_accept_dense(const double* edges, int edge_begin, int edge_end, int64_t y0, int64_t x0,
+                           int64_t ny, int64_t nx, int stride, int ps, double threshold, uint8_t* mask_u8,
+                           double* area_out, void* stream);
+DH_API int dh_compact_coords(const uint8_t* mask_u8, int64_t y0, int64_t x0, int64_t ny, int64_t nx, int stride,
+                      int32_t* coords_out, int32_t* n_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * F/G  AnnoRegionRndSampler._gen_single_proc + _patches_one_region (region_samplers.py:484-591)
+ * Sampling tables (built on the host by region_samplers.AnnoRegionRndSampler, float64 exactly as
+ * _calc_area_weights / _calc_weights :339-482); all pointers are device pointers:
+ *   T "tables" (1 in global mode, one per image with one_image_for_batch);
+ *   tbl_cls_off int32 [T+1]      -> classes usable in table t: tbl_cls[tbl_cls_off[t] .. )
+ *   cat_off     int32 [T*C+1]    -> regions of (table t, class c): cat_region / cat_cdf slices
+ *   cat_cdf     float64          -> inclusive cumulative weights (last = 1)
+ *   img_cdf     float64 [T]      -> table (image) weights, used when T > 1
+ *   reg_bbox    float64 [R][4]   -> polygon.bounds (x0, y0, x1, y1); reg_area float64 [R]
+ *   reg_image   int32  [R], img_hw int32 [M][2] (layer h, w of the region's image)
+ * One warp per group of k = patches_from_one_region slots (group g = local slots [g*k, g*k+k));
+ * 32 attempts are evaluated in parallel per slot and the lowest accepted attempt index wins, so
+ * the result equals the reference's sequential rejection loop driven by the same Philox stream
+ * (counters: DESIGN.md "Philox contract"). A group whose region fails (too small, empty range,
+ * miss limit) redraws class and region, up to max_redraw times (the reference's except/continue).
+ * slot_offset = global index of local slot 0 (batch_index * batch_size): disjoint ranges give
+ * independent streams, which is how ranks shard the sampler.
+ * Outputs per slot: coords (y,x) int32, label int64 (class index), image int32, status u8.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dh_region_tables {
+    const double* edges;
+    const int32_t* edge_off;
+    const double* reg_bbox;
+    const double* reg_area;
+    const int32_t* reg_image;
+    const int32_t* img_hw;
+    const int32_t* tbl_cls_off;
+    const int32_t* tbl_cls;
+    const int32_t* cat_off;
+    const int32_t* cat_region;
+    const double* cat_cdf;
+    const double* img_cdf;
+    int32_t n_tables;
+    int32_t n_classes;
+    int32_t n_regions;
+    int32_t n_images;
+} dh_region_tables;
+
+DH_API int dh_region_sample(const dh_region_tables* tables_host, int64_t n_slots, int k, int ps, double threshold,
+                     int miss_limit, int max_redraw, int fixed_class, int64_t slots_per_table_draw,
+                     uint64_t seed, uint64_t slot_offset, int32_t* coords_out, int64_t* label_out,
+                     int32_t* image_out, uint8_t* status_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * R  polygon rasterisation (north-star item (a); anno/utils.py:308-320 is the visual analogue).
+ * label_out[my][mx] = 1 + index of the LAST polygon whose interior contains the centre of mask
+ * pixel (my, mx) (even-odd rule, float64), 0 if none. Pixel centre = ((mx+0.5)*scale, (my+0.5)*scale).
+ * ------------------------------------------------------------------------------------------ */
+DH_API int dh_rasterize_polygons(const double* edges, const int32_t* edge_off, const double* reg_bbox, int n_regions,
+                          double scale, int32_t* label_out, int64_t mh, int64_t mw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPHISTO_B200_H */

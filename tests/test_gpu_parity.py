@@ -1,0 +1,293 @@
+"""Parity of the sm_100a kernels (called through the C-ABI) against the CPU oracle and the golden vectors
+generated from the unmodified reference. Bit-exact for bytes / indices / fp32 sums; 1e-5 for the atomic scatter."""
+
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cover as ocover
+from oracle import dense as odense
+from oracle import region as oregion
+from oracle import stitch as ostitch
+from oracle import synth
+from oracle.make_golden import DENSE_CASES, PIXEL_CASES, STITCH_CASES, region_polygons
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from deephisto_b200 import _lib, ops
+
+    _lib.require_device()  # fails loudly without a B200 / the built library
+    return ops
+
+
+def bits(t: torch.Tensor) -> np.ndarray:
+    if t.dtype == torch.bfloat16:
+        return t.view(torch.int16).cpu().numpy()
+    if t.dtype == torch.float32:
+        return t.view(torch.int32).cpu().numpy()
+    return t.cpu().numpy()
+
+
+# ---- synthetic slide -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("hw", [(64, 48), (37, 53), (300, 261), (1000, 777)])
+def test_synth_slide_matches_oracle(ops, hw):
+    H, W = hw
+    for seed in (0, 7, (5 << 32) | 11):
+        dev = ops.DeviceSlide.synthetic(H, W, seed)
+        assert dev.pitch % 16 == 0
+        assert np.array_equal(dev.to_numpy(), synth.synth_slide(H, W, seed))
+
+
+# ---- A1 dense coordinates --------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", DENSE_CASES)
+def test_dense_coords_bit_exact(ops, golden, case):
+    z, man = golden
+    H, W, ps, stride, B = case
+    got = ops.dense_coords(H, W, ps, stride, B).cpu().numpy()
+    assert np.array_equal(got, z[f"dense_{H}x{W}_ps{ps}_s{stride}_b{B}_coords"])
+    part = ops.dense_coords(H, W, ps, stride, B, first=5, count=len(got) - 9).cpu().numpy()
+    assert np.array_equal(part, got[5:-4])
+
+
+def test_dense_coords_full_size(ops, golden):
+    _, man = golden
+    for H, W, ps, stride, B in [(40000, 40000, 224, 112, 64), (100000, 100000, 224, 112, 64)]:
+        got = ops.dense_coords(H, W, ps, stride, B).cpu().numpy()
+        e = man[f"dense_{H}x{W}_ps{ps}_s{stride}_b{B}"]
+        assert len(got) == e["n_padded"] and sha(got) == e["coords_sha256"]
+
+
+# ---- A2 gather + normalise ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", PIXEL_CASES)
+def test_gather_matches_reference_golden(ops, golden, case):
+    """fp32 NHWC batches == the tensors the unmodified FullImageDenseSampler.generator_torch() yielded."""
+    z, man = golden
+    H, W, ps, stride, B = case
+    key = f"dense_{H}x{W}_ps{ps}_s{stride}_b{B}"
+    slide = ops.DeviceSlide.synthetic(H, W, 0)
+    coords = ops.dense_coords(H, W, ps, stride, B)
+    want = man[key]["batch_sha256"]
+    # one launch over all patches, digested per reference batch
+    feats = ops.gather_normalize(slide, coords, ps).cpu().numpy()
+    for i, dg in enumerate(want):
+        assert sha(feats[i * B : (i + 1) * B]) == dg, f"batch {i}"
+    csum = feats.reshape(-1, 3).sum(axis=0, dtype=np.float64)
+    assert np.allclose(csum, man[key]["channel_sum_f64"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("ps", [224, 32, 20, 7])          # 20: ps%4==0 only; 7: generic scalar kernel
+@pytest.mark.parametrize("layout", ["NHWC", "NCHW"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.uint8])
+def test_gather_variants_vs_oracle(ops, ps, layout, dtype):
+    H, W = 523, 611  # odd width -> padded pitch
+    host = synth.synth_slide(H, W, 3)
+    slide = ops.DeviceSlide.from_numpy(host)
+    rng = np.random.default_rng(ps)
+    B = 19
+    coords = np.stack([rng.integers(0, H - ps + 1, B), rng.integers(0, W - ps + 1, B)], 1).astype(np.int32)
+    coords[0] = (0, 0)
+    coords[1] = (H - ps, W - ps)
+    coords[2] = (-3, 5)              # partly outside: zero fill
+    coords[3] = (H - ps + 4, W - 5)
+    cdev = torch.from_numpy(coords).cuda()
+    raw = odense.gather(host, coords, ps)
+    if dtype == torch.uint8:
+        got = ops.gather_normalize(slide, cdev, ps, dtype=dtype, layout=layout)
+        want = raw if layout == "NHWC" else np.ascontiguousarray(raw.transpose(0, 3, 1, 2))
+        assert np.array_equal(got.cpu().numpy(), want)
+        return
+    flips = torch.from_numpy((np.arange(B) % 4).astype(np.uint8)).cuda()
+    for scale255, mean, std, flip in [(True, None, None, None), (False, None, None, None),
+                                      (True, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), None), (True, None, None, flips)]:
+        got = ops.gather_normalize(slide, cdev, ps, dtype=dtype, layout=layout, scale255=scale255, mean=mean, std=std, flip=flip)
+        want = odense.normalize(raw, scale255, mean, std, layout, None if flip is None else flip.cpu().numpy())
+        want_t = torch.from_numpy(want).to(dtype)  # bf16: round-to-nearest-even of the fp32 value
+        assert got.shape == want_t.shape
+        assert np.array_equal(bits(got), bits(want_t)), (scale255, mean, flip is not None)
+
+
+def test_gather_out_index_and_value_range(ops):
+    H, W, ps = 400, 400, 64
+    slide = ops.DeviceSlide.synthetic(H, W, 1)
+    host = synth.synth_slide(H, W, 1)
+    coords = torch.tensor([[0, 0], [10, 20], [300, 336], [77, 5]], dtype=torch.int32, device="cuda")
+    out = torch.full((6, ps, ps, 3), -1.0, device="cuda")
+    idx = torch.tensor([5, 0, 3, 1], dtype=torch.int32, device="cuda")
+    ops.gather_normalize(slide, coords, ps, out=out, out_index=idx)
+    want = odense.normalize(odense.gather(host, coords.cpu().numpy(), ps))
+    got = out.cpu().numpy()
+    for b, s in enumerate([5, 0, 3, 1]):
+        assert np.array_equal(got[s], want[b])
+    assert (got[2] == -1).all() and (got[4] == -1).all()
+    # all 256 byte values: exact IEEE division on the device
+    ramp = np.arange(256, dtype=np.uint8).repeat(3).reshape(1, 256, 3).repeat(4, 0)
+    rs = ops.DeviceSlide.from_numpy(np.ascontiguousarray(ramp))
+    f = ops.gather_normalize(rs, torch.zeros((1, 2), dtype=torch.int32, device="cuda"), 4)
+    g = ops.gather_normalize(rs, torch.tensor([[0, 252]], dtype=torch.int32, device="cuda"), 4)
+    assert np.array_equal(f.cpu().numpy()[0, 0, :, 0], (np.arange(4, dtype=np.float32) / np.float32(255)))
+    assert np.array_equal(g.cpu().numpy()[0, 0, :, 0], (np.arange(252, 256).astype(np.float32) / np.float32(255)))
+    full = ops.gather_normalize(rs, torch.tensor([[0, 4 * i] for i in range(64)], dtype=torch.int32, device="cuda"), 4).cpu().numpy()
+    assert np.array_equal(full[:, 0, :, 1].reshape(-1), np.arange(256).astype(np.float32) / np.float32(255))
+
+
+def test_gather_full_size_properties(ops):
+    """BASELINE C1 size (8192^2, stride 224): dense non-overlapping patches tile the slide, so the uint8 gather is a
+    permutation of the covered pixels and re-assembling it reproduces the slide exactly."""
+    H = W = 8192
+    ps = 224
+    slide = ops.DeviceSlide.synthetic(H, W, 0)
+    coords = ops.dense_coords(H, W, ps, ps, 16)
+    n, _ = ops.dense_count(H, W, ps, ps, 16)
+    raw = ops.gather_normalize(slide, coords[:n], ps, dtype=torch.uint8)
+    host = slide.storage.view(H, slide.pitch)[:, : 3 * W].view(H, W, 3)
+    ny = nx = 36
+    main = raw[: ny * nx].view(ny, nx, ps, ps, 3).permute(0, 2, 1, 3, 4).reshape(ny * ps, nx * ps, 3)
+    assert torch.equal(main, host[: ny * ps, : nx * ps])
+    assert torch.equal(raw[n - 1], host[H - ps :, W - ps :])
+    f32 = ops.gather_normalize(slide, coords[:n], ps)
+    bf = ops.gather_normalize(slide, coords[:n], ps, dtype=torch.bfloat16, layout="NCHW")
+    assert torch.equal(f32, raw.to(torch.float32) / 255)
+    assert torch.equal(bf, (raw.to(torch.float32) / 255).permute(0, 3, 1, 2).to(torch.bfloat16))
+
+
+# ---- A4 stitch -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", STITCH_CASES)
+def test_stitch_dense_bit_exact(ops, golden, case):
+    z, man = golden
+    H, W, ps, stride, B, n, ds = case
+    key = f"stitch_{H}x{W}_ps{ps}_s{stride}_b{B}_n{n}"
+    logits = torch.from_numpy(z[key + "_logits"]).cuda()
+    coords, _ = odense.dense_coords(H, W, ps, stride, B)
+    for d in ds:
+        s, cnt, am = ops.stitch_dense(logits, H, W, ps, stride, d, B, want_count=True, want_argmax=True)
+        e = man[f"{key}_d{d}"]
+        assert sha(s.cpu().numpy()) == e["sum_sha256"], d
+        assert sha(am.cpu().numpy()) == e["argmax_sha256"], d
+        _, ocnt, _ = ostitch.stitch(z[key + "_logits"], coords, H, W, ps, d)
+        assert np.array_equal(cnt.cpu().numpy().astype(np.int64), ocnt)
+        # argmax-only and band modes
+        _, _, am2 = ops.stitch_dense(logits, H, W, ps, stride, d, B, want_sum=False, want_argmax=True)
+        assert torch.equal(am, am2)
+        dh = H // d
+        r0, r1 = dh // 3, dh - dh // 5
+        sb, cb, ab = ops.stitch_dense(logits, H, W, ps, stride, d, B, row_begin=r0, row_end=r1, want_count=True, want_argmax=True)
+        assert torch.equal(sb, s[r0:r1]) and torch.equal(cb, cnt[r0:r1]) and torch.equal(ab, am[r0:r1])
+        # finalize: argmax of the sum map (first maximum) and count-normalised map
+        norm, am3 = ops.stitch_finalize(s, cnt, want_norm=True)
+        assert torch.equal(am3, am)
+        assert np.array_equal(norm.cpu().numpy(), ostitch.normalize(s.cpu().numpy(), ocnt))
+
+
+def test_stitch_scatter_vs_oracle(ops):
+    H, W, ps, d, n = 1500, 1300, 224, 16, 5
+    rng = np.random.default_rng(0)
+    P = 300
+    coords = np.stack([rng.integers(0, H - ps + 1, P), rng.integers(0, W - ps + 1, P)], 1).astype(np.int32)
+    logits = rng.standard_normal((P, n)).astype(np.float32)
+    want, wcnt, _ = ostitch.stitch(logits, coords, H, W, ps, d)
+    s = torch.zeros((H // d, W // d, n), device="cuda")
+    c = torch.zeros((H // d, W // d), dtype=torch.int32, device="cuda")
+    ops.stitch_scatter(torch.from_numpy(logits).cuda(), torch.from_numpy(coords).cuda(), ps, d, s, c)
+    got = s.cpu().numpy()
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 1e-5 * scale  # fp32 accumulation order only
+    assert np.array_equal(c.cpu().numpy().astype(np.int64), wcnt)
+    # band: rows [20, 60)
+    sb = torch.zeros((40, W // d, n), device="cuda")
+    ops.stitch_scatter(torch.from_numpy(logits).cuda(), torch.from_numpy(coords).cuda(), ps, d, sb, None, row_offset=20)
+    assert np.abs(sb.cpu().numpy() - want[20:60]).max() <= 1e-5 * scale
+
+
+# ---- B coverage sampler -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(700, 900, 224, 16, 3), (2048, 2048, 224, 64, 0), (300, 5000, 224, 7, 11)])
+def test_cover_sampler_bit_exact_vs_oracle(ops, cfg):
+    H, W, ps, B, seed = cfg
+    st = ops.CoverState(H, W, ps, 16, 2, B, seed)
+    ref = ocover.CoverSampler(H, W, ps, B, seed)
+    filled = 0.0
+    it = 0
+    while filled < 1:
+        c, nz = st.next_coords()
+        rc, filled = ref.next_coords()
+        assert np.array_equal(c.cpu().numpy(), rc), f"batch {it}"
+        assert int(nz.item()) / (st.dh * st.dw) == filled
+        it += 1
+        assert it < 2000
+    assert np.array_equal(st.accum.cpu().numpy().astype(np.int64), ref.accum)
+
+
+# ---- C/D regions ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(region_polygons().keys()))
+def test_region_accept_dense_bit_exact(ops, golden, name):
+    from deephisto_b200 import geometry
+
+    z, _ = golden
+    verts = z[f"region_{name}_verts"].astype(np.float64)
+    for layer in (1, 2):
+        v = oregion.scale_vertices(verts, layer)
+        edges_h = geometry.build_edges(v)
+        assert np.array_equal(edges_h, oregion.build_edges(v))
+        edges = torch.from_numpy(edges_h.reshape(-1)).cuda()
+        for ps, stride, ri in ((224, 112, 0.75), (224, 56, 0.5), (64, 32, 0.95)):
+            y0, x0, ny, nx = oregion.dense_candidates(v, (2048 // layer, 2048 // layer), ps, stride)
+            want_c, want_m, want_a = oregion.coords_dense(v, (2048 // layer, 2048 // layer), ps, stride, ri)
+            mask, area = ops.region_accept_dense(edges, 0, len(edges_h), y0, x0, ny, nx, stride, ps, ps * ps * ri, want_area=True)
+            assert np.array_equal(area.cpu().numpy(), want_a)     # every float64 op reproduced
+            assert np.array_equal(mask.cpu().numpy(), want_m)
+            got = ops.compact_coords(mask, y0, x0, ny, nx, stride).cpu().numpy()
+            assert np.array_equal(got, z[f"region_{name}_l{layer}_ps{ps}_s{stride}_ri{ri}"])
+
+
+def _tables(polys_per_image, hw, one_image, device="cuda"):
+    from deephisto_b200.patch_samplers.region_samplers import build_tables
+
+    return build_tables([(hw, p) for p in polys_per_image], layer=1, area_influence=0.5, classes=None, one_image_for_batch=one_image,
+                        device=device)
+
+
+@pytest.mark.parametrize("one_image", [True, False])
+def test_region_sample_bit_exact_vs_oracle(ops, one_image):
+    hw = (6000, 6000)
+    imgs = [synth.synth_polygons(12, *hw, seed=1, rmin=300, rmax=900), synth.synth_polygons(7, *hw, seed=2, rmin=200, rmax=700, n_classes=3)]
+    tables, regions, classes = _tables(imgs, hw, one_image)
+    rs = oregion.RegionSet([(hw, p) for p in imgs], layer=1, one_image_for_batch=one_image)
+    assert classes == rs.classes
+    for (n_slots, k, ri, seed, off, spt) in [(256, 4, 0.75, 9, 0, 128), (70, 3, 0.9, 1, 1000, 35), (33, 32, 0.5, 2, 7, 33)]:
+        c, lab, img, st = ops.region_sample(tables.struct, n_slots, k, 224, 224 * 224 * ri, seed=seed, slot_offset=off, slots_per_table_draw=spt)
+        oc, olab, oimg, ost = oregion.sample(rs, n_slots, k, 224, ri, seed=seed, slot_offset=off, slots_per_table_draw=spt)
+        assert np.array_equal(st.cpu().numpy(), ost) and (ost == 0).all()
+        assert np.array_equal(c.cpu().numpy(), oc)
+        assert np.array_equal(lab.cpu().numpy(), olab)
+        assert np.array_equal(img.cpu().numpy(), oimg)
+
+
+def test_region_sample_failure_status(ops):
+    hw = (3000, 3000)
+    tiny = [{"class": "A", "vertices": [[10.0, 10.0], [100.0, 10.0], [100.0, 100.0], [10.0, 100.0]]}]  # area < ps*ps*ri
+    tables, _, _ = _tables([tiny], hw, False)
+    c, lab, img, st = ops.region_sample(tables.struct, 8, 4, 224, 224 * 224 * 0.75, max_redraw=3)
+    assert (st.cpu().numpy() == 1).all() and (lab.cpu().numpy() == -1).all()
+
+
+def test_rasterize_vs_oracle(ops):
+    from deephisto_b200 import geometry
+
+    polys = [np.asarray(p["vertices"]) for p in synth.synth_polygons(6, 4000, 4000, seed=4, rmin=300, rmax=900)]
+    edges = [geometry.build_edges(v) for v in polys]
+    bbox = [geometry.polygon_bounds(v) for v in polys]
+    off = np.zeros(len(edges) + 1, np.int32)
+    off[1:] = np.cumsum([len(e) for e in edges])
+    lab = ops.rasterize_polygons(torch.from_numpy(np.concatenate(edges).reshape(-1)).cuda(), torch.from_numpy(off).cuda(),
+                                 torch.from_numpy(np.asarray(bbox).reshape(-1)).cuda(), 16.0, 250, 250)
+    want = oregion.rasterize(edges, bbox, 16.0, 250, 250)
+    assert np.array_equal(lab.cpu().numpy(), want)
+    assert len(np.unique(want)) > 2
