@@ -229,6 +229,8 @@ def region_accept_dense(edges: torch.Tensor, edge_begin: int, edge_end: int, y0:
     _need_cuda(edges, "edges", torch.float64)
     mask = torch.empty(max(ny * nx, 0), dtype=torch.uint8, device=edges.device)
     area = torch.empty(max(ny * nx, 0), dtype=torch.float64, device=edges.device) if want_area else None
+    if ny <= 0 or nx <= 0:
+        return mask, area
     with torch.cuda.device(edges.device):
         check(lib.dh_region_accept_dense(edges.data_ptr(), edge_begin, edge_end, y0, x0, ny, nx, stride, ps, float(threshold),
                                          mask.data_ptr(), _ptr(area), _stream()), "dh_region_accept_dense")

@@ -312,18 +312,23 @@ def sample(rs: RegionSet, n_slots: int, k: int, ps: int, ri: float = 0.75, miss_
                 continue
             ok_group = True
             got = []
-            att = np.arange(miss_limit, dtype=np.uint64)
             for s in range(kk):
                 gs = g0 + s
-                pa = philox4x32_10(gs & 0xFFFFFFFF, gs >> 32, (np.uint64(rd) << np.uint64(16)) | att, STREAM_ATTEMPT, k0, k1)
-                xs = xlo + bounded(pa[0], xhi - xlo)
-                ys = ylo + bounded(pa[1], yhi - ylo)
-                ok = clip_area(rs.edges[region], xs, ys, ps) > thr          # :133-134 strict
-                hit = np.flatnonzero(ok)
-                if len(hit) == 0:
+                hit_yx = None
+                for a0 in range(0, miss_limit, 32):                         # 32 attempts at a time, first accepted wins (kernel order)
+                    att = np.arange(a0, min(a0 + 32, miss_limit), dtype=np.uint64)
+                    pa = philox4x32_10(gs & 0xFFFFFFFF, gs >> 32, (np.uint64(rd) << np.uint64(16)) | att, STREAM_ATTEMPT, k0, k1)
+                    xs = xlo + bounded(pa[0], xhi - xlo)
+                    ys = ylo + bounded(pa[1], yhi - ylo)
+                    ok = clip_area(rs.edges[region], xs, ys, ps) > thr      # :133-134 strict
+                    hit = np.flatnonzero(ok)
+                    if len(hit):
+                        hit_yx = (int(ys[hit[0]]), int(xs[hit[0]]))
+                        break
+                if hit_yx is None:
                     ok_group = False
                     break
-                got.append((int(ys[hit[0]]), int(xs[hit[0]])))
+                got.append(hit_yx)
             if not ok_group:
                 fail = 1
                 continue

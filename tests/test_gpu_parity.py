@@ -54,8 +54,9 @@ def test_dense_coords_bit_exact(ops, golden, case):
     H, W, ps, stride, B = case
     got = ops.dense_coords(H, W, ps, stride, B).cpu().numpy()
     assert np.array_equal(got, z[f"dense_{H}x{W}_ps{ps}_s{stride}_b{B}_coords"])
-    part = ops.dense_coords(H, W, ps, stride, B, first=5, count=len(got) - 9).cpu().numpy()
-    assert np.array_equal(part, got[5:-4])
+    a, b = len(got) // 3, len(got) - len(got) // 4
+    part = ops.dense_coords(H, W, ps, stride, B, first=a, count=b - a).cpu().numpy()
+    assert np.array_equal(part, got[a:b])
 
 
 def test_dense_coords_full_size(ops, golden):
@@ -81,7 +82,7 @@ def test_gather_matches_reference_golden(ops, golden, case):
     for i, dg in enumerate(want):
         assert sha(feats[i * B : (i + 1) * B]) == dg, f"batch {i}"
     csum = feats.reshape(-1, 3).sum(axis=0, dtype=np.float64)
-    assert np.allclose(csum, man[key]["channel_sum_f64"], rtol=1e-12)
+    assert np.allclose(csum, man[key]["channel_sum_f64"], rtol=1e-9)  # same values (digests), different summation order
 
 
 @pytest.mark.parametrize("ps", [224, 32, 20, 7])          # 20: ps%4==0 only; 7: generic scalar kernel
@@ -155,8 +156,11 @@ def test_gather_full_size_properties(ops):
     assert torch.equal(raw[n - 1], host[H - ps :, W - ps :])
     f32 = ops.gather_normalize(slide, coords[:n], ps)
     bf = ops.gather_normalize(slide, coords[:n], ps, dtype=torch.bfloat16, layout="NCHW")
-    assert torch.equal(f32, raw.to(torch.float32) / 255)
-    assert torch.equal(bf, (raw.to(torch.float32) / 255).permute(0, 3, 1, 2).to(torch.bfloat16))
+    # torch's CUDA `x / 255` multiplies by a rounded reciprocal (not IEEE division): build the expected values on the CPU
+    lut = (torch.arange(256, dtype=torch.float32) / 255).cuda()
+    want = lut[raw.long()]
+    assert torch.equal(f32, want)
+    assert torch.equal(bf, want.permute(0, 3, 1, 2).to(torch.bfloat16))
 
 
 # ---- A4 stitch -------------------------------------------------------------------------------------------------
