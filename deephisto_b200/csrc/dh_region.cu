@@ -138,6 +138,17 @@ __device__ __forceinline__ int cdf_search(const double* __restrict__ cdf, int lo
 }
 
 constexpr int kSampleWarps = 4;
+constexpr int kSmemEdges = 96;  // edges of the group's region staged per warp (larger polygons read the rest from L1/L2)
+
+// clip area with the first `n_sm` edges in shared memory and the remainder in global memory (same order, same ops)
+__device__ __forceinline__ double clip_area_staged(const double* __restrict__ sm_edges, int n_sm, const double* __restrict__ edges,
+                                                   int e0, int e1, double x, double y, double ps) {
+    const double xa = x, xb = x + ps, ya = y, yb = y + ps;
+    double acc = 0.0;
+    for (int e = 0; e < n_sm; ++e) acc = acc + edge_term(sm_edges + e * kEdgeStride, xa, xb, ya, yb);
+    for (int e = e0 + n_sm; e < e1; ++e) acc = acc + edge_term(edges + (int64_t)e * kEdgeStride, xa, xb, ya, yb);
+    return fabs(acc);
+}
 
 __global__ void __launch_bounds__(kSampleWarps * 32) region_sample_kernel(RegionTablesDev T, int64_t n_slots, int k, int ps, double thr,
                                                                          int miss_limit, int max_redraw, int fixed_class,
@@ -145,13 +156,22 @@ __global__ void __launch_bounds__(kSampleWarps * 32) region_sample_kernel(Region
                                                                          uint64_t slot_offset, int32_t* __restrict__ coords_out,
                                                                          int64_t* __restrict__ label_out, int32_t* __restrict__ image_out,
                                                                          uint8_t* __restrict__ status_out) {
+    __shared__ double s_edges[kSampleWarps][kSmemEdges * kEdgeStride];
     const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
     const int64_t n_groups = (n_slots + k - 1) / k;
-    const int64_t group = (int64_t)blockIdx.x * kSampleWarps + (threadIdx.x >> 5);
+    const int64_t group = (int64_t)blockIdx.x * kSampleWarps + wib;
     if (group >= n_groups) return;
     const int64_t s0 = group * k;
     const int kk = (int)((n_slots - s0) < k ? (n_slots - s0) : k);
     const uint64_t g0 = slot_offset + (uint64_t)s0;  // global index of the group's first slot
+    double* my_edges = s_edges[wib];
+
+    // lanes = k slots x apr attempts per round; slot of this lane and its attempt sub-index
+    const int apr = 32 / k;
+    const int slot = lane / apr, sub = lane - slot * apr;
+    const bool lane_live = slot < kk;
+    const unsigned slot_mask = (apr == 32 ? 0xffffffffu : ((1u << apr) - 1u)) << (slot * apr & 31);
 
     // table (image) choice: one draw per chunk of slots_per_table_draw global slots
     int table = 0;
@@ -161,6 +181,7 @@ __global__ void __launch_bounds__(kSampleWarps * 32) region_sample_kernel(Region
         table = cdf_search(T.img_cdf, 0, T.n_tables, u01(pt.v[0]));
     }
     const int cls_lo = T.tbl_cls_off[table], ncls = T.tbl_cls_off[table + 1] - cls_lo;
+    const uint64_t gs = g0 + (uint64_t)(lane_live ? slot : 0);
 
     uint8_t fail = DH_SLOT_MISS_LIMIT;
     for (int rd = 0; rd < max_redraw; ++rd) {
@@ -190,31 +211,36 @@ __global__ void __launch_bounds__(kSampleWarps * 32) region_sample_kernel(Region
         const uint32_t xr = (uint32_t)(xhi - xlo), yr = (uint32_t)(yhi - ylo);
         const int e0 = T.edge_off[region], e1 = T.edge_off[region + 1];
 
-        bool group_ok = true;
-        int my_y = 0, my_x = 0;  // lane s keeps the result of slot s (k <= 32)
-        for (int s = 0; s < kk && group_ok; ++s) {
-            const uint64_t gs = g0 + (uint64_t)s;
-            bool found = false;
-            for (int a0 = 0; a0 < miss_limit && !found; a0 += 32) {
-                const int a = a0 + lane;
+        // stage the region's edge table in shared memory (coalesced), once per draw
+        const int n_sm = (e1 - e0) < kSmemEdges ? (e1 - e0) : kSmemEdges;
+        __syncwarp();
+        for (int i = lane; i < n_sm * kEdgeStride; i += 32) my_edges[i] = T.edges[(int64_t)e0 * kEdgeStride + i];
+        __syncwarp();
+
+        // every round evaluates attempts [a0, a0 + apr) of all unfinished slots at once; per slot the lowest accepted attempt
+        // index wins, which is what the reference's sequential rejection loop returns for the same draws
+        bool done = !lane_live;
+        int my_y = 0, my_x = 0;
+        unsigned pending = __ballot_sync(0xffffffffu, !done);
+        for (int a0 = 0; a0 < miss_limit && pending; a0 += apr) {
+            const int a = a0 + sub;
+            bool ok = false;
+            int x = 0, y = 0;
+            if (!done && a < miss_limit) {
                 Philox4 pa = philox4x32_10((uint32_t)gs, (uint32_t)(gs >> 32), ((uint32_t)rd << 16) | (uint32_t)a, kStreamAttempt, key0, key1);
-                const int x = (int)(xlo + (int64_t)bounded_u32(pa.v[0], xr));
-                const int y = (int)(ylo + (int64_t)bounded_u32(pa.v[1], yr));
-                bool ok = false;
-                if (a < miss_limit) ok = clip_area(T.edges, e0, e1, (double)x, (double)y, dps) > thr;
-                unsigned bal = __ballot_sync(0xffffffffu, ok);
-                if (bal) {
-                    int src = __ffs(bal) - 1;
-                    int yy = __shfl_sync(0xffffffffu, y, src), xx = __shfl_sync(0xffffffffu, x, src);
-                    if (lane == s) { my_y = yy; my_x = xx; }
-                    found = true;
-                }
+                x = (int)(xlo + (int64_t)bounded_u32(pa.v[0], xr));
+                y = (int)(ylo + (int64_t)bounded_u32(pa.v[1], yr));
+                ok = clip_area_staged(my_edges, n_sm, T.edges, e0, e1, (double)x, (double)y, dps) > thr;
             }
-            if (!found) group_ok = false;
+            const unsigned hits = __ballot_sync(0xffffffffu, ok) & slot_mask;
+            const int src = hits ? __ffs(hits) - 1 : lane;
+            const int yy = __shfl_sync(0xffffffffu, y, src), xx = __shfl_sync(0xffffffffu, x, src);
+            if (!done && hits) { my_y = yy; my_x = xx; done = true; }
+            pending = __ballot_sync(0xffffffffu, !done);
         }
-        if (!group_ok) { fail = DH_SLOT_MISS_LIMIT; continue; }
-        if (lane < kk) {
-            const int64_t o = s0 + lane;
+        if (pending) { fail = DH_SLOT_MISS_LIMIT; continue; }
+        if (lane_live && sub == 0) {
+            const int64_t o = s0 + slot;
             coords_out[2 * o] = my_y;
             coords_out[2 * o + 1] = my_x;
             if (label_out) label_out[o] = cls;
@@ -223,8 +249,8 @@ __global__ void __launch_bounds__(kSampleWarps * 32) region_sample_kernel(Region
         }
         return;
     }
-    if (lane < kk) {
-        const int64_t o = s0 + lane;
+    if (lane_live && sub == 0) {
+        const int64_t o = s0 + slot;
         coords_out[2 * o] = 0;
         coords_out[2 * o + 1] = 0;
         if (label_out) label_out[o] = -1;

@@ -284,3 +284,9 @@ def rasterize_polygons(edges: torch.Tensor, edge_off: torch.Tensor, reg_bbox: to
         check(lib.dh_rasterize_polygons(edges.data_ptr(), edge_off.data_ptr(), reg_bbox.data_ptr(), edge_off.numel() - 1, float(scale),
                                         out.data_ptr(), mh, mw, _stream()), "dh_rasterize_polygons")
     return out
+
+
+def set_gather_variant(variant: str = "auto") -> None:
+    """Profiling switch: "auto" (TMA-staged kernel when the shape allows), "direct" (LDG/STG kernel), "tma" (fail if unsupported)."""
+    lib = _lib.load()
+    check(lib.dh_gather_set_variant({"auto": 0, "direct": 1, "tma": 2}[variant]), "dh_gather_set_variant")

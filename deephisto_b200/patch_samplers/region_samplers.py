@@ -280,9 +280,13 @@ class AnnoRegionRndSampler:
                         max_workers: int = None, cls_idx: int = None) -> Iterator[tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         """Reference :685-738: yields (features [B,ps,ps,3] float32 in [0,1], labels int64 [B], coords float32 [B,2] (y,x))."""
         batch_no = 0
-        for nb in self._split_chunks(n_batches, batches_per_worker):
+        chunk = batch_size * batches_per_worker
+        # Coordinates are counter-based (Philox keyed by the global slot index), so several worker-sized chunks can be drawn by
+        # ONE launch with identical results -- as long as the groups of k slots do not straddle a chunk boundary.
+        ahead = max(1, 32 // batches_per_worker) * batches_per_worker if chunk % self.patches_from_one_region == 0 else batches_per_worker
+        for nb in self._split_chunks(n_batches, ahead):
             first_slot = self._slot_cursor
-            coords, labels, images = self.sample_coords(batch_size * nb, batch_size * batches_per_worker, cls_idx)
+            coords, labels, images = self.sample_coords(batch_size * nb, chunk, cls_idx)
             for i in range(nb):
                 sl = slice(i * batch_size, (i + 1) * batch_size)
                 flip = self._batch_flip(first_slot // max(batch_size, 1) + i, batch_size)

@@ -37,12 +37,13 @@ def _worker(args):
     n_slots, k, ps, ri, seed, slot_offset, spt = args
     rs, slide = _G["rs"], _G["slide"]
     coords, labels, images, status = region.sample(rs, n_slots, k, ps, ri, seed=seed, slot_offset=slot_offset, slots_per_table_draw=spt)
-    res = []
-    for (y, x), lab in zip(coords.tolist(), labels.tolist()):
+    feats = []
+    for (y, x) in coords.tolist():
         data = slide[y : y + ps, x : x + ps, :]                                   # :513-520
-        features = torch.tensor(data, dtype=torch.float32) / 255                  # :616
-        res.append((features, torch.tensor(lab, dtype=torch.int64), torch.tensor([y, x], dtype=torch.float32)))
-    return res
+        feats.append((torch.tensor(data, dtype=torch.float32) / 255).numpy())     # :616
+    # Transport: plain numpy through the result pipe. (The reference returns torch tensors, which torch.multiprocessing moves
+    # through /dev/shm file descriptors; containers with a small /dev/shm kill the workers, and it is not faster.)
+    return np.stack(feats), labels.astype(np.int64), coords.astype(np.float32)
 
 
 def _ping(_):
@@ -71,10 +72,10 @@ class AnnotatedRndCPU:
             jobs.append((batch_size * nb, k, ps, ri, seed, off, batch_size * batches_per_worker))
             off += batch_size * nb
         results = map(_worker, jobs) if self.pool is None else self.pool.map(_worker, jobs)
-        for lst in results:
-            for i in range(0, len(lst), batch_size):
-                el = lst[i : i + batch_size]
-                yield torch.stack([e[0] for e in el]), torch.stack([e[1] for e in el]), torch.stack([e[2] for e in el])
+        for feats, labels, coords in results:
+            for i in range(0, len(feats), batch_size):                             # :729-735 stack per batch
+                yield (torch.from_numpy(feats[i : i + batch_size]), torch.from_numpy(labels[i : i + batch_size]),
+                       torch.from_numpy(coords[i : i + batch_size]))
 
     def close(self):
         if self.pool is not None:

@@ -295,3 +295,30 @@ def test_rasterize_vs_oracle(ops):
     want = oregion.rasterize(edges, bbox, 16.0, 250, 250)
     assert np.array_equal(lab.cpu().numpy(), want)
     assert len(np.unique(want)) > 2
+
+
+@pytest.mark.parametrize("variant", ["direct", "tma"])
+@pytest.mark.parametrize("ps", [224, 64, 16, 256, 112, 20])
+def test_gather_kernel_variants_agree_with_oracle(ops, variant, ps):
+    """Both gather kernels (direct LDG/STG and TMA-staged) against the oracle, all layouts / dtypes, flips, out-of-slide patches."""
+    H, W = 700, 900
+    host = synth.synth_slide(H, W, 11)
+    slide = ops.DeviceSlide.from_numpy(host)
+    rng = np.random.default_rng(ps)
+    B = 37
+    coords = np.stack([rng.integers(0, H - ps + 1, B), rng.integers(0, W - ps + 1, B)], 1).astype(np.int32)
+    coords[0], coords[1], coords[2], coords[3] = (0, 0), (H - ps, W - ps), (-5, 7), (H - ps + 9, W - 3)
+    cdev = torch.from_numpy(coords).cuda()
+    raw = odense.gather(host, coords, ps)
+    flips = torch.from_numpy(rng.integers(0, 4, B).astype(np.uint8)).cuda()
+    ops.set_gather_variant(variant)
+    try:
+        for layout in ("NHWC", "NCHW"):
+            for dtype in (torch.float32, torch.bfloat16):
+                for scale255, mean, std, flip in [(True, None, None, None), (False, None, None, None),
+                                                  (True, (0.5, 0.4, 0.3), (0.2, 0.25, 0.3), None), (True, None, None, flips)]:
+                    got = ops.gather_normalize(slide, cdev, ps, dtype=dtype, layout=layout, scale255=scale255, mean=mean, std=std, flip=flip)
+                    want = odense.normalize(raw, scale255, mean, std, layout, None if flip is None else flip.cpu().numpy())
+                    assert np.array_equal(bits(got), bits(torch.from_numpy(want).to(dtype))), (layout, dtype, scale255, mean, flip is not None)
+    finally:
+        ops.set_gather_variant("auto")
