@@ -54,6 +54,7 @@ SIGNATURES = {
     "dh_last_error": (C.c_char_p, []),
     "dh_device_check": (C.c_int, []),
     "dh_synth_slide": (C.c_int, [_vp, _i64, _i64, _i64, _u64, _vp]),
+    "dh_synth_slide_rows": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i64, _u64, _vp]),
     "dh_dense_count": (_i64, [_i64, _i64, _i32, _i32, _i32, C.POINTER(_i64)]),
     "dh_dense_coords": (C.c_int, [_i64, _i64, _i32, _i32, _i32, _i64, _i64, _vp, _vp]),
     "dh_gather_normalize": (

@@ -84,13 +84,14 @@ __host__ __device__ __forceinline__ uint32_t bounded_u32(uint32_t r, uint32_t n)
 #endif
 }
 
-// exact float(v)/255.0f for v in 0..255: one Newton correction of v * RN(1/255) is correctly
-// rounded for all 256 inputs (checked exhaustively in tests/test_oracle_cpu.py and on the GPU).
+// exact float(v)/255.0f for v in 0..255 in two operations: 1/255 split into RN(1/255) + a float32 tail, the tail product
+// rounded once and the head product added unrounded by the FMA. The result is the correctly rounded quotient for all 256
+// inputs (v/255 is never within 2^-33 relative of a rounding boundary, the split's error is ~2^-46; checked exhaustively
+// with exact rationals in tests/test_oracle_cpu.py and on the GPU in tests/test_gpu_parity.py).
 __device__ __forceinline__ float div255_exact(float x) {
-    const float rcp = 0x1.010102p-8f;  // RN(1/255) = 0.003921568859368563
-    float q = __fmul_rn(x, rcp);
-    float e = __fmaf_rn(-255.0f, q, x);
-    return __fmaf_rn(e, rcp, q);
+    const float rcp_hi = 0x1.010102p-8f;    // RN(1/255)
+    const float rcp_lo = -0x1.fdfdfep-33f;  // RN(1/255 - rcp_hi)
+    return __fmaf_rn(x, rcp_hi, __fmul_rn(x, rcp_lo));
 }
 
 }  // namespace dh

@@ -79,7 +79,8 @@ __host__ __device__ __forceinline__ uint32_t synth_word(uint64_t widx, uint32_t 
     return fmix32(fmix32(a) + b * 0x9E3779B9u);
 }
 
-__global__ void synth_slide_kernel(uint8_t* __restrict__ slide, int64_t H, int64_t W, int64_t pitch, uint32_t seed_lo,
+// writes rows [y0, y0 + H) of the logical slide into a buffer whose row 0 is slide row y0
+__global__ void synth_slide_kernel(uint8_t* __restrict__ slide, int64_t y0, int64_t H, int64_t W, int64_t pitch, uint32_t seed_lo,
                                    uint32_t seed_hi, bool aligned) {
     const int64_t row_bytes = 3 * W;
     const int64_t words_per_row = (row_bytes + 3) / 4;
@@ -87,7 +88,7 @@ __global__ void synth_slide_kernel(uint8_t* __restrict__ slide, int64_t H, int64
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         int64_t y = t / words_per_row;
         int64_t j = t - y * words_per_row;
-        uint64_t k0 = (uint64_t)y * (uint64_t)row_bytes + 4ull * j;
+        uint64_t k0 = (uint64_t)(y0 + y) * (uint64_t)row_bytes + 4ull * j;
         uint64_t wi = k0 >> 2;
         uint32_t sh = (uint32_t)(k0 & 3) * 8u;
         uint32_t h0 = synth_word(wi, seed_lo, seed_hi);
@@ -148,12 +149,20 @@ extern "C" DH_API int dh_dense_coords(int64_t H, int64_t W, int ps, int stride, 
     return DH_OK;
 }
 
-extern "C" DH_API int dh_synth_slide(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, uint64_t seed, void* stream) {
+extern "C" DH_API int dh_synth_slide_rows(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, int64_t y0, int64_t rows, uint64_t seed,
+                                          void* stream) {
     DH_REQUIRE(slide, "dh_synth_slide: null pointer");
     DH_REQUIRE(H > 0 && W > 0 && pitch >= 3 * W, "dh_synth_slide: bad shape");
+    DH_REQUIRE(y0 >= 0 && rows >= 0 && y0 + rows <= H, "dh_synth_slide: rows [%lld, %lld) outside the %lld-row slide", (long long)y0,
+               (long long)(y0 + rows), (long long)H);
+    if (rows == 0) return DH_OK;
     bool aligned = (reinterpret_cast<uintptr_t>(slide) % 4 == 0) && (pitch % 4 == 0);
     int grid = kNumSMs * 16;
-    synth_slide_kernel<<<grid, 256, 0, as_stream(stream)>>>(slide, H, W, pitch, (uint32_t)seed, (uint32_t)(seed >> 32), aligned);
+    synth_slide_kernel<<<grid, 256, 0, as_stream(stream)>>>(slide, y0, rows, W, pitch, (uint32_t)seed, (uint32_t)(seed >> 32), aligned);
     DH_CHECK_LAUNCH("synth_slide_kernel");
     return DH_OK;
+}
+
+extern "C" DH_API int dh_synth_slide(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, uint64_t seed, void* stream) {
+    return dh_synth_slide_rows(slide, H, W, pitch, 0, H, seed, stream);
 }

@@ -296,7 +296,7 @@ static int g_variant = 0;
 
 int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, const int32_t* coords, const int32_t* out_index,
                       int64_t B, int ps, void* out, int out_dtype, int out_layout, int scale255, const float* mean3, const float* std3,
-                      const uint8_t* flip, cudaStream_t st);
+                      const uint8_t* flip, int debug, cudaStream_t st);
 
 template <typename OutT>
 static void launch_vec(const GatherParams& p, bool nchw, int grid, cudaStream_t st) {
@@ -316,7 +316,7 @@ static void launch_vec(const GatherParams& p, bool nchw, int grid, cudaStream_t 
 using namespace dh;
 
 extern "C" DH_API int dh_gather_set_variant(int variant) {
-    if (variant < 0 || variant > 2) { set_error("dh_gather_set_variant: variant must be 0, 1 or 2"); return DH_ERR_INVALID; }
+    if (variant < 0 || variant > 6) { set_error("dh_gather_set_variant: variant must be 0..6"); return DH_ERR_INVALID; }
     g_variant = variant;
     return DH_OK;
 }
@@ -349,9 +349,9 @@ extern "C" DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64
     const bool nchw = out_layout == DH_NCHW;
     if (g_variant != 1) {  // TMA-staged kernel whenever the shape allows it
         int rc = gather_tma_launch(slide, H, W, pitch, coords, out_index, B, ps, out, out_dtype, out_layout, p.scale255,
-                                   mean3_host ? p.mean : nullptr, mean3_host ? p.stdv : nullptr, flip, st);
+                                   mean3_host ? p.mean : nullptr, mean3_host ? p.stdv : nullptr, flip, g_variant >= 3 ? (g_variant == 6 ? 4 : g_variant - 2) : 0, st);
         if (rc != DH_ERR_UNSUPPORTED) return rc;
-        if (g_variant == 2) { set_error("dh_gather_normalize: shape not supported by the TMA-staged kernel (needs ps %% 4 == 0, pitch %% 16 == 0, f32/bf16 output)"); return rc; }
+        if (g_variant >= 2) { set_error("dh_gather_normalize: shape not supported by the TMA-staged kernel (needs ps %% 4 == 0 for f32, ps %% 8 == 0 for bf16, pitch %% 16 == 0)"); return rc; }
     }
     const size_t esz = out_dtype == DH_F32 ? 4 : (out_dtype == DH_BF16 ? 2 : 1);
     const bool aligned = (reinterpret_cast<uintptr_t>(slide) % 4 == 0) && (pitch % 4 == 0) && (ps % 4 == 0) &&

@@ -1,26 +1,39 @@
-// K1 (TMA-engine variant): fused patch gather + normalise with the patch rows staged through shared memory by
-// asynchronous bulk copies (cp.async.bulk.shared.global -> SASS UBLKCP, executed by the TMA unit) behind an
-// mbarrier ring, S tiles ahead of the consumers.
+// K1 (TMA-engine variant): fused patch gather + normalise, warp-specialised.
 //
-// Why: the direct LDG kernel (dh_gather.cu) is latency-bound -- ncu shows ~70 % of its stall samples on the
-// funnel-shift that consumes the two global loads (profiles/r01_gather.md). Here the loads are issued by one thread,
-// complete asynchronously, and the SM only does LDS -> convert -> one coalesced 16-byte store per 4 outputs.
+// One producer warp stages patch rows in shared memory with asynchronous bulk copies
+// (cp.async.bulk.shared.global -> SASS UBLKCP, executed by the TMA unit) behind a ring of full/empty
+// mbarriers; seven consumer warps do LDS -> byte unpack -> exact /255 -> one coalesced 16-byte store per
+// unit. There is no block-wide barrier in the steady state.
 //
-// Alignment: a patch row starts at byte 3*x of its slide row, which is arbitrary, while bulk copies (and TMA tensor
-// tiles: measured on B200, a cp.async.bulk.tensor whose innermost start byte is not a multiple of 16 faults with
-// "illegal instruction") need 16-byte aligned global addresses. So each row copy starts at the 16-byte boundary below
-// 3*x (a = 3*x mod 16 extra leading bytes) and the consumers realign with a funnel shift of two LDS words.
-// The copy never leaves the slide row: its end is roundup16(3*x + 3*ps) <= pitch when the patch is inside the slide.
-// Patches that are not entirely inside the slide (zero fill) take a guarded global-load path in the same kernel.
+// History (profiles/r01_gather.md): the direct LDG kernel (dh_gather.cu) was latency-bound; the first TMA
+// version was ISSUE-bound -- 81 warp instructions per 16-byte store, most of it per-tile bookkeeping done by
+// every thread (64-bit division, coordinate loads, guarded register arrays) plus a __syncthreads per tile
+// (33 % of stall samples). Here the per-tile work is done once by the producer and handed over through a
+// 32-byte header in shared memory, the consumer loop is ~26 instructions per store, and stages are recycled
+// through mbarriers.
 //
-// Tile = R consecutive output rows of one patch; persistent CTAs walk tiles round-robin.
+// Alignment: a patch row starts at byte 3*x of its slide row, which is arbitrary, while bulk copies need
+// 16-byte aligned global addresses and sizes (a cp.async.bulk.tensor tile whose innermost start is not a
+// multiple of 16 bytes faults on B200: profiles/tma_probe.py). So each row copy starts at the 16-byte boundary
+// below 3*x (a = 3*x mod 16 extra leading bytes) and the consumers realign with a funnel shift of LDS words.
+// The copy never leaves the slide row: its end is roundup16(3*x + 3*ps) <= pitch when the patch is inside
+// the slide. Patches that are not entirely inside the slide (zero fill) and horizontally flipped patches take a
+// guarded byte path in the same kernel.
+//
+// Tile = R consecutive output rows of one patch; persistent CTAs walk tiles round-robin (no division in the loop).
+// Unit = 16 bytes of output: NHWC 4 (f32) / 8 (bf16) consecutive elements of a patch row; NCHW 4 / 8 consecutive
+// pixels -> one 16-byte store into each of the three channel planes.
+#include <stdlib.h>
+
 #include "dh_common.cuh"
 
 namespace dh {
 
-constexpr int kTmaThreads = 256;
-constexpr int kTmaStages = 4;
-constexpr int kTmaMaxUnits = 8;  // units per thread per tile
+constexpr int kConsumerWarps = 7;
+constexpr int kConsumers = 32 * kConsumerWarps;   // 224: divides the 1344 units of an 8-row 224-wide fp32 NHWC tile
+constexpr int kTmaThreads = kConsumers + 32;      // warp 0 = producer
+constexpr int kTmaMaxStages = 8;                  // ring depth is a launch parameter (p.stages <= kTmaMaxStages)
+constexpr int kTmaMaxUnits = 6;                   // units per consumer thread per tile
 
 struct TmaGatherParams {
     const uint8_t* slide;
@@ -33,11 +46,23 @@ struct TmaGatherParams {
     int ps;
     int R;            // rows per tile
     int tiles_per_patch;
-    int row_pitch;    // bytes per staged row in shared memory (multiple of 16, >= 3*ps + 16)
-    int affine;
+    int row_pitch;    // bytes per staged row in shared memory (multiple of 16, >= 3*ps + 32)
+    int units_per_row;
+    int stages;       // depth of the stage ring
+    int debug;        // profiling only: 1 = producer skips the bulk loads, 2 = consumers skip the stores, 4 = default-policy stores
     float mean[3];
     float stdv[3];
 };
+
+// per-stage header written by the producer (plain st.shared, published by its mbarrier arrive)
+struct __align__(16) TileMeta {
+    long long out_off;  // element offset of the tile's first output element (plane 0 for NCHW)
+    int y, x;           // patch origin
+    int flags;          // DH_FLIP_H | DH_FLIP_V | kInside
+    int tr;             // tile index inside the patch
+    int pad[2];
+};
+constexpr int kInside = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -46,6 +71,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0;
@@ -62,16 +90,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (TMA unit, SASS UBLKCP)
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
-// float(v) for a byte without the XU pipe: 0x4B000000 | v is the float 8388608 + v
-__device__ __forceinline__ float byte_to_float(uint32_t word, uint32_t sel) {
-    // sel = 0x744k: byte k of `word` in the low byte, 0x00 0x00 0x4B above it
-    return __uint_as_float(__byte_perm(word, 0x4B000000u, sel)) - 8388608.0f;
+// float(v) for a byte without the conversion pipe: 0x4B000000 | v is the float 8388608 + v
+// (k is a compile-time constant after unrolling: one PRMT + one FADD)
+// `magic` = 0x4B000000 held in a register so that the selector is the PRMT immediate
+__device__ __forceinline__ float byte_f(uint32_t word, int k, uint32_t magic) {
+    return __uint_as_float(__byte_perm(word, magic, 0x7440u + (uint32_t)k)) - 8388608.0f;
+}
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
 }
 
 template <bool SCALE, bool AFFINE>
@@ -85,189 +124,217 @@ __device__ __forceinline__ float norm_f(float f, int c, const TmaGatherParams& p
     return f;
 }
 
-template <typename OutT>
-__device__ __forceinline__ void store4(OutT* dst, float a, float b, float c, float d);
-template <>
-__device__ __forceinline__ void store4<float>(float* dst, float a, float b, float c, float d) {
-    __stcs(reinterpret_cast<float4*>(dst), make_float4(a, b, c, d));
-}
-template <>
-__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b, float c, float d) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-    uint2 v;
-    v.x = *reinterpret_cast<uint32_t*>(&lo);
-    v.y = *reinterpret_cast<uint32_t*>(&hi);
-    __stcs(reinterpret_cast<uint2*>(dst), v);
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
 }
 
-struct TileInfo {
-    int64_t patch, slot;
-    int tr, y, x;
-    uint32_t fl;
-    bool inside;
-};
-
-__device__ __forceinline__ TileInfo tile_info(const TmaGatherParams& p, int64_t t) {
-    TileInfo ti;
-    ti.patch = t / p.tiles_per_patch;
-    ti.tr = (int)(t - ti.patch * p.tiles_per_patch);
-    ti.y = __ldg(p.coords + 2 * ti.patch);
-    ti.x = __ldg(p.coords + 2 * ti.patch + 1);
-    ti.slot = p.out_index ? (int64_t)__ldg(p.out_index + ti.patch) : ti.patch;
-    ti.fl = p.flip ? (uint32_t)__ldg(p.flip + ti.patch) : 0u;
-    ti.inside = (ti.y >= 0) && (ti.x >= 0) && ((int64_t)ti.y + p.ps <= p.H) && ((int64_t)ti.x + p.ps <= p.W);
-    return ti;
+// 16-byte streaming store of 4 floats / 8 bf16
+__device__ __forceinline__ void store_unit(float* dst, const float (&f)[4], bool plain = false) {
+    if (plain) *reinterpret_cast<float4*>(dst) = make_float4(f[0], f[1], f[2], f[3]);
+    else __stcs(reinterpret_cast<float4*>(dst), make_float4(f[0], f[1], f[2], f[3]));
+}
+__device__ __forceinline__ void store_unit(__nv_bfloat16* dst, const float (&f)[8], bool plain = false) {
+    uint4 v;
+    v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]); v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
+    if (plain) *reinterpret_cast<uint4*>(dst) = v;
+    else __stcs(reinterpret_cast<uint4*>(dst), v);
 }
 
-template <typename OutT, bool NCHW, bool SCALE, bool AFFINE>
+template <typename OutT> struct UnitOf { static constexpr int kElems = 16 / (int)sizeof(OutT); };
+
+template <typename OutT, bool NCHW, bool SCALE, bool AFFINE, bool FULL>
 __global__ void __launch_bounds__(kTmaThreads) gather_tma_kernel(const TmaGatherParams p) {
+    constexpr int E = UnitOf<OutT>::kElems;          // elements (NHWC) or pixels (NCHW) per unit: 4 or 8
+    constexpr int IN_BYTES = NCHW ? 3 * E : E;       // input bytes per unit
+    constexpr int NW = IN_BYTES / 4;                 // aligned words per unit after the funnel shift
+    // FULL: every consumer thread owns exactly KU units of every tile (the ps = 224 shapes) -> no per-unit guards
+    constexpr int KU = FULL ? (NCHW ? (E == 4 ? 4 : 2) : 6) : kTmaMaxUnits;
     extern __shared__ __align__(128) uint8_t stages[];
-    __shared__ __align__(8) uint64_t full[kTmaStages];
+    __shared__ __align__(16) TileMeta meta[kTmaMaxStages];
+    __shared__ __align__(8) uint64_t full[kTmaMaxStages];
+    __shared__ __align__(8) uint64_t empty[kTmaMaxStages];
+
     const int R = p.R, ps = p.ps, RP = p.row_pitch;
     const int row_bytes = 3 * ps;
     const int stage_bytes = R * RP;
-
-    const int64_t n_tiles = p.B * (int64_t)p.tiles_per_patch;
-    const int64_t first = blockIdx.x;
-    const int64_t stride = gridDim.x;
-    const int64_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+    const int tpp = p.tiles_per_patch;
+    const int S = p.stages;
+    const int64_t n_tiles = p.B * (int64_t)tpp;
+    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t plane = (int64_t)ps * ps;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // warp 0 issues the R row copies of my i-th tile into stage i % S (lane r copies row r; lane 0 arms the barrier first)
-    auto issue = [&](int64_t i) {
-        const TileInfo ti = tile_info(p, first + i * stride);
-        const int s = (int)(i % kTmaStages);
-        if (!ti.inside) {  // guarded path reads global memory directly: nothing to stage, but the phase must still complete
-            if (threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
-            return;
-        }
-        const int a = (3 * ti.x) & 15;
-        const uint32_t bytes = (uint32_t)((a + row_bytes + 15) & ~15);
-        const int lane = threadIdx.x;
-        if (lane == 0) mbar_expect_tx(&full[s], bytes * (uint32_t)R);
-        __syncwarp();
-        if (lane < R) {
-            const int orow = ti.tr * R + lane;                                   // output row of the patch
-            const int srow = (ti.fl & DH_FLIP_V) ? ps - 1 - orow : orow;         // source row
-            const uint8_t* src = p.slide + (int64_t)(ti.y + srow) * p.pitch + ((3 * (int64_t)ti.x) & ~(int64_t)15);
-            bulk_load(stages + (size_t)s * stage_bytes + (size_t)lane * RP, src, bytes, &full[s]);
-        }
-    };
-
     if (threadIdx.x < 32) {
-        for (int64_t i = 0; i < kTmaStages - 1 && i < my_tiles; ++i) issue(i);
+        // ---------------- producer warp ----------------
+        const int lane = threadIdx.x;
+        int64_t patch = blockIdx.x / tpp;                      // once; the loop advances (patch, tr) incrementally
+        int tr = (int)(blockIdx.x - patch * tpp);
+        const int64_t dq = gridDim.x / tpp;
+        const int dr = (int)(gridDim.x - dq * tpp);
+        const uint32_t stage0 = smem_u32(stages);
+        int s = 0;
+        uint32_t ph = 1;  // a fresh mbarrier passes a wait on parity 1: the first S tiles do not wait
+        for (int64_t i = 0; i < my_tiles; ++i) {
+            mbar_wait(&empty[s], ph);
+            const int y = __ldg(p.coords + 2 * patch);
+            const int x = __ldg(p.coords + 2 * patch + 1);
+            const uint32_t fl = p.flip ? (uint32_t)__ldg(p.flip + patch) : 0u;
+            const bool inside = (y >= 0) && (x >= 0) && ((int64_t)y + ps <= p.H) && ((int64_t)x + ps <= p.W);
+            const int a = (3 * x) & 15;
+            const uint32_t bytes = (uint32_t)((a + row_bytes + 15) & ~15);
+            const bool stage_it = inside && !(p.debug & 1);
+            if (lane == 0) {
+                const int64_t slot = p.out_index ? (int64_t)__ldg(p.out_index + patch) : patch;
+                TileMeta m;
+                m.out_off = slot * 3 * plane + (int64_t)tr * R * (NCHW ? ps : row_bytes);
+                m.y = y; m.x = x; m.flags = (int)fl | (inside ? kInside : 0); m.tr = tr; m.pad[0] = m.pad[1] = 0;
+                meta[s] = m;
+                if (stage_it) mbar_expect_tx(&full[s], bytes * (uint32_t)R);
+                else mbar_arrive(&full[s]);  // guarded path reads global memory directly: nothing to stage
+            }
+            __syncwarp();
+            if (stage_it && lane < R) {
+                const int orow = tr * R + lane;                                // output row of the patch
+                const int srow = (fl & DH_FLIP_V) ? ps - 1 - orow : orow;      // source row
+                const uint8_t* src = p.slide + (int64_t)(y + srow) * p.pitch + ((3 * (int64_t)x) & ~(int64_t)15);
+                bulk_load(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s]);
+            }
+            tr += dr; patch += dq;
+            if (tr >= tpp) { tr -= tpp; ++patch; }
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
+        return;
     }
 
-    // per-thread unit geometry is the same for every tile
-    const int units_per_row = NCHW ? ps / 4 : row_bytes / 4;
-    const int units_per_tile = R * units_per_row;
-    int u_row[kTmaMaxUnits], u_col[kTmaMaxUnits], s_off[kTmaMaxUnits], o_off[kTmaMaxUnits];
+    // ---------------- consumer warps ----------------
+    const int tid = threadIdx.x - 32;
+    const int upr = p.units_per_row;
+    const int units_per_tile = R * upr;
+    // per-thread unit geometry is the same for every tile: unit u_k = tid + k * kConsumers
+    uint32_t s_off[kTmaMaxUnits];
+    int cph[kTmaMaxUnits];
+    int nu = 0;
 #pragma unroll
     for (int k = 0; k < kTmaMaxUnits; ++k) {
-        int u = threadIdx.x + k * kTmaThreads;
-        int r = u / units_per_row;
-        u_row[k] = u < units_per_tile ? r : -1;
-        u_col[k] = u - r * units_per_row;                       // unit index inside the row
-        s_off[k] = r * RP + (NCHW ? 12 : 4) * u_col[k];         // byte offset of the unit in the stage (before the +a shift)
-        o_off[k] = NCHW ? r * ps + 4 * u_col[k] : r * row_bytes + 4 * u_col[k];
+        const int u = tid + k * kConsumers;
+        const int r = u / upr, c = u - r * upr;
+        s_off[k] = (uint32_t)(r * RP + IN_BYTES * c);
+        cph[k] = (E * c) % 3;                    // channel of the unit's first element (NHWC, AFFINE only)
+        if (u < units_per_tile) nu = k + 1;
     }
+    const uint32_t stage0 = smem_u32(stages);
+    const uint32_t magic = opaque_u32(0x4B000000u);
+    OutT* const out_base = reinterpret_cast<OutT*>(p.out) + (int64_t)E * tid;
 
-    const int64_t plane = (int64_t)ps * ps;
+    int s = 0;
+    uint32_t ph = 0;
     for (int64_t i = 0; i < my_tiles; ++i) {
-        if (threadIdx.x < 32 && i + kTmaStages - 1 < my_tiles) issue(i + kTmaStages - 1);
-        const TileInfo ti = tile_info(p, first + i * stride);
-        const bool fv = ti.fl & DH_FLIP_V, fh = ti.fl & DH_FLIP_H;
-        const int s = (int)(i % kTmaStages);
-        const uint8_t* src = stages + (size_t)s * stage_bytes;
-        const int a = (3 * ti.x) & 15;
-        const uint32_t sh = (uint32_t)(a & 3) * 8u;
-        const int a4 = a & ~3;
-        mbar_wait(&full[s], (uint32_t)((i / kTmaStages) & 1));
-
-        OutT* outp = reinterpret_cast<OutT*>(p.out) + ti.slot * 3 * plane + (int64_t)ti.tr * R * (NCHW ? ps : row_bytes);
-        if (ti.inside && !fh) {
+        mbar_wait(&full[s], ph);
+        const TileMeta m = meta[s];
+        const uint32_t sbase = stage0 + (uint32_t)(s * stage_bytes);
+        OutT* const o = out_base + m.out_off;
+        if ((m.flags & (kInside | DH_FLIP_H)) == kInside) {
             // fast path: aligned LDS words + funnel shift
+            const int a = (3 * m.x) & 15;
+            const uint32_t sh = (uint32_t)(a & 3) * 8u;
+            const uint32_t abase = sbase + (uint32_t)(a & ~3);
 #pragma unroll
-            for (int k = 0; k < kTmaMaxUnits; ++k) {
-                if (u_row[k] >= 0) {
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + s_off[k] + a4);
+            for (int k = 0; k < KU; ++k) {
+                if (FULL || k < nu) {
+                    uint32_t q[NW + 1], w[NW];
+#pragma unroll
+                    for (int j = 0; j <= NW; ++j) q[j] = lds32(abase + s_off[k] + 4 * j);
+#pragma unroll
+                    for (int j = 0; j < NW; ++j) w[j] = __funnelshift_r(q[j], q[j + 1], sh);
+                    OutT* const ok = o + k * (kConsumers * E);
                     if (!NCHW) {
-                        const uint32_t w = __funnelshift_r(wp[0], wp[1], sh);
-                        const int c0 = (4 * u_col[k]) % 3, c1 = c0 == 2 ? 0 : c0 + 1, c2 = c1 == 2 ? 0 : c1 + 1;
-                        float f0 = norm_f<SCALE, AFFINE>(byte_to_float(w, 0x7440), c0, p);
-                        float f1 = norm_f<SCALE, AFFINE>(byte_to_float(w, 0x7441), c1, p);
-                        float f2 = norm_f<SCALE, AFFINE>(byte_to_float(w, 0x7442), c2, p);
-                        float f3 = norm_f<SCALE, AFFINE>(byte_to_float(w, 0x7443), c0, p);
-                        store4<OutT>(outp + o_off[k], f0, f1, f2, f3);
+                        float f[E];
+                        int c = cph[k];
+#pragma unroll
+                        for (int j = 0; j < E; ++j) {
+                            f[j] = norm_f<SCALE, AFFINE>(byte_f(w[j >> 2], j & 3, magic), c, p);
+                            if (AFFINE) c = c == 2 ? 0 : c + 1;
+                        }
+                        if (!(p.debug & 2) || f[0] == 12345.f) store_unit(ok, f, p.debug & 4);
                     } else {
-                        const uint32_t q0 = wp[0], q1 = wp[1], q2 = wp[2], q3 = wp[3];
-                        const uint32_t w0 = __funnelshift_r(q0, q1, sh), w1 = __funnelshift_r(q1, q2, sh), w2 = __funnelshift_r(q2, q3, sh);
-                        // bytes: w0 = R0 G0 B0 R1 | w1 = G1 B1 R2 G2 | w2 = B2 R3 G3 B3
-                        OutT* o = outp + o_off[k];
-                        store4<OutT>(o, norm_f<SCALE, AFFINE>(byte_to_float(w0, 0x7440), 0, p), norm_f<SCALE, AFFINE>(byte_to_float(w0, 0x7443), 0, p),
-                                     norm_f<SCALE, AFFINE>(byte_to_float(w1, 0x7442), 0, p), norm_f<SCALE, AFFINE>(byte_to_float(w2, 0x7441), 0, p));
-                        store4<OutT>(o + plane, norm_f<SCALE, AFFINE>(byte_to_float(w0, 0x7441), 1, p), norm_f<SCALE, AFFINE>(byte_to_float(w1, 0x7440), 1, p),
-                                     norm_f<SCALE, AFFINE>(byte_to_float(w1, 0x7443), 1, p), norm_f<SCALE, AFFINE>(byte_to_float(w2, 0x7442), 1, p));
-                        store4<OutT>(o + 2 * plane, norm_f<SCALE, AFFINE>(byte_to_float(w0, 0x7442), 2, p), norm_f<SCALE, AFFINE>(byte_to_float(w1, 0x7441), 2, p),
-                                     norm_f<SCALE, AFFINE>(byte_to_float(w2, 0x7440), 2, p), norm_f<SCALE, AFFINE>(byte_to_float(w2, 0x7443), 2, p));
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float f[E];
+#pragma unroll
+                            for (int j = 0; j < E; ++j) {
+                                const int b = 3 * j + ch;  // byte of pixel j, channel ch
+                                f[j] = norm_f<SCALE, AFFINE>(byte_f(w[b >> 2], b & 3, magic), ch, p);
+                            }
+                            if (!(p.debug & 2) || f[0] == 12345.f) store_unit(ok + ch * plane, f, p.debug & 4);
+                        }
                     }
                 }
             }
         } else {
             // slow path: horizontally flipped patches (bytes from the stage) and patches that overhang the slide (guarded global loads)
-            // (recomputes the unit geometry from the unit index so that the register arrays above are never indexed dynamically)
-            for (int u = threadIdx.x; u < units_per_tile; u += kTmaThreads) {
-                const int ur = u / units_per_row, uc = u - ur * units_per_row;
-                const int orow = ti.tr * R + ur;
+            const bool inside = m.flags & kInside, fv = m.flags & DH_FLIP_V, fh = m.flags & DH_FLIP_H;
+            const int a = (3 * m.x) & 15;
+            for (int u = tid; u < units_per_tile; u += kConsumers) {
+                const int ur = u / upr, uc = u - ur * upr;
+                const int orow = m.tr * R + ur;
                 const int srow = fv ? ps - 1 - orow : orow;
                 auto pix = [&](int scol, int ch) -> float {
                     uint32_t v = 0;
-                    if (ti.inside) {
-                        v = src[ur * RP + a + 3 * scol + ch];
+                    if (inside) {
+                        v = stages[(size_t)s * stage_bytes + ur * RP + a + 3 * scol + ch];
                     } else {
-                        const int64_t yy = (int64_t)ti.y + srow, xx = (int64_t)ti.x + scol;
+                        const int64_t yy = (int64_t)m.y + srow, xx = (int64_t)m.x + scol;
                         if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v = __ldg(p.slide + yy * p.pitch + 3 * xx + ch);
                     }
                     return norm_f<SCALE, AFFINE>((float)v, ch, p);
                 };
+                OutT* const ou = reinterpret_cast<OutT*>(p.out) + m.out_off + (int64_t)E * u;
                 if (!NCHW) {
-                    float f[4];
+                    float f[E];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int e = 4 * uc + j, col = e / 3, ch = e - 3 * col;
+                    for (int j = 0; j < E; ++j) {
+                        const int e = E * uc + j, col = e / 3, ch = e - 3 * col;
                         f[j] = pix(fh ? ps - 1 - col : col, ch);
                     }
-                    store4<OutT>(outp + ur * row_bytes + 4 * uc, f[0], f[1], f[2], f[3]);
+                    store_unit(ou, f);
                 } else {
-                    const int col = 4 * uc;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float f[4];
+                    for (int ch = 0; ch < 3; ++ch) {
+                        float f[E];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) f[j] = pix(fh ? ps - 1 - (col + j) : col + j, c);
-                        store4<OutT>(outp + ur * ps + col + c * plane, f[0], f[1], f[2], f[3]);
+                        for (int j = 0; j < E; ++j) f[j] = pix(fh ? ps - 1 - (E * uc + j) : E * uc + j, ch);
+                        store_unit(ou + ch * plane, f);
                     }
                 }
             }
         }
-        __syncthreads();  // every thread is done with stage s before warp 0 refills it (next iteration)
+        __syncwarp();  // all lanes of this warp are done reading stage s
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);
+        if (++s == S) { s = 0; ph ^= 1u; }
     }
 }
 
-// persistent grid = SMs x resident CTAs of this instantiation (registers decide: 3 or 4 per SM), so every CTA is co-resident
+// persistent grid = SMs x resident CTAs of this instantiation, so every CTA is co-resident
 template <typename K>
 static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_t smem, cudaStream_t st) {
     static int occ_cache[64] = {0};  // per instantiation, indexed by shared-memory size in KB
     int& occ = occ_cache[(smem >> 10) & 63];
     if (occ == 0) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTmaThreads, smem);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTmaThreads, smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
         if (occ < 1) occ = 1;
+        if (occ > 4) occ = 4;
     }
     const int64_t want = (int64_t)kNumSMs * occ;
     const int grid = (int)(n_tiles < want ? n_tiles : want);
@@ -278,33 +345,44 @@ static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_
 // Returns DH_ERR_UNSUPPORTED (without touching the error string) when the shape does not fit this kernel.
 int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, const int32_t* coords, const int32_t* out_index,
                       int64_t B, int ps, void* out, int out_dtype, int out_layout, int scale255, const float* mean3, const float* std3,
-                      const uint8_t* flip, cudaStream_t st) {
+                      const uint8_t* flip, int debug, cudaStream_t st) {
     const bool nchw = out_layout == DH_NCHW;
     if (out_dtype == DH_U8) return DH_ERR_UNSUPPORTED;
-    if (ps % 4 != 0 || pitch % 16 != 0 || reinterpret_cast<uintptr_t>(slide) % 16 != 0) return DH_ERR_UNSUPPORTED;
-    const size_t esz = out_dtype == DH_F32 ? 4 : 2;
-    if (reinterpret_cast<uintptr_t>(out) % (4 * esz) != 0) return DH_ERR_UNSUPPORTED;
+    const int E = out_dtype == DH_F32 ? 4 : 8;
+    if (ps % E != 0 || pitch % 16 != 0 || reinterpret_cast<uintptr_t>(slide) % 16 != 0) return DH_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(out) % 16 != 0) return DH_ERR_UNSUPPORTED;
     const int row_bytes = 3 * ps;
-    const int row_pitch = ((15 + row_bytes + 15) & ~15) + 16;  // largest copy + one spare word for the funnel shift
-    const int units_per_row = nchw ? ps / 4 : row_bytes / 4;
+    if (!nchw && row_bytes % E != 0) return DH_ERR_UNSUPPORTED;
+    const int row_pitch = ((15 + row_bytes + 15) & ~15) + 16;  // largest copy + one spare 16-byte line for the funnel shift
+    const int units_per_row = nchw ? ps / E : row_bytes / E;
     int R = 0;
     for (int r = 32; r >= 1; --r)
-        if (ps % r == 0 && r * units_per_row <= kTmaThreads * kTmaMaxUnits && r * row_pitch <= 11 * 1024) { R = r; break; }
+        if (ps % r == 0 && r * units_per_row <= kConsumers * kTmaMaxUnits && r * row_pitch <= 12 * 1024) { R = r; break; }
     if (!R) return DH_ERR_UNSUPPORTED;
+    if (B * (int64_t)(ps / R) >= (1ll << 40)) return DH_ERR_UNSUPPORTED;
 
     TmaGatherParams p{};
     p.slide = slide; p.H = H; p.W = W; p.pitch = pitch;
     p.coords = coords; p.out_index = out_index; p.flip = flip; p.out = out; p.B = B; p.ps = ps; p.R = R;
-    p.tiles_per_patch = ps / R; p.row_pitch = row_pitch; p.affine = mean3 ? 1 : 0;
+    p.tiles_per_patch = ps / R; p.row_pitch = row_pitch; p.units_per_row = units_per_row; p.debug = debug;
     for (int c = 0; c < 3; ++c) { p.mean[c] = mean3 ? mean3[c] : 0.f; p.stdv[c] = std3 ? std3[c] : 1.f; }
-    const size_t smem = (size_t)kTmaStages * R * row_pitch;
+    const bool affine = mean3 != nullptr;
+    const char* env = getenv("DH_GATHER_STAGES");  // profiling override
+    const int env_stages = env ? atoi(env) : 0;
+    int stages = env_stages >= 2 && env_stages <= kTmaMaxStages ? env_stages : 4;
+    while (stages > 2 && (size_t)stages * R * row_pitch > 56 * 1024) --stages;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * R * row_pitch;
     const int64_t n_tiles = B * (int64_t)p.tiles_per_patch;
     int rc_launch = DH_OK;
-#define DH_TMA(T, N, S, A) rc_launch = launch_one(gather_tma_kernel<T, N, S, A>, p, n_tiles, smem, st)
+    // every consumer thread owns exactly KU units (see the kernel): true for ps = 224 in all four output modes
+    const bool full_units = R * units_per_row == kConsumers * (nchw ? (E == 4 ? 4 : 2) : 6);
+#define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st) \
+                                            : launch_one(gather_tma_kernel<T, N, S, A, false>, p, n_tiles, smem, st)
 #define DH_TMA_SA(T, N)                                                                  \
     do {                                                                                 \
-        if (scale255) { if (p.affine) DH_TMA(T, N, true, true); else DH_TMA(T, N, true, false); } \
-        else          { if (p.affine) DH_TMA(T, N, false, true); else DH_TMA(T, N, false, false); } \
+        if (scale255) { if (affine) DH_TMA(T, N, true, true); else DH_TMA(T, N, true, false); } \
+        else          { if (affine) DH_TMA(T, N, false, true); else DH_TMA(T, N, false, false); } \
     } while (0)
     if (out_dtype == DH_F32) { if (nchw) DH_TMA_SA(float, true); else DH_TMA_SA(float, false); }
     else                     { if (nchw) DH_TMA_SA(__nv_bfloat16, true); else DH_TMA_SA(__nv_bfloat16, false); }

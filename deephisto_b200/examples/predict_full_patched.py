@@ -1,0 +1,333 @@
+"""Whole-slide patched prediction and stitching -- drop-in for the reference's `examples/predict_full_patched.py`.
+
+Same names and call signatures as the reference: `ImagePredictorPatched(psim_path, patch_sampler, batch_predictor, anno,
+layer, downscale=4).process()` (:22-63), `batch_predictor(patches, model, device)` (:66-78),
+`perform_and_save_visualizations` (:81-113), `load_model` (:116-126). What changes is where the work happens:
+
+  reference (per batch)                                     here
+  np.stack(u8)/255 -> tensor -> .to(device) -> permute       dh_gather_normalize writes the NCHW batch from the HBM-resident slide
+  model(features).detach().cpu().numpy()                     logits stay in HBM ([n_padded, n] float32 buffer)
+  python loop  prediction[y//d:(y+ps)//d, ...] += logits_i   dh_stitch_dense (reference order, bit-exact sums) / dh_stitch_scatter
+  np.argmax(prediction, axis=2)                              fused into the stitch epilogue
+
+`process()` picks the path from what it is given:
+  * a FullImageDenseSampler / FullImageRndSampler OBJECT of this package + a DeviceBatchPredictor -> device pipeline;
+  * anything else (the reference's usage: an iterator of (list[Patch], progress) and a callable list[Patch] -> ndarray)
+    -> the same control flow as the reference with the accumulation done by dh_stitch_scatter on the device.
+Multi-GPU (BASELINE config 4): `process(rank=r, world=G)` computes the row band of deephisto_b200/bands.py and
+assembles the bands with an NCCL all-gather (`torch.distributed` must be initialised)."""
+
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+
+from .. import bands, ops
+from ..anno.utils import AnnoDescription
+from ..patch_samplers.full_samplers import FullImageDenseSampler, FullImageRndSampler, SamplerExecutionMode
+from ..slide import Patch, open_slide
+
+
+def get_model(n_classes: int, pretrained: bool = False) -> torch.nn.Module:
+    """models/patch_cls_simple/model.py:5-11: torchvision ResNet18 with the final layer replaced. The reference asks for
+    ImageNet weights (a download); offline the default is random initialisation (weights come from load_model)."""
+    import torch.nn as nn
+    from torchvision import models
+
+    model = models.resnet18(weights=models.ResNet18_Weights.DEFAULT if pretrained else None)
+    model.fc = nn.Linear(model.fc.in_features, n_classes)
+    return model
+
+
+def load_model(weights_path: Path, device, n_classes: int = 5) -> torch.nn.Module:
+    """Reference :116-126."""
+    model = get_model(n_classes=n_classes).to(device)
+    model.load_state_dict(torch.load(weights_path, weights_only=True, map_location=device))
+    model.to(device).eval()
+    return model
+
+
+class DeviceBatchPredictor:
+    """features -> logits on the device. Called with a CUDA NCHW batch it returns CUDA float32 logits [B, n]; called with a
+    list[Patch] (the reference's batch_predictor contract, :66-78) it uploads the uint8 pixels, normalises them with
+    dh_gather_normalize and returns a numpy array like the reference.
+
+    dtype float32 keeps torch's defaults (what the reference runs on a GPU); bfloat16 runs the CNN in bf16 channels_last."""
+
+    def __init__(self, model: torch.nn.Module, device="cuda", dtype=torch.float32, channels_last: bool = True):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.channels_last = channels_last and dtype != torch.float32
+        model = model.to(self.device).eval()
+        if dtype != torch.float32:
+            model = model.to(dtype)
+        if self.channels_last:
+            model = model.to(memory_format=torch.channels_last)
+        self.model = model
+
+    @torch.no_grad()
+    def logits(self, features: torch.Tensor) -> torch.Tensor:
+        if self.channels_last:
+            features = features.contiguous(memory_format=torch.channels_last)
+        return self.model(features).float()
+
+    def features_from_patches(self, patches: list[Patch]) -> torch.Tensor:
+        """uint8 patch pixels -> [B,3,ps,ps] in [0,1] through the gather kernel: the stacked batch is a (B*ps) x ps 'slide'."""
+        ps = patches[0].patch_size
+        stack = np.stack([np.asarray(p.data) for p in patches]).reshape(len(patches) * ps, ps, 3)
+        slide = ops.DeviceSlide.from_numpy(stack, self.device)
+        coords = torch.arange(len(patches), dtype=torch.int32, device=self.device).mul_(ps).reshape(-1, 1)
+        coords = torch.cat([coords, torch.zeros_like(coords)], 1).contiguous()
+        return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NCHW", scale255=True)
+
+    def __call__(self, batch):
+        if isinstance(batch, torch.Tensor):
+            return self.logits(batch)
+        return self.logits(self.features_from_patches(batch)).cpu().numpy()
+
+
+def batch_predictor(patches: list[Patch], model, device) -> np.ndarray:
+    """Reference :66-78 (same signature and return type); the /255, NHWC->NCHW and float conversion run in the gather kernel."""
+    key = (id(model), str(device))
+    pred = _PREDICTORS.get(key)
+    if pred is None:
+        pred = _PREDICTORS[key] = DeviceBatchPredictor(model, device)
+    return pred(patches)
+
+
+_PREDICTORS: dict = {}
+
+
+class ImagePredictorPatched:
+    def __init__(self, psim_path, patch_sampler, batch_predictor: Callable, anno: AnnoDescription, layer: int, downscale: int = 4,
+                 *, device="cuda", cnn_batch: Optional[int] = None, progress: bool = False):
+        self.patch_sampler = patch_sampler
+        self.batch_predictor = batch_predictor
+        self.anno = anno
+        self.layer = layer
+        self.downscale = downscale
+        self._device = torch.device(device)
+        self._cnn_batch = cnn_batch
+        self._progress = progress
+        if isinstance(patch_sampler, (FullImageDenseSampler, FullImageRndSampler)):
+            self.h, self.w = patch_sampler.h, patch_sampler.w
+        else:
+            with open_slide(psim_path) as psim:
+                self.h, self.w = psim.layer_size(self.layer)
+        self.last_sum_map: Optional[torch.Tensor] = None      # kept when process_device(want_sum=True)
+
+    # ---- reference entry point --------------------------------------------------------------------------------------
+    def process(self, rank: Optional[int] = None, world: Optional[int] = None) -> np.ndarray:
+        """int64 [h//d, w//d] class map, like the reference's np.argmax(prediction, axis=2) (:62)."""
+        return self.process_device(rank=rank, world=world)["argmax"].cpu().numpy().astype(np.int64)
+
+    def process_device(self, want_sum: bool = False, want_count: bool = False, rank: Optional[int] = None,
+                       world: Optional[int] = None) -> dict:
+        fast = isinstance(self.batch_predictor, DeviceBatchPredictor)
+        if fast and isinstance(self.patch_sampler, FullImageDenseSampler):
+            if world is not None and world > 1:
+                return self._dense_banded(rank, world, want_sum)
+            return self._dense_device(want_sum, want_count)
+        if world is not None and world > 1:
+            raise ValueError("row-band sharding needs a FullImageDenseSampler object and a DeviceBatchPredictor")
+        if fast and isinstance(self.patch_sampler, FullImageRndSampler):
+            return self._scatter_device(self._rnd_batches(), want_sum, want_count)
+        return self._scatter_device(self._host_batches(), want_sum, want_count)
+
+    # ---- dense, device resident, bit-exact sums -----------------------------------------------------------------------
+    def _logits_for(self, sampler: FullImageDenseSampler, slide, logits: torch.Tensor, first: int, count: int, y_off: int = 0):
+        """Fill logits[first:first+count] for entries [first, first+count) of the padded dense enumeration."""
+        pred: DeviceBatchPredictor = self.batch_predictor
+        step = self._cnn_batch or max(sampler.batch_size, 512)
+        ps = sampler.patch_size
+        for a in range(first, first + count, step):
+            c = min(step, first + count - a)
+            coords = ops.dense_coords(sampler.h, sampler.w, ps, sampler.stride, sampler.batch_size, first=a, count=c, device=self._device)
+            if y_off:
+                coords[:, 0] -= y_off
+            feats = ops.gather_normalize(slide, coords, ps, dtype=pred.dtype, layout="NCHW", scale255=True)
+            logits[a : a + c] = pred.logits(feats)
+
+    def _dense_device(self, want_sum: bool, want_count: bool) -> dict:
+        s: FullImageDenseSampler = self.patch_sampler
+        n = len(self.anno.anno_classes)
+        logits = torch.empty((s.n_padded, n), dtype=torch.float32, device=self._device)
+        self._logits_for(s, s._slide, logits, 0, s.n_padded)
+        sum_map, cnt, amax = ops.stitch_dense(logits, s.h, s.w, s.patch_size, s.stride, self.downscale, s.batch_size,
+                                              want_sum=want_sum, want_count=want_count, want_argmax=True)
+        self.last_sum_map = sum_map
+        return {"argmax": amax, "sum": sum_map, "count": cnt, "logits": logits}
+
+    def dense_band_local(self, rank: int, world: int, want_sum: bool = False) -> dict:
+        """The work of ONE rank of a row-band sharded prediction, without the exchange step: logits of the band's patches
+        (halo patch rows recomputed), then the band of the stitched map, padded to `plan.rows_max` rows."""
+        s: FullImageDenseSampler = self.patch_sampler
+        n = len(self.anno.anno_classes)
+        d = self.downscale
+        plan = bands.plan_band(s.h, s.w, s.patch_size, s.stride, d, s.batch_size, rank, world)
+        logits = torch.zeros((s.n_padded, n), dtype=torch.float32, device=self._device)
+        if plan.patch_ranges:
+            slide, y_off = s.band_slide(plan.slide_y0, plan.slide_y1)
+            for first, count in plan.patch_ranges:
+                self._logits_for(s, slide, logits, first, count, y_off)
+        dw = s.w // d
+        amax_band = torch.zeros((plan.rows_max, dw), dtype=torch.uint8, device=self._device)
+        sum_band = torch.zeros((plan.rows_max, dw, n), dtype=torch.float32, device=self._device) if want_sum else None
+        if plan.row_end > plan.row_begin:
+            sm, _, am = ops.stitch_dense(logits, s.h, s.w, s.patch_size, s.stride, d, s.batch_size, row_begin=plan.row_begin,
+                                         row_end=plan.row_end, want_sum=want_sum, want_argmax=True)
+            amax_band[: plan.row_end - plan.row_begin] = am
+            if want_sum:
+                sum_band[: plan.row_end - plan.row_begin] = sm
+        return {"argmax_band": amax_band, "sum_band": sum_band, "logits": logits, "plan": plan}
+
+    def _dense_banded(self, rank: int, world: int, want_sum: bool) -> dict:
+        import torch.distributed as dist
+
+        s: FullImageDenseSampler = self.patch_sampler
+        dh = s.h // self.downscale
+        loc = self.dense_band_local(rank, world, want_sum)
+        # the one exchange step: band maps are disjoint row ranges -> all-gather, then drop the padding rows
+        out = {"argmax": assemble_bands(loc["argmax_band"], dh, world, dist), "sum": None, "count": None, "logits": loc["logits"],
+               "plan": loc["plan"]}
+        if want_sum:
+            out["sum"] = assemble_bands(loc["sum_band"], dh, world, dist)
+        self.last_sum_map = out["sum"]
+        return out
+
+    # ---- arbitrary coordinates: scatter-accumulate ------------------------------------------------------------------------
+    def _rnd_batches(self):
+        s: FullImageRndSampler = self.patch_sampler
+        pred: DeviceBatchPredictor = self.batch_predictor
+        for coords, progress in s.coords_generator():
+            feats = ops.gather_normalize(s._slide, coords, s.patch_size, dtype=pred.dtype, layout="NCHW", scale255=True)
+            yield pred.logits(feats), coords, s.patch_size, progress
+
+    def _host_batches(self):
+        """The reference's loop (:47-54): any iterator of (list[Patch], progress) and any callable list[Patch] -> [B, n]."""
+        for patches, progress in self.patch_sampler:
+            preds = self.batch_predictor(patches)
+            lg = torch.as_tensor(np.asarray(preds) if not isinstance(preds, torch.Tensor) else preds, dtype=torch.float32).to(self._device)
+            coords = torch.tensor([[p.pos_y, p.pos_x] for p in patches], dtype=torch.int32, device=self._device)
+            yield lg, coords, patches[0].patch_size, progress
+
+    def _scatter_device(self, batches, want_sum: bool, want_count: bool) -> dict:
+        d = self.downscale
+        dh, dw = self.h // d, self.w // d
+        n = len(self.anno.anno_classes)
+        sum_map = torch.zeros((dh, dw, n), dtype=torch.float32, device=self._device)
+        cnt = torch.zeros((dh, dw), dtype=torch.int32, device=self._device) if want_count else None
+        bar = None
+        if self._progress:
+            from tqdm import tqdm
+
+            bar = tqdm(total=100, desc="Predicting", unit="step")
+        for lg, coords, ps, progress in batches:
+            ops.stitch_scatter(lg.contiguous(), coords.contiguous(), ps, d, sum_map, cnt)
+            if bar is not None:
+                bar.n = round(progress * 100, 2)
+                bar.refresh()
+        _, amax = ops.stitch_finalize(sum_map, None, want_norm=False, want_argmax=True)
+        self.last_sum_map = sum_map
+        return {"argmax": amax, "sum": sum_map if want_sum else None, "count": cnt, "logits": None}
+
+
+def assemble_bands(band: torch.Tensor, dh: int, world: int, dist) -> torch.Tensor:
+    """All-gather equal-height (padded) row bands and keep rows [r*dh//G, (r+1)*dh//G) of each: [dh, ...]. Works with
+    NCCL (CUDA tensors) and gloo (CPU tensors; used by the world_size-2 CPU tests)."""
+    rows_max = band.shape[0]
+    gathered = torch.empty((world * rows_max,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+    dist.all_gather_into_tensor(gathered, band.contiguous())
+    heights = [bands.band_rows(dh, r, world)[1] - bands.band_rows(dh, r, world)[0] for r in range(world)]
+    if all(hh == rows_max for hh in heights):
+        return gathered
+    return torch.cat([gathered[r * rows_max : r * rows_max + heights[r]] for r in range(world)], 0)
+
+
+def colorize(pred: torch.Tensor | np.ndarray, anno_dsc: AnnoDescription) -> np.ndarray:
+    """Class map -> RGB by class colour (reference :89-95)."""
+    pred = torch.as_tensor(pred)
+    lut = torch.zeros((256, 3), dtype=torch.uint8)
+    for a in anno_dsc.anno_classes:
+        lut[a.id] = torch.tensor(a.color, dtype=torch.uint8)
+    return lut.to(pred.device)[pred.long()].cpu().numpy()
+
+
+def perform_and_save_visualizations(img_path, anno_dsc: AnnoDescription, pred: np.ndarray, out_dir: Path = Path(".")):
+    """Reference :81-113: colourised mask, downscaled slide, 0.6/0.4 overlay, saved as JPEG."""
+    from PIL import Image
+
+    out_dir.mkdir(exist_ok=True, parents=True)
+    stem = Path(img_path).stem if isinstance(img_path, (str, Path)) else "slide"
+    h, w = pred.shape[:2]
+    colored = colorize(pred, anno_dsc)
+    Image.fromarray(colored).save(out_dir / f"{stem}_mask.jpg", quality=95)
+    with open_slide(img_path) as psim:
+        img = np.asarray(psim.get_region((0, 0), (psim.height, psim.width), target_hw=(h, w)))
+    Image.fromarray(img).save(out_dir / f"{stem}.jpg", quality=95)
+    alpha = 0.6
+    Image.fromarray((img * alpha + colored * (1 - alpha)).astype(np.uint8)).save(out_dir / f"{stem}_overlay.jpg", quality=95)
+
+
+def main(argv=None):
+    """python -m deephisto_b200.examples.predict_full_patched --synthetic H W [--weights best_model.pth] (reference :129-183)."""
+    import argparse
+    import os
+    import time
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--image", default=None, help=".npy slide (uint8 [H,W,3]) or .psi when psimage is installed")
+    ap.add_argument("--synthetic", type=int, nargs=2, metavar=("H", "W"), default=None)
+    ap.add_argument("--weights", default=None)
+    ap.add_argument("--layer", type=int, default=1)
+    ap.add_argument("--stride", type=int, default=112)
+    ap.add_argument("--downscale", type=int, default=16)
+    ap.add_argument("--random-sampler", action="store_true", help="the reference's default (coverage-driven random sampling)")
+    ap.add_argument("--bf16", action="store_true")
+    ap.add_argument("--out", default="./output/")
+    args = ap.parse_args(argv)
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    anno_dsc = AnnoDescription.with_known_colors({"AT": (245, 119, 34), "BG": (153, 255, 255), "LP": (64, 170, 72), "MM": (255, 0, 0),
+                                                  "TUM": (33, 67, 156)})
+    if args.weights:
+        model = load_model(args.weights, device)
+    else:
+        torch.manual_seed(0)
+        model = get_model(5).to(device).eval()
+    from ..slide import SyntheticSlide
+
+    src = SyntheticSlide(*args.synthetic) if args.synthetic else args.image
+    if src is None:
+        ap.error("give --image or --synthetic H W")
+    mode = SamplerExecutionMode.INMEMORY_SINGLEPROC
+    if args.random_sampler:
+        sampler = FullImageRndSampler(src, layer=args.layer, patch_size=224, batch_size=64, mode=mode, device=device)
+    else:
+        sampler = FullImageDenseSampler(src, layer=args.layer, patch_size=224, batch_size=64, mode=mode, stride=args.stride, device=device,
+                                        lazy_slide=world > 1)
+    predictor = ImagePredictorPatched(src, patch_sampler=sampler, batch_predictor=DeviceBatchPredictor(model, device, torch.bfloat16 if args.bf16 else torch.float32),
+                                      anno=anno_dsc, layer=args.layer, downscale=args.downscale, device=device)
+    t0 = time.perf_counter()
+    pred = predictor.process(rank=rank, world=world) if world > 1 else predictor.process()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        print(f"{sampler.h} x {sampler.w} slide -> {pred.shape} class map in {dt:.3f} s ({sampler.h * sampler.w / dt / 1e9:.3f} Gpx/s, {world} GPU)")
+        if not args.synthetic:
+            perform_and_save_visualizations(src, anno_dsc, pred, out_dir=Path(args.out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,12 +61,14 @@ class DeviceSlide:
         return s
 
     @classmethod
-    def synthetic(cls, H: int, W: int, seed: int = 0, device="cuda") -> "DeviceSlide":
-        """Counter-hash slide generated on the device (oracle/synth.py restates the bytes)."""
+    def synthetic(cls, H: int, W: int, seed: int = 0, device="cuda", y0: int = 0, rows: Optional[int] = None) -> "DeviceSlide":
+        """Counter-hash slide generated on the device (oracle/synth.py restates the bytes). With y0 / rows only that row band
+        of the H x W slide is generated; the returned slide has `rows` rows and row 0 is slide row y0."""
         lib = _lib.require_device()
-        s = cls.empty(H, W, device)
+        rows = H - y0 if rows is None else rows
+        s = cls.empty(rows, W, device)
         with torch.cuda.device(s.storage.device):
-            check(lib.dh_synth_slide(s.storage.data_ptr(), H, W, s.pitch, seed, _stream()), "dh_synth_slide")
+            check(lib.dh_synth_slide_rows(s.storage.data_ptr(), H, W, s.pitch, y0, rows, seed, _stream()), "dh_synth_slide_rows")
         return s
 
     def to_numpy(self) -> np.ndarray:
@@ -289,4 +291,5 @@ def rasterize_polygons(edges: torch.Tensor, edge_off: torch.Tensor, reg_bbox: to
 def set_gather_variant(variant: str = "auto") -> None:
     """Profiling switch: "auto" (TMA-staged kernel when the shape allows), "direct" (LDG/STG kernel), "tma" (fail if unsupported)."""
     lib = _lib.load()
-    check(lib.dh_gather_set_variant({"auto": 0, "direct": 1, "tma": 2}[variant]), "dh_gather_set_variant")
+    check(lib.dh_gather_set_variant({"auto": 0, "direct": 1, "tma": 2, "tma_noload": 3, "tma_nostore": 4, "tma_nomem": 5, "tma_plainstore": 6}[variant]),
+          "dh_gather_set_variant")

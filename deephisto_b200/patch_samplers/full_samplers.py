@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from .. import ops
-from ..slide import Patch, layer_to_device, open_slide
+from ..slide import Patch, band_to_device, layer_to_device, open_slide
 
 
 class SamplerExecutionMode(Enum):
@@ -126,15 +126,19 @@ class FullImageDenseSampler:
     `stride=None` means stride = patch_size (the reference would raise a TypeError in `range`)."""
 
     def __init__(self, psimage_path: Path, layer: int, patch_size: int, batch_size: int, mode: SamplerExecutionMode,
-                 stride: int = None, *, device="cuda"):
+                 stride: int = None, *, device="cuda", lazy_slide: bool = False):
+        """`lazy_slide=True` (row-band sharding, BASELINE config 4) does not upload the whole layer: each rank uploads only
+        the rows of its band through `band_slide`."""
         self._psim_path = psimage_path
         self.mode = mode
-        src = open_slide(psimage_path)
-        with src as psim:
+        self._src = open_slide(psimage_path)
+        self._slide_dev = None
+        with self._src as psim:
             self.layer = layer
             psim._assert_layer(layer)
             self.h, self.w = psim.layer_size(self.layer)
-            self._slide = layer_to_device(psim, layer, device)
+            if not lazy_slide:
+                self._slide_dev = layer_to_device(psim, layer, device)
         self.patch_size = patch_size
         self.batch_size = batch_size
         self.stride = patch_size if stride is None else stride
@@ -144,6 +148,21 @@ class FullImageDenseSampler:
 
     def __len__(self) -> int:
         return self.n_padded // self.batch_size
+
+    @property
+    def _slide(self):
+        if self._slide_dev is None:
+            with self._src as psim:
+                self._slide_dev = layer_to_device(psim, self.layer, self._device)
+        return self._slide_dev
+
+    def band_slide(self, y0: int, y1: int):
+        """(DeviceSlide holding rows [y0, y1) of the layer, y0): what a rank needs for its row band plus the patch-size halo.
+        A slide that is already resident is used as it is (offset 0)."""
+        if self._slide_dev is not None:
+            return self._slide_dev, 0
+        with self._src as psim:
+            return band_to_device(psim, self.layer, y0, y1, self._device), y0
 
     def coords_device(self) -> torch.Tensor:
         """int32 [n_padded, 2] device tensor of all (y, x) in reference order, padding included."""

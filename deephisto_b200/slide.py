@@ -104,6 +104,10 @@ class SyntheticSlide:
             self._dev[key] = DeviceSlide.synthetic(self.height, self.width, self.seed, device)
         return self._dev[key]
 
+    def device_band(self, y0: int, y1: int, device="cuda") -> DeviceSlide:
+        """Rows [y0, y1) generated directly in HBM (no full-slide buffer)."""
+        return DeviceSlide.synthetic(self.height, self.width, self.seed, device, y0=y0, rows=y1 - y0)
+
     def get_region_from_layer(self, layer: int, p0, p1) -> np.ndarray:
         self._assert_layer(layer)
         (y0, x0), (y1, x1) = p0, p1
@@ -177,4 +181,18 @@ def layer_to_device(src, layer: int, device="cuda") -> DeviceSlide:
         return src.device_slide(device)
     h, w = src.layer_size(layer)
     arr = np.asarray(src.get_region_from_layer(layer, (0, 0), (h, w)))
+    return DeviceSlide.from_numpy(arr, device)
+
+
+def band_to_device(src, layer: int, y0: int, y1: int, device="cuda") -> DeviceSlide:
+    """Upload rows [y0, y1) of layer `layer` (a row band with its halo); row 0 of the result is slide row y0."""
+    if isinstance(src, DeviceSlideSource):
+        src._assert_layer(layer)
+        s = src.dev
+        return DeviceSlide(s.storage[y0 * s.pitch : y1 * s.pitch], y1 - y0, s.W, s.pitch)
+    if isinstance(src, SyntheticSlide):
+        src._assert_layer(layer)
+        return src.device_band(y0, y1, device)
+    h, w = src.layer_size(layer)
+    arr = np.asarray(src.get_region_from_layer(layer, (y0, 0), (y1, w)))
     return DeviceSlide.from_numpy(arr, device)

@@ -65,6 +65,9 @@ DH_API int dh_device_check(void);
  * for benchmark inputs (no 30 GB host->device copy for the 100k x 100k case).
  * ------------------------------------------------------------------------------------------ */
 DH_API int dh_synth_slide(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, uint64_t seed, void* stream);
+/* rows [y0, y0+rows) of the same H x W slide into a buffer whose row 0 is slide row y0 (row bands) */
+DH_API int dh_synth_slide_rows(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, int64_t y0, int64_t rows, uint64_t seed,
+                               void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * A1  FullImageDenseSampler._create_batched_coords (full_samplers.py:374-404)
@@ -97,7 +100,9 @@ DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64_t W, int64
                         int scale255, const float* mean3_host, const float* std3_host, const uint8_t* flip,
                         void* stream);
 
-/* Variant selector for profiling: 0 = auto, 1 = direct (LDG/STG) kernel, 2 = TMA-staged kernel. */
+/* Variant selector for profiling: 0 = auto, 1 = direct (LDG/STG) kernel, 2 = TMA-staged kernel;
+ * 3 / 4 / 5 = TMA-staged kernel with the loads / the stores / both switched off (WRONG RESULTS: ceiling measurements only);
+ * 6 = TMA-staged kernel with default-policy instead of streaming stores. */
 DH_API int dh_gather_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------

@@ -1,0 +1,136 @@
+"""Row-band partition of whole-slide prediction (deephisto_b200/bands.py): host logic against the CPU oracle, and the
+exchange step (all-gather of band maps) over gloo with world_size 2 -- no GPU."""
+
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from deephisto_b200 import bands
+from oracle import dense as odense
+from oracle import stitch as ostitch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+CASES = [  # (H, W, ps, stride, d, batch)
+    (2048, 2048, 224, 112, 16, 64),
+    (1000, 777, 224, 100, 3, 7),
+    (1000, 777, 224, 100, 16, 7),
+    (300, 260, 32, 48, 4, 5),      # stride > ps: gaps between patches
+    (224, 500, 224, 64, 8, 3),     # h == ps: no main-grid rows
+    (448, 448, 224, 224, 1, 4),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_patch_origin_matches_oracle(case):
+    H, W, ps, stride, d, B = case
+    g = bands.dense_grid(H, W, ps, stride, B)
+    coords, n = odense.dense_coords(H, W, ps, stride, B)
+    assert (g.N, g.n_padded) == (n, len(coords))
+    got = np.array([bands.patch_origin(g, i) for i in range(g.n_padded)], dtype=np.int32)
+    assert np.array_equal(got, coords)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("case", CASES)
+def test_band_plan_reproduces_full_map(case, world):
+    """Stitching only the patches a band's plan lists gives exactly the full map's rows of that band (bit-exact sums:
+    within a band the accumulation order is the reference's), and the band's slide rows contain every listed patch."""
+    H, W, ps, stride, d, B = case
+    coords, _ = odense.dense_coords(H, W, ps, stride, B)
+    rng = np.random.default_rng(5)
+    logits = rng.standard_normal((len(coords), 4)).astype(np.float32)
+    full, fcnt, famax = ostitch.stitch(logits, coords, H, W, ps, d)
+    dh = H // d
+    covered = 0
+    for rank in range(world):
+        plan = bands.plan_band(H, W, ps, stride, d, B, rank, world)
+        assert (plan.row_begin, plan.row_end) == bands.band_rows(dh, rank, world)
+        idx = bands.patch_indices(plan)
+        assert len(idx) == len(set(idx)) == plan.n_patches
+        masked = np.zeros_like(logits)
+        masked[idx] = logits[idx]
+        # zeroed logits still ADD 0.0 in the oracle loop; a patch outside the plan must not touch the band at all
+        keep = np.zeros(len(coords), bool)
+        keep[idx] = True
+        band, bcnt, bamax = ostitch.stitch(logits[keep], coords[keep], H, W, ps, d, plan.row_begin, plan.row_end)
+        assert np.array_equal(band.view(np.uint32), full[plan.row_begin:plan.row_end].view(np.uint32))
+        assert np.array_equal(bcnt, fcnt[plan.row_begin:plan.row_end])
+        for i in idx:
+            y, _ = coords[i]
+            assert plan.slide_y0 <= y and y + ps <= plan.slide_y1
+        assert plan.rows_max >= plan.row_end - plan.row_begin
+        covered += plan.row_end - plan.row_begin
+    assert covered == dh
+
+
+def test_band_halo_overhead_is_small_at_full_size():
+    """100k x 100k, stride 112, 8 ranks (BASELINE config 4): the recomputed halo patch rows stay under 3 %."""
+    H = W = 100000
+    g = bands.dense_grid(H, W, 224, 112, 64)
+    total = sum(bands.plan_band(H, W, 224, 112, 16, 64, r, 8).n_patches for r in range(8))
+    assert g.n_padded <= total < 1.03 * g.n_padded
+    p = bands.plan_band(H, W, 224, 112, 16, 64, 3, 8)
+    assert p.slide_y1 - p.slide_y0 < H // 8 + 3 * 224
+
+
+WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from deephisto_b200 import bands
+from deephisto_b200.examples.predict_full_patched import assemble_bands
+from oracle import dense as odense, stitch as ostitch
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+for (H, W, ps, stride, d, B) in [(1000, 777, 224, 100, 3, 7), (2048, 2048, 224, 112, 16, 64)]:
+    coords, _ = odense.dense_coords(H, W, ps, stride, B)
+    logits = np.random.default_rng(9).standard_normal((len(coords), 5)).astype(np.float32)
+    full, _, famax = ostitch.stitch(logits, coords, H, W, ps, d)
+    plan = bands.plan_band(H, W, ps, stride, d, B, rank, world)
+    keep = np.zeros(len(coords), bool); keep[bands.patch_indices(plan)] = True
+    band, _, bamax = ostitch.stitch(logits[keep], coords[keep], H, W, ps, d, plan.row_begin, plan.row_end)
+    pad = torch.zeros((plan.rows_max,) + band.shape[1:]); pad[: len(band)] = torch.from_numpy(band)
+    apad = torch.zeros((plan.rows_max, band.shape[1]), dtype=torch.uint8); apad[: len(band)] = torch.from_numpy(bamax.astype(np.uint8))
+    got = assemble_bands(pad, H // d, world, dist)
+    agot = assemble_bands(apad, H // d, world, dist)
+    assert got.shape == full.shape, (got.shape, full.shape)
+    assert np.array_equal(got.numpy().view(np.uint32), full.view(np.uint32))
+    assert np.array_equal(agot.numpy(), famax.astype(np.uint8))
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_band_assembly_gloo_world2(tmp_path):
+    import subprocess
+
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(ROOT)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        outs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in out, out[-2000:]

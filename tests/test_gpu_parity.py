@@ -315,6 +315,10 @@ def test_gather_kernel_variants_agree_with_oracle(ops, variant, ps):
     try:
         for layout in ("NHWC", "NCHW"):
             for dtype in (torch.float32, torch.bfloat16):
+                if variant == "tma" and dtype == torch.bfloat16 and ps % 8 != 0:
+                    with pytest.raises(Exception, match="not supported by the TMA-staged kernel"):   # 16-byte bf16 units need ps % 8 == 0
+                        ops.gather_normalize(slide, cdev, ps, dtype=dtype, layout=layout)
+                    continue
                 for scale255, mean, std, flip in [(True, None, None, None), (False, None, None, None),
                                                   (True, (0.5, 0.4, 0.3), (0.2, 0.25, 0.3), None), (True, None, None, flips)]:
                     got = ops.gather_normalize(slide, cdev, ps, dtype=dtype, layout=layout, scale255=scale255, mean=mean, std=std, flip=flip)
