@@ -3,18 +3,24 @@
 
 Default workload = BASELINE.json configs[1]: `examples.sample_annotated_rnd --torch` -- random 224x224 patches inside
 50 synthetic annotation polygons on a 32768 x 32768 synthetic slide, batch 256, fp32 NHWC features in [0,1] + int64
-labels + (y,x) coords, exactly what AnnoRegionRndSampler.torch_generator yields. One step = one batch:
-    dh_region_sample (Philox draws + exact clip-area acceptance, 256 slots)  ->  dh_gather_normalize (256 patches).
+labels + (y,x) coords, exactly what AnnoRegionRndSampler.torch_generator yields. One step = one batch of 256 patches.
+The device pipeline prefetches CHUNK (16) batches per pair of launches:
+    dh_region_sample (Philox draws + exact clip-area acceptance, 16 x 256 slots)  ->  dh_gather_normalize (16 x 256 patches)
+so a K-step run is ceil(K/16) chunk pairs (the last one partial) and every batch is a contiguous slice of the chunk buffer.
 
   value     patches/s over all ranks, inputs (slide, polygon tables) resident in HBM, CUDA-event timed, max over ranks
-  e2e       the same metric through the public Python API (AnnoRegionRndSampler.torch_generator), every step ending
-            with the device->host read of the step's labels and coordinates into pinned memory (the features stay
-            in HBM for the consumer CNN; `features_to_host` also reports the PCIe-bound variant)
+  e2e       the same metric through the public Python API (AnnoRegionRndSampler.torch_generator) starting from a slide in
+            PINNED HOST memory: its upload to HBM is inside the timed region (once per run -- the slide then stays resident,
+            which is the product's design), and every step ends with the device->host read of the step's labels and
+            coordinates; features stay in HBM for the consumer CNN (`features_to_host` also reports the PCIe-bound variant)
   roofline  dominant kernel (gather+normalise): algorithmic bytes / CUDA-event time of that kernel vs measured HBM peak
   cpu_baseline / --impl reference: the reference's CPU path (oracle/cpu_pipeline.py restates
             AnnoRegionRndSampler.torch_generator; the reference itself needs psimage + shapely, which do not exist)
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload annotated_rnd|dense|predict]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload annotated_rnd|predict]
+
+`--workload predict` (BASELINE configs[2]/[3]): whole-slide patched prediction, ResNet18 (torch/cuDNN) on a synthetic
+40k x 40k slide (1 GPU) or 100k x 100k slide row-band sharded over N GPUs; metric = gigapixels/s; one step = one slide.
 """
 
 from __future__ import annotations
@@ -37,9 +43,9 @@ PATCH_IN = PS * PS * 3                 # 150 528 B uint8 read per patch
 SLIDE_HW = (32768, 32768)
 N_POLY = 50
 BATCH = 256
+CHUNK = 16                             # batches prefetched per (sample, gather) launch pair
 K_PER_REGION = 4
 RI = 0.75
-L2_BYTES = 126 * 1024 * 1024
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -81,7 +87,12 @@ class ClockSampler(threading.Thread):
                 self.samples.append((sm, reasons, util))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.01)
+
+    def finish(self):
+        self.stop_flag = True
+        self.join(timeout=1)
+        return self.summary()
 
     def summary(self):
         if not self.ok or not self.samples:
@@ -99,91 +110,106 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": self.max_sm, "reasons": seen, "samples": len(busy)}
 
 
+def dist_env():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
 # --------------------------------------------------------------------------------------------------------------------
-# CPU legs (run in a process that never touched CUDA: they fork worker pools)
-def cpu_leg_annotated(steps: int, warmup: int, workers: int | None, budget_s: float | None):
-    from oracle import cpu_pipeline, synth
-    from deephisto_b200.synthetic import synth_polygons
-
-    H, W = SLIDE_HW
-    cores = workers or os.cpu_count()
-    path = synth.synth_slide_shared(H, W, 0, workers=cores, return_path=True)
-    images = [((H, W), synth_polygons(N_POLY, H, W, seed=0))]
-    pipe = cpu_pipeline.AnnotatedRndCPU(path, (H, W, 3), images, layer=1, one_image_for_batch=True, max_workers=cores)
-
-    def run(n_batches, seed):
-        t0 = time.perf_counter()
-        n = 0
-        for f, l, c in pipe.batches(PS, BATCH, n_batches, batches_per_worker=2, k=K_PER_REGION, ri=RI, seed=seed):
-            n += f.shape[0]
-        return n, time.perf_counter() - t0
-
-    try:
-        return _cpu_leg_run(run, steps, warmup, cores, budget_s, H, W)
-    finally:
-        pipe.close()
-
-
-def _cpu_leg_run(run, steps, warmup, cores, budget_s, H, W):
-    if warmup > 0:
-        run(max(2, min(warmup, 2 * cores)), seed=1)        # page-cache / import warm-up, untimed
-    if budget_s is not None:                                # bounded sample: grow until ~budget seconds of CPU work
-        n_batches = 2 * cores
-        while True:
-            n, dt = run(n_batches, seed=2)
-            if dt >= budget_s / 2 or n_batches >= 4096:
-                break
-            n_batches = int(min(4096, max(n_batches * 2, n_batches * budget_s / max(dt, 1e-3))))
-    else:
-        n_batches = steps
-        n, dt = run(n_batches, seed=2)
-    return {"value": n / dt, "unit": "patches/s", "cores": cores, "kind": "port",
-            "sample": f"{n_batches} batches x {BATCH} patches of the same workload ({H}x{W} slide in host RAM, {N_POLY} polygons), "
-                      f"{cores} worker processes x 2 batches per job like the reference's spawn ProcessPoolExecutor (pool start-up excluded); {dt:.2f} s",
-            "seconds": dt, "steps": n_batches}
-
-
-def reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    r = cpu_leg_annotated(args.steps, args.warmup, None, None)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(r["steps"], 1), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": r["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "oracle port of AnnoRegionRndSampler.torch_generator (region_samplers.py:685-738): the reference cannot run here "
-                "(psimage and shapely are not installable); CPU tensors are left on the host as the reference yields them",
-    }
-    print(json.dumps(line), flush=True)
-
-
+# CPU legs (run in a process that never touched CUDA: they start worker pools)
 METRIC = "patches/sec sampled+normalised"
 CONFIG = {
     "workload": "examples.sample_annotated_rnd --torch (BASELINE configs[1]): 224x224 random patches inside 50 synthetic polygons, "
                 "32768x32768 uint8 RGB slide, batch 256, patches_from_one_region 4, region_intersection 0.75, fp32 NHWC /255",
-    "slide": list(SLIDE_HW), "patch": PS, "batch": BATCH, "polygons": N_POLY,
-    "l2_policy": "inputs larger than L2: random patches of a 3.2 GB slide; each step writes a 193 MB batch (> 126 MB L2)",
+    "slide": list(SLIDE_HW), "patch": PS, "batch": BATCH, "polygons": N_POLY, "chunk_batches": CHUNK,
+    "l2_policy": "inputs larger than L2: random patches of a 3.2 GB slide; every gather launch writes a 2.5 GB chunk (16 batches of "
+                 "154 MB) into one of two alternating buffers (126 MB L2)",
 }
+
+
+def cpu_pipe(cores):
+    from oracle import cpu_pipeline, synth
+    from deephisto_b200.synthetic import synth_polygons
+
+    H, W = SLIDE_HW
+    path = synth.synth_slide_shared(H, W, 0, workers=cores, return_path=True)
+    images = [((H, W), synth_polygons(N_POLY, H, W, seed=0))]
+    return cpu_pipeline.AnnotatedRndCPU(path, (H, W, 3), images, layer=1, one_image_for_batch=True, max_workers=cores)
+
+
+def cpu_run(pipe, batch, n_batches, seed):
+    t0 = time.perf_counter()
+    n = 0
+    for f, l, c in pipe.batches(PS, batch, n_batches, batches_per_worker=2, k=K_PER_REGION, ri=RI, seed=seed):
+        n += f.shape[0]
+    return n, time.perf_counter() - t0
+
+
+def cpu_leg_bounded(budget_s: float):
+    """cpu_baseline of our arm: ~budget_s seconds of the reference's CPU path on the same workload (batch 256)."""
+    cores = os.cpu_count()
+    pipe = cpu_pipe(cores)
+    try:
+        cpu_run(pipe, BATCH, 2 * cores, seed=1)                     # page-cache / import warm-up, untimed
+        n_batches = 2 * cores
+        while True:
+            n, dt = cpu_run(pipe, BATCH, n_batches, seed=2)
+            if dt >= budget_s / 2 or n_batches >= 4096:
+                break
+            n_batches = int(min(4096, max(n_batches * 2, n_batches * budget_s / max(dt, 1e-3))))
+    finally:
+        pipe.close()
+    H, W = SLIDE_HW
+    return {"value": n / dt, "unit": "patches/s", "cores": cores, "kind": "port",
+            "sample": f"{n_batches} batches x {BATCH} patches of the same workload ({H}x{W} slide in host RAM, {N_POLY} polygons), {cores} "
+                      f"worker processes x 2 batches per job like the reference's spawn ProcessPoolExecutor (pool start-up excluded); {dt:.2f} s"}
+
+
+def reference_arm(args):
+    """The reference's CPU implementation of the path on the host cores, K steps; a step is a bounded sample (a batch of
+    `sample` <= 256 patches) so that the whole run ends within a few minutes."""
+    world, rank, _ = dist_env()
+    if rank != 0:
+        return
+    if args.workload == "predict":
+        return reference_arm_predict(args)
+    cores = os.cpu_count()
+    pipe = cpu_pipe(cores)
+    try:
+        n, dt = cpu_run(pipe, BATCH, max(2 * cores, min(args.warmup, 4 * cores)), seed=1)      # warm-up, also calibrates the sample
+        rate = n / dt
+        sample = int(max(K_PER_REGION, min(BATCH, rate * args.ref_budget / max(args.steps, 1)) // K_PER_REGION * K_PER_REGION))
+        n, dt = cpu_run(pipe, sample, args.steps, seed=2)
+    finally:
+        pipe.close()
+    H, W = SLIDE_HW
+    value = n / dt
+    desc = (f"{args.steps} steps x {sample} patches (bounded sample of the 256-patch batch) of the same workload ({H}x{W} slide in host RAM, "
+            f"{N_POLY} polygons), {cores} worker processes x 2 batches per job like the reference's spawn ProcessPoolExecutor (pool start-up "
+            f"excluded); {dt:.2f} s")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle port of AnnoRegionRndSampler.torch_generator (region_samplers.py:685-738): the reference itself cannot run "
+                "(psimage and shapely are neither vendored nor installable); CPU tensors are left on the host as the reference yields them",
+    }
+    print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------------------------
 def ours(args):
-    import numpy as np
     import torch
     import torch.distributed as dist
 
-    from deephisto_b200 import _lib, ops
+    from deephisto_b200 import _lib
     from deephisto_b200.patch_samplers.region_samplers import AnnoRegionRndSampler, build_tables
-    from deephisto_b200.slide import SyntheticSlide
+    from deephisto_b200.slide import PinnedSlide, SyntheticSlide
     from deephisto_b200.synthetic import synth_polygons
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local = dist_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -191,88 +217,97 @@ def ours(args):
     lib = _lib.require_device()
     K, Wm = args.steps, args.warmup
     H, W = SLIDE_HW
-    sampler_src = SyntheticSlide(H, W, seed=0)
-    slide = sampler_src.device_slide(dev)
+    source = SyntheticSlide(H, W, seed=0)
+    slide = source.device_slide(dev)
     polys = synth_polygons(N_POLY, H, W, seed=0)
     tables, _, classes = build_tables([((H, W), polys)], layer=1, area_influence=0.5, classes=None, one_image_for_batch=True, device=dev)
     thr = PS * PS * RI
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- device-resident loop through the C-ABI, outputs preallocated ---------------------------------------------------
-    # Coordinates are counter-based (Philox keyed by the global slot index): one dh_region_sample launch draws the next
-    # AHEAD batches (identical results to per-batch launches), then each step gathers one batch of 256 patches.
-    AHEAD = 16
-    coords = torch.empty((2, AHEAD * BATCH, 2), dtype=torch.int32, device=dev)
-    labels = torch.empty((2, AHEAD * BATCH), dtype=torch.int64, device=dev)
-    images = torch.empty((2, AHEAD * BATCH), dtype=torch.int32, device=dev)
-    status = torch.zeros((2, AHEAD * BATCH), dtype=torch.uint8, device=dev)
-    nbuf = 3
-    feats = [torch.empty((BATCH, PS, PS, 3), dtype=torch.float32, device=dev) for _ in range(nbuf)]
+    # Coordinates are counter-based (Philox keyed by the global slot index): one dh_region_sample launch draws CHUNK batches
+    # (identical results to per-batch launches), one dh_gather_normalize launch writes their features.
+    n_slots = CHUNK * BATCH
+    coords = torch.empty((2, n_slots, 2), dtype=torch.int32, device=dev)
+    labels = torch.empty((2, n_slots), dtype=torch.int64, device=dev)
+    images = torch.empty((2, n_slots), dtype=torch.int32, device=dev)
+    status = torch.zeros((2, n_slots), dtype=torch.uint8, device=dev)
+    feats = torch.empty((2, n_slots, PS, PS, 3), dtype=torch.float32, device=dev)
     tstruct = C.byref(tables.struct)
     sp, gp = lib.dh_region_sample, lib.dh_gather_normalize
-    fps = [f.data_ptr() for f in feats]
-    cptr = [coords[0].data_ptr(), coords[1].data_ptr()]
     sl_ptr, pitch = slide.storage.data_ptr(), slide.pitch
     fail = torch.zeros(1, dtype=torch.uint8, device=dev)
     launches = [0]
 
-    def step(i, ev=None):
-        # rank r draws from its own Philox slot range (rank << 40): disjoint streams, no data-path collective
-        buf = (i // AHEAD) & 1
-        rc = 0
-        if i % AHEAD == 0:
-            off = (rank << 40) + i * BATCH
-            rc = sp(tstruct, AHEAD * BATCH, K_PER_REGION, PS, thr, 500, 64, -1, 2 * BATCH, 0, off, coords[buf].data_ptr(),
-                    labels[buf].data_ptr(), images[buf].data_ptr(), status[buf].data_ptr(), stream)
-            launches[0] += 1
+    def chunk(first_step, n_batches, ev=None):
+        """Steps [first_step, first_step + n_batches): rank r draws from its own Philox slot range (rank << 40) -- disjoint
+        streams, no data-path collective."""
+        buf = (first_step // CHUNK) & 1
+        n = n_batches * BATCH
+        off = (rank << 40) + first_step * BATCH
+        rc = sp(tstruct, n, K_PER_REGION, PS, thr, 500, 64, -1, 2 * BATCH, 0, off, coords[buf].data_ptr(), labels[buf].data_ptr(),
+                images[buf].data_ptr(), status[buf].data_ptr(), stream)
         if ev is not None:
             ev[0].record()
-        rc |= gp(sl_ptr, H, W, pitch, cptr[buf] + (i % AHEAD) * BATCH * 8, None, BATCH, PS, fps[i % nbuf], 0, 0, 1, None, None, None, stream)
-        launches[0] += 1
+        rc |= gp(sl_ptr, H, W, pitch, coords[buf].data_ptr(), None, n, PS, feats[buf].data_ptr(), 0, 0, 1, None, None, None, stream)
         if ev is not None:
             ev[1].record()
+        launches[0] += 2
         if rc:
             raise RuntimeError(_lib.last_error())
 
-    sampler_thread = ClockSampler(local)
-    sampler_thread.start()
-    Wm = (Wm + AHEAD - 1) // AHEAD * AHEAD          # keep the sampling launches aligned with the timed region
-    for i in range(Wm):
-        step(i)
+    def run_steps(first, n_steps, evs=None):
+        done = 0
+        while done < n_steps:
+            nb = min(CHUNK, n_steps - done)
+            e = None
+            if evs is not None:
+                e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), nb)
+                evs.append(e)
+            chunk(first + done, nb, e)
+            done += nb
+        return done
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    Wm = max(Wm, 3)
+    run_steps(0, Wm)
     torch.maximum(fail, status.max().reshape(1), out=fail)
     torch.cuda.synchronize()
     launches[0] = 0
+    first_timed = (Wm + CHUNK - 1) // CHUNK * CHUNK                 # keep chunk boundaries aligned with the buffers
     if world > 1:
         dist.barrier()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    evs = []
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_start.record()
-    for i in range(K):
-        step(Wm + i, evs[i])
+    run_steps(first_timed, K, evs)
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms_total = t_start.elapsed_time(t_end)
-    gather_ms = sorted(a.elapsed_time(b) for a, b in evs)
-    gather_avg_ms = sum(gather_ms) / len(gather_ms)
-    if int(fail.item()) != 0 or int(status.max().item()) != 0:
+    gather_ms = [(a.elapsed_time(b), nb) for a, b, nb in evs]
+    gather_total_ms = sum(m for m, _ in gather_ms)
+    torch.maximum(fail, status.max().reshape(1), out=fail)
+    if int(fail.item()) != 0:
         raise RuntimeError("region sampling reported failed slots")
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * K * BATCH / (ms_total / 1e3)
+    del feats, coords, labels, images, status
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the public API ---------------------------------------------------------------------------
-    api = AnnoRegionRndSampler([(sampler_src, polys)], layer=1, patch_size=PS, patches_from_one_region=K_PER_REGION,
-                               one_image_for_batch=True, seed=1 + rank, device=dev, verbose=False)
+    # ---- end to end through the public API, slide starting in pinned host memory -----------------------------------------
+    host_slide = PinnedSlide.from_device(slide)                       # setup (not timed): the slide as it sits in host RAM
     h_labels = torch.empty(BATCH, dtype=torch.int64).pin_memory()
     h_coords = torch.empty((BATCH, 2), dtype=torch.float32).pin_memory()
     d2h = h_labels.numel() * 8 + h_coords.numel() * 4
 
-    def run_api(n_batches, to_host=False, h_feats=None):
+    def run_api(api, n_batches, to_host=False, h_feats=None):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for f, l, c in api.torch_generator(batch_size=BATCH, n_batches=n_batches, batches_per_worker=2):
@@ -280,49 +315,65 @@ def ours(args):
             h_coords.copy_(c, non_blocking=True)
             if to_host:
                 h_feats.copy_(f, non_blocking=True)
-            torch.cuda.current_stream().synchronize()      # the consumer reads this step's result
+            torch.cuda.current_stream().synchronize()                 # the consumer reads this step's result
         return time.perf_counter() - t0
 
-    run_api(max(Wm, 4))
+    def new_api(src, seed):
+        return AnnoRegionRndSampler([(src, polys)], layer=1, patch_size=PS, patches_from_one_region=K_PER_REGION, one_image_for_batch=True,
+                                    seed=seed, device=dev, verbose=False)
+
+    warm = new_api(source, 1 + rank)
+    run_api(warm, max(Wm, CHUNK))                                    # warm-up of the API path (allocator, kernels), resident slide
+    del warm, slide
+    source._dev.clear()
+    torch.cuda.empty_cache()
+    api = new_api(host_slide, 101 + rank)                              # polygon parsing / table build: constructor, not timed (as in the reference)
     if world > 1:
         dist.barrier()
-    e2e_s = run_api(K)
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_s = run_api(api, K)                                          # includes the one-time H2D upload of the 3.2 GB slide
+    steady_s = run_api(api, K)                                       # same call again: slide already resident
+    t = torch.tensor([e2e_s, steady_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * K * BATCH / float(t.item())
+    e2e_value, steady_value = (world * K * BATCH / float(x) for x in t.tolist())
     h_feats = torch.empty((BATCH, PS, PS, 3), dtype=torch.float32).pin_memory()
     kh = max(4, min(K, 32))
-    run_api(2, True, h_feats)
-    e2e_host_s = run_api(kh, True, h_feats)
-    sampler_thread.stop_flag = True
-    sampler_thread.join(timeout=1)
+    run_api(api, 2, True, h_feats)
+    e2e_host_s = run_api(api, kh, True, h_feats)
+    clk = clocks.finish()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
-    alg_bytes = BATCH * (PATCH_IN + PATCH_IN * 4)
-    achieved = alg_bytes / (gather_avg_ms / 1e3) / 1e9
+    alg_bytes_batch = BATCH * (PATCH_IN + PATCH_IN * 4)
+    alg_total = alg_bytes_batch * sum(nb for _, nb in gather_ms)
+    achieved = alg_total / (gather_total_ms / 1e3) / 1e9
+    full = [m for m, nb in gather_ms if nb == CHUNK]
     traffic = None
     tf = ROOT / "profiles" / "gather_traffic.json"
     if tf.exists():
-        traffic = json.loads(tf.read_text()).get("gather_nhwc_f32_bytes_per_launch")
+        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+    slide_bytes = host_slide.nbytes
     line = {
         "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": dict(CONFIG, parallelism=f"replicated slide, batches sharded by rank (x{world})"),
+        "data": "synthetic", "config": dict(CONFIG, parallelism=f"replicated slide, batches sharded by rank (x{world}), no data-path collective"),
         "gigapixels_per_s": value * PS * PS / 1e9,
-        "roofline": {"bound": "hbm", "kernel": "gather_nhwc_vec<float> (dh_gather_normalize)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms_avg": gather_avg_ms, "kernel_ms_median": gather_ms[len(gather_ms) // 2],
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
-        "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h,
-                "api": "AnnoRegionRndSampler.torch_generator(batch_size=256) -> CUDA features; labels+coords read back per step",
+        "roofline": {"bound": "hbm", "kernel": "gather_tma_kernel<float, NHWC, /255> (dh_gather_normalize), one launch per 16-batch chunk",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes_batch * CHUNK, "algorithmic_bytes_per_patch": PATCH_IN * 5,
+                     "kernel_ms_avg_full_chunk": (sum(full) / len(full)) if full else None, "launches_timed": len(gather_ms),
+                     "kernel_ms_per_batch": gather_total_ms / max(sum(nb for _, nb in gather_ms), 1), "frac_of_nominal_8TBs": achieved / 8000.0},
+        "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": slide_bytes / K, "d2h_bytes_per_step": d2h,
+                "api": "AnnoRegionRndSampler.torch_generator(batch_size=256, n_batches=K) over a slide in pinned host memory: the timed region "
+                       "contains the one-time H2D upload of the slide (h2d_bytes_total), K batches, and per step the D2H read of labels+coords",
+                "h2d_bytes_total": slide_bytes, "seconds": e2e_s,
+                "steady_state": {"value": steady_value, "unit": "patches/s", "note": "the same call repeated with the slide already resident"},
                 "features_to_host": {"value": kh * BATCH / e2e_host_s, "unit": "patches/s", "d2h_bytes_per_step": d2h + h_feats.numel() * 4}},
         "gpu_launches": launches[0],
-        "clocks": sampler_thread.summary(),
+        "clocks": clk,
     }
     if world == 1 and not args.no_cpu_baseline:
         out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--cpu-leg", "--cpu-budget", str(args.cpu_budget)],
@@ -336,25 +387,165 @@ def ours(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# whole-slide patched prediction (BASELINE configs[2] / [3])
+def predict_config(world, args):
+    hw = tuple(args.slide) if args.slide else ((40000, 40000) if world == 1 else (100000, 100000))
+    return hw, {
+        "workload": f"examples.predict_full_patched (BASELINE configs[{2 if world == 1 else 3}]): patch_cls_simple ResNet18 (random init, seed 0, "
+                    f"{'bf16 channels_last' if args.bf16 else 'fp32, torch defaults (TF32 convolutions)'}) on a synthetic {hw[0]}x{hw[1]} slide, "
+                    f"224x224 patches at stride 112, dense sampler batch 64 (CNN batch {args.cnn_batch}), stitch downscale 16, argmax map",
+        "slide": list(hw), "patch": PS, "stride": 112, "downscale": 16, "cnn_batch": args.cnn_batch,
+        "l2_policy": "inputs larger than L2: each step re-reads the whole slide band (GBs) from HBM",
+    }
+
+
+def ours_predict(args):
+    import torch
+    import torch.distributed as dist
+
+    from deephisto_b200 import _lib, bands
+    from deephisto_b200.anno.utils import AnnoDescription
+    from deephisto_b200.examples import predict_full_patched as pfp
+    from deephisto_b200.patch_samplers import full_samplers as fs
+    from deephisto_b200.slide import SyntheticSlide
+
+    world, rank, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device()
+    (H, W), cfg = predict_config(world, args)
+    torch.manual_seed(0)
+    model = pfp.get_model(5)
+    pred = pfp.DeviceBatchPredictor(model, dev, torch.bfloat16 if args.bf16 else torch.float32)
+    anno = AnnoDescription.with_auto_colors(["AT", "BG", "LP", "MM", "TUM"])
+    src = SyntheticSlide(H, W, seed=0)
+    mode = fs.SamplerExecutionMode.INMEMORY_SINGLEPROC
+    sampler = fs.FullImageDenseSampler(src, 1, PS, 64, mode, stride=112, device=dev, lazy_slide=True)
+    plan = bands.plan_band(H, W, PS, 112, 16, 64, rank, world)
+    # the band of the slide (with its patch-size halo) is made resident once, like the reference loads the layer in its constructor
+    band, y_off = sampler.band_slide(plan.slide_y0, plan.slide_y1)
+    sampler.band_slide = lambda y0, y1: (band, y_off)
+    ipp = pfp.ImagePredictorPatched(src, sampler, pred, anno, layer=1, downscale=16, device=dev, cnn_batch=args.cnn_batch)
+    K, Wm = args.steps, max(1, min(args.warmup, 2))
+
+    def step():
+        return ipp.process_device(rank=rank, world=world)["argmax"] if world > 1 else ipp.dense_band_local(0, 1)["argmax_band"]
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    for _ in range(Wm):
+        out = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(K):
+        out = step()
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    # e2e: the public call, class map read back to the host every step (what process() returns)
+    h_map = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(K):
+        h_map.copy_(step(), non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clk = clocks.finish()
+    if rank == 0:
+        gpx = H * W / 1e9
+        g = bands.dense_grid(H, W, PS, 112, 64)
+        line = {
+            "metric": "WSI gigapixels/sec patched predict", "value": K * gpx / (ms_total / 1e3), "unit": "Gpx/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16" if args.bf16 else "f32", "data": "synthetic",
+            "config": dict(cfg, parallelism=f"row bands x{world} with patch-size halo (recomputed halo patch rows), NCCL all-gather of the u8 class-map bands"),
+            "patches_per_s": K * g.n_padded / (ms_total / 1e3), "patches_per_slide": g.n_padded, "patches_this_rank": plan.n_patches,
+            "e2e": {"value": K * gpx / e2e_s, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(h_map.numel()),
+                    "api": "ImagePredictorPatched.process_device (band resident in HBM), class map copied to pinned host memory every step"},
+            "roofline": None, "gpu_launches": None, "clocks": clk,
+            "note": "CNN-bound (torch/cuDNN ResNet18): see profiles/ for the gather and stitch kernel shares",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_arm_predict(args):
+    """ImagePredictorPatched.process + batch_predictor restated on the CPU (oracle), 2048 x 2048 crop, model on the host cores."""
+    import numpy as np
+    import torch
+
+    from deephisto_b200.examples.predict_full_patched import get_model
+    from oracle import cpu_pipeline, stitch as ostitch, synth
+
+    H = W = 2048
+    slide = synth.synth_slide(H, W, 0)
+    torch.manual_seed(0)
+    model = get_model(5).eval()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(max(1, min(args.steps, 2))):
+        logits, coords = [], []
+        for feats, c, _ in cpu_pipeline.dense_batches(slide, PS, 112, 64):
+            with torch.no_grad():
+                logits.append(model(feats.permute(0, 3, 1, 2).contiguous()).numpy())
+            coords.append(c.numpy().astype(np.int64))
+        ostitch.stitch(np.concatenate(logits), np.concatenate(coords), H, W, PS, 16)
+        n += 1
+    dt = time.perf_counter() - t0
+    val = n * H * W / 1e9 / dt
+    print(json.dumps({"impl": "reference", "metric": "WSI gigapixels/sec patched predict", "value": val, "unit": "Gpx/s", "n_gpus": args.gpus,
+                      "steps": n, "warmup": 0, "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic", "config": {"workload": "oracle port of examples.predict_full_patched on a 2048x2048 crop, CPU ResNet18"},
+                      "cpu_baseline": {"value": val, "unit": "Gpx/s", "cores": torch.get_num_threads(), "kind": "port", "sample": f"{n} x 2048x2048 crop"},
+                      "e2e": {"value": val, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="annotated_rnd", choices=["annotated_rnd", "predict"])
+    ap.add_argument("--slide", type=int, nargs=2, default=None, help="predict workload: slide H W")
+    ap.add_argument("--bf16", action="store_true", help="predict workload: run the CNN in bf16 channels_last")
+    ap.add_argument("--cnn-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the bounded cpu_baseline sample")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="--impl reference: target seconds for the K timed steps")
     ap.add_argument("--cpu-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
+    if args.steps is None:
+        args.steps = 3 if args.workload == "predict" else 640
+    if args.warmup is None:
+        args.warmup = 1 if args.workload == "predict" else 32
+    args.warmup = max(args.warmup, 3) if args.workload != "predict" else args.warmup
     if args.cpu_leg:
-        r = cpu_leg_annotated(0, 1, None, args.cpu_budget)
-        print(json.dumps({k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}), flush=True)
+        print(json.dumps(cpu_leg_bounded(args.cpu_budget)), flush=True)
         return
     if args.impl == "reference":
         reference_arm(args)
         return
-    ours(args)
+    if args.workload == "predict":
+        ours_predict(args)
+    else:
+        ours(args)
 
 
 if __name__ == "__main__":

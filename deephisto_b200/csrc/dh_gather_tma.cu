@@ -369,7 +369,7 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     const bool affine = mean3 != nullptr;
     const char* env = getenv("DH_GATHER_STAGES");  // profiling override
     const int env_stages = env ? atoi(env) : 0;
-    int stages = env_stages >= 2 && env_stages <= kTmaMaxStages ? env_stages : 4;
+    int stages = env_stages >= 2 && env_stages <= kTmaMaxStages ? env_stages : 2;  // measured: a shallow ring interferes least with the store stream (profiles/r01_gather.md)
     while (stages > 2 && (size_t)stages * R * row_pitch > 56 * 1024) --stages;
     p.stages = stages;
     const size_t smem = (size_t)stages * R * row_pitch;

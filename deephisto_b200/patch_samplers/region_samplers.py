@@ -279,25 +279,31 @@ class AnnoRegionRndSampler:
     def torch_generator(self, batch_size: int, n_batches: int, batches_per_worker: int = 2, transforms: callable = None,
                         max_workers: int = None, cls_idx: int = None) -> Iterator[tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         """Reference :685-738: yields (features [B,ps,ps,3] float32 in [0,1], labels int64 [B], coords float32 [B,2] (y,x))."""
-        batch_no = 0
         chunk = batch_size * batches_per_worker
         # Coordinates are counter-based (Philox keyed by the global slot index), so several worker-sized chunks can be drawn by
-        # ONE launch with identical results -- as long as the groups of k slots do not straddle a chunk boundary.
-        ahead = max(1, 32 // batches_per_worker) * batches_per_worker if chunk % self.patches_from_one_region == 0 else batches_per_worker
+        # ONE launch with identical results -- as long as the groups of k slots do not straddle a chunk boundary. The features of
+        # all prefetched batches are then written by ONE gather launch (short launches cannot fill HBM: profiles/r01_gather.md);
+        # every yielded batch is a contiguous slice of that buffer. Prefetch depth: <= 32 batches and <= ~2.5 GB of features.
+        ps = self.patch_size
+        per_batch = batch_size * ps * ps * 3 * torch.empty((), dtype=self._out_dtype).element_size()
+        ahead = batches_per_worker
+        if chunk % self.patches_from_one_region == 0:
+            ahead = max(1, min(32, (5 << 29) // max(per_batch, 1)) // batches_per_worker) * batches_per_worker
         for nb in self._split_chunks(n_batches, ahead):
             first_slot = self._slot_cursor
             coords, labels, images = self.sample_coords(batch_size * nb, chunk, cls_idx)
+            flip = None
+            if self._flips:
+                flip = torch.cat([self._batch_flip(first_slot // max(batch_size, 1) + i, batch_size) for i in range(nb)])
+            features = self._gather(coords, images, self._out_dtype, self._out_layout, flip)
+            coords_f = coords.to(torch.float32)
             for i in range(nb):
                 sl = slice(i * batch_size, (i + 1) * batch_size)
-                flip = self._batch_flip(first_slot // max(batch_size, 1) + i, batch_size)
-                features = self._gather(coords[sl], images[sl], self._out_dtype, self._out_layout, flip)
+                f = features[sl]
                 if transforms is not None:
-                    features = transforms(features)
-                batch_no += 1
-                if batch_no % 64 == 0:
-                    self._check_failures()
-                yield features, labels[sl], coords[sl].to(torch.float32)
-        self._check_failures()
+                    f = transforms(f)
+                yield f, labels[sl], coords_f[sl]
+            self._check_failures()
 
     def structs_generator(self, batch_size: int, n_batches: int, batches_per_worker: int = 2, max_workers: int = None,
                           cls_idx: int = None) -> Iterator[list[tuple[Patch, int]]]:

@@ -4,7 +4,7 @@ The reference talks to `psimage.PSImage` (full_samplers.py:35-38,55,176-180; reg
 501,513-520; predict_full_patched.py:37-38,103-105): context manager, `_assert_layer`, `layer_size`,
 `get_region_from_layer(layer, (y0,x0), (y1,x1))`, `get_region`, `height`, `width`, `close`. psimage is not
 part of the reference tree, so every sampler here accepts, wherever the reference takes a `.psi` path:
-  * a `DeviceSlide` (already resident in HBM), a `SyntheticSlide`, a uint8 numpy array [H,W,3],
+  * a `DeviceSlide` (already resident in HBM), a `SyntheticSlide`, a `PinnedSlide` (pinned host memory), a uint8 numpy array [H,W,3],
   * a path to a `.npy` file holding such an array,
   * any object with the PSImage duck type above (including a real psimage.PSImage if it is installed),
   * a `.psi` path when the `psimage` package is importable.
@@ -115,9 +115,73 @@ class SyntheticSlide:
         return s.storage.view(s.H, s.pitch)[y0:y1, 3 * x0 : 3 * x1].cpu().numpy().reshape(y1 - y0, x1 - x0, 3)
 
 
+class PinnedSlide:
+    """A slide layer held in PINNED host memory with the device row pitch (uint8 [H, pitch], pitch % 16 == 0): the upload to
+    HBM is one asynchronous cudaMemcpy at PCIe speed (a pageable numpy array goes through a staging copy first). Layer 1 only."""
+
+    def __init__(self, host, H: int, W: int, pitch: int):
+        import torch
+
+        if not (isinstance(host, torch.Tensor) and host.dtype == torch.uint8 and host.is_pinned() and host.numel() >= H * pitch):
+            raise ValueError("PinnedSlide needs a pinned uint8 tensor of at least H * pitch bytes")
+        self.host, self.height, self.width, self.pitch = host, int(H), int(W), int(pitch)
+
+    @classmethod
+    def from_numpy(cls, arr: np.ndarray) -> "PinnedSlide":
+        import torch
+
+        H, W, _ = arr.shape
+        pitch = DeviceSlide.pitch_for(W)
+        host = torch.empty(H * pitch, dtype=torch.uint8).pin_memory()
+        host.view(H, pitch)[:, : 3 * W].copy_(torch.from_numpy(np.ascontiguousarray(arr)).view(H, 3 * W))
+        return cls(host, H, W, pitch)
+
+    @classmethod
+    def from_device(cls, dev: DeviceSlide) -> "PinnedSlide":
+        import torch
+
+        host = torch.empty(dev.H * dev.pitch, dtype=torch.uint8).pin_memory()
+        host.copy_(dev.storage[: dev.H * dev.pitch])
+        return cls(host, dev.H, dev.W, dev.pitch)
+
+    @property
+    def nbytes(self) -> int:
+        return self.height * self.pitch
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def close(self):
+        pass
+
+    def _assert_layer(self, layer: int):
+        if layer != 1:
+            raise ValueError("a PinnedSlide holds exactly one layer; pass layer=1")
+
+    def layer_size(self, layer: int):
+        self._assert_layer(layer)
+        return self.height, self.width
+
+    def get_region_from_layer(self, layer: int, p0, p1) -> np.ndarray:
+        self._assert_layer(layer)
+        (y0, x0), (y1, x1) = p0, p1
+        return self.host.view(-1, self.pitch)[y0:y1, 3 * x0 : 3 * x1].numpy().reshape(y1 - y0, x1 - x0, 3)
+
+    def to_device(self, device="cuda", y0: int = 0, y1: int = None) -> DeviceSlide:
+        import torch
+
+        y1 = self.height if y1 is None else y1
+        storage = torch.empty((y1 - y0) * self.pitch, dtype=torch.uint8, device=device)
+        storage.copy_(self.host[y0 * self.pitch : y1 * self.pitch], non_blocking=True)
+        return DeviceSlide(storage, y1 - y0, self.width, self.pitch)
+
+
 def open_slide(source):
     """Return a PSImage-duck-typed object for `source` (see module docstring)."""
-    if isinstance(source, (ArraySlide, SyntheticSlide, DeviceSlideSource)):
+    if isinstance(source, (ArraySlide, SyntheticSlide, DeviceSlideSource, PinnedSlide)):
         return source
     if isinstance(source, DeviceSlide):
         return DeviceSlideSource(source)
@@ -179,6 +243,9 @@ def layer_to_device(src, layer: int, device="cuda") -> DeviceSlide:
     if isinstance(src, SyntheticSlide):
         src._assert_layer(layer)
         return src.device_slide(device)
+    if isinstance(src, PinnedSlide):
+        src._assert_layer(layer)
+        return src.to_device(device)
     h, w = src.layer_size(layer)
     arr = np.asarray(src.get_region_from_layer(layer, (0, 0), (h, w)))
     return DeviceSlide.from_numpy(arr, device)
@@ -193,6 +260,9 @@ def band_to_device(src, layer: int, y0: int, y1: int, device="cuda") -> DeviceSl
     if isinstance(src, SyntheticSlide):
         src._assert_layer(layer)
         return src.device_band(y0, y1, device)
+    if isinstance(src, PinnedSlide):
+        src._assert_layer(layer)
+        return src.to_device(device, y0, y1)
     h, w = src.layer_size(layer)
     arr = np.asarray(src.get_region_from_layer(layer, (y0, 0), (y1, w)))
     return DeviceSlide.from_numpy(arr, device)
