@@ -144,7 +144,7 @@ __device__ __forceinline__ void store_unit(__nv_bfloat16* dst, const float (&f)[
 template <typename OutT> struct UnitOf { static constexpr int kElems = 16 / (int)sizeof(OutT); };
 
 template <typename OutT, bool NCHW, bool SCALE, bool AFFINE, bool FULL>
-__global__ void __launch_bounds__(kTmaThreads) gather_tma_kernel(const TmaGatherParams p) {
+__global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGatherParams p) {
     constexpr int E = UnitOf<OutT>::kElems;          // elements (NHWC) or pixels (NCHW) per unit: 4 or 8
     constexpr int IN_BYTES = NCHW ? 3 * E : E;       // input bytes per unit
     constexpr int NW = IN_BYTES / 4;                 // aligned words per unit after the funnel shift
@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kTmaThreads) gather_tma_kernel(const TmaGather
     const int units_per_tile = R * upr;
     // per-thread unit geometry is the same for every tile: unit u_k = tid + k * kConsumers
     uint32_t s_off[kTmaMaxUnits];
+    uint32_t s_mirror[kTmaMaxUnits];   // s_off of the mirrored unit of the same row = s_mirror - s_off (NCHW horizontal flip)
     int cph[kTmaMaxUnits];
     int nu = 0;
 #pragma unroll
@@ -228,6 +229,7 @@ __global__ void __launch_bounds__(kTmaThreads) gather_tma_kernel(const TmaGather
         const int u = tid + k * kConsumers;
         const int r = u / upr, c = u - r * upr;
         s_off[k] = (uint32_t)(r * RP + IN_BYTES * c);
+        s_mirror[k] = (uint32_t)(2 * r * RP + IN_BYTES * (upr - 1));
         cph[k] = (E * c) % 3;                    // channel of the unit's first element (NHWC, AFFINE only)
         if (u < units_per_tile) nu = k + 1;
     }
@@ -242,17 +244,20 @@ __global__ void __launch_bounds__(kTmaThreads) gather_tma_kernel(const TmaGather
         const TileMeta m = meta[s];
         const uint32_t sbase = stage0 + (uint32_t)(s * stage_bytes);
         OutT* const o = out_base + m.out_off;
-        if ((m.flags & (kInside | DH_FLIP_H)) == kInside) {
-            // fast path: aligned LDS words + funnel shift
+        if ((m.flags & kInside) && (NCHW || !(m.flags & DH_FLIP_H))) {
+            // fast path: aligned LDS words + funnel shift. A horizontal flip in NCHW mode reads the mirrored unit of the row and
+            // reverses the pixel order inside the unit (compile-time byte permutation); in NHWC mode it takes the byte path.
             const int a = (3 * m.x) & 15;
             const uint32_t sh = (uint32_t)(a & 3) * 8u;
             const uint32_t abase = sbase + (uint32_t)(a & ~3);
+            const bool fh = NCHW && (m.flags & DH_FLIP_H);
 #pragma unroll
             for (int k = 0; k < KU; ++k) {
                 if (FULL || k < nu) {
                     uint32_t q[NW + 1], w[NW];
+                    const uint32_t so = fh ? s_mirror[k] - s_off[k] : s_off[k];
 #pragma unroll
-                    for (int j = 0; j <= NW; ++j) q[j] = lds32(abase + s_off[k] + 4 * j);
+                    for (int j = 0; j <= NW; ++j) q[j] = lds32(abase + so + 4 * j);
 #pragma unroll
                     for (int j = 0; j < NW; ++j) w[j] = __funnelshift_r(q[j], q[j + 1], sh);
                     OutT* const ok = o + k * (kConsumers * E);
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(kTmaThreads) gather_tma_kernel(const TmaGather
                             if (AFFINE) c = c == 2 ? 0 : c + 1;
                         }
                         if (!(p.debug & 2) || f[0] == 12345.f) store_unit(ok, f, p.debug & 4);
-                    } else {
+                    } else if (!fh) {
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
                             float f[E];
@@ -275,6 +280,17 @@ __global__ void __launch_bounds__(kTmaThreads) gather_tma_kernel(const TmaGather
                                 f[j] = norm_f<SCALE, AFFINE>(byte_f(w[b >> 2], b & 3, magic), ch, p);
                             }
                             if (!(p.debug & 2) || f[0] == 12345.f) store_unit(ok + ch * plane, f, p.debug & 4);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ch = 0; ch < 3; ++ch) {
+                            float f[E];
+#pragma unroll
+                            for (int j = 0; j < E; ++j) {
+                                const int b = 3 * (E - 1 - j) + ch;  // output pixel j = source pixel E-1-j of the mirrored unit
+                                f[j] = norm_f<SCALE, AFFINE>(byte_f(w[b >> 2], b & 3, magic), ch, p);
+                            }
+                            store_unit(ok + ch * plane, f, p.debug & 4);
                         }
                     }
                 }
