@@ -200,6 +200,21 @@ def reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------------------------------
+MODES = {
+    # BASELINE configs[1]
+    "annotated_rnd": dict(batch=BATCH, chunk=CHUNK, dtype="f32", torch_dtype="float32", layout="NHWC", dcode=0, lcode=0, esize=4, flips=False,
+                          config=CONFIG, kernel="gather_tma_kernel<float, NHWC, /255> (dh_gather_normalize), one launch per 16-batch chunk"),
+    # BASELINE configs[4]: the input pipeline of models.patch_cls_simple.train at 8k patches/step, bf16 NCHW with the batch-level
+    # random H/V flips of train.py:71-81 fused into the gather
+    "train_input": dict(batch=8192, chunk=1, dtype="bf16", torch_dtype="bfloat16", layout="NCHW", dcode=1, lcode=1, esize=2, flips=True,
+                        config=dict(CONFIG, workload="models.patch_cls_simple.train input pipeline (BASELINE configs[4]): on-device annotated random sampling, "
+                                    "8192 patches per step, bf16 NCHW /255 with batch-level random H/V flips (train.py:71-81), same slide and polygons "
+                                    "as configs[1]", batch=8192, chunk_batches=1,
+                                    l2_policy="inputs larger than L2: random patches of a 3.2 GB slide; every step writes a 2.5 GB batch"),
+                        kernel="gather_tma_kernel<bf16, NCHW, /255> with flips (dh_gather_normalize), one launch per 8192-patch step"),
+}
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -216,6 +231,9 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.require_device()
     K, Wm = args.steps, args.warmup
+    mode = MODES[args.workload]
+    BATCH, CHUNK = mode["batch"], mode["chunk"]        # shadow the module-level defaults
+    out_dtype = getattr(torch, mode["torch_dtype"])
     H, W = SLIDE_HW
     source = SyntheticSlide(H, W, seed=0)
     slide = source.device_slide(dev)
@@ -232,7 +250,13 @@ def ours(args):
     labels = torch.empty((2, n_slots), dtype=torch.int64, device=dev)
     images = torch.empty((2, n_slots), dtype=torch.int32, device=dev)
     status = torch.zeros((2, n_slots), dtype=torch.uint8, device=dev)
-    feats = torch.empty((2, n_slots, PS, PS, 3), dtype=torch.float32, device=dev)
+    feats = torch.empty((2, n_slots, PS, PS, 3) if mode["layout"] == "NHWC" else (2, n_slots, 3, PS, PS), dtype=out_dtype, device=dev)
+    # one H and one V coin per batch, like torchvision's flips of the whole [B,3,H,W] tensor (train.py:71-81)
+    flip_bits = None
+    if mode["flips"]:
+        n_coins = (max(Wm, 3) + CHUNK + K) * 2 + 4 * CHUNK
+        coins = torch.randint(0, 4, (n_coins,), generator=torch.Generator().manual_seed(7 + rank), dtype=torch.uint8)
+        flip_bits = coins.repeat_interleave(BATCH).to(dev)
     tstruct = C.byref(tables.struct)
     sp, gp = lib.dh_region_sample, lib.dh_gather_normalize
     sl_ptr, pitch = slide.storage.data_ptr(), slide.pitch
@@ -249,7 +273,9 @@ def ours(args):
                 images[buf].data_ptr(), status[buf].data_ptr(), stream)
         if ev is not None:
             ev[0].record()
-        rc |= gp(sl_ptr, H, W, pitch, coords[buf].data_ptr(), None, n, PS, feats[buf].data_ptr(), 0, 0, 1, None, None, None, stream)
+        fl = None if flip_bits is None else flip_bits.data_ptr() + first_step * BATCH
+        rc |= gp(sl_ptr, H, W, pitch, coords[buf].data_ptr(), None, n, PS, feats[buf].data_ptr(), mode["dcode"], mode["lcode"], 1, None, None, fl,
+                 stream)
         if ev is not None:
             ev[1].record()
         launches[0] += 2
@@ -320,7 +346,7 @@ def ours(args):
 
     def new_api(src, seed):
         return AnnoRegionRndSampler([(src, polys)], layer=1, patch_size=PS, patches_from_one_region=K_PER_REGION, one_image_for_batch=True,
-                                    seed=seed, device=dev, verbose=False)
+                                    seed=seed, device=dev, verbose=False, out_dtype=out_dtype, out_layout=mode["layout"], flips=mode["flips"])
 
     warm = new_api(source, 1 + rank)
     run_api(warm, max(Wm, CHUNK))                                    # warm-up of the API path (allocator, kernels), resident slide
@@ -336,8 +362,8 @@ def ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value, steady_value = (world * K * BATCH / float(x) for x in t.tolist())
-    h_feats = torch.empty((BATCH, PS, PS, 3), dtype=torch.float32).pin_memory()
-    kh = max(4, min(K, 32))
+    h_feats = torch.empty((BATCH, PS, PS, 3) if mode["layout"] == "NHWC" else (BATCH, 3, PS, PS), dtype=out_dtype).pin_memory()
+    kh = max(2, min(K, 32 if BATCH <= 256 else 4))
     run_api(api, 2, True, h_feats)
     e2e_host_s = run_api(api, kh, True, h_feats)
     clk = clocks.finish()
@@ -347,35 +373,35 @@ def ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
-    alg_bytes_batch = BATCH * (PATCH_IN + PATCH_IN * 4)
+    alg_bytes_batch = BATCH * (PATCH_IN + PATCH_IN * mode["esize"])
     alg_total = alg_bytes_batch * sum(nb for _, nb in gather_ms)
     achieved = alg_total / (gather_total_ms / 1e3) / 1e9
     full = [m for m, nb in gather_ms if nb == CHUNK]
     traffic = None
     tf = ROOT / "profiles" / "gather_traffic.json"
-    if tf.exists():
+    if tf.exists() and args.workload == "annotated_rnd":               # ncu capture of exactly this kernel / launch shape
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
     slide_bytes = host_slide.nbytes
     line = {
         "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": dict(CONFIG, parallelism=f"replicated slide, batches sharded by rank (x{world}), no data-path collective"),
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": mode["dtype"],
+        "data": "synthetic", "config": dict(mode["config"], parallelism=f"replicated slide, batches sharded by rank (x{world}), no data-path collective"),
         "gigapixels_per_s": value * PS * PS / 1e9,
-        "roofline": {"bound": "hbm", "kernel": "gather_tma_kernel<float, NHWC, /255> (dh_gather_normalize), one launch per 16-batch chunk",
+        "roofline": {"bound": "hbm", "kernel": mode["kernel"],
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes_batch * CHUNK, "algorithmic_bytes_per_patch": PATCH_IN * 5,
+                     "algorithmic_bytes_per_launch": alg_bytes_batch * CHUNK, "algorithmic_bytes_per_patch": PATCH_IN * (1 + mode["esize"]),
                      "kernel_ms_avg_full_chunk": (sum(full) / len(full)) if full else None, "launches_timed": len(gather_ms),
                      "kernel_ms_per_batch": gather_total_ms / max(sum(nb for _, nb in gather_ms), 1), "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": slide_bytes / K, "d2h_bytes_per_step": d2h,
-                "api": "AnnoRegionRndSampler.torch_generator(batch_size=256, n_batches=K) over a slide in pinned host memory: the timed region "
+                "api": f"AnnoRegionRndSampler.torch_generator(batch_size={BATCH}, n_batches=K) over a slide in pinned host memory: the timed region "
                        "contains the one-time H2D upload of the slide (h2d_bytes_total), K batches, and per step the D2H read of labels+coords",
                 "h2d_bytes_total": slide_bytes, "seconds": e2e_s,
                 "steady_state": {"value": steady_value, "unit": "patches/s", "note": "the same call repeated with the slide already resident"},
-                "features_to_host": {"value": kh * BATCH / e2e_host_s, "unit": "patches/s", "d2h_bytes_per_step": d2h + h_feats.numel() * 4}},
+                "features_to_host": {"value": kh * BATCH / e2e_host_s, "unit": "patches/s", "d2h_bytes_per_step": d2h + h_feats.numel() * mode["esize"]}},
         "gpu_launches": launches[0],
         "clocks": clk,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "annotated_rnd":
         out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--cpu-leg", "--cpu-budget", str(args.cpu_budget)],
                              capture_output=True, text=True)
         try:
@@ -522,7 +548,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="annotated_rnd", choices=["annotated_rnd", "predict"])
+    ap.add_argument("--workload", default="annotated_rnd", choices=["annotated_rnd", "train_input", "predict"])
     ap.add_argument("--slide", type=int, nargs=2, default=None, help="predict workload: slide H W")
     ap.add_argument("--bf16", action="store_true", help="predict workload: run the CNN in bf16 channels_last")
     ap.add_argument("--cnn-batch", type=int, default=1024)
@@ -532,9 +558,9 @@ def main():
     ap.add_argument("--cpu-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 3 if args.workload == "predict" else 640
+        args.steps = {"predict": 3, "train_input": 40}.get(args.workload, 640)
     if args.warmup is None:
-        args.warmup = 1 if args.workload == "predict" else 32
+        args.warmup = {"predict": 1, "train_input": 4}.get(args.workload, 32)
     args.warmup = max(args.warmup, 3) if args.workload != "predict" else args.warmup
     if args.cpu_leg:
         print(json.dumps(cpu_leg_bounded(args.cpu_budget)), flush=True)

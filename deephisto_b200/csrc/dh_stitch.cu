@@ -133,6 +133,180 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_kernel(const floa
     }
 }
 
+// ---- aligned fast path ------------------------------------------------------------------------------
+// When dw*n is a multiple of 4 floats and the column tile is a multiple of 4 cells, every row segment of a tile starts on
+// a 16-byte boundary: a thread keeps its float4s (and count / argmax words) of the current row class IN REGISTERS and the
+// per-row work is just the stores. The row class (which patch rows cover map row i) is advanced incrementally -- no division
+// in the row loop (the first version of this kernel spent its time on two 64-bit divisions per row per thread:
+// profiles/r01_stitch.md).
+constexpr int kStitchV = 2;  // float4 per thread per row
+
+struct RowClass {
+    int64_t lo_raw, hi_raw;  // unclamped main-grid row range covering the current map row
+    int64_t rem_lo, rem_hi;
+    __device__ __forceinline__ void init(int64_t i, int ps, int stride, int d) {
+        const int64_t e = (i + 1) * (int64_t)d;
+        hi_raw = (e - 1) / stride;
+        rem_hi = (e - 1) - hi_raw * stride;
+        const int64_t u = e - ps + stride - 1;  // lo = max(0, floor(u / stride))
+        if (u >= 0) { lo_raw = u / stride; rem_lo = u - lo_raw * stride; }
+        else        { lo_raw = 0; rem_lo = u; }
+    }
+    // number of consecutive map rows, starting at the current one, with the same (lo_raw, hi_raw)
+    __device__ __forceinline__ int64_t run_length(int stride, int d) const {
+        const int64_t a = (stride - rem_hi + d - 1) / d;  // rows until hi_raw changes (rem_hi < stride)
+        const int64_t b = (stride - rem_lo + d - 1) / d;  // rows until lo_raw changes (rem_lo may be negative)
+        return a < b ? a : b;
+    }
+    __device__ __forceinline__ void advance(int64_t rows, int stride, int d) {
+        rem_hi += rows * d;
+        if (rem_hi >= stride) { int64_t q = rem_hi / stride; hi_raw += q; rem_hi -= q * stride; }
+        rem_lo += rows * d;
+        if (rem_lo >= stride) { int64_t q = rem_lo / stride; lo_raw += q; rem_lo -= q * stride; }
+    }
+};
+
+template <bool WITH_SUM, bool WITH_ARGMAX, bool WITH_COUNT>
+__global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(const float* __restrict__ logits, StitchGrid g,
+                                                                              float* __restrict__ sum_map,
+                                                                              uint32_t* __restrict__ count_map,
+                                                                              uint8_t* __restrict__ argmax_map,
+                                                                              int64_t row_begin, int64_t row_end, int tj_max,
+                                                                              int rows_per_block, int amax_vec) {
+    extern __shared__ __align__(16) float smem[];
+    const int n = g.n;
+    float* vals = smem;                                                       // [tj_max * n]
+    uint32_t* cnts = reinterpret_cast<uint32_t*>(smem + tj_max * n);          // [tj_max]
+    uint8_t* amax = reinterpret_cast<uint8_t*>(cnts + tj_max);                // [tj_max] (tj_max % 16 == 0)
+
+    const int64_t j0 = (int64_t)blockIdx.x * tj_max;
+    const int tj = (int)((g.dw - j0) < tj_max ? (g.dw - j0) : tj_max);
+    const int64_t i0 = row_begin + (int64_t)blockIdx.y * rows_per_block;
+    const int64_t i1 = (i0 + rows_per_block) < row_end ? (i0 + rows_per_block) : row_end;
+    const int nvec = (tj * n) >> 2;  // (tj * n) % 4 == 0 by construction
+    const int tid = threadIdx.x;
+
+    RowClass rc;
+    rc.init(i0, g.ps, g.stride, g.d);
+    float4 vreg[kStitchV];
+    uint32_t creg[2] = {0, 0};
+    uint32_t areg[2] = {0, 0};
+    float* out_row = WITH_SUM ? sum_map + ((i0 - row_begin) * g.dw + j0) * n : nullptr;
+    int64_t cell_row = (i0 - row_begin) * g.dw + j0;
+    const int64_t row_floats = g.dw * n;
+    int64_t i = i0;
+    while (i < i1) {
+        // rows [i, i + run) share one class: same covering patch rows, same side of the last-row boundary
+        Cover cy;
+        cy.lo = rc.lo_raw;
+        cy.hi = rc.hi_raw > g.ny - 1 ? g.ny - 1 : rc.hi_raw;
+        cy.last = i >= g.lastrow_cell;
+        int64_t run = rc.run_length(g.stride, g.d);
+        if (!cy.last && i + run > g.lastrow_cell) run = g.lastrow_cell - i;
+        if (i + run > i1) run = i1 - i;
+        {
+            __syncthreads();  // previous class has been read into registers by everybody
+            for (int t = tid; t < tj; t += kStitchThreads) {
+                const int64_t j = j0 + t;
+                Cover cx = cover_1d(j, g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+                const int64_t main_n = g.ny * g.nx;
+                float best = 0.f;
+                int best_c = 0;
+                for (int c = 0; c < n; ++c) {
+                    float acc = 0.f;
+                    for (int64_t gy = cy.lo; gy <= cy.hi; ++gy)
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, __ldg(logits + (gy * g.nx + gx) * n + c));
+                    if (cx.last)
+                        for (int64_t gy = cy.lo; gy <= cy.hi; ++gy) acc = __fadd_rn(acc, __ldg(logits + (main_n + gy) * n + c));
+                    if (cy.last)
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, __ldg(logits + (main_n + g.ny + gx) * n + c));
+                    if (cx.last && cy.last)
+                        for (int64_t k = 0; k <= g.pads; ++k) acc = __fadd_rn(acc, __ldg(logits + (g.N - 1 + k) * n + c));
+                    if (WITH_SUM) vals[t * n + c] = acc;
+                    if (WITH_ARGMAX) {
+                        if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; best_c = c; }  // np.argmax: first maximum; NaN wins
+                    }
+                }
+                if (WITH_COUNT) {
+                    int64_t ry = cy.hi >= cy.lo ? cy.hi - cy.lo + 1 : 0;
+                    int64_t rx = cx.hi >= cx.lo ? cx.hi - cx.lo + 1 : 0;
+                    cnts[t] = (uint32_t)(ry * rx + (cx.last ? ry : 0) + (cy.last ? rx : 0) + ((cx.last && cy.last) ? 1 + g.pads : 0));
+                }
+                if (WITH_ARGMAX) amax[t] = (uint8_t)best_c;
+            }
+            __syncthreads();
+            if (WITH_SUM) {
+#pragma unroll
+                for (int v = 0; v < kStitchV; ++v) {
+                    const int q = tid + v * kStitchThreads;
+                    if (q < nvec) vreg[v] = reinterpret_cast<const float4*>(vals)[q];
+                }
+            }
+            if (WITH_COUNT) {
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const int t = tid + v * kStitchThreads;
+                    if (t < tj) creg[v] = cnts[t];
+                }
+            }
+            if (WITH_ARGMAX) {
+                if (amax_vec) {  // 4 cells per 32-bit store (dw % 4 == 0, so j0 and the row starts are 4-byte aligned)
+                    if (tid < ((tj + 3) >> 2)) areg[0] = reinterpret_cast<const uint32_t*>(amax)[tid];
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const int t = tid + v * kStitchThreads;
+                        if (t < tj) areg[v] = amax[t];
+                    }
+                }
+            }
+        }
+        // stream the class out: nothing but stores and pointer increments per row
+        if (WITH_SUM) {
+            float4* o0 = reinterpret_cast<float4*>(out_row) + tid;
+            const bool h0 = tid < nvec, h1 = tid + kStitchThreads < nvec;
+            for (int64_t r = 0; r < run; ++r) {
+                if (h0) __stcs(o0, vreg[0]);
+                if (h1) __stcs(o0 + kStitchThreads, vreg[1]);
+                o0 = reinterpret_cast<float4*>(reinterpret_cast<float*>(o0) + row_floats);
+            }
+            out_row += run * row_floats;
+        }
+        if (WITH_COUNT) {
+            uint32_t* c0 = count_map + cell_row + tid;
+            const bool h0 = tid < tj, h1 = tid + kStitchThreads < tj;
+            for (int64_t r = 0; r < run; ++r) {
+                if (h0) c0[0] = creg[0];
+                if (h1) c0[kStitchThreads] = creg[1];
+                c0 += g.dw;
+            }
+        }
+        if (WITH_ARGMAX) {
+            if (amax_vec) {
+                uint8_t* a0 = argmax_map + cell_row;
+                for (int64_t r = 0; r < run; ++r) {
+                    if (tid < (tj >> 2)) reinterpret_cast<uint32_t*>(a0)[tid] = areg[0];
+                    else if (tid == (tj >> 2) && (tj & 3)) {
+                        for (int b = 0; b < (tj & 3); ++b) a0[(tj & ~3) + b] = (uint8_t)(areg[0] >> (8 * b));
+                    }
+                    a0 += g.dw;
+                }
+            } else {
+                uint8_t* a0 = argmax_map + cell_row + tid;
+                const bool h0 = tid < tj, h1 = tid + kStitchThreads < tj;
+                for (int64_t r = 0; r < run; ++r) {
+                    if (h0) a0[0] = (uint8_t)areg[0];
+                    if (h1) a0[kStitchThreads] = (uint8_t)areg[1];
+                    a0 += g.dw;
+                }
+            }
+        }
+        cell_row += run * g.dw;
+        i += run;
+        rc.advance(run, g.stride, g.d);
+    }
+}
+
 // ---- scatter (arbitrary coordinates) ------------------------------------------------------------
 __global__ void __launch_bounds__(256) stitch_scatter_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords,
                                                              int64_t P, int ps, int d, int n, float* __restrict__ sum_map,
@@ -214,11 +388,33 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
     DH_REQUIRE(!sum_map || reinterpret_cast<uintptr_t>(sum_map) % 16 == 0, "dh_stitch_dense: sum_map must be 16-byte aligned");
     DH_REQUIRE(!argmax_u8 || n <= 256, "dh_stitch_dense: argmax_u8 needs n <= 256");
     if (row_end == row_begin || g.dw == 0) return DH_OK;
+    const int64_t rows = row_end - row_begin;
+    cudaStream_t st = as_stream(stream);
+    const bool s = sum_map != nullptr, a = argmax_u8 != nullptr, c = count_map != nullptr;
+    if (!s || (g.dw * n) % 4 == 0) {
+        // aligned fast path: column tile = multiple of 16 cells with at most kStitchV float4 per thread per row
+        int tj = (kStitchThreads * 4 * kStitchV / n) & ~15;
+        if (tj > 2 * kStitchThreads) tj = 2 * kStitchThreads;
+        if (tj < 16) tj = 16;  // n <= 64 -> 16 * 64 / 4 = 256 vectors: still one per thread
+        const int64_t col_tiles = (g.dw + tj - 1) / tj;
+        int64_t rpb = rows * col_tiles / ((int64_t)kNumSMs * 8);
+        rpb = rpb < 4 ? 4 : (rpb > 128 ? 128 : rpb);
+        const int64_t row_groups = (rows + rpb - 1) / rpb;
+        DH_REQUIRE(row_groups <= 65535, "dh_stitch_dense: too many row groups (%lld); stitch in bands", (long long)row_groups);
+        const int amax_vec = (a && g.dw % 4 == 0 && reinterpret_cast<uintptr_t>(argmax_u8) % 4 == 0) ? 1 : 0;
+        dim3 grid((unsigned)col_tiles, (unsigned)row_groups);
+        size_t smem = (size_t)tj * n * sizeof(float) + (size_t)tj * sizeof(uint32_t) + (size_t)tj;
+#define DH_STA(S, A, C) stitch_dense_aligned_kernel<S, A, C><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, (int)rpb, amax_vec)
+        if (s) { if (a) { if (c) DH_STA(true, true, true); else DH_STA(true, true, false); } else { if (c) DH_STA(true, false, true); else DH_STA(true, false, false); } }
+        else   { if (a) { if (c) DH_STA(false, true, true); else DH_STA(false, true, false); } else { DH_STA(false, false, true); } }
+#undef DH_STA
+        DH_CHECK_LAUNCH("stitch_dense_aligned_kernel");
+        return DH_OK;
+    }
     int tj = 2048 / n;
     tj = tj / 32 * 32;
     if (tj > 256) tj = 256;
     if (tj < 32) tj = 32;
-    const int64_t rows = row_end - row_begin;
     const int64_t col_tiles = (g.dw + tj - 1) / tj;
     // enough row groups to fill the machine a few times over, but long enough to reuse a row class
     int rpb = 32;
@@ -227,9 +423,7 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
     DH_REQUIRE(row_groups <= 65535, "dh_stitch_dense: too many row groups (%lld); stitch in bands", (long long)row_groups);
     dim3 grid((unsigned)col_tiles, (unsigned)row_groups);
     size_t smem = (size_t)(4 * (tj * n + 4)) * sizeof(float) + (size_t)tj * sizeof(uint32_t) + (size_t)tj;
-    cudaStream_t st = as_stream(stream);
 #define DH_ST(S, A, C) stitch_dense_kernel<S, A, C><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, rpb)
-    const bool s = sum_map != nullptr, a = argmax_u8 != nullptr, c = count_map != nullptr;
     if (s) { if (a) { if (c) DH_ST(true, true, true); else DH_ST(true, true, false); } else { if (c) DH_ST(true, false, true); else DH_ST(true, false, false); } }
     else   { if (a) { if (c) DH_ST(false, true, true); else DH_ST(false, true, false); } else { DH_ST(false, false, true); } }
 #undef DH_ST
