@@ -114,6 +114,25 @@ def dist_env():
     return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def init_nccl(dev):
+    """init_process_group + first collective with fd 1 pointed at stderr: NCCL prints its version banner on stdout, which
+    must carry exactly one JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.all_reduce(torch.zeros(1, device=dev))
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 # --------------------------------------------------------------------------------------------------------------------
 # CPU legs (run in a process that never touched CUDA: they start worker pools)
 METRIC = "patches/sec sampled+normalised"
@@ -228,7 +247,7 @@ def ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     lib = _lib.require_device()
     K, Wm = args.steps, args.warmup
     mode = MODES[args.workload]
@@ -440,7 +459,7 @@ def ours_predict(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl(dev)
     _lib.require_device()
     (H, W), cfg = predict_config(world, args)
     torch.manual_seed(0)

@@ -1,0 +1,278 @@
+"""The host mirror of the reference's sampler classes (deephisto_b200/patch_samplers) on the GPU: yielded shapes, dtypes and
+values against the CPU oracle / golden vectors, seeded determinism, error behaviour. These read like the reference's own
+example scripts (examples/sample_full_dense.py, sample_full_random.py, sample_annotated_rnd.py, sample_annotated_dense.py)."""
+
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cover as ocover
+from oracle import dense as odense
+from oracle import region as oregion
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    import deephisto_b200
+    from deephisto_b200 import _lib
+    from deephisto_b200.patch_samplers import full_samplers as fs
+    from deephisto_b200.patch_samplers import region_samplers as rs
+
+    _lib.require_device()
+    return deephisto_b200, fs, rs
+
+
+MODE = None
+
+
+def _mode(fs):
+    return fs.SamplerExecutionMode.INMEMORY_SINGLEPROC
+
+
+# ---- examples/sample_full_dense.py ------------------------------------------------------------------------------------
+def test_full_dense_sampler_api(api, golden, tmp_path):
+    _, fs, _ = api
+    z, man = golden
+    H, W, ps, stride, B = 1000, 777, 224, 100, 7
+    host = synth.synth_slide(H, W, 0)
+    npy = tmp_path / "slide.npy"
+    np.save(npy, host)
+    for source in (host, str(npy)):                                            # numpy array and .npy path (the psimage seam)
+        s = fs.FullImageDenseSampler(source, layer=1, patch_size=ps, batch_size=B, mode=_mode(fs), stride=stride)
+        assert (s.h, s.w) == (H, W)
+        key = f"dense_{H}x{W}_ps{ps}_s{stride}_b{B}"
+        want = z[key + "_coords"]
+        bc = s._create_batched_coords()                                        # same return type as the reference's method
+        assert isinstance(bc, list) and isinstance(bc[0][0], tuple) and len(bc[0]) == B
+        assert np.array_equal(np.array([c for b in bc for c in b], dtype=np.int32), want)
+        n = 0
+        last_progress = -1.0
+        for feats, coords, progress in s.generator_torch():
+            assert feats.is_cuda and feats.dtype == torch.float32 and tuple(feats.shape) == (B, ps, ps, 3)
+            assert coords.dtype == torch.float32 and tuple(coords.shape) == (B, 2)
+            assert np.array_equal(coords.cpu().numpy(), want[n * B : (n + 1) * B].astype(np.float32))
+            exp = odense.normalize(odense.gather(host, want[n * B : (n + 1) * B], ps))
+            assert np.array_equal(feats.cpu().numpy(), exp)
+            assert progress == n / len(s) and progress > last_progress       # never reaches 1.0
+            last_progress = progress
+            n += 1
+        assert n == len(s) == len(want) // B
+    # list[Patch] protocol of generator() / __iter__
+    s = fs.FullImageDenseSampler(host, 1, ps, B, _mode(fs), stride)
+    patches, progress = next(iter(s))
+    assert len(patches) == B and progress == 0.0
+    p = patches[3]
+    assert (p.layer, p.patch_size) == (1, ps) and p.data.dtype == np.uint8 and p.data.shape == (ps, ps, 3)
+    assert np.array_equal(p.data, host[p.pos_y : p.pos_y + ps, p.pos_x : p.pos_x + ps])
+    # stride=None means stride = patch_size; bf16 NCHW with mean/std is an extra
+    s2 = fs.FullImageDenseSampler(host, 1, 224, 4, _mode(fs))
+    assert s2.stride == 224
+    f, _, _ = next(s2.generator_torch(dtype=torch.bfloat16, layout="NCHW", mean=(0.5, 0.5, 0.5), std=(0.25, 0.25, 0.25)))
+    assert f.dtype == torch.bfloat16 and tuple(f.shape) == (4, 3, 224, 224)
+
+
+# ---- examples/sample_full_random.py -----------------------------------------------------------------------------------
+def test_full_rnd_sampler_api_and_coverage(api):
+    _, fs, _ = api
+    H, W, ps, B = 1100, 900, 224, 16
+    host = synth.synth_slide(H, W, 2)
+    s = fs.FullImageRndSampler(host, layer=1, patch_size=ps, batch_size=B, mode=_mode(fs), seed=11)
+    assert (s.dh, s.dw, s.dense_level) == (H // 16, W // 16, 2)
+    oracle = ocover.CoverSampler(H, W, ps, B, seed=11)
+    ratios = []
+    for feats, coords, filled in s.generator_torch():
+        assert feats.is_cuda and tuple(feats.shape) == (B, ps, ps, 3) and feats.dtype == torch.float32
+        oc, _ = oracle.next_coords()
+        c = coords.cpu().numpy()
+        assert np.array_equal(c, np.asarray(oc, dtype=np.float32))             # bit-identical to the CPU restatement of the Philox stream
+        assert (c[:, 0] >= 0).all() and (c[:, 0] <= H - ps).all() and (c[:, 1] >= 0).all() and (c[:, 1] <= W - ps).all()
+        # the reference does NOT divide by 255 here (full_samplers.py:286)
+        exp = odense.gather(host, c.astype(np.int32), ps).astype(np.float32)
+        assert np.array_equal(feats.cpu().numpy(), exp)
+        ratios.append(filled)
+    assert ratios[-1] == 1.0 and all(b >= a for a, b in zip(ratios, ratios[1:]))
+    assert s._filled_ratio == ratios
+    acc = s._accum
+    assert acc.shape == (s.dh, s.dw) and (acc > 0).all()
+    assert np.array_equal(acc, oracle.accum.astype(np.float32))
+    # list[Patch] protocol
+    s2 = fs.FullImageRndSampler(host, 1, ps, B, _mode(fs), seed=11)
+    patches, filled = next(iter(s2))
+    assert len(patches) == B and 0 < filled < 1 and patches[0].data.shape == (ps, ps, 3)
+    f, _, _ = next(fs.FullImageRndSampler(host, 1, ps, B, _mode(fs), seed=11).generator_torch(normalize=True))
+    assert float(f.max()) <= 1.0
+
+
+# ---- examples/sample_annotated_rnd.py ---------------------------------------------------------------------------------
+def _dataset(tmp_path, n_images=2):
+    hw = (5000, 4600)
+    items, polys_all = [], []
+    for j in range(n_images):
+        polys = synth.synth_polygons(9 + 3 * j, *hw, seed=20 + j, rmin=300, rmax=800, n_classes=4)
+        anno = tmp_path / f"img{j}.json"
+        anno.write_text(json.dumps(polys))                                      # the reference's JSON schema (region_samplers.py:218-227)
+        items.append((synth.synth_slide(*hw, seed=30 + j), anno))
+        polys_all.append(polys)
+    return hw, items, polys_all
+
+
+@pytest.mark.parametrize("one_image", [False, True])
+def test_anno_region_rnd_sampler_torch_generator(api, tmp_path, one_image):
+    _, _, rs = api
+    hw, items, polys_all = _dataset(tmp_path)
+    ps, B, k, ri = 224, 24, 4, 0.75
+    s = rs.AnnoRegionRndSampler(items, layer=1, patch_size=ps, region_intersection=ri, patches_from_one_region=k, one_image_for_batch=one_image,
+                                seed=5, verbose=False)
+    assert s.classes == sorted({p["class"] for polys in polys_all for p in polys})
+    assert len(s) == int(sum(r.area for regs in s.regions.values() for r in regs) / (ps * ps))
+    ors = oregion.RegionSet([(hw, p) for p in polys_all], layer=1, one_image_for_batch=one_image)
+    n_batches, bpw = 7, 2
+    oc, olab, oimg, ost = [], [], [], []
+    off = 0
+    for nb in [bpw] * (n_batches // bpw) + ([n_batches % bpw] if n_batches % bpw else []):   # the reference's worker chunks (:722-728)
+        c, l, i, st = oregion.sample(ors, B * nb, k, ps, ri, seed=5, slot_offset=off, slots_per_table_draw=B * bpw)
+        off += B * nb
+        oc.append(c), olab.append(l), oimg.append(i), ost.append(st)
+    oc, olab, oimg = np.concatenate(oc), np.concatenate(olab), np.concatenate(oimg)
+    assert (np.concatenate(ost) == 0).all()
+    got = list(s.torch_generator(batch_size=B, n_batches=n_batches, batches_per_worker=bpw))
+    assert len(got) == n_batches
+    for b, (f, l, c) in enumerate(got):
+        sl = slice(b * B, (b + 1) * B)
+        assert f.is_cuda and f.dtype == torch.float32 and tuple(f.shape) == (B, ps, ps, 3)
+        assert l.dtype == torch.int64 and tuple(l.shape) == (B,) and c.dtype == torch.float32 and tuple(c.shape) == (B, 2)
+        assert np.array_equal(c.cpu().numpy(), oc[sl].astype(np.float32))
+        assert np.array_equal(l.cpu().numpy(), olab[sl])
+        fh = f.cpu().numpy()
+        for q in range(0, B, 5):                                                # pixels come from the image the slot drew
+            y, x = oc[sl][q]
+            img = items[int(oimg[sl][q])][0]
+            assert np.array_equal(fh[q], odense.normalize(img[None, y : y + ps, x : x + ps])[0])
+    if one_image:                                                               # one image per worker chunk (:544-552)
+        for w0 in range(0, n_batches * B, B * bpw):
+            assert len(set(oimg[w0 : w0 + B * bpw].tolist())) == 1
+    # every accepted patch satisfies the reference's criterion: area(polygon ∩ patch) > ri * ps^2 for a region of its class and image
+    names = s.classes
+    for q in range(0, len(oc), 7):
+        y, x = oc[q]
+        areas = [float(oregion.clip_area(oregion.build_edges(np.asarray(p["vertices"], dtype=np.float64)), float(x), float(y), float(ps)))
+                 for p in polys_all[int(oimg[q])] if p["class"] == names[int(olab[q])]]
+        assert max(areas) > ri * ps * ps
+    # seeded determinism; a different seed gives different coordinates
+    again = list(rs.AnnoRegionRndSampler(items, 1, ps, ri, k, one_image_for_batch=one_image, seed=5, verbose=False).torch_generator(B, n_batches, bpw))
+    assert all(torch.equal(a[2], b[2]) and torch.equal(a[1], b[1]) and torch.equal(a[0], b[0]) for a, b in zip(got, again))
+    other = next(rs.AnnoRegionRndSampler(items, 1, ps, ri, k, one_image_for_batch=one_image, seed=6, verbose=False).torch_generator(B, 1))
+    assert not torch.equal(other[2], got[0][2])
+
+
+def test_anno_region_rnd_sampler_extras_and_structs(api, tmp_path):
+    _, _, rs = api
+    hw, items, polys_all = _dataset(tmp_path, 1)
+    ps, B = 224, 8
+    base = rs.AnnoRegionRndSampler(items, 1, ps, seed=3, verbose=False)
+    f0, l0, c0 = next(base.torch_generator(B, 1))
+    # fused layout / dtype / batch-level flips (train.py:71-81): same coordinates, features = flipped NCHW bf16 of the plain ones
+    aug = rs.AnnoRegionRndSampler(items, 1, ps, seed=3, verbose=False, out_dtype=torch.bfloat16, out_layout="NCHW", flips=True)
+    seen = set()
+    gen_a = aug.torch_generator(B, 12)
+    gen_b = rs.AnnoRegionRndSampler(items, 1, ps, seed=3, verbose=False).torch_generator(B, 12)
+    for (fa, la, ca), (fb, lb, cb) in zip(gen_a, gen_b):
+        assert torch.equal(ca, cb) and torch.equal(la, lb)
+        ref = fb.permute(0, 3, 1, 2)
+        cands = {0: ref, 1: ref.flip(3), 2: ref.flip(2), 3: ref.flip(2).flip(3)}
+        hit = [bits for bits, t in cands.items() if torch.equal(fa, t.to(torch.bfloat16))]
+        assert hit, "augmented batch is not a whole-batch H/V flip of the plain batch"
+        seen.add(hit[0])
+    assert len(seen) >= 2
+    # structs_generator: list[(Patch, class_index)] with uint8 data (reference :641-683); cls_idx restricts the class (0 is class 0, Q5)
+    batches = list(base.structs_generator(batch_size=6, n_batches=3, cls_idx=0))
+    assert [len(b) for b in batches] == [6, 6, 6]
+    host = items[0][0]
+    for patch, cls in batches[1]:
+        assert cls == 0 and patch.data.dtype == np.uint8
+        assert np.array_equal(patch.data, host[patch.pos_y : patch.pos_y + ps, patch.pos_x : patch.pos_x + ps])
+    with pytest.raises(ValueError):
+        next(base.torch_generator(4, 1, cls_idx=99))
+    # iterable dataset yields (features [ps,ps,3], label, (y, x)) -- not (y, y) (Q6)
+    it = iter(base.torch_iterable_dataset())
+    f, l, c = next(it)
+    assert tuple(f.shape) == (ps, ps, 3) and c.shape == (2,)
+
+
+def test_region_annotation_errors_and_dense(api):
+    _, _, rs = api
+    hw = (3000, 3000)
+    small = np.array([[10.0, 10.0], [120.0, 10.0], [120.0, 130.0], [10.0, 130.0]])
+    r = rs.RegionAnnotation("x.psi", 0, "A", small, layer=1, layer_size=hw)
+    with pytest.raises(RuntimeError, match="Region is too small."):
+        r._extract_patch_coords_rnd(224, 4)
+    with pytest.raises(RuntimeError, match="Invalid region shape"):
+        rs.RegionAnnotation("x.psi", 0, "A", np.zeros((4, 3)), 1, hw)
+    with pytest.raises(RuntimeError, match="Invalid region dtype"):
+        rs.RegionAnnotation("x.psi", 0, "A", small.astype(np.float32), 1, hw)
+    # thin sliver: area above the threshold but no position reaches 95 % coverage -> miss limit
+    sliver = np.array([[100.0, 100.0], [2900.0, 100.0], [2900.0, 130.0], [100.0, 130.0]])
+    rr = rs.RegionAnnotation("x.psi", 1, "A", sliver, 1, hw)
+    with pytest.raises(RuntimeError, match="Miss limit reached"):
+        rr._extract_patch_coords_rnd(224, 2, region_intersection=0.95, miss_limit=50)
+    star = np.asarray(synth.synth_polygons(1, *hw, seed=8, rmin=700, rmax=900)[0]["vertices"])
+    big = rs.RegionAnnotation("x.psi", 2, "B", star, 1, hw)
+    got = big._extract_patch_coords_rnd(224, 9)
+    assert len(got) == 9 and isinstance(got[0], tuple)
+    e = oregion.build_edges(star)
+    for y, x in got:
+        assert float(oregion.clip_area(e, float(x), float(y), 224.0)) > 0.75 * 224 * 224
+    dense = big._extract_patch_coords_dense(224, 56, 0.6)
+    assert dense == [tuple(c) for c in oregion.coords_dense(star, hw, 224, 56, 0.6)[0].tolist()] and len(dense) > 10
+    # layer = 2: vertices are divided by the layer (region_samplers.py:68)
+    half = rs.RegionAnnotation("x.psi", 3, "B", star, 2, (hw[0] // 2, hw[1] // 2))
+    assert abs(half.area - big.area / 4) < 1e-6 * big.area
+    assert half._extract_patch_coords_dense(64, 32) == [tuple(c) for c in oregion.coords_dense(star / 2, (1500, 1500), 64, 32)[0].tolist()]
+
+
+# ---- examples/sample_annotated_dense.py -------------------------------------------------------------------------------
+def test_anno_region_dense_sampler(api, tmp_path):
+    _, _, rs = api
+    hw, items, polys_all = _dataset(tmp_path, 2)
+    ps, stride, ri = 224, 150, 0.8
+    s = rs.AnnoRegionDenseSampler(items, layer=1, patch_size=ps, stride=stride, region_intersection=ri, verbose=False)
+    want = []                                                                   # classes sorted, regions in file order (reference :866-871)
+    got = [(p.pos_y, p.pos_x, c, p.data) for p, c in s.structs_generator()]
+    for ci, cls in enumerate(s.classes):
+        for reg in s.regions[cls]:
+            v = np.asarray(reg.vertices, dtype=np.float64)
+            for y, x in oregion.coords_dense(v, hw, ps, stride, ri)[0].tolist():
+                want.append((y, x, ci, reg._region.image))
+    assert [(y, x, c) for y, x, c, _ in got] == [(y, x, c) for y, x, c, _ in want]
+    assert len(got) > 50
+    for (y, x, c, data), (_, _, _, img) in list(zip(got, want))[::11]:
+        assert np.array_equal(data, items[img][0][y : y + ps, x : x + ps])
+    n_dev = sum(len(c) for _, c, _ in s.region_batches(dtype=torch.bfloat16, layout="NCHW"))
+    assert n_dev == len(got)
+
+
+def test_install_dropin_registers_reference_module_names(api):
+    deephisto_b200, fs, rs = api
+    import sys
+
+    saved = {k: sys.modules.get(k) for k in ("patch_samplers", "patch_samplers.full_samplers", "patch_samplers.region_samplers", "examples",
+                                              "examples.predict_full_patched", "anno", "anno.utils")}
+    try:
+        deephisto_b200.install_dropin()
+        from patch_samplers.full_samplers import FullImageDenseSampler, SamplerExecutionMode  # noqa: F401  (the reference's import lines)
+        from patch_samplers.region_samplers import AnnoRegionRndSampler  # noqa: F401
+        from examples.predict_full_patched import ImagePredictorPatched, batch_predictor, load_model  # noqa: F401
+        from anno.utils import AnnoDescription  # noqa: F401
+
+        assert FullImageDenseSampler is fs.FullImageDenseSampler and AnnoRegionRndSampler is rs.AnnoRegionRndSampler
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
