@@ -4,6 +4,7 @@ arithmetic happens in the hand-written sm_100a kernels of libdeephisto_b200.so).
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from typing import Optional, Sequence
 
 import numpy as np
@@ -56,7 +57,9 @@ class DeviceSlide:
             raise ValueError("slide must be uint8 [H, W, 3]")
         H, W, _ = arr.shape
         s = cls.empty(H, W, device)
-        src = torch.from_numpy(np.ascontiguousarray(arr)).view(H, 3 * W)
+        with warnings.catch_warnings():                     # read-only sources (np.load(mmap_mode="r")) are only read from
+            warnings.filterwarnings("ignore", message="The given NumPy array is not writable")
+            src = torch.from_numpy(np.ascontiguousarray(arr)).view(H, 3 * W)
         s.storage.view(H, s.pitch)[:, : 3 * W].copy_(src, non_blocking=False)
         return s
 

@@ -160,7 +160,7 @@ def test_anno_region_rnd_sampler_torch_generator(api, tmp_path, one_image):
     names = s.classes
     for q in range(0, len(oc), 7):
         y, x = oc[q]
-        areas = [float(oregion.clip_area(oregion.build_edges(np.asarray(p["vertices"], dtype=np.float64)), float(x), float(y), float(ps)))
+        areas = [float(np.ravel(oregion.clip_area(oregion.build_edges(np.asarray(p["vertices"], dtype=np.float64)), float(x), float(y), float(ps)))[0])
                  for p in polys_all[int(oimg[q])] if p["class"] == names[int(olab[q])]]
         assert max(areas) > ri * ps * ps
     # seeded determinism; a different seed gives different coordinates
@@ -226,7 +226,7 @@ def test_region_annotation_errors_and_dense(api):
     assert len(got) == 9 and isinstance(got[0], tuple)
     e = oregion.build_edges(star)
     for y, x in got:
-        assert float(oregion.clip_area(e, float(x), float(y), 224.0)) > 0.75 * 224 * 224
+        assert float(np.ravel(oregion.clip_area(e, float(x), float(y), 224.0))[0]) > 0.75 * 224 * 224
     dense = big._extract_patch_coords_dense(224, 56, 0.6)
     assert dense == [tuple(c) for c in oregion.coords_dense(star, hw, 224, 56, 0.6)[0].tolist()] and len(dense) > 10
     # layer = 2: vertices are divided by the layer (region_samplers.py:68)
