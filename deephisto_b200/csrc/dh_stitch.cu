@@ -355,6 +355,47 @@ __global__ void __launch_bounds__(256) stitch_finalize_kernel(const float* __res
     }
 }
 
+// ---- prediction post-processing ---------------------------------------------------------
+// Reference: examples/predict_full_patched.py:81-113 perform_and_save_visualizations
+//   colored_image[pred == anno.id] = anno.color                      -> class-colour LUT
+//   img = psim.get_region((0,0), (H,W), target_hw=(h,w))             -> slide thumbnail [h][w][3]
+//   (img * alpha + colored_image * (1 - alpha)).astype(np.uint8)     -> overlay, float64 arithmetic, truncation
+// The thumbnail here is the exact integer AREA AVERAGE of the d x d slide block under every map cell, rounded half up:
+// (sum + d*d/2) / (d*d). (psimage's own resampling filter is unknown -- the package is not in the reference tree -- so the
+// thumbnail is this build's definition; the LUT and the blend follow the reference arithmetic exactly.)
+// One thread per (cell, channel); a warp covers ~11 neighbouring cells, so the d x d x 3 byte block of the slide is read from
+// DRAM once and re-touched through L1. Algorithmic bytes: dh*d * dw*d * 3 read + up to 3 * dh*dw*3 written.
+__global__ void __launch_bounds__(256) colorize_overlay_kernel(const uint8_t* __restrict__ argmax_map, const uint8_t* __restrict__ slide,
+                                                               int64_t pitch, int64_t dh, int64_t dw, int d,
+                                                               const uint8_t* __restrict__ lut, double alpha,
+                                                               uint8_t* __restrict__ mask_out, uint8_t* __restrict__ thumb_out,
+                                                               uint8_t* __restrict__ overlay_out) {
+    const int64_t row_elems = dw * 3;
+    const int64_t total = dh * row_elems;
+    const uint32_t area = (uint32_t)d * (uint32_t)d;
+    const double beta = __dsub_rn(1.0, alpha);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / row_elems;
+        const int64_t e = t - i * row_elems;   // 3*j + c
+        const int64_t j = e / 3;
+        const int c = (int)(e - 3 * j);
+        const uint32_t col = lut[3 * (uint32_t)argmax_map[i * dw + j] + c];
+        if (mask_out) mask_out[t] = (uint8_t)col;
+        if (thumb_out || overlay_out) {
+            const uint8_t* src = slide + (i * d) * pitch + 3 * (j * d) + c;
+            uint32_t sum = 0;
+            for (int r = 0; r < d; ++r) {
+                const uint8_t* row = src + (int64_t)r * pitch;
+#pragma unroll 4
+                for (int px = 0; px < d; ++px) sum += __ldg(row + 3 * px);
+            }
+            const uint32_t img = (sum + area / 2) / area;
+            if (thumb_out) thumb_out[t] = (uint8_t)img;
+            if (overlay_out) overlay_out[t] = (uint8_t)(int)__dadd_rn(__dmul_rn((double)img, alpha), __dmul_rn((double)col, beta));
+        }
+    }
+}
+
 static int make_stitch_grid(int64_t H, int64_t W, int ps, int stride, int d, int n, int batch_size, StitchGrid* g) {
     DH_REQUIRE(ps > 0 && stride > 0 && d > 0, "stitch: ps, stride and downscale must be positive");
     DH_REQUIRE(n > 0 && n <= 64, "stitch: n classes %d outside 1..64", n);
@@ -458,5 +499,26 @@ extern "C" DH_API int dh_stitch_finalize(const float* sum_map, const uint32_t* c
     int grid = (int)(blocks < (int64_t)kNumSMs * 16 ? blocks : (int64_t)kNumSMs * 16);
     stitch_finalize_kernel<<<grid, 256, 0, as_stream(stream)>>>(sum_map, count_map, cells, n, norm_map, argmax_u8);
     DH_CHECK_LAUNCH("stitch_finalize_kernel");
+    return DH_OK;
+}
+
+extern "C" DH_API int dh_colorize_overlay(const uint8_t* argmax_u8, const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, int64_t dh_,
+                                          int64_t dw_, int d, const uint8_t* lut_rgb, double alpha, uint8_t* mask_out, uint8_t* thumb_out,
+                                          uint8_t* overlay_out, void* stream) {
+    DH_REQUIRE(argmax_u8 && lut_rgb, "dh_colorize_overlay: null class map or colour table");
+    DH_REQUIRE(mask_out || thumb_out || overlay_out, "dh_colorize_overlay: no output requested");
+    DH_REQUIRE(dh_ >= 0 && dw_ >= 0 && d >= 1 && d <= 4096, "dh_colorize_overlay: bad sizes");
+    if (thumb_out || overlay_out) {
+        DH_REQUIRE(slide, "dh_colorize_overlay: the thumbnail and the overlay need the slide");
+        DH_REQUIRE(dh_ * d <= H && dw_ * d <= W && pitch >= 3 * W, "dh_colorize_overlay: map %lldx%lld at downscale %d does not fit the %lldx%lld slide",
+                   (long long)dh_, (long long)dw_, d, (long long)H, (long long)W);
+    }
+    if (dh_ == 0 || dw_ == 0) return DH_OK;
+    const int64_t total = dh_ * dw_ * 3;
+    const int64_t blocks = (total + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)kNumSMs * 32 ? blocks : (int64_t)kNumSMs * 32);
+    colorize_overlay_kernel<<<grid, 256, 0, as_stream(stream)>>>(argmax_u8, slide, pitch, dh_, dw_, d, lut_rgb, alpha, mask_out, thumb_out,
+                                                                overlay_out);
+    DH_CHECK_LAUNCH("colorize_overlay_kernel");
     return DH_OK;
 }

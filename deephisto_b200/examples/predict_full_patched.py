@@ -247,29 +247,35 @@ def assemble_bands(band: torch.Tensor, dh: int, world: int, dist) -> torch.Tenso
     return torch.cat([gathered[r * rows_max : r * rows_max + heights[r]] for r in range(world)], 0)
 
 
-def colorize(pred: torch.Tensor | np.ndarray, anno_dsc: AnnoDescription) -> np.ndarray:
-    """Class map -> RGB by class colour (reference :89-95)."""
-    pred = torch.as_tensor(pred)
+def visualize_device(pred_u8: torch.Tensor, slide, anno_dsc: AnnoDescription, d: int, alpha: float = 0.6):
+    """(mask, thumbnail, overlay) uint8 [h,w,3] CUDA tensors for a class map u8 [h,w] and the full-resolution DeviceSlide it was
+    predicted from at total downscale d: one launch of dh_colorize_overlay (reference :89-110)."""
     lut = torch.zeros((256, 3), dtype=torch.uint8)
     for a in anno_dsc.anno_classes:
         lut[a.id] = torch.tensor(a.color, dtype=torch.uint8)
-    return lut.to(pred.device)[pred.long()].cpu().numpy()
+    return ops.colorize_overlay(pred_u8.contiguous(), lut.to(pred_u8.device), slide, d, alpha, want_mask=True, want_thumb=True, want_overlay=True)
 
 
-def perform_and_save_visualizations(img_path, anno_dsc: AnnoDescription, pred: np.ndarray, out_dir: Path = Path(".")):
-    """Reference :81-113: colourised mask, downscaled slide, 0.6/0.4 overlay, saved as JPEG."""
+def perform_and_save_visualizations(img_path, anno_dsc: AnnoDescription, pred: np.ndarray, out_dir: Path = Path("."), *, device="cuda"):
+    """Reference :81-113: colourised mask, downscaled slide, 0.6/0.4 overlay, saved as JPEG. The three images are computed on
+    the device from the full-resolution layer in one pass; only the JPEG encoding (PIL) is host work."""
     from PIL import Image
+
+    from ..slide import layer_to_device
 
     out_dir.mkdir(exist_ok=True, parents=True)
     stem = Path(img_path).stem if isinstance(img_path, (str, Path)) else "slide"
     h, w = pred.shape[:2]
-    colored = colorize(pred, anno_dsc)
-    Image.fromarray(colored).save(out_dir / f"{stem}_mask.jpg", quality=95)
     with open_slide(img_path) as psim:
-        img = np.asarray(psim.get_region((0, 0), (psim.height, psim.width), target_hw=(h, w)))
-    Image.fromarray(img).save(out_dir / f"{stem}.jpg", quality=95)
-    alpha = 0.6
-    Image.fromarray((img * alpha + colored * (1 - alpha)).astype(np.uint8)).save(out_dir / f"{stem}_overlay.jpg", quality=95)
+        full = layer_to_device(psim, 1, device)
+    d = min(full.H // h, full.W // w)
+    if d < 1:
+        raise ValueError("the class map is larger than the slide")
+    pred_u8 = torch.as_tensor(np.asarray(pred)).to(torch.uint8).to(device)
+    mask, thumb, over = visualize_device(pred_u8, full, anno_dsc, d)
+    Image.fromarray(mask.cpu().numpy()).save(out_dir / f"{stem}_mask.jpg", quality=95)
+    Image.fromarray(thumb.cpu().numpy()).save(out_dir / f"{stem}.jpg", quality=95)
+    Image.fromarray(over.cpu().numpy()).save(out_dir / f"{stem}_overlay.jpg", quality=95)
 
 
 def main(argv=None):

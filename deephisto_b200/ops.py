@@ -200,6 +200,26 @@ def stitch_finalize(sum_map: torch.Tensor, count_map: Optional[torch.Tensor] = N
     return norm, amax
 
 
+def colorize_overlay(argmax: torch.Tensor, lut_rgb: torch.Tensor, slide: Optional[DeviceSlide] = None, d: int = 1, alpha: float = 0.6,
+                     want_mask: bool = True, want_thumb: bool = False, want_overlay: bool = False):
+    """Class map u8 [dh,dw] -> (mask, thumbnail, overlay), each uint8 [dh,dw,3] or None (predict_full_patched.py:81-113)."""
+    lib = _lib.require_device()
+    _need_cuda(argmax, "argmax", torch.uint8)
+    _need_cuda(lut_rgb, "lut_rgb", torch.uint8)
+    if lut_rgb.numel() != 768:
+        raise ValueError("lut_rgb must be uint8 [256, 3]")
+    if (want_thumb or want_overlay) and slide is None:
+        raise ValueError("the thumbnail and the overlay need the slide")
+    dh, dw = argmax.shape
+    mk = lambda want: torch.empty((dh, dw, 3), dtype=torch.uint8, device=argmax.device) if want else None  # noqa: E731
+    mask, thumb, over = mk(want_mask), mk(want_thumb), mk(want_overlay)
+    with torch.cuda.device(argmax.device):
+        check(lib.dh_colorize_overlay(argmax.data_ptr(), None if slide is None else slide.storage.data_ptr(), 0 if slide is None else slide.H,
+                                      0 if slide is None else slide.W, 0 if slide is None else slide.pitch, dh, dw, d, lut_rgb.data_ptr(),
+                                      float(alpha), _ptr(mask), _ptr(thumb), _ptr(over), _stream()), "dh_colorize_overlay")
+    return mask, thumb, over
+
+
 class CoverState:
     """Device state of the coverage-driven random sampler (accumulator + scratch)."""
 

@@ -133,6 +133,18 @@ DH_API int dh_stitch_finalize(const float* sum_map, const uint32_t* count_map, i
                        float* norm_map, uint8_t* argmax_u8, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Prediction post-processing: perform_and_save_visualizations (examples/predict_full_patched.py:81-113).
+ *   mask    [dh][dw][3] = lut_rgb[class]                                   (:89-95)
+ *   thumb   [dh][dw][3] = integer area average of the d x d slide block under the cell, rounded half up
+ *                         (stands in for psim.get_region(..., target_hw=(h, w)), :103-104; psimage's filter is unknown)
+ *   overlay [dh][dw][3] = uint8(thumb * alpha + mask * (1 - alpha)), float64, truncated   (:108-110, alpha = 0.6)
+ * lut_rgb: device uint8 [256][3]. Any of the three outputs may be NULL; slide may be NULL when only the mask is requested.
+ * ------------------------------------------------------------------------------------------ */
+DH_API int dh_colorize_overlay(const uint8_t* argmax_u8, const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, int64_t dh,
+                               int64_t dw, int d, const uint8_t* lut_rgb, double alpha, uint8_t* mask_out, uint8_t* thumb_out,
+                               uint8_t* overlay_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * B1-B3  FullImageRndSampler (full_samplers.py:81-94,105-114,125-162,263-274)
  * Coverage-driven random sampling on the 1/speedup coarse accumulator.
  * One call = one batch: eligible cells (accum < dense_level) are compacted in index order, topped

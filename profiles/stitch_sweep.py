@@ -66,6 +66,15 @@ for d in (16, 4, 2, 1):
         rows.append({"kernel": "stitch_finalize", "d": d, "outputs": "argmax", "ms": ms, "alg_MB": alg / 1e6, "GBs": alg / ms / 1e6, "frac_of_measured": alg / ms / 1e6 / peak})
         del sum_map
     torch.cuda.empty_cache()
+# prediction post-processing: class-colour mask + area-average thumbnail + overlay in one pass over the slide
+slide = ops.DeviceSlide.synthetic(H, W, 0)
+lut = torch.randint(0, 256, (256, 3), dtype=torch.uint8, device="cuda")
+for d in (16, 4):
+    dh, dw = H // d, W // d
+    am = torch.randint(0, N, (dh, dw), dtype=torch.uint8, device="cuda")
+    ms = timeit(lambda: ops.colorize_overlay(am, lut, slide, d, want_mask=True, want_thumb=True, want_overlay=True), 10)
+    alg = dh * d * dw * d * 3 + dh * dw * (1 + 9)
+    rows.append({"kernel": "colorize_overlay", "d": d, "outputs": "mask+thumb+overlay", "ms": ms, "alg_MB": alg / 1e6, "GBs": alg / ms / 1e6, "frac_of_measured": alg / ms / 1e6 / peak})
 print(json.dumps({"peak_gbs": peak, "case": f"{H}x{W} ps{PS} stride{STRIDE} n{N}, {npad} patches", "rows": rows}, indent=1))
 for r in rows:
     print(f'{r["kernel"]:16s} d={r["d"]:2d} {r["outputs"]:18s} {r["ms"]:9.3f} ms {r["alg_MB"]:10.1f} MB {r["GBs"]:8.0f} GB/s  {r["frac_of_measured"]:.3f}', file=sys.stderr)
