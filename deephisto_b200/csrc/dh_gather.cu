@@ -316,7 +316,7 @@ static void launch_vec(const GatherParams& p, bool nchw, int grid, cudaStream_t 
 using namespace dh;
 
 extern "C" DH_API int dh_gather_set_variant(int variant) {
-    if (variant < 0 || variant > 6) { set_error("dh_gather_set_variant: variant must be 0..6"); return DH_ERR_INVALID; }
+    if (variant < 0 || variant > 9) { set_error("dh_gather_set_variant: variant must be 0..9"); return DH_ERR_INVALID; }
     g_variant = variant;
     return DH_OK;
 }
@@ -349,7 +349,7 @@ extern "C" DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64
     const bool nchw = out_layout == DH_NCHW;
     if (g_variant != 1) {  // TMA-staged kernel whenever the shape allows it
         int rc = gather_tma_launch(slide, H, W, pitch, coords, out_index, B, ps, out, out_dtype, out_layout, p.scale255,
-                                   mean3_host ? p.mean : nullptr, mean3_host ? p.stdv : nullptr, flip, g_variant >= 3 ? (g_variant == 6 ? 4 : g_variant - 2) : 0, st);
+                                   mean3_host ? p.mean : nullptr, mean3_host ? p.stdv : nullptr, flip, g_variant >= 3 ? (g_variant == 6 ? 4 : (g_variant == 7 ? 8 : (g_variant == 8 ? 16 : (g_variant == 9 ? 24 : g_variant - 2)))) : 0, st);
         if (rc != DH_ERR_UNSUPPORTED) return rc;
         if (g_variant >= 2) { set_error("dh_gather_normalize: shape not supported by the TMA-staged kernel (needs ps %% 4 == 0 for f32, ps %% 8 == 0 for bf16, pitch %% 16 == 0)"); return rc; }
     }

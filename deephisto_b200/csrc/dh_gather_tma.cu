@@ -49,7 +49,7 @@ struct TmaGatherParams {
     int row_pitch;    // bytes per staged row in shared memory (multiple of 16, >= 3*ps + 32)
     int units_per_row;
     int stages;       // depth of the stage ring
-    int debug;        // profiling only: 1 = producer skips the bulk loads, 2 = consumers skip the stores, 4 = default-policy stores
+    int debug;        // profiling only: 1 = no bulk loads, 2 = no stores, 4 = default-policy stores, 8 = contiguous tiles per CTA, 16 = evict-first loads
     float mean[3];
     float stdv[3];
 };
@@ -93,6 +93,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -161,7 +166,13 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
     const int tpp = p.tiles_per_patch;
     const int S = p.stages;
     const int64_t n_tiles = p.B * (int64_t)tpp;
-    const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // tile assignment: round-robin over the grid (default) or one contiguous range per CTA (debug bit 8, profiling)
+    const bool blocked = p.debug & 8;
+    const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const int64_t first_tile = blocked ? (int64_t)blockIdx.x * per_cta : (int64_t)blockIdx.x;
+    const int64_t tile_step = blocked ? 1 : (int64_t)gridDim.x;
+    const int64_t my_tiles = blocked ? (first_tile >= n_tiles ? 0 : (n_tiles - first_tile < per_cta ? n_tiles - first_tile : per_cta))
+                                     : (first_tile < n_tiles ? (n_tiles - first_tile + gridDim.x - 1) / gridDim.x : 0);
     const int64_t plane = (int64_t)ps * ps;
 
     if (threadIdx.x == 0) {
@@ -176,10 +187,12 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
     if (threadIdx.x < 32) {
         // ---------------- producer warp ----------------
         const int lane = threadIdx.x;
-        int64_t patch = blockIdx.x / tpp;                      // once; the loop advances (patch, tr) incrementally
-        int tr = (int)(blockIdx.x - patch * tpp);
-        const int64_t dq = gridDim.x / tpp;
-        const int dr = (int)(gridDim.x - dq * tpp);
+        int64_t patch = first_tile / tpp;                      // once; the loop advances (patch, tr) incrementally
+        int tr = (int)(first_tile - patch * tpp);
+        const int64_t dq = tile_step / tpp;
+        const int dr = (int)(tile_step - dq * tpp);
+        uint64_t policy = 0;
+        if (p.debug & 16) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         const uint32_t stage0 = smem_u32(stages);
         int s = 0;
         uint32_t ph = 1;  // a fresh mbarrier passes a wait on parity 1: the first S tiles do not wait
@@ -206,7 +219,8 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                 const int orow = tr * R + lane;                                // output row of the patch
                 const int srow = (fl & DH_FLIP_V) ? ps - 1 - orow : orow;      // source row
                 const uint8_t* src = p.slide + (int64_t)(y + srow) * p.pitch + ((3 * (int64_t)x) & ~(int64_t)15);
-                bulk_load(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s]);
+                if (p.debug & 16) bulk_load_hint(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s], policy);
+                else bulk_load(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s]);
             }
             tr += dr; patch += dq;
             if (tr >= tpp) { tr -= tpp; ++patch; }

@@ -396,6 +396,58 @@ __global__ void __launch_bounds__(256) colorize_overlay_kernel(const uint8_t* __
     }
 }
 
+// Vector variant for d % 4 == 0 (VW = 1: 32-bit loads) and d % 16 == 0 (VW = 4: 128-bit loads): one thread per CELL reads its
+// 3*d-byte row segments as words; a group of 3 words is 4 RGB pixels with the channel phases (0,1,2,0)(1,2,0,1)(2,0,1,2), so the
+// per-channel sums are nine DP4A with constant byte masks.
+__device__ __forceinline__ void rgb_sums3(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t& r, uint32_t& g, uint32_t& b) {
+    r = __dp4a(w0, 0x01000001u, r); g = __dp4a(w0, 0x00000100u, g); b = __dp4a(w0, 0x00010000u, b);
+    r = __dp4a(w1, 0x00010000u, r); g = __dp4a(w1, 0x01000001u, g); b = __dp4a(w1, 0x00000100u, b);
+    r = __dp4a(w2, 0x00000100u, r); g = __dp4a(w2, 0x00010000u, g); b = __dp4a(w2, 0x01000001u, b);
+}
+
+template <int VW>
+__global__ void __launch_bounds__(256) colorize_overlay_vec_kernel(const uint8_t* __restrict__ argmax_map, const uint8_t* __restrict__ slide,
+                                                                   int64_t pitch, int64_t dh, int64_t dw, int d,
+                                                                   const uint8_t* __restrict__ lut, double alpha,
+                                                                   uint8_t* __restrict__ mask_out, uint8_t* __restrict__ thumb_out,
+                                                                   uint8_t* __restrict__ overlay_out) {
+    const int64_t total = dh * dw;
+    const uint32_t area = (uint32_t)d * (uint32_t)d;
+    const double beta = __dsub_rn(1.0, alpha);
+    const int groups = d / 4;  // groups of 3 words (12 bytes = 4 pixels) per row segment
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / dw, j = t - i * dw;
+        const uint8_t* src = slide + (i * d) * pitch + 3 * (j * d);
+        uint32_t sr = 0, sg = 0, sb = 0;
+        for (int r = 0; r < d; ++r) {
+            const uint8_t* row = src + (int64_t)r * pitch;
+            if (VW == 4) {
+                const uint4* q = reinterpret_cast<const uint4*>(row);
+                for (int k = 0; k < groups / 4; ++k) {  // 3 x 16 bytes = 4 groups
+                    const uint4 a = __ldg(q + 3 * k), b = __ldg(q + 3 * k + 1), c = __ldg(q + 3 * k + 2);
+                    rgb_sums3(a.x, a.y, a.z, sr, sg, sb);
+                    rgb_sums3(a.w, b.x, b.y, sr, sg, sb);
+                    rgb_sums3(b.z, b.w, c.x, sr, sg, sb);
+                    rgb_sums3(c.y, c.z, c.w, sr, sg, sb);
+                }
+            } else {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(row);
+                for (int k = 0; k < groups; ++k) rgb_sums3(__ldg(q + 3 * k), __ldg(q + 3 * k + 1), __ldg(q + 3 * k + 2), sr, sg, sb);
+            }
+        }
+        const uint32_t cls = argmax_map[t];
+        const uint32_t sum[3] = {sr, sg, sb};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t col = lut[3 * cls + c];
+            const uint32_t img = (sum[c] + area / 2) / area;
+            if (mask_out) mask_out[3 * t + c] = (uint8_t)col;
+            if (thumb_out) thumb_out[3 * t + c] = (uint8_t)img;
+            if (overlay_out) overlay_out[3 * t + c] = (uint8_t)(int)__dadd_rn(__dmul_rn((double)img, alpha), __dmul_rn((double)col, beta));
+        }
+    }
+}
+
 static int make_stitch_grid(int64_t H, int64_t W, int ps, int stride, int d, int n, int batch_size, StitchGrid* g) {
     DH_REQUIRE(ps > 0 && stride > 0 && d > 0, "stitch: ps, stride and downscale must be positive");
     DH_REQUIRE(n > 0 && n <= 64, "stitch: n classes %d outside 1..64", n);
@@ -514,6 +566,19 @@ extern "C" DH_API int dh_colorize_overlay(const uint8_t* argmax_u8, const uint8_
                    (long long)dh_, (long long)dw_, d, (long long)H, (long long)W);
     }
     if (dh_ == 0 || dw_ == 0) return DH_OK;
+    if ((thumb_out || overlay_out) && d % 4 == 0 && pitch % 16 == 0 && reinterpret_cast<uintptr_t>(slide) % 16 == 0 && d <= 256) {
+        const int64_t cells = dh_ * dw_;  // d <= 256: the per-channel sums (255 * d * d) fit 32 bits
+        const int64_t blocks = (cells + 255) / 256;
+        const int grid = (int)(blocks < (int64_t)kNumSMs * 32 ? blocks : (int64_t)kNumSMs * 32);
+        if (d % 16 == 0)
+            colorize_overlay_vec_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(argmax_u8, slide, pitch, dh_, dw_, d, lut_rgb, alpha, mask_out,
+                                                                             thumb_out, overlay_out);
+        else
+            colorize_overlay_vec_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(argmax_u8, slide, pitch, dh_, dw_, d, lut_rgb, alpha, mask_out,
+                                                                             thumb_out, overlay_out);
+        DH_CHECK_LAUNCH("colorize_overlay_vec_kernel");
+        return DH_OK;
+    }
     const int64_t total = dh_ * dw_ * 3;
     const int64_t blocks = (total + 255) / 256;
     const int grid = (int)(blocks < (int64_t)kNumSMs * 32 ? blocks : (int64_t)kNumSMs * 32);

@@ -314,5 +314,5 @@ def rasterize_polygons(edges: torch.Tensor, edge_off: torch.Tensor, reg_bbox: to
 def set_gather_variant(variant: str = "auto") -> None:
     """Profiling switch: "auto" (TMA-staged kernel when the shape allows), "direct" (LDG/STG kernel), "tma" (fail if unsupported)."""
     lib = _lib.load()
-    check(lib.dh_gather_set_variant({"auto": 0, "direct": 1, "tma": 2, "tma_noload": 3, "tma_nostore": 4, "tma_nomem": 5, "tma_plainstore": 6}[variant]),
+    check(lib.dh_gather_set_variant({"auto": 0, "direct": 1, "tma": 2, "tma_noload": 3, "tma_nostore": 4, "tma_nomem": 5, "tma_plainstore": 6, "tma_blocked": 7, "tma_evictfirst": 8, "tma_blocked_evictfirst": 9}[variant]),
           "dh_gather_set_variant")

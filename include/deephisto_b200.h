@@ -102,7 +102,8 @@ DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64_t W, int64
 
 /* Variant selector for profiling: 0 = auto, 1 = direct (LDG/STG) kernel, 2 = TMA-staged kernel;
  * 3 / 4 / 5 = TMA-staged kernel with the loads / the stores / both switched off (WRONG RESULTS: ceiling measurements only);
- * 6 = TMA-staged kernel with default-policy instead of streaming stores. */
+ * 6 = TMA-staged kernel with default-policy instead of streaming stores; 7 / 8 / 9 = contiguous tile range per CTA /
+ * L2 evict-first hint on the bulk loads / both (correct results; profiling). */
 DH_API int dh_gather_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------

@@ -52,7 +52,7 @@ for B in (256, 1024, 4096):
     for dtype in (torch.float32, torch.bfloat16):
         for layout in ("NHWC", "NCHW"):
             rows.append(run(B, dtype, layout))
-for v in ("direct", "tma_noload", "tma_nostore", "tma_nomem", "tma_plainstore"):
+for v in ("direct", "tma_noload", "tma_nostore", "tma_nomem", "tma_plainstore", "tma_blocked", "tma_evictfirst", "tma_blocked_evictfirst"):
     rows.append(run(256, torch.float32, "NHWC", v))
     rows.append(run(4096, torch.float32, "NHWC", v))
 import os
