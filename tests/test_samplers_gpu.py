@@ -276,3 +276,23 @@ def test_install_dropin_registers_reference_module_names(api):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@pytest.mark.parametrize("script,extra", [
+    ("sample_full_dense", ["--synthetic", "1100", "900", "--quiet"]),
+    ("sample_full_random", ["--synthetic", "1100", "900", "--quiet"]),
+    ("sample_annotated_rnd", ["--torch", "--synthetic", "6000", "6000", "-n", "6", "--quiet"]),
+    ("sample_annotated_rnd", ["--synthetic", "6000", "6000", "-n", "4", "--quiet"]),
+    ("sample_annotated_dense", ["--synthetic", "6000", "6000", "--polygons", "3", "--stride", "200"]),
+    ("predict_full_patched", ["--synthetic", "1500", "1300", "--downscale", "16"]),
+])
+def test_example_entry_points_run(script, extra):
+    """The reference's `python -m examples.<name>` entry points (README.md:19-32) run end to end on synthetic inputs."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, "-m", f"deephisto_b200.examples.{script}", *extra], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert ("items/s" in out.stdout) or ("Gpx/s" in out.stdout)
