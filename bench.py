@@ -486,12 +486,15 @@ def ours_predict(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    ipp.stage_events = {}                                            # CUDA events per stage: our kernels vs torch's CNN
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(K):
         out = step()
     t1.record()
     torch.cuda.synchronize()
+    stage_ms = {k: v / K for k, v in ipp.stage_ms().items()}
+    ipp.stage_events = None
     if world > 1:
         dist.barrier()
     t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)

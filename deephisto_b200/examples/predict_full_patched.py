@@ -118,6 +118,29 @@ class ImagePredictorPatched:
             with open_slide(psim_path) as psim:
                 self.h, self.w = psim.layer_size(self.layer)
         self.last_sum_map: Optional[torch.Tensor] = None      # kept when process_device(want_sum=True)
+        self.stage_events: Optional[dict] = None              # set to {} to collect CUDA events per stage (bench breakdown)
+
+    def _mark(self, stage: str):
+        """(start, end) CUDA events appended to stage_events[stage]; a no-op context when profiling is off."""
+        import contextlib
+
+        if self.stage_events is None:
+            return contextlib.nullcontext()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.stage_events.setdefault(stage, []).append((a, b))
+
+        @contextlib.contextmanager
+        def ctx():
+            a.record()
+            yield
+            b.record()
+
+        return ctx()
+
+    def stage_ms(self) -> dict:
+        """Total milliseconds per stage from the collected events (synchronises)."""
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in (self.stage_events or {}).items()}
 
     # ---- reference entry point --------------------------------------------------------------------------------------
     def process(self, rank: Optional[int] = None, world: Optional[int] = None) -> np.ndarray:
@@ -145,11 +168,13 @@ class ImagePredictorPatched:
         ps = sampler.patch_size
         for a in range(first, first + count, step):
             c = min(step, first + count - a)
-            coords = ops.dense_coords(sampler.h, sampler.w, ps, sampler.stride, sampler.batch_size, first=a, count=c, device=self._device)
-            if y_off:
-                coords[:, 0] -= y_off
-            feats = ops.gather_normalize(slide, coords, ps, dtype=pred.dtype, layout="NCHW", scale255=True)
-            logits[a : a + c] = pred.logits(feats)
+            with self._mark("coords+gather"):
+                coords = ops.dense_coords(sampler.h, sampler.w, ps, sampler.stride, sampler.batch_size, first=a, count=c, device=self._device)
+                if y_off:
+                    coords[:, 0] -= y_off
+                feats = ops.gather_normalize(slide, coords, ps, dtype=pred.dtype, layout="NCHW", scale255=True)
+            with self._mark("cnn"):
+                logits[a : a + c] = pred.logits(feats)
 
     def _dense_device(self, want_sum: bool, want_count: bool) -> dict:
         s: FullImageDenseSampler = self.patch_sampler
@@ -177,11 +202,12 @@ class ImagePredictorPatched:
         amax_band = torch.zeros((plan.rows_max, dw), dtype=torch.uint8, device=self._device)
         sum_band = torch.zeros((plan.rows_max, dw, n), dtype=torch.float32, device=self._device) if want_sum else None
         if plan.row_end > plan.row_begin:
-            sm, _, am = ops.stitch_dense(logits, s.h, s.w, s.patch_size, s.stride, d, s.batch_size, row_begin=plan.row_begin,
-                                         row_end=plan.row_end, want_sum=want_sum, want_argmax=True)
-            amax_band[: plan.row_end - plan.row_begin] = am
-            if want_sum:
-                sum_band[: plan.row_end - plan.row_begin] = sm
+            with self._mark("stitch"):
+                sm, _, am = ops.stitch_dense(logits, s.h, s.w, s.patch_size, s.stride, d, s.batch_size, row_begin=plan.row_begin,
+                                             row_end=plan.row_end, want_sum=want_sum, want_argmax=True)
+                amax_band[: plan.row_end - plan.row_begin] = am
+                if want_sum:
+                    sum_band[: plan.row_end - plan.row_begin] = sm
         return {"argmax_band": amax_band, "sum_band": sum_band, "logits": logits, "plan": plan}
 
     def _dense_banded(self, rank: int, world: int, want_sum: bool) -> dict:
@@ -191,10 +217,11 @@ class ImagePredictorPatched:
         dh = s.h // self.downscale
         loc = self.dense_band_local(rank, world, want_sum)
         # the one exchange step: band maps are disjoint row ranges -> all-gather, then drop the padding rows
-        out = {"argmax": assemble_bands(loc["argmax_band"], dh, world, dist), "sum": None, "count": None, "logits": loc["logits"],
-               "plan": loc["plan"]}
-        if want_sum:
-            out["sum"] = assemble_bands(loc["sum_band"], dh, world, dist)
+        with self._mark("assemble (NCCL all-gather)"):
+            out = {"argmax": assemble_bands(loc["argmax_band"], dh, world, dist), "sum": None, "count": None, "logits": loc["logits"],
+                   "plan": loc["plan"]}
+            if want_sum:
+                out["sum"] = assemble_bands(loc["sum_band"], dh, world, dist)
         self.last_sum_map = out["sum"]
         return out
 
