@@ -110,6 +110,18 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": self.max_sm, "reasons": seen, "samples": len(busy)}
 
 
+# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, the samplers' "Image H x W"
+# prints, worker processes) is pointed at stderr for the life of the process.
+sys.stdout.flush()
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def dist_env():
     return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
@@ -215,7 +227,7 @@ def reference_arm(args):
         "note": "oracle port of AnnoRegionRndSampler.torch_generator (region_samplers.py:685-738): the reference itself cannot run "
                 "(psimage and shapely are neither vendored nor installable); CPU tensors are left on the host as the reference yields them",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -427,7 +439,7 @@ def ours(args):
             line["cpu_baseline"] = json.loads(out.stdout.strip().splitlines()[-1])
         except Exception:
             line["cpu_baseline"] = {"error": (out.stderr or out.stdout)[-400:]}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -501,11 +513,19 @@ def ours_predict(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    # e2e: the public call, class map read back to the host every step (what process() returns)
+    # e2e: every step uploads this rank's slide band from PINNED HOST memory, runs the public call and reads the class map back
+    # (what process() returns) -- the reference likewise reads the layer from storage in its constructor (full_samplers.py:53-55)
+    from deephisto_b200.slide import PinnedSlide
+
+    host_band = PinnedSlide.from_device(band)                         # setup, not timed
     h_map = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
+    del band
+    resident = {}
+    sampler.band_slide = lambda y0, y1: (resident["band"], y_off)
     torch.cuda.synchronize()
     w0 = time.perf_counter()
     for _ in range(K):
+        resident["band"] = host_band.to_device(dev)
         h_map.copy_(step(), non_blocking=True)
         torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
@@ -523,12 +543,13 @@ def ours_predict(args):
             "dtype": "bf16" if args.bf16 else "f32", "data": "synthetic",
             "config": dict(cfg, parallelism=f"row bands x{world} with patch-size halo (recomputed halo patch rows), NCCL all-gather of the u8 class-map bands"),
             "patches_per_s": K * g.n_padded / (ms_total / 1e3), "patches_per_slide": g.n_padded, "patches_this_rank": plan.n_patches,
-            "e2e": {"value": K * gpx / e2e_s, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(h_map.numel()),
-                    "api": "ImagePredictorPatched.process_device (band resident in HBM), class map copied to pinned host memory every step"},
+            "e2e": {"value": K * gpx / e2e_s, "unit": "Gpx/s", "h2d_bytes_per_step": int(host_band.nbytes), "d2h_bytes_per_step": int(h_map.numel()),
+                    "api": "per step: this rank's slide band uploaded from pinned host memory, ImagePredictorPatched.process_device, class map "
+                           "copied to pinned host memory (h2d/d2h bytes are per rank)"},
             "roofline": None, "gpu_launches": None, "clocks": clk,
             "note": "CNN-bound (torch/cuDNN ResNet18): see profiles/ for the gather and stitch kernel shares",
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -557,11 +578,11 @@ def reference_arm_predict(args):
         n += 1
     dt = time.perf_counter() - t0
     val = n * H * W / 1e9 / dt
-    print(json.dumps({"impl": "reference", "metric": "WSI gigapixels/sec patched predict", "value": val, "unit": "Gpx/s", "n_gpus": args.gpus,
+    emit({"impl": "reference", "metric": "WSI gigapixels/sec patched predict", "value": val, "unit": "Gpx/s", "n_gpus": args.gpus,
                       "steps": n, "warmup": 0, "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                       "dtype": "f32", "data": "synthetic", "config": {"workload": "oracle port of examples.predict_full_patched on a 2048x2048 crop, CPU ResNet18"},
                       "cpu_baseline": {"value": val, "unit": "Gpx/s", "cores": torch.get_num_threads(), "kind": "port", "sample": f"{n} x 2048x2048 crop"},
-                      "e2e": {"value": val, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+                      "e2e": {"value": val, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def main():
@@ -585,7 +606,7 @@ def main():
         args.warmup = {"predict": 1, "train_input": 4}.get(args.workload, 32)
     args.warmup = max(args.warmup, 3) if args.workload != "predict" else args.warmup
     if args.cpu_leg:
-        print(json.dumps(cpu_leg_bounded(args.cpu_budget)), flush=True)
+        emit(cpu_leg_bounded(args.cpu_budget))
         return
     if args.impl == "reference":
         reference_arm(args)

@@ -148,7 +148,8 @@ __device__ __forceinline__ void store_unit(__nv_bfloat16* dst, const float (&f)[
 
 template <typename OutT> struct UnitOf { static constexpr int kElems = 16 / (int)sizeof(OutT); };
 
-template <typename OutT, bool NCHW, bool SCALE, bool AFFINE, bool FULL>
+// DBG: profiling instantiation (p.debug switches; only fp32 NHWC /255 FULL is built with it). Production kernels carry none of it.
+template <typename OutT, bool NCHW, bool SCALE, bool AFFINE, bool FULL, bool DBG = false>
 __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGatherParams p) {
     constexpr int E = UnitOf<OutT>::kElems;          // elements (NHWC) or pixels (NCHW) per unit: 4 or 8
     constexpr int IN_BYTES = NCHW ? 3 * E : E;       // input bytes per unit
@@ -165,9 +166,10 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
     const int stage_bytes = R * RP;
     const int tpp = p.tiles_per_patch;
     const int S = p.stages;
+    const int dbg = DBG ? p.debug : 0;
     const int64_t n_tiles = p.B * (int64_t)tpp;
     // tile assignment: round-robin over the grid (default) or one contiguous range per CTA (debug bit 8, profiling)
-    const bool blocked = p.debug & 8;
+    const bool blocked = dbg & 8;
     const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
     const int64_t first_tile = blocked ? (int64_t)blockIdx.x * per_cta : (int64_t)blockIdx.x;
     const int64_t tile_step = blocked ? 1 : (int64_t)gridDim.x;
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
         const int64_t dq = tile_step / tpp;
         const int dr = (int)(tile_step - dq * tpp);
         uint64_t policy = 0;
-        if (p.debug & 16) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        if (dbg & 16) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
         const uint32_t stage0 = smem_u32(stages);
         int s = 0;
         uint32_t ph = 1;  // a fresh mbarrier passes a wait on parity 1: the first S tiles do not wait
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             const bool inside = (y >= 0) && (x >= 0) && ((int64_t)y + ps <= p.H) && ((int64_t)x + ps <= p.W);
             const int a = (3 * x) & 15;
             const uint32_t bytes = (uint32_t)((a + row_bytes + 15) & ~15);
-            const bool stage_it = inside && !(p.debug & 1);
+            const bool stage_it = inside && !(dbg & 1);
             if (lane == 0) {
                 const int64_t slot = p.out_index ? (int64_t)__ldg(p.out_index + patch) : patch;
                 TileMeta m;
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                 const int orow = tr * R + lane;                                // output row of the patch
                 const int srow = (fl & DH_FLIP_V) ? ps - 1 - orow : orow;      // source row
                 const uint8_t* src = p.slide + (int64_t)(y + srow) * p.pitch + ((3 * (int64_t)x) & ~(int64_t)15);
-                if (p.debug & 16) bulk_load_hint(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s], policy);
+                if (dbg & 16) bulk_load_hint(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s], policy);
                 else bulk_load(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s]);
             }
             tr += dr; patch += dq;
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                             f[j] = norm_f<SCALE, AFFINE>(byte_f(w[j >> 2], j & 3, magic), c, p);
                             if (AFFINE) c = c == 2 ? 0 : c + 1;
                         }
-                        if (!(p.debug & 2) || f[0] == 12345.f) store_unit(ok, f, p.debug & 4);
+                        if (!(dbg & 2) || f[0] == 12345.f) store_unit(ok, f, dbg & 4);
                     } else if (!fh) {
 #pragma unroll
                         for (int ch = 0; ch < 3; ++ch) {
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                                 const int b = 3 * j + ch;  // byte of pixel j, channel ch
                                 f[j] = norm_f<SCALE, AFFINE>(byte_f(w[b >> 2], b & 3, magic), ch, p);
                             }
-                            if (!(p.debug & 2) || f[0] == 12345.f) store_unit(ok + ch * plane, f, p.debug & 4);
+                            if (!(dbg & 2) || f[0] == 12345.f) store_unit(ok + ch * plane, f, dbg & 4);
                         }
                     } else {
 #pragma unroll
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                                 const int b = 3 * (E - 1 - j) + ch;  // output pixel j = source pixel E-1-j of the mirrored unit
                                 f[j] = norm_f<SCALE, AFFINE>(byte_f(w[b >> 2], b & 3, magic), ch, p);
                             }
-                            store_unit(ok + ch * plane, f, p.debug & 4);
+                            store_unit(ok + ch * plane, f, dbg & 4);
                         }
                     }
                 }
@@ -414,7 +416,10 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
         if (scale255) { if (affine) DH_TMA(T, N, true, true); else DH_TMA(T, N, true, false); } \
         else          { if (affine) DH_TMA(T, N, false, true); else DH_TMA(T, N, false, false); } \
     } while (0)
-    if (out_dtype == DH_F32) { if (nchw) DH_TMA_SA(float, true); else DH_TMA_SA(float, false); }
+    if (debug) {  // profiling switches exist for one instantiation only
+        if (!(out_dtype == DH_F32 && !nchw && scale255 && !affine && full_units)) return DH_ERR_UNSUPPORTED;
+        rc_launch = launch_one(gather_tma_kernel<float, false, true, false, true, true>, p, n_tiles, smem, st);
+    } else if (out_dtype == DH_F32) { if (nchw) DH_TMA_SA(float, true); else DH_TMA_SA(float, false); }
     else                     { if (nchw) DH_TMA_SA(__nv_bfloat16, true); else DH_TMA_SA(__nv_bfloat16, false); }
 #undef DH_TMA_SA
 #undef DH_TMA

@@ -54,3 +54,49 @@ def test_no_cpu_fallback_without_gpu():
 
     with pytest.raises(_lib.DeepHistoError):
         ops.gather_normalize(None, torch.zeros((1, 2), dtype=torch.int32), 8)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No CPU fallback: with the shared library absent every compute entry point raises (checked in a fresh interpreter)."""
+    import os
+    import sys
+
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from deephisto_b200 import _lib\n"
+            "try:\n    _lib.load()\nexcept _lib.DeepHistoError as e:\n    print('RAISED', 'no CPU fallback' in str(e).lower() or 'not found' in str(e))\n") % str(ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, DEEPHISTO_B200_LIB=str(tmp_path / "nope.so")))
+    assert "RAISED True" in out.stdout, out.stdout + out.stderr
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under deephisto_b200/ may import it."""
+    offenders = []
+    for p in (ROOT / "deephisto_b200").rglob("*.py"):
+        txt = p.read_text()
+        if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M):
+            offenders.append(str(p))
+    assert not offenders, offenders
+
+
+def test_slide_sources_host_side():
+    """The psimage seam (deephisto_b200/slide.py): duck-typed sources agree on layer sizes and regions without touching the GPU."""
+    import numpy as np
+
+    from deephisto_b200 import slide as sl
+
+    a = np.arange(40 * 30 * 3, dtype=np.uint8).reshape(40, 30, 3)
+    s = sl.open_slide(a)
+    assert isinstance(s, sl.ArraySlide) and s.layer_size(1) == (40, 30) and s.layer_size(2) == (20, 15)
+    assert np.array_equal(s.get_region_from_layer(1, (3, 4), (10, 9)), a[3:10, 4:9])
+    assert np.array_equal(s.get_region_from_layer(2, (0, 0), (20, 15)), a[::2, ::2])
+    assert s.get_region((0, 0), (40, 30), target_hw=(10, 6)).shape == (10, 6, 3)
+    with pytest.raises(ValueError):
+        sl.ArraySlide(a.astype(np.float32))
+    with pytest.raises(TypeError):
+        sl.open_slide(42)
+    with pytest.raises(RuntimeError, match="psimage"):
+        sl.open_slide("missing.psi")
+    syn = sl.SyntheticSlide(64, 48, seed=3)
+    assert syn.layer_size(1) == (64, 48)
+    with pytest.raises(ValueError):
+        syn.layer_size(2)
