@@ -546,8 +546,10 @@ def ours_predict(args):
             "e2e": {"value": K * gpx / e2e_s, "unit": "Gpx/s", "h2d_bytes_per_step": int(host_band.nbytes), "d2h_bytes_per_step": int(h_map.numel()),
                     "api": "per step: this rank's slide band uploaded from pinned host memory, ImagePredictorPatched.process_device, class map "
                            "copied to pinned host memory (h2d/d2h bytes are per rank)"},
+            "stage_ms_per_step_rank0": stage_ms,
             "roofline": None, "gpu_launches": None, "clocks": clk,
-            "note": "CNN-bound (torch/cuDNN ResNet18): see profiles/ for the gather and stitch kernel shares",
+            "note": "CNN-bound (torch/cuDNN ResNet18, not part of the rebuilt path): stage_ms_per_step_rank0 separates this repo's kernels "
+                    "(coords+gather, stitch, assemble) from the CNN",
         }
         emit(line)
     if world > 1:

@@ -81,7 +81,10 @@ def area_weights(areas, area_influence: float) -> np.ndarray:
         target = np.array(inv) / sum(inv)
         f = -area_influence
     w = w_default + (target - w_default) * f
-    return w / sum(w.tolist())
+    # NB the reference writes `sum(w)` over a NUMPY array here and `sum(areas)` over a list of Python floats above: on the
+    # Python 3.12 it pins (environment.yaml) the builtin sum is Neumaier-compensated for exact floats only, so the two sums round
+    # differently. Both spellings are kept as they are (tests/golden/golden_weights_v1.json pins the result bit for bit).
+    return w / sum(w)
 
 
 @dataclass

@@ -161,6 +161,48 @@ def region_goldens(rs_mod, im, out: dict, manifest: dict):
         out[f"region_{name}_verts"] = verts
 
 
+WEIGHT_CASES = [  # (area_influence, one_image_for_batch)
+    (0.5, True), (0.5, False), (0.0, True), (-0.7, False), (1.0, True), (-1.0, True),
+]
+
+
+def weights_dataset(tmp: Path):
+    """Two synthetic images with 11 and 7 polygons in 4 / 3 classes, written in the reference's JSON schema."""
+    hw = (6000, 5000)
+    items, polys_all = [], []
+    for j, (n, ncls) in enumerate(((11, 4), (7, 3))):
+        polys = synth.synth_polygons(n, *hw, seed=50 + j, rmin=250, rmax=900, n_classes=ncls)
+        anno = tmp / f"w{j}.json"
+        anno.write_text(json.dumps(polys))
+        items.append((Path(f"weights_img{j}"), anno))
+        polys_all.append(polys)
+    return hw, items, polys_all
+
+
+def weights_goldens(rs_mod, im, manifest: dict):
+    """AnnoRegionRndSampler.__init__ (unmodified: _parse_annotations :194-249, _calc_weights :395-482, _calc_area_weights
+    :339-378) on a synthetic two-image dataset; the weight tables it computes are the golden values of row F."""
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        hw, items, polys_all = weights_dataset(Path(td))
+        for path, _ in items:
+            im.register(path, np.zeros(hw + (3,), np.uint8))
+        out = {"hw": list(hw), "cases": []}
+        for infl, one in WEIGHT_CASES:
+            s = rs_mod.AnnoRegionRndSampler(items, layer=1, patch_size=224, region_area_influence=infl, one_image_for_batch=one)
+            out["cases"].append({
+                "area_influence": infl, "one_image_for_batch": one, "classes": list(s.classes), "len": len(s),
+                "reg_w_all": {c: np.asarray(w).tolist() for c, w in s._reg_w_all.items()},
+                "reg_w_per_img": [{c: np.asarray(w).tolist() for c, w in d.items()} for d in s._reg_w_per_img],
+                "img_w": {c: np.asarray(w).tolist() for c, w in s._img_w.items()},
+                "img_w_all": np.asarray(s._img_w_all).tolist(),
+                "areas_all": {c: [r.area for r in regs] for c, regs in s.regions.items()},
+            })
+    (OUT / "golden_weights_v1.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+    manifest["weights"] = {"file": "golden_weights_v1.json", "cases": len(out["cases"])}
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     out, manifest = {}, {}
@@ -170,6 +212,7 @@ def main():
         dense_goldens(fs, im, out, manifest)
         stitch_goldens(pfp, fs, im, out, manifest)
         region_goldens(rs, im, out, manifest)
+        weights_goldens(rs, im, manifest)
     np.savez_compressed(OUT / "golden_v1.npz", **out)
     (OUT / "golden_v1.json").write_text(json.dumps(manifest, indent=1, sort_keys=True))
     print(f"wrote {OUT / 'golden_v1.npz'} ({(OUT / 'golden_v1.npz').stat().st_size / 1e6:.2f} MB), {len(out)} arrays, {len(manifest)} manifest entries")

@@ -326,3 +326,87 @@ def test_gather_kernel_variants_agree_with_oracle(ops, variant, ps):
                     assert np.array_equal(bits(got), bits(torch.from_numpy(want).to(dtype))), (layout, dtype, scale255, mean, flip is not None)
     finally:
         ops.set_gather_variant("auto")
+
+
+# ---- BASELINE full sizes through size-independent properties ---------------------------------------------------------------
+def test_stitch_full_size_properties(ops):
+    """40k x 40k / stride 112 (BASELINE configs[2], 127 488 padded patches): with all logits = 1 the sum map IS the count map
+    (small integers, exact in fp32); bands concatenate to the full map; total mass = sum of clipped patch footprints."""
+    H = W = 40000
+    ps, stride, B, n = 224, 112, 64, 5
+    N, npad = ops.dense_count(H, W, ps, stride, B)
+    ones = torch.ones((npad, n), device="cuda")
+    for d in (16, 4):
+        s, cnt, am = ops.stitch_dense(ones, H, W, ps, stride, d, B, want_count=True, want_argmax=True)
+        dh, dw = H // d, W // d
+        assert tuple(s.shape) == (dh, dw, n) and int(am.max()) == 0
+        assert torch.equal(s[..., 0], cnt.to(torch.float32)) and torch.equal(s[..., n - 1], s[..., 0])
+        assert int(cnt.min()) >= 1                                           # every cell is covered
+        coords = ops.dense_coords(H, W, ps, stride, B).cpu().numpy().astype(np.int64)
+        fy = np.minimum((coords[:, 0] + ps) // d, dh) - coords[:, 0] // d
+        fx = np.minimum((coords[:, 1] + ps) // d, dw) - coords[:, 1] // d
+        assert int(cnt.sum(dtype=torch.int64)) == int((fy * fx).sum())
+        r0, r1 = dh // 3 + 1, dh // 3 + 1 + 257
+        sb, cb, _ = ops.stitch_dense(ones, H, W, ps, stride, d, B, row_begin=r0, row_end=r1, want_count=True)
+        assert torch.equal(sb, s[r0:r1]) and torch.equal(cb, cnt[r0:r1])
+        # random logits: finalize(argmax) of the sum map == fused argmax
+        g = torch.Generator(device="cuda").manual_seed(d)
+        lg = torch.randn((npad, n), generator=g, device="cuda")
+        s2, _, am2 = ops.stitch_dense(lg, H, W, ps, stride, d, B, want_argmax=True)
+        _, am3 = ops.stitch_finalize(s2)
+        assert torch.equal(am2, am3)
+        del s, cnt, am, s2, sb, cb
+        torch.cuda.empty_cache()
+
+
+def test_region_sampling_full_size_properties(ops):
+    """BASELINE configs[1] shape: 32768^2 slide, 50 synthetic polygons, 1000 batches of 256 slots in one launch. Every slot succeeds,
+    every origin keeps the patch inside the slide and satisfies the acceptance criterion (oracle clip area on a subsample); classes
+    are drawn uniformly (region_samplers.py:555-560); launch splitting does not change the stream."""
+    from deephisto_b200.patch_samplers.region_samplers import build_tables
+    from deephisto_b200.synthetic import synth_polygons
+
+    H = W = 32768
+    ps, k, ri = 224, 4, 0.75
+    polys = synth_polygons(50, H, W, seed=0)
+    tables, regions, classes = build_tables([((H, W), polys)], layer=1, area_influence=0.5, classes=None, one_image_for_batch=True)
+    n = 256 * 1000
+    c, lab, img, st = ops.region_sample(tables.struct, n, k, ps, ps * ps * ri, seed=42, slots_per_table_draw=512)
+    assert int(st.max()) == 0
+    cy, cx = c[:, 0], c[:, 1]
+    assert int(cy.min()) >= 0 and int(cx.min()) >= 0 and int(cy.max()) <= H - ps and int(cx.max()) <= W - ps
+    hist = torch.bincount(lab, minlength=len(classes)).cpu().numpy()
+    assert hist.sum() == n and np.abs(hist / n - 1 / len(classes)).max() < 0.01
+    # groups of k slots share one region: consecutive slots of a group carry the same label
+    assert torch.equal(lab.view(-1, k)[:, 0].repeat_interleave(k), lab)
+    cn, labn = c.cpu().numpy(), lab.cpu().numpy()
+    by_class = {ci: [oregion.build_edges(np.asarray(p["vertices"], dtype=np.float64)) for p in polys if p["class"] == cls] for ci, cls in enumerate(classes)}
+    for q in range(0, n, 997):
+        y, x = cn[q]
+        best = max(float(np.ravel(oregion.clip_area(e, float(x), float(y), float(ps)))[0]) for e in by_class[int(labn[q])])
+        assert best > ri * ps * ps
+    # the same slots drawn by two launches with offsets give the same coordinates
+    a, _, _, _ = ops.region_sample(tables.struct, 4096, k, ps, ps * ps * ri, seed=42, slot_offset=0, slots_per_table_draw=512)
+    b, _, _, _ = ops.region_sample(tables.struct, 4096, k, ps, ps * ps * ri, seed=42, slot_offset=4096, slots_per_table_draw=512)
+    assert torch.equal(torch.cat([a, b]), c[:8192])
+
+
+def test_cover_sampler_full_size_terminates(ops):
+    """8192^2 slide (BASELINE configs[0] size), batch 256: coverage reaches 1.0, every origin is inside the clamp range, the
+    accumulator equals the footprint histogram of the yielded coordinates."""
+    H = W = 8192
+    ps, B, sp = 224, 256, 16
+    st = ops.CoverState(H, W, ps, sp, 2, B, seed=7)
+    cells = (H // sp) * (W // sp)
+    acc = torch.zeros((H // sp, W // sp), dtype=torch.int32, device="cuda")
+    filled, batches = 0.0, 0
+    while filled < 1.0:
+        coords, nonzero = st.next_coords()
+        assert int(coords.min()) >= 0 and int(coords[:, 0].max()) <= H - ps and int(coords[:, 1].max()) <= W - ps
+        ones = torch.ones((B, 1), device="cuda")
+        ops.stitch_scatter(ones, coords, ps, sp, None, acc)                 # the stitcher's footprint == the sampler's (y//s:(y+ps)//s)
+        filled = int(nonzero.item()) / cells
+        batches += 1
+        assert batches < 5000
+    assert torch.equal(acc, st.accum)
+    assert batches * B >= 2 * cells / ((ps // sp) ** 2) * 0.5 and int(st.accum.min()) >= 1
