@@ -426,7 +426,7 @@ def ours(args):
         "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": slide_bytes / K, "d2h_bytes_per_step": d2h,
                 "api": f"AnnoRegionRndSampler.torch_generator(batch_size={BATCH}, n_batches=K) over a slide in pinned host memory: the timed region "
                        "contains the one-time H2D upload of the slide (h2d_bytes_total), K batches, and per step the D2H read of labels+coords",
-                "h2d_bytes_total": slide_bytes, "seconds": e2e_s,
+                "h2d_bytes_total": slide_bytes, "host_memory_pinned": bool(host_slide.pinned), "seconds": e2e_s,
                 "steady_state": {"value": steady_value, "unit": "patches/s", "note": "the same call repeated with the slide already resident"},
                 "features_to_host": {"value": kh * BATCH / e2e_host_s, "unit": "patches/s", "d2h_bytes_per_step": d2h + h_feats.numel() * mode["esize"]}},
         "gpu_launches": launches[0],

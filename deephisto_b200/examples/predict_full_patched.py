@@ -227,11 +227,27 @@ class ImagePredictorPatched:
 
     # ---- arbitrary coordinates: scatter-accumulate ------------------------------------------------------------------------
     def _rnd_batches(self):
+        """Coverage-driven random sampling (the reference's default, :156-163). The sampler's batches depend on each other through
+        the coverage accumulator, the CNN does not feed back into them: coordinates of several sampler batches are collected
+        and sent through gather + CNN together (the reference's batch of 64 leaves the tensor cores mostly idle)."""
         s: FullImageRndSampler = self.patch_sampler
         pred: DeviceBatchPredictor = self.batch_predictor
-        for coords, progress in s.coords_generator():
+        target = self._cnn_batch or max(s.batch_size, 1024)
+        pending, n_pending, progress = [], 0, 0.0
+
+        def flush():
+            coords = pending[0] if len(pending) == 1 else torch.cat(pending)
             feats = ops.gather_normalize(s._slide, coords, s.patch_size, dtype=pred.dtype, layout="NCHW", scale255=True)
-            yield pred.logits(feats), coords, s.patch_size, progress
+            return pred.logits(feats), coords, s.patch_size, progress
+
+        for coords, progress in s.coords_generator():
+            pending.append(coords)
+            n_pending += len(coords)
+            if n_pending >= target:
+                yield flush()
+                pending, n_pending = [], 0
+        if pending:
+            yield flush()
 
     def _host_batches(self):
         """The reference's loop (:47-54): any iterator of (list[Patch], progress) and any callable list[Patch] -> [B, n]."""

@@ -122,9 +122,20 @@ class PinnedSlide:
     def __init__(self, host, H: int, W: int, pitch: int):
         import torch
 
-        if not (isinstance(host, torch.Tensor) and host.dtype == torch.uint8 and host.is_pinned() and host.numel() >= H * pitch):
-            raise ValueError("PinnedSlide needs a pinned uint8 tensor of at least H * pitch bytes")
+        if not (isinstance(host, torch.Tensor) and host.dtype == torch.uint8 and not host.is_cuda and host.numel() >= H * pitch):
+            raise ValueError("PinnedSlide needs a host uint8 tensor of at least H * pitch bytes")
         self.host, self.height, self.width, self.pitch = host, int(H), int(W), int(pitch)
+        self.pinned = host.is_pinned()      # False only when page-locking failed (_host_buffer): uploads then go through staging
+
+    @staticmethod
+    def _host_buffer(nbytes: int):
+        import torch
+
+        buf = torch.empty(nbytes, dtype=torch.uint8)
+        try:
+            return buf.pin_memory()
+        except RuntimeError:               # page-locking refused (ulimit / small host): keep a pageable buffer
+            return buf
 
     @classmethod
     def from_numpy(cls, arr: np.ndarray) -> "PinnedSlide":
@@ -132,7 +143,7 @@ class PinnedSlide:
 
         H, W, _ = arr.shape
         pitch = DeviceSlide.pitch_for(W)
-        host = torch.empty(H * pitch, dtype=torch.uint8).pin_memory()
+        host = cls._host_buffer(H * pitch)
         host.view(H, pitch)[:, : 3 * W].copy_(torch.from_numpy(np.ascontiguousarray(arr)).view(H, 3 * W))
         return cls(host, H, W, pitch)
 
@@ -140,7 +151,7 @@ class PinnedSlide:
     def from_device(cls, dev: DeviceSlide) -> "PinnedSlide":
         import torch
 
-        host = torch.empty(dev.H * dev.pitch, dtype=torch.uint8).pin_memory()
+        host = cls._host_buffer(dev.H * dev.pitch)
         host.copy_(dev.storage[: dev.H * dev.pitch])
         return cls(host, dev.H, dev.W, dev.pitch)
 

@@ -410,3 +410,24 @@ def test_cover_sampler_full_size_terminates(ops):
         assert batches < 5000
     assert torch.equal(acc, st.accum)
     assert batches * B >= 2 * cells / ((ps // sp) ** 2) * 0.5 and int(st.accum.min()) >= 1
+
+
+@pytest.mark.parametrize("layout", ["NHWC", "NCHW"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gather_writes_only_its_output_canary(ops, layout, dtype):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds writes are checked with canaries: the output is a view in
+    the middle of a larger buffer filled with a sentinel, for batch sizes that leave partial tiles / partial waves."""
+    H, W, ps = 2000, 1800, 224
+    slide = ops.DeviceSlide.synthetic(H, W, 3)
+    for B in (1, 5, 149, 593):
+        g = torch.Generator(device="cuda").manual_seed(B)
+        coords = torch.stack([torch.randint(0, H - ps + 1, (B,), generator=g, device="cuda"), torch.randint(0, W - ps + 1, (B,), generator=g, device="cuda")], 1).to(torch.int32)
+        n = B * ps * ps * 3
+        pad = 4096
+        big = torch.full((n + 2 * pad,), 7.0, dtype=dtype, device="cuda")
+        shape = (B, ps, ps, 3) if layout == "NHWC" else (B, 3, ps, ps)
+        out = big[pad : pad + n].view(shape)
+        flips = torch.randint(0, 4, (B,), generator=g, device="cuda").to(torch.uint8)
+        ops.gather_normalize(slide, coords, ps, dtype=dtype, layout=layout, flip=flips, out=out)
+        assert bool((big[:pad] == 7.0).all()) and bool((big[pad + n :] == 7.0).all())
+        assert float(out.float().max()) <= 1.0                                # every element was written ([0,1] after /255)
