@@ -190,8 +190,18 @@ class FullImageDenseSampler:
     def generator_torch(self, dtype=torch.float32, layout: str = "NHWC", mean=None,
                         std=None) -> Iterator[tuple[torch.Tensor, torch.Tensor, float]]:
         """features [B,ps,ps,3] float32 in [0,1] (bit-identical to `.astype(float32) / 255`, :441-443),
-        coords float32 [B,2] (y, x), progress i / n_batches (never reaches 1.0, like the reference)."""
-        for coords, progress in self.coords_generator():
-            features = ops.gather_normalize(self._slide, coords, self.patch_size, dtype=dtype, layout=layout, scale255=True,
+        coords float32 [B,2] (y, x), progress i / n_batches (never reaches 1.0, like the reference).
+
+        Up to 64 batches (<= ~2.5 GB of features) are gathered by ONE launch and yielded as contiguous slices: short launches
+        cannot fill HBM (profiles/r01_gather.md)."""
+        coords = self.coords_device()
+        coords_f = coords.to(torch.float32)
+        n_batches, B, ps = len(self), self.batch_size, self.patch_size
+        per_batch = B * ps * ps * 3 * torch.empty((), dtype=dtype).element_size()
+        ahead = max(1, min(64, (5 << 29) // max(per_batch, 1)))
+        for b0 in range(0, n_batches, ahead):
+            nb = min(ahead, n_batches - b0)
+            features = ops.gather_normalize(self._slide, coords[b0 * B : (b0 + nb) * B], ps, dtype=dtype, layout=layout, scale255=True,
                                             mean=mean, std=std)
-            yield features, coords.to(torch.float32), progress
+            for i, f in enumerate(features.view((nb, B) + tuple(features.shape[1:])).unbind(0)):
+                yield f, coords_f[(b0 + i) * B : (b0 + i + 1) * B], (b0 + i) / n_batches
