@@ -450,7 +450,8 @@ def predict_config(world, args):
     hw = tuple(args.slide) if args.slide else ((40000, 40000) if world == 1 else (100000, 100000))
     return hw, {
         "workload": f"examples.predict_full_patched (BASELINE configs[{2 if world == 1 else 3}]): patch_cls_simple ResNet18 (random init, seed 0, "
-                    f"{'bf16 channels_last' if args.bf16 else 'fp32, torch defaults (TF32 convolutions)'}) on a synthetic {hw[0]}x{hw[1]} slide, "
+                    f"{'bf16 channels_last' if args.bf16 else 'fp32, torch defaults (TF32 convolutions)'}{', BatchNorm folded' if args.fold_bn else ''}"
+                    f"{', cudnn.benchmark' if args.cudnn_benchmark else ''}) on a synthetic {hw[0]}x{hw[1]} slide, "
                     f"224x224 patches at stride 112, dense sampler batch 64 (CNN batch {args.cnn_batch}), stitch downscale 16, argmax map",
         "slide": list(hw), "patch": PS, "stride": 112, "downscale": 16, "cnn_batch": args.cnn_batch,
         "l2_policy": "inputs larger than L2: each step re-reads the whole slide band (GBs) from HBM",
@@ -476,7 +477,8 @@ def ours_predict(args):
     (H, W), cfg = predict_config(world, args)
     torch.manual_seed(0)
     model = pfp.get_model(5)
-    pred = pfp.DeviceBatchPredictor(model, dev, torch.bfloat16 if args.bf16 else torch.float32)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+    pred = pfp.DeviceBatchPredictor(model, dev, torch.bfloat16 if args.bf16 else torch.float32, fold_bn=bool(args.fold_bn))
     anno = AnnoDescription.with_auto_colors(["AT", "BG", "LP", "MM", "TUM"])
     src = SyntheticSlide(H, W, seed=0)
     mode = fs.SamplerExecutionMode.INMEMORY_SINGLEPROC
@@ -597,6 +599,8 @@ def main():
     ap.add_argument("--slide", type=int, nargs=2, default=None, help="predict workload: slide H W")
     ap.add_argument("--bf16", action="store_true", help="predict workload: run the CNN in bf16 channels_last")
     ap.add_argument("--cnn-batch", type=int, default=1024)
+    ap.add_argument("--fold-bn", action="store_true", help="predict workload: fold eval-mode BatchNorm into the convolutions")
+    ap.add_argument("--cudnn-benchmark", action="store_true", help="predict workload: torch.backends.cudnn.benchmark = True")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the bounded cpu_baseline sample")
     ap.add_argument("--ref-budget", type=float, default=60.0, help="--impl reference: target seconds for the K timed steps")

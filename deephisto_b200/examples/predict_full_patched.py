@@ -57,11 +57,15 @@ class DeviceBatchPredictor:
 
     dtype float32 keeps torch's defaults (what the reference runs on a GPU); bfloat16 runs the CNN in bf16 channels_last."""
 
-    def __init__(self, model: torch.nn.Module, device="cuda", dtype=torch.float32, channels_last: bool = True):
+    def __init__(self, model: torch.nn.Module, device="cuda", dtype=torch.float32, channels_last: bool = True, fold_bn: bool = False):
+        """fold_bn=True folds every eval-mode BatchNorm into the preceding convolution (torch.nn.utils.fusion): the same
+        function with ~20 fewer memory-bound elementwise kernels per forward; logits change at rounding level only."""
         self.device = torch.device(device)
         self.dtype = dtype
         self.channels_last = channels_last and dtype != torch.float32
         model = model.to(self.device).eval()
+        if fold_bn:
+            model = fold_batchnorm(model)
         if dtype != torch.float32:
             model = model.to(dtype)
         if self.channels_last:
@@ -87,6 +91,28 @@ class DeviceBatchPredictor:
         if isinstance(batch, torch.Tensor):
             return self.logits(batch)
         return self.logits(self.features_from_patches(batch)).cpu().numpy()
+
+
+def fold_batchnorm(model: torch.nn.Module) -> torch.nn.Module:
+    """A copy of an eval-mode torchvision ResNet with conv+bn pairs fused (conv1/bn1, every block's conv/bn and downsample)."""
+    import copy
+
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+
+    m = copy.deepcopy(model).eval()
+
+    def fuse_pairs(mod):
+        names = [n for n, _ in mod.named_children()]
+        for a, b in zip(names, names[1:]):
+            ca, cb = getattr(mod, a), getattr(mod, b)
+            if isinstance(ca, torch.nn.Conv2d) and isinstance(cb, torch.nn.BatchNorm2d):
+                setattr(mod, a, fuse_conv_bn_eval(ca, cb))
+                setattr(mod, b, torch.nn.Identity())
+        for child in mod.children():
+            fuse_pairs(child)
+
+    fuse_pairs(m)
+    return m
 
 
 def batch_predictor(patches: list[Patch], model, device) -> np.ndarray:

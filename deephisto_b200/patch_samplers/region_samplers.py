@@ -202,6 +202,7 @@ class AnnoRegionRndSampler:
         assert names == self.classes
         self._slides = [None] * len(img_anno_paths)
         self._slot_cursor = 0
+        self._producer = None          # CUDA stream the prefetch groups of torch_generator run on
         self._fail = torch.zeros(1, dtype=torch.uint8, device=device) if torch.device(device).type == "cuda" else None
         if verbose:
             self._print_anno_stats(self.regions)
@@ -239,18 +240,21 @@ class AnnoRegionRndSampler:
             raise RuntimeError("region sampling failed for some slots after max_redraw redraws "
                                "(regions too small for the patch size / intersection, or miss limit reached)")
 
-    def sample_coords(self, n_slots: int, slots_per_image_draw: int, cls_idx: int = None, slot_offset: int = None):
-        """(coords int32 [n,2], labels int64 [n], images int32 [n]) on the device for one worker-sized chunk (:525-591)."""
+    def _sample_raw(self, n_slots: int, slots_per_image_draw: int, cls_idx: int = None, slot_offset: int = None):
         if cls_idx is not None and not (0 <= cls_idx < len(self.classes)):
             raise ValueError(f"cls_idx {cls_idx} out of range")
         if slot_offset is None:
             slot_offset = self._slot_cursor
             self._slot_cursor += n_slots
         ps = self.patch_size
-        coords, labels, images, status = ops.region_sample(
+        return ops.region_sample(
             self._tables.struct, n_slots, self.patches_from_one_region, ps, ps * ps * self.region_intersection, miss_limit=500,
             max_redraw=64, fixed_class=-1 if cls_idx is None else cls_idx, slots_per_table_draw=max(slots_per_image_draw, 1),
             seed=self._seed, slot_offset=slot_offset, device=self._device)
+
+    def sample_coords(self, n_slots: int, slots_per_image_draw: int, cls_idx: int = None, slot_offset: int = None):
+        """(coords int32 [n,2], labels int64 [n], images int32 [n]) on the device for one worker-sized chunk (:525-591)."""
+        coords, labels, images, status = self._sample_raw(n_slots, slots_per_image_draw, cls_idx, slot_offset)
         torch.maximum(self._fail, status.max().reshape(1), out=self._fail)
         return coords, labels, images
 
@@ -280,30 +284,59 @@ class AnnoRegionRndSampler:
                         max_workers: int = None, cls_idx: int = None) -> Iterator[tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         """Reference :685-738: yields (features [B,ps,ps,3] float32 in [0,1], labels int64 [B], coords float32 [B,2] (y,x))."""
         chunk = batch_size * batches_per_worker
+        if cls_idx is not None and not (0 <= cls_idx < len(self.classes)):
+            raise ValueError(f"cls_idx {cls_idx} out of range")
         # Coordinates are counter-based (Philox keyed by the global slot index), so several worker-sized chunks can be drawn by
         # ONE launch with identical results -- as long as the groups of k slots do not straddle a chunk boundary. The features of
         # all prefetched batches are then written by ONE gather launch (short launches cannot fill HBM: profiles/r01_gather.md);
         # every yielded batch is a contiguous slice of that buffer. Prefetch depth: <= 32 batches and <= ~2.5 GB of features.
+        # The launches run on a PRODUCER STREAM, one prefetch group ahead of the batches being yielded: the consumer's own work on
+        # the current stream (its CNN step, its read-back of labels) overlaps with the sampling of the next group instead of
+        # queueing behind it -- the role the reference gives to its ProcessPoolExecutor workers (:721-738).
         ps = self.patch_size
         per_batch = batch_size * ps * ps * 3 * torch.empty((), dtype=self._out_dtype).element_size()
         ahead = batches_per_worker
         if chunk % self.patches_from_one_region == 0:
             ahead = max(1, min(32, (5 << 29) // max(per_batch, 1)) // batches_per_worker) * batches_per_worker
-        for nb in self._split_chunks(n_batches, ahead):
-            first_slot = self._slot_cursor
-            coords, labels, images = self.sample_coords(batch_size * nb, chunk, cls_idx)
-            flip = None
-            if self._flips:
-                flip = torch.cat([self._batch_flip(first_slot // max(batch_size, 1) + i, batch_size) for i in range(nb)])
-            features = self._gather(coords, images, self._out_dtype, self._out_layout, flip)
-            coords_f = coords.to(torch.float32)
-            for i in range(nb):
-                sl = slice(i * batch_size, (i + 1) * batch_size)
-                f = features[sl]
+        groups = self._split_chunks(n_batches, ahead)
+        on_gpu = torch.device(self._device).type == "cuda"
+        cur = torch.cuda.current_stream(self._device) if on_gpu else None
+        if on_gpu and self._producer is None:
+            self._producer = torch.cuda.Stream(self._device)
+            self._producer.wait_stream(cur)                 # tables (and anything else set up on the caller's stream) are complete
+
+        def launch(nb):
+            """Enqueue one prefetch group on the producer stream; returns its tensors and the event that marks them ready."""
+            with torch.cuda.stream(self._producer):
+                first_slot = self._slot_cursor
+                coords, labels, images, status = self._sample_raw(batch_size * nb, chunk, cls_idx)
+                flip = None
+                if self._flips:
+                    flip = torch.cat([self._batch_flip(first_slot // max(batch_size, 1) + i, batch_size) for i in range(nb)])
+                features = self._gather(coords, images, self._out_dtype, self._out_layout, flip)
+                group = {"features": features, "labels": labels, "coords": coords.to(torch.float32), "fail": status.max()}
+                ready = torch.cuda.Event()
+                ready.record(self._producer)
+            for t in group.values():
+                t.record_stream(cur)                         # allocated on the producer stream, consumed on the caller's
+            return group, ready
+
+        pending = launch(groups[0]) if groups else None
+        for gi, nb in enumerate(groups):
+            group, ready = pending
+            pending = launch(groups[gi + 1]) if gi + 1 < len(groups) else None
+            cur.wait_event(ready)
+            if int(group["fail"].item()) != 0:
+                raise RuntimeError("region sampling failed for some slots after max_redraw redraws "
+                                   "(regions too small for the patch size / intersection, or miss limit reached)")
+            feats = group["features"]
+            fv = feats.view((nb, batch_size) + tuple(feats.shape[1:])).unbind(0)
+            lv = group["labels"].view(nb, batch_size).unbind(0)
+            cv = group["coords"].view(nb, batch_size, 2).unbind(0)
+            for f, l, c in zip(fv, lv, cv):
                 if transforms is not None:
                     f = transforms(f)
-                yield f, labels[sl], coords_f[sl]
-            self._check_failures()
+                yield f, l, c
 
     def structs_generator(self, batch_size: int, n_batches: int, batches_per_worker: int = 2, max_workers: int = None,
                           cls_idx: int = None) -> Iterator[list[tuple[Patch, int]]]:
