@@ -61,6 +61,10 @@ SIGNATURES = {
         C.c_int,
         [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp],
     ),
+    "dh_gather_normalize_multi": (
+        C.c_int,
+        [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _i32, C.POINTER(C.c_float), C.POINTER(C.c_float), _vp, _vp],
+    ),
     "dh_gather_set_variant": (C.c_int, [_i32]),
     "dh_stitch_dense": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _i64, _vp]),
     "dh_stitch_dense_ex": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _vp]),

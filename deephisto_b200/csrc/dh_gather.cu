@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(kThreads) gather_generic(const GatherParams p)
 
 static int g_variant = 0;
 
-int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, const int32_t* coords, const int32_t* out_index,
+int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, const int64_t* slides_dev, int n_slides,
+                      const int32_t* image, const int32_t* coords, const int32_t* out_index,
                       int64_t B, int ps, void* out, int out_dtype, int out_layout, int scale255, const float* mean3, const float* std3,
                       const uint8_t* flip, int debug, cudaStream_t st);
 
@@ -348,7 +349,7 @@ extern "C" DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64
     }
     const bool nchw = out_layout == DH_NCHW;
     if (g_variant != 1) {  // TMA-staged kernel whenever the shape allows it
-        int rc = gather_tma_launch(slide, H, W, pitch, coords, out_index, B, ps, out, out_dtype, out_layout, p.scale255,
+        int rc = gather_tma_launch(slide, H, W, pitch, nullptr, 1, nullptr, coords, out_index, B, ps, out, out_dtype, out_layout, p.scale255,
                                    mean3_host ? p.mean : nullptr, mean3_host ? p.stdv : nullptr, flip, g_variant >= 3 ? (g_variant == 6 ? 4 : (g_variant == 7 ? 8 : (g_variant == 8 ? 16 : (g_variant == 9 ? 24 : g_variant - 2)))) : 0, st);
         if (rc != DH_ERR_UNSUPPORTED) return rc;
         if (g_variant >= 2) { set_error("dh_gather_normalize: shape not supported by the TMA-staged kernel (needs ps %% 4 == 0 for f32, ps %% 8 == 0 for bf16, pitch %% 16 == 0)"); return rc; }
@@ -375,4 +376,33 @@ extern "C" DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64
     else { if (nchw) gather_generic<uint8_t, true><<<grid, kThreads, 0, st>>>(p); else gather_generic<uint8_t, false><<<grid, kThreads, 0, st>>>(p); }
     DH_CHECK_LAUNCH("gather_generic");
     return DH_OK;
+}
+
+extern "C" DH_API int dh_gather_normalize_multi(const int64_t* slides_host, const int64_t* slides_dev, int n_slides,
+                                                const int32_t* image_of_patch, const int32_t* coords, const int32_t* out_index, int64_t B,
+                                                int ps, void* out, int out_dtype, int out_layout, int scale255,
+                                                const float* mean3_host, const float* std3_host, const uint8_t* flip, void* stream) {
+    DH_REQUIRE(slides_host && slides_dev && image_of_patch && coords && out, "dh_gather_normalize_multi: null pointer");
+    DH_REQUIRE(n_slides >= 1, "dh_gather_normalize_multi: empty slide table");
+    DH_REQUIRE(ps > 0 && ps <= 8192 && B >= 0, "dh_gather_normalize_multi: bad patch size / batch");
+    DH_REQUIRE(out_dtype == DH_F32 || out_dtype == DH_BF16, "dh_gather_normalize_multi: output must be f32 or bf16");
+    DH_REQUIRE(out_layout == DH_NHWC || out_layout == DH_NCHW, "dh_gather_normalize_multi: bad layout %d", out_layout);
+    DH_REQUIRE((mean3_host == nullptr) == (std3_host == nullptr), "dh_gather_normalize_multi: mean and std must both be given or both be NULL");
+    DH_REQUIRE(reinterpret_cast<uintptr_t>(slides_dev) % 16 == 0, "dh_gather_normalize_multi: the device slide table must be 16-byte aligned");
+    for (int i = 0; i < n_slides; ++i) {
+        const int64_t* d = slides_host + 4 * i;
+        DH_REQUIRE(d[0] != 0 && d[1] > 0 && d[2] > 0 && d[3] >= 3 * d[2], "dh_gather_normalize_multi: bad descriptor of slide %d", i);
+        if (d[0] % 16 != 0 || d[3] % 16 != 0) {
+            set_error("dh_gather_normalize_multi: slide %d is not 16-byte aligned (data, pitch): gather it with dh_gather_normalize", i);
+            return DH_ERR_UNSUPPORTED;
+        }
+    }
+    if (mean3_host) for (int c = 0; c < 3; ++c) DH_REQUIRE(std3_host[c] != 0.f, "dh_gather_normalize_multi: std[%d] == 0", c);
+    if (B == 0) return DH_OK;
+    int rc = gather_tma_launch(reinterpret_cast<const uint8_t*>(slides_host[0]), slides_host[1], slides_host[2], slides_host[3], slides_dev, n_slides,
+                               image_of_patch, coords, out_index, B, ps, out, out_dtype, out_layout, scale255 ? 1 : 0, mean3_host, std3_host, flip,
+                               0, as_stream(stream));
+    if (rc == DH_ERR_UNSUPPORTED)
+        set_error("dh_gather_normalize_multi: patch size %d not supported by the TMA-staged kernel (needs ps %% 4 == 0 for f32, ps %% 8 == 0 for bf16)", ps);
+    return rc;
 }

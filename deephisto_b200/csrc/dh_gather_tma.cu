@@ -38,6 +38,9 @@ constexpr int kTmaMaxUnits = 6;                   // units per consumer thread p
 struct TmaGatherParams {
     const uint8_t* slide;
     int64_t H, W, pitch;
+    const int64_t* slides;   // multi-slide mode: device table [n_slides][4] = {data pointer, H, W, pitch}, else NULL
+    const int32_t* image;    // multi-slide mode: slide index of every patch
+    int n_slides;
     const int32_t* coords;
     const int32_t* out_index;
     const uint8_t* flip;
@@ -99,6 +102,20 @@ __device__ __forceinline__ void bulk_load_hint(uint32_t dst, const void* src, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
+}
+struct SlideRef {
+    const uint8_t* data;
+    int64_t H, W, pitch;
+};
+// the slide a patch reads from: the launch's single slide, or entry `img` of the device table (multi-slide datasets)
+__device__ __forceinline__ SlideRef slide_of(const TmaGatherParams& p, int img) {
+    SlideRef r;
+    if (p.slides == nullptr) { r.data = p.slide; r.H = p.H; r.W = p.W; r.pitch = p.pitch; return r; }
+    img = img < 0 ? 0 : (img >= p.n_slides ? p.n_slides - 1 : img);
+    const longlong2* t = reinterpret_cast<const longlong2*>(p.slides + 4 * (int64_t)img);
+    const longlong2 a = __ldg(t), b = __ldg(t + 1);
+    r.data = reinterpret_cast<const uint8_t*>(a.x); r.H = a.y; r.W = b.x; r.pitch = b.y;
+    return r;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     uint32_t v;
@@ -219,7 +236,9 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             const int y = __ldg(p.coords + 2 * patch);
             const int x = __ldg(p.coords + 2 * patch + 1);
             const uint32_t fl = p.flip ? (uint32_t)__ldg(p.flip + patch) : 0u;
-            const bool inside = (y >= 0) && (x >= 0) && ((int64_t)y + ps <= p.H) && ((int64_t)x + ps <= p.W);
+            const int img = p.image ? __ldg(p.image + patch) : 0;
+            const SlideRef sl = slide_of(p, img);
+            const bool inside = (y >= 0) && (x >= 0) && ((int64_t)y + ps <= sl.H) && ((int64_t)x + ps <= sl.W);
             const int a = (3 * x) & 15;
             const uint32_t bytes = (uint32_t)((a + row_bytes + 15) & ~15);
             const bool stage_it = inside && !(dbg & 1);
@@ -227,7 +246,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                 const int64_t slot = p.out_index ? (int64_t)__ldg(p.out_index + patch) : patch;
                 TileMeta m;
                 m.out_off = slot * 3 * plane + (int64_t)tr * R * (NCHW ? ps : row_bytes);
-                m.y = y; m.x = x; m.flags = (int)fl | (inside ? kInside : 0); m.tr = tr; m.pad[0] = m.pad[1] = 0;
+                m.y = y; m.x = x; m.flags = (int)fl | (inside ? kInside : 0); m.tr = tr; m.pad[0] = img; m.pad[1] = 0;
                 meta[s] = m;
                 if (stage_it) mbar_expect_tx(&full[s], bytes * (uint32_t)R);
                 else mbar_arrive(&full[s]);  // guarded path reads global memory directly: nothing to stage
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             if (stage_it && lane < R) {
                 const int orow = tr * R + lane;                                // output row of the patch
                 const int srow = (fl & DH_FLIP_V) ? ps - 1 - orow : orow;      // source row
-                const uint8_t* src = p.slide + (int64_t)(y + srow) * p.pitch + ((3 * (int64_t)x) & ~(int64_t)15);
+                const uint8_t* src = sl.data + (int64_t)(y + srow) * sl.pitch + ((3 * (int64_t)x) & ~(int64_t)15);
                 if (dbg & 16) bulk_load_hint(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s], policy);
                 else bulk_load(stage0 + (uint32_t)(s * stage_bytes + lane * RP), src, bytes, &full[s]);
             }
@@ -344,6 +363,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             // slow path: horizontally flipped patches (bytes from the stage) and patches that overhang the slide (guarded global loads)
             const bool inside = m.flags & kInside, fv = m.flags & DH_FLIP_V, fh = m.flags & DH_FLIP_H;
             const int a = (3 * m.x) & 15;
+            const SlideRef sl = slide_of(p, m.pad[0]);
             for (int u = tid; u < units_per_tile; u += kConsumers) {
                 const int ur = u / upr, uc = u - ur * upr;
                 const int orow = m.tr * R + ur;
@@ -354,7 +374,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                         v = stages[(size_t)s * stage_bytes + ur * RP + a + 3 * scol + ch];
                     } else {
                         const int64_t yy = (int64_t)m.y + srow, xx = (int64_t)m.x + scol;
-                        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) v = __ldg(p.slide + yy * p.pitch + 3 * xx + ch);
+                        if (yy >= 0 && yy < sl.H && xx >= 0 && xx < sl.W) v = __ldg(sl.data + yy * sl.pitch + 3 * xx + ch);
                     }
                     return norm_f<SCALE, AFFINE>((float)v, ch, p);
                 };
@@ -404,7 +424,8 @@ static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_
 }
 
 // Returns DH_ERR_UNSUPPORTED (without touching the error string) when the shape does not fit this kernel.
-int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, const int32_t* coords, const int32_t* out_index,
+int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch, const int64_t* slides_dev, int n_slides,
+                      const int32_t* image, const int32_t* coords, const int32_t* out_index,
                       int64_t B, int ps, void* out, int out_dtype, int out_layout, int scale255, const float* mean3, const float* std3,
                       const uint8_t* flip, int debug, cudaStream_t st) {
     const bool nchw = out_layout == DH_NCHW;
@@ -424,6 +445,7 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
 
     TmaGatherParams p{};
     p.slide = slide; p.H = H; p.W = W; p.pitch = pitch;
+    p.slides = slides_dev; p.image = slides_dev ? image : nullptr; p.n_slides = n_slides;
     p.coords = coords; p.out_index = out_index; p.flip = flip; p.out = out; p.B = B; p.ps = ps; p.R = R;
     p.tiles_per_patch = ps / R; p.row_pitch = row_pitch; p.units_per_row = units_per_row; p.debug = debug;
     for (int c = 0; c < 3; ++c) { p.mean[c] = mean3 ? mean3[c] : 0.f; p.stdv[c] = std3 ? std3[c] : 1.f; }

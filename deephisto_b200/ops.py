@@ -140,6 +140,41 @@ def gather_normalize(slide: DeviceSlide, coords: torch.Tensor, ps: int, *, dtype
     return out
 
 
+class SlideTable:
+    """Descriptor table of several resident slides for gather_normalize_multi (one launch over a multi-image dataset)."""
+
+    def __init__(self, slides: Sequence[DeviceSlide]):
+        self.slides = list(slides)
+        rows = [[s.storage.data_ptr(), s.H, s.W, s.pitch] for s in self.slides]
+        self.host = np.ascontiguousarray(np.asarray(rows, dtype=np.int64))
+        self.dev = torch.from_numpy(self.host).to(self.slides[0].device)
+
+
+def gather_normalize_multi(table: SlideTable, images: torch.Tensor, coords: torch.Tensor, ps: int, *, dtype=torch.float32, layout: str = "NHWC",
+                           scale255: bool = True, mean: Optional[Sequence[float]] = None, std: Optional[Sequence[float]] = None,
+                           flip: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Patch b is read from slide images[b] of the table at coords[b]: ONE launch for a batch that spans several slides."""
+    lib = _lib.require_device()
+    _need_cuda(coords, "coords", torch.int32)
+    _need_cuda(images, "images", torch.int32)
+    B = coords.shape[0]
+    lay = {"NHWC": DH_NHWC, "NCHW": DH_NCHW}[layout]
+    shape = (B, ps, ps, 3) if lay == DH_NHWC else (B, 3, ps, ps)
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=coords.device)
+    if flip is not None:
+        _need_cuda(flip, "flip", torch.uint8)
+    m = s = None
+    if mean is not None or std is not None:
+        m = (C.c_float * 3)(*(mean if mean is not None else (0.0, 0.0, 0.0)))
+        s = (C.c_float * 3)(*(std if std is not None else (1.0, 1.0, 1.0)))
+    with torch.cuda.device(coords.device):
+        check(lib.dh_gather_normalize_multi(table.host.ctypes.data, table.dev.data_ptr(), len(table.slides), images.data_ptr(), coords.data_ptr(),
+                                            None, B, ps, out.data_ptr(), _DTYPES[dtype], lay, int(bool(scale255)), m, s, _ptr(flip), _stream()),
+              "dh_gather_normalize_multi")
+    return out
+
+
 def stitch_dense(logits: torch.Tensor, H: int, W: int, ps: int, stride: int, d: int, batch_size: int, *, row_begin: int = 0,
                  row_end: Optional[int] = None, want_sum: bool = True, want_count: bool = False, want_argmax: bool = False):
     """Deterministic stitch of dense-sampler logits [Npad, n] -> (sum [rows,dw,n] f32, count u32, argmax u8)."""

@@ -203,6 +203,7 @@ class AnnoRegionRndSampler:
         self._slides = [None] * len(img_anno_paths)
         self._slot_cursor = 0
         self._producer = None          # CUDA stream the prefetch groups of torch_generator run on
+        self._slide_table = None       # ops.SlideTable over all images (multi-image datasets)
         self._fail = torch.zeros(1, dtype=torch.uint8, device=device) if torch.device(device).type == "cuda" else None
         if verbose:
             self._print_anno_stats(self.regions)
@@ -263,6 +264,12 @@ class AnnoRegionRndSampler:
         if len(self._slides) == 1:
             return ops.gather_normalize(self._slide(0), coords, ps, dtype=dtype, layout=layout, scale255=scale255, mean=self._mean,
                                         std=self._std, flip=flip)
+        if dtype != torch.uint8 and ps % (4 if dtype == torch.float32 else 8) == 0:
+            # one launch over all source slides (descriptor table in HBM); every image of the dataset is made resident on first use
+            if self._slide_table is None:
+                self._slide_table = ops.SlideTable([self._slide(j) for j in range(len(self._slides))])
+            return ops.gather_normalize_multi(self._slide_table, images, coords, ps, dtype=dtype, layout=layout, scale255=scale255,
+                                              mean=self._mean, std=self._std, flip=flip)
         shape = (len(coords), ps, ps, 3) if layout == "NHWC" else (len(coords), 3, ps, ps)
         out = torch.empty(shape, dtype=dtype, device=coords.device)
         for j in torch.unique(images).tolist():                                                  # one gather per source slide

@@ -100,6 +100,16 @@ DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64_t W, int64
                         int scale255, const float* mean3_host, const float* std3_host, const uint8_t* flip,
                         void* stream);
 
+/* The same gather over SEVERAL resident slides in one launch (datasets of many images, region_samplers.py:484-523 opens the
+ * image of every region): slides_dev is a device table int64 [n_slides][4] = {data pointer, H, W, pitch} (16-byte aligned),
+ * slides_host the same table in host memory (validated here), image_of_patch the slide index of every patch (device int32 [B]).
+ * Needs every slide 16-byte aligned with pitch % 16 == 0 and a patch size the TMA-staged kernel takes (ps % 4 == 0 for f32,
+ * ps % 8 == 0 for bf16); otherwise returns DH_ERR_UNSUPPORTED and the caller gathers slide by slide. */
+DH_API int dh_gather_normalize_multi(const int64_t* slides_host, const int64_t* slides_dev, int n_slides,
+                                     const int32_t* image_of_patch, const int32_t* coords, const int32_t* out_index, int64_t B, int ps,
+                                     void* out, int out_dtype, int out_layout, int scale255, const float* mean3_host,
+                                     const float* std3_host, const uint8_t* flip, void* stream);
+
 /* Variant selector for profiling: 0 = auto, 1 = direct (LDG/STG) kernel, 2 = TMA-staged kernel;
  * 3 / 4 / 5 = TMA-staged kernel with the loads / the stores / both switched off (WRONG RESULTS: ceiling measurements only);
  * 6 = TMA-staged kernel with default-policy instead of streaming stores; 7 / 8 / 9 = contiguous tile range per CTA /

@@ -431,3 +431,26 @@ def test_gather_writes_only_its_output_canary(ops, layout, dtype):
         ops.gather_normalize(slide, coords, ps, dtype=dtype, layout=layout, flip=flips, out=out)
         assert bool((big[:pad] == 7.0).all()) and bool((big[pad + n :] == 7.0).all())
         assert float(out.float().max()) <= 1.0                                # every element was written ([0,1] after /255)
+
+
+@pytest.mark.parametrize("layout,dtype", [("NHWC", torch.float32), ("NCHW", torch.bfloat16), ("NCHW", torch.float32)])
+def test_gather_multi_slide_one_launch(ops, layout, dtype):
+    """dh_gather_normalize_multi: a batch whose patches come from three resident slides of different sizes (descriptor table in
+    HBM) equals the per-slide oracle gather -- flips, overhanging patches (zero fill) and both kernel paths included."""
+    ps, B = 64, 61
+    shapes = [(500, 700), (333, 401), (900, 260)]
+    hosts = [synth.synth_slide(h, w, 40 + i) for i, (h, w) in enumerate(shapes)]
+    table = ops.SlideTable([ops.DeviceSlide.from_numpy(a) for a in hosts])
+    rng = np.random.default_rng(3)
+    images = rng.integers(0, 3, B).astype(np.int32)
+    coords = np.stack([[rng.integers(0, shapes[i][0] - ps + 1), rng.integers(0, shapes[i][1] - ps + 1)] for i in images]).astype(np.int32)
+    coords[0], images[0] = (-7, 3), 1                      # overhangs slide 1: zero fill
+    coords[1], images[1] = (900 - ps + 5, 260 - 9), 2      # overhangs slide 2
+    flips = rng.integers(0, 4, B).astype(np.uint8)
+    got = ops.gather_normalize_multi(table, torch.from_numpy(images).cuda(), torch.from_numpy(coords).cuda(), ps, dtype=dtype, layout=layout,
+                                     flip=torch.from_numpy(flips).cuda())
+    want = np.stack([odense.normalize(odense.gather(hosts[images[b]], coords[b : b + 1], ps), True, None, None, layout, flips[b : b + 1])[0]
+                     for b in range(B)])
+    assert np.array_equal(bits(got), bits(torch.from_numpy(want).to(dtype)))
+    with pytest.raises(Exception, match="not supported"):
+        ops.gather_normalize_multi(table, torch.from_numpy(images).cuda(), torch.from_numpy(coords).cuda(), 30)
