@@ -607,7 +607,9 @@ def main():
     ap.add_argument("--cpu-leg", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = {"predict": 3, "train_input": 40}.get(args.workload, 640)
+        # default job = 2500 batches of 256 = 640 000 patches, the size of the reference's own training run (config.yaml: 50 epochs,
+        # batch 64; train.py:142: 200 steps per epoch): the slide is uploaded once and stays resident for the whole job
+        args.steps = {"predict": 3, "train_input": 40}.get(args.workload, 2500)
     if args.warmup is None:
         args.warmup = {"predict": 1, "train_input": 4}.get(args.workload, 32)
     args.warmup = max(args.warmup, 3) if args.workload != "predict" else args.warmup
