@@ -167,10 +167,10 @@ def cpu_pipe(cores):
     return cpu_pipeline.AnnotatedRndCPU(path, (H, W, 3), images, layer=1, one_image_for_batch=True, max_workers=cores)
 
 
-def cpu_run(pipe, batch, n_batches, seed):
+def cpu_run(pipe, batch, n_batches, seed, batches_per_worker=2):
     t0 = time.perf_counter()
     n = 0
-    for f, l, c in pipe.batches(PS, batch, n_batches, batches_per_worker=2, k=K_PER_REGION, ri=RI, seed=seed):
+    for f, l, c in pipe.batches(PS, batch, n_batches, batches_per_worker=batches_per_worker, k=K_PER_REGION, ri=RI, seed=seed):
         n += f.shape[0]
     return n, time.perf_counter() - t0
 
@@ -209,14 +209,17 @@ def reference_arm(args):
         n, dt = cpu_run(pipe, BATCH, max(2 * cores, min(args.warmup, 4 * cores)), seed=1)      # warm-up, also calibrates the sample
         rate = n / dt
         sample = int(max(K_PER_REGION, min(BATCH, rate * args.ref_budget / max(args.steps, 1)) // K_PER_REGION * K_PER_REGION))
-        n, dt = cpu_run(pipe, sample, args.steps, seed=2)
+        # keep the reference's worker-job size (2 batches of 256 = 512 patches per job, region_samplers.py:722-728): the result pipe of
+        # the process pool is part of the path, and smaller jobs would make it look ~2x faster than it is at batch 256
+        bpw = max(2, (2 * BATCH) // sample)
+        n, dt = cpu_run(pipe, sample, args.steps, seed=2, batches_per_worker=bpw)
     finally:
         pipe.close()
     H, W = SLIDE_HW
     value = n / dt
     desc = (f"{args.steps} steps x {sample} patches (bounded sample of the 256-patch batch) of the same workload ({H}x{W} slide in host RAM, "
-            f"{N_POLY} polygons), {cores} worker processes x 2 batches per job like the reference's spawn ProcessPoolExecutor (pool start-up "
-            f"excluded); {dt:.2f} s")
+            f"{N_POLY} polygons), {cores} worker processes, {bpw} sampled batches (= {bpw * sample} patches, the reference's 2 x 256) per job like the "
+            f"reference's spawn ProcessPoolExecutor (pool start-up excluded); {dt:.2f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
@@ -432,6 +435,8 @@ def ours(args):
         "gpu_launches": launches[0],
         "clocks": clk,
     }
+    if args.with_training and args.workload == "train_input":
+        line["training_consumer"] = training_consumer(api, dev, BATCH, torch)
     if world == 1 and not args.no_cpu_baseline and args.workload == "annotated_rnd":
         out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--cpu-leg", "--cpu-budget", str(args.cpu_budget)],
                              capture_output=True, text=True)
@@ -442,6 +447,50 @@ def ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def training_consumer(api, dev, batch, torch, steps=3, micro=1024):
+    """BASELINE configs[4] in full: the sampler feeding a bf16 ResNet18 training step (models/patch_cls_simple/train.py:153-172:
+    forward, cross-entropy, backward, Adam 1e-4) at `batch` patches per step, micro-batched. Two measurements, same model:
+    (a) every step reuses one resident batch (no input pipeline at all), (b) every step consumes a fresh batch from
+    AnnoRegionRndSampler.torch_generator (sampling + gather of the next batch run on the producer stream). (b) / (a) is the
+    cost of the input pipeline as the training loop sees it."""
+    from deephisto_b200.examples.predict_full_patched import get_model
+
+    torch.manual_seed(0)
+    model = get_model(5).to(dev).to(memory_format=torch.channels_last).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    def train_step(f, l):
+        opt.zero_grad(set_to_none=True)
+        for a in range(0, f.shape[0], micro):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = model(f[a : a + micro].contiguous(memory_format=torch.channels_last))
+                loss = loss_fn(out.float(), l[a : a + micro]) * (min(micro, f.shape[0] - a) / f.shape[0])
+            loss.backward()
+        opt.step()
+        return loss
+
+    gen = api.torch_generator(batch_size=batch, n_batches=2 * steps + 2, batches_per_worker=2)
+    f0, l0, _ = next(gen)
+    train_step(f0, l0)                                               # warm-up (cuDNN algorithm selection, allocator)
+    torch.cuda.synchronize()
+    res = {}
+    for name in ("resident_batch", "fresh_batch_per_step"):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            if name == "fresh_batch_per_step":
+                f0, l0, _ = next(gen)
+            loss = train_step(f0, l0)
+        t1.record()
+        torch.cuda.synchronize()
+        res[name] = {"patches_per_s": steps * batch / (t0.elapsed_time(t1) / 1e3), "ms_per_step": t0.elapsed_time(t1) / steps}
+    res["input_pipeline_overhead"] = res["resident_batch"]["patches_per_s"] / res["fresh_batch_per_step"]["patches_per_s"] - 1.0
+    res["final_loss"] = float(loss.item()) * 1.0
+    res["note"] = f"ResNet18 bf16 autocast channels_last, Adam, {batch} patches per step in micro-batches of {micro}, {steps} steps each"
+    return res
 
 
 # --------------------------------------------------------------------------------------------------------------------
@@ -601,6 +650,7 @@ def main():
     ap.add_argument("--cnn-batch", type=int, default=1024)
     ap.add_argument("--fold-bn", action="store_true", help="predict workload: fold eval-mode BatchNorm into the convolutions")
     ap.add_argument("--cudnn-benchmark", action="store_true", help="predict workload: torch.backends.cudnn.benchmark = True")
+    ap.add_argument("--with-training", action="store_true", help="train_input workload: also time a ResNet18 bf16 training step fed by the sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the bounded cpu_baseline sample")
     ap.add_argument("--ref-budget", type=float, default=60.0, help="--impl reference: target seconds for the K timed steps")
