@@ -40,3 +40,25 @@ def annotated_dataset(args, n_polygons: int = 50):
         return get_img_ano_paths(Path(args.dataset), args.sample)
     h, w = args.synthetic or args._default_hw
     return [(SyntheticSlide(h, w, seed=0), synth_polygons(n_polygons, h, w, seed=0))]
+
+
+class Throughput:
+    """Wall-clock items/s counter for the example drivers (the reference prints `items/s` in its annotated examples)."""
+
+    def __init__(self):
+        import time
+
+        self._clock = time.perf_counter
+        self.start = self._clock()
+        self.items = 0
+
+    def add(self, n: int):
+        self.items += int(n)
+
+    def report(self, extra: str = ""):
+        import torch
+
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dt = self._clock() - self.start
+        print(f"{self.items / dt} items/s{extra}")
