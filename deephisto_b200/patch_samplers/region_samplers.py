@@ -324,15 +324,16 @@ class AnnoRegionRndSampler:
                 group = {"features": features, "labels": labels, "coords": coords.to(torch.float32), "fail": status.max()}
                 ready = torch.cuda.Event()
                 ready.record(self._producer)
-            for t in group.values():
-                t.record_stream(cur)                         # allocated on the producer stream, consumed on the caller's
             return group, ready
 
         pending = launch(groups[0]) if groups else None
         for gi, nb in enumerate(groups):
             group, ready = pending
             pending = launch(groups[gi + 1]) if gi + 1 < len(groups) else None
+            cur = torch.cuda.current_stream(self._device)    # the stream the caller consumes this group on
             cur.wait_event(ready)
+            for t in group.values():
+                t.record_stream(cur)                         # allocated on the producer stream, used on the caller's
             if int(group["fail"].item()) != 0:
                 raise RuntimeError("region sampling failed for some slots after max_redraw redraws "
                                    "(regions too small for the patch size / intersection, or miss limit reached)")
