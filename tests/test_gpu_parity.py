@@ -454,3 +454,32 @@ def test_gather_multi_slide_one_launch(ops, layout, dtype):
     assert np.array_equal(bits(got), bits(torch.from_numpy(want).to(dtype)))
     with pytest.raises(Exception, match="not supported"):
         ops.gather_normalize_multi(table, torch.from_numpy(images).cuda(), torch.from_numpy(coords).cuda(), 30)
+
+
+def test_empty_inputs_and_error_reporting(ops):
+    """Empty batches are no-ops; invalid arguments come back as negative status codes with a message (no exceptions from C,
+    no partial launches)."""
+    from deephisto_b200 import _lib
+
+    slide = ops.DeviceSlide.synthetic(300, 300, 0)
+    empty = torch.zeros((0, 2), dtype=torch.int32, device="cuda")
+    for layout in ("NHWC", "NCHW"):
+        out = ops.gather_normalize(slide, empty, 64, layout=layout)
+        assert out.numel() == 0
+    assert ops.dense_coords(300, 300, 64, 32, 4, first=5, count=0).shape == (0, 2)
+    lg = torch.zeros((0, 5), device="cuda")
+    sm = torch.zeros((10, 10, 5), device="cuda")
+    ops.stitch_scatter(lg, empty, 64, 16, sm, None)                      # P = 0
+    assert float(sm.abs().max()) == 0.0
+    with pytest.raises(_lib.DeepHistoError, match="patch size"):
+        ops.gather_normalize(slide, torch.zeros((1, 2), dtype=torch.int32, device="cuda"), 0)
+    with pytest.raises(ValueError, match="smaller than patch"):
+        ops.dense_count(100, 100, 224, 112, 64)
+    with pytest.raises(_lib.DeepHistoError, match="rows"):
+        ops.stitch_dense(torch.zeros((ops.dense_count(300, 300, 64, 32, 4)[1], 5), device="cuda"), 300, 300, 64, 32, 16, 4, row_begin=5, row_end=99)
+    with pytest.raises(_lib.DeepHistoError, match="batch size"):
+        ops.CoverState(64, 64, 32, 16, 2, 4096, seed=0).next_coords()
+    with pytest.raises(_lib.DeepHistoError, match="must be a CUDA tensor"):
+        ops.gather_normalize(slide, torch.zeros((1, 2), dtype=torch.int32), 64)
+    with pytest.raises(TypeError):
+        ops.gather_normalize(slide, torch.zeros((1, 2), dtype=torch.int64, device="cuda"), 64)
