@@ -415,7 +415,7 @@ static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTmaThreads, smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
         if (occ < 1) occ = 1;
-        if (occ > 4) occ = 4;
+        if (occ > 3) occ = 3;  // measured (profiles/r01_gather.md): 3 resident CTAs per SM beat 4 (and 5, 6) -- less concurrency, less HBM read/write interference
     }
     const int64_t want = (int64_t)kNumSMs * occ;
     const int grid = (int)(n_tiles < want ? n_tiles : want);
