@@ -163,22 +163,6 @@ __device__ __forceinline__ void store_unit(__nv_bfloat16* dst, const float (&f)[
     else __stcs(reinterpret_cast<uint4*>(dst), v);
 }
 
-// DH_GATHER_ORDER (compile-time experiment, profiles/r01_gather.md): 0 = the compiler orders loads and stores freely;
-// 1 = stores are volatile asm, so each unit's store stays where the source puts it (spread between the units' math);
-// 2 = as 1, with the LDS of unit k+1 issued before the math of unit k.
-#ifndef DH_GATHER_ORDER
-#define DH_GATHER_ORDER 0
-#endif
-#if DH_GATHER_ORDER
-__device__ __forceinline__ void store_unit_ordered(float* dst, const float (&f)[4]) {
-    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
-}
-__device__ __forceinline__ void store_unit_ordered(__nv_bfloat16* dst, const float (&f)[8]) {
-    const uint32_t a = pack_bf16(f[0], f[1]), b = pack_bf16(f[2], f[3]), c = pack_bf16(f[4], f[5]), d = pack_bf16(f[6], f[7]);
-    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-#endif
-
 template <typename OutT> struct UnitOf { static constexpr int kElems = 16 / (int)sizeof(OutT); };
 
 // DBG: profiling instantiation (p.debug switches; only fp32 NHWC /255 FULL is built with it). Production kernels carry none of it.
@@ -302,25 +286,14 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             const uint32_t sh = (uint32_t)(a & 3) * 8u;
             const uint32_t abase = sbase + (uint32_t)(a & ~3);
             const bool fh = NCHW && (m.flags & DH_FLIP_H);
-#if DH_GATHER_ORDER
-#define DH_STORE(ptr, vals) do { if (DBG) { if (!(dbg & 2) || (vals)[0] == 12345.f) store_unit(ptr, vals, dbg & 4); } else { store_unit_ordered(ptr, vals); __syncwarp(); } } while (0)
-#else
 #define DH_STORE(ptr, vals) do { if (!(dbg & 2) || (vals)[0] == 12345.f) store_unit(ptr, vals, dbg & 4); } while (0)
-#endif
-            uint32_t qq[2][NW + 1];
-            auto load_unit = [&](int k, uint32_t (&q)[NW + 1]) {
-                const uint32_t so = fh ? s_mirror[k] - s_off[k] : s_off[k];
-#pragma unroll
-                for (int j = 0; j <= NW; ++j) q[j] = lds32(abase + so + 4 * j);
-            };
-            if (DH_GATHER_ORDER == 2 && (FULL || nu > 0)) load_unit(0, qq[0]);
 #pragma unroll
             for (int k = 0; k < KU; ++k) {
-                if (DH_GATHER_ORDER == 2 && k + 1 < KU && (FULL || k + 1 < nu)) load_unit(k + 1, qq[(k + 1) & 1]);
                 if (FULL || k < nu) {
-                    uint32_t (&q)[NW + 1] = qq[k & 1];
-                    uint32_t w[NW];
-                    if (DH_GATHER_ORDER != 2) load_unit(k, q);
+                    uint32_t q[NW + 1], w[NW];
+                    const uint32_t so = fh ? s_mirror[k] - s_off[k] : s_off[k];
+#pragma unroll
+                    for (int j = 0; j <= NW; ++j) q[j] = lds32(abase + so + 4 * j);
 #pragma unroll
                     for (int j = 0; j < NW; ++j) w[j] = __funnelshift_r(q[j], q[j + 1], sh);
                     OutT* const ok = o + k * (kConsumers * E);
