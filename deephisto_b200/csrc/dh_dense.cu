@@ -137,6 +137,7 @@ extern "C" DH_API int dh_dense_coords(int64_t H, int64_t W, int ps, int stride, 
     DenseGrid g;
     int rc = make_grid(H, W, ps, stride, batch_size, &g);
     if (rc != DH_OK) return rc;
+    if (count == 0 && first >= 0 && first <= g.Npad) return DH_OK;
     DH_REQUIRE(coords_out, "dh_dense_coords: null output");
     DH_REQUIRE(first >= 0 && count >= 0 && first + count <= g.Npad, "dh_dense_coords: range [%lld, %lld) outside the %lld padded patches",
                (long long)first, (long long)(first + count), (long long)g.Npad);

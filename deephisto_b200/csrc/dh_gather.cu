@@ -326,6 +326,7 @@ extern "C" DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64
                                    const int32_t* out_index, int64_t B, int ps, void* out, int out_dtype,
                                    int out_layout, int scale255, const float* mean3_host, const float* std3_host,
                                    const uint8_t* flip, void* stream) {
+    if (B == 0) return DH_OK;  // an empty batch is a no-op (empty tensors have null data pointers)
     DH_REQUIRE(slide && coords && out, "dh_gather_normalize: null pointer");
     DH_REQUIRE(H > 0 && W > 0 && pitch >= 3 * W, "dh_gather_normalize: bad slide shape H=%lld W=%lld pitch=%lld",
                (long long)H, (long long)W, (long long)pitch);
@@ -382,6 +383,7 @@ extern "C" DH_API int dh_gather_normalize_multi(const int64_t* slides_host, cons
                                                 const int32_t* image_of_patch, const int32_t* coords, const int32_t* out_index, int64_t B,
                                                 int ps, void* out, int out_dtype, int out_layout, int scale255,
                                                 const float* mean3_host, const float* std3_host, const uint8_t* flip, void* stream) {
+    if (B == 0) return DH_OK;
     DH_REQUIRE(slides_host && slides_dev && image_of_patch && coords && out, "dh_gather_normalize_multi: null pointer");
     DH_REQUIRE(n_slides >= 1, "dh_gather_normalize_multi: empty slide table");
     DH_REQUIRE(ps > 0 && ps <= 8192 && B >= 0, "dh_gather_normalize_multi: bad patch size / batch");

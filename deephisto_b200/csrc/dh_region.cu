@@ -319,6 +319,7 @@ extern "C" DH_API int dh_region_sample(const dh_region_tables* t, int64_t n_slot
                                 int max_redraw, int fixed_class, int64_t slots_per_table_draw, uint64_t seed,
                                 uint64_t slot_offset, int32_t* coords_out, int64_t* label_out, int32_t* image_out,
                                 uint8_t* status_out, void* stream) {
+    if (n_slots <= 0) return DH_OK;
     DH_REQUIRE(t && coords_out, "dh_region_sample: null pointer");
     DH_REQUIRE(t->edges && t->edge_off && t->reg_bbox && t->reg_area && t->reg_image && t->img_hw && t->tbl_cls_off && t->tbl_cls &&
                    t->cat_off && t->cat_region && t->cat_cdf,

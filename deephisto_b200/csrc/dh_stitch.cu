@@ -531,6 +531,7 @@ extern "C" DH_API int dh_stitch_dense(const float* logits, int64_t H, int64_t W,
 
 extern "C" DH_API int dh_stitch_scatter(const float* logits, const int32_t* coords, int64_t P, int ps, int d, int n, float* sum_map,
                                  uint32_t* count_map, int64_t rows, int64_t dw, int64_t row_offset, void* stream) {
+    if (P == 0) return DH_OK;  // nothing to add (empty tensors have null data pointers)
     DH_REQUIRE(logits && coords, "dh_stitch_scatter: null input");
     DH_REQUIRE(sum_map || count_map, "dh_stitch_scatter: no output requested");
     DH_REQUIRE(ps > 0 && d > 0 && n > 0 && rows >= 0 && dw >= 0 && P >= 0 && row_offset >= 0, "dh_stitch_scatter: bad sizes");
