@@ -472,7 +472,7 @@ def test_empty_inputs_and_error_reporting(ops):
     ops.stitch_scatter(lg, empty, 64, 16, sm, None)                      # P = 0
     assert float(sm.abs().max()) == 0.0
     with pytest.raises(_lib.DeepHistoError, match="patch size"):
-        ops.gather_normalize(slide, torch.zeros((1, 2), dtype=torch.int32, device="cuda"), 0)
+        ops.gather_normalize(slide, torch.zeros((1, 2), dtype=torch.int32, device="cuda"), 8200, dtype=torch.uint8)      # > 8192
     with pytest.raises(ValueError, match="smaller than patch"):
         ops.dense_count(100, 100, 224, 112, 64)
     with pytest.raises(_lib.DeepHistoError, match="rows"):
