@@ -203,6 +203,42 @@ def weights_goldens(rs_mod, im, manifest: dict):
     manifest["weights"] = {"file": "golden_weights_v1.json", "cases": len(out["cases"])}
 
 
+STAT_COVER_CASES = [(1100, 900, 224, 16), (2048, 2048, 224, 64)]     # (H, W, ps, batch)
+STAT_SEEDS = list(range(12))
+
+
+def statistics_goldens(fs, rs_mod, im, manifest: dict):
+    """Row B / C statistics of the UNMODIFIED reference with its global numpy RNG seeded (np.random.seed): the random streams
+    cannot be compared draw by draw with the Philox streams of the new build, their distributions can.
+      cover:  FullImageRndSampler.generator() (full_samplers.py:263-274) -- batches until filled_ratio reaches 1, mean accumulator value
+      region: RegionAnnotation._extract_patch_coords_rnd (region_samplers.py:82-143) -- mean / std of the accepted (y, x)"""
+    mode = fs.SamplerExecutionMode.INMEMORY_SINGLEPROC
+    out = {"seeds": STAT_SEEDS, "cover": [], "region": []}
+    for H, W, ps, B in STAT_COVER_CASES:
+        key = f"stat_cover_{H}x{W}"
+        im.register(key, np.zeros((H, W, 3), np.uint8))
+        n_batches, mean_acc, first_ratio = [], [], []
+        for seed in STAT_SEEDS:
+            np.random.seed(seed)
+            s = fs.FullImageRndSampler(key, layer=1, patch_size=ps, batch_size=B, mode=mode)
+            ratios = [fr for _patches, fr in s.generator()]
+            n_batches.append(len(ratios))
+            first_ratio.append(ratios[0])
+            mean_acc.append(float(s._accum.mean()))
+        out["cover"].append({"H": H, "W": W, "ps": ps, "batch": B, "n_batches": n_batches, "mean_accum": mean_acc, "first_ratio": first_ratio})
+    polys = region_polygons()
+    for name in ("star", "convex", "frac"):
+        verts = polys[name].astype(np.float64)
+        reg = rs_mod.RegionAnnotation(Path("regions"), 0, "X", verts, layer=1, layer_size=(2048, 2048))
+        for ps, ri in ((224, 0.75), (64, 0.95)):
+            np.random.seed(123)
+            c = np.asarray(reg._extract_patch_coords_rnd(ps, 6000, ri, miss_limit=500), dtype=np.float64)
+            out["region"].append({"polygon": name, "ps": ps, "ri": ri, "n": len(c), "mean_yx": c.mean(0).tolist(), "std_yx": c.std(0).tolist(),
+                                  "min_yx": c.min(0).tolist(), "max_yx": c.max(0).tolist()})
+    (OUT / "golden_stats_v1.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+    manifest["statistics"] = {"file": "golden_stats_v1.json"}
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     out, manifest = {}, {}
@@ -213,6 +249,7 @@ def main():
         stitch_goldens(pfp, fs, im, out, manifest)
         region_goldens(rs, im, out, manifest)
         weights_goldens(rs, im, manifest)
+        statistics_goldens(fs, rs, im, manifest)
     np.savez_compressed(OUT / "golden_v1.npz", **out)
     (OUT / "golden_v1.json").write_text(json.dumps(manifest, indent=1, sort_keys=True))
     print(f"wrote {OUT / 'golden_v1.npz'} ({(OUT / 'golden_v1.npz').stat().st_size / 1e6:.2f} MB), {len(out)} arrays, {len(manifest)} manifest entries")

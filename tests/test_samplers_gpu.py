@@ -296,3 +296,51 @@ def test_example_entry_points_run(script, extra):
     out = subprocess.run([sys.executable, "-m", f"deephisto_b200.examples.{script}", *extra], cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert ("items/s" in out.stdout) or ("Gpx/s" in out.stdout)
+
+
+# ---- statistical parity with the UNMODIFIED reference's random samplers (its RNG seeded; tests/golden/golden_stats_v1.json) -----
+def _stats():
+    from pathlib import Path
+
+    return json.loads((Path(__file__).resolve().parent / "golden" / "golden_stats_v1.json").read_text())
+
+
+def test_cover_sampler_statistics_match_reference(api):
+    """FullImageRndSampler draws from Philox instead of the reference's global numpy RNG, so parity is distributional: over 12
+    seeds the number of batches to full coverage, the coverage after the first batch and the mean accumulator value agree with
+    the reference's own runs (full_samplers.py:263-274, np.random.seed(0..11))."""
+    _, fs, _ = api
+    gold = _stats()
+    for case in gold["cover"]:
+        H, W, ps, B = case["H"], case["W"], case["ps"], case["batch"]
+        slide = np.zeros((H, W, 3), np.uint8)
+        nb, first, macc = [], [], []
+        for seed in gold["seeds"]:
+            s = fs.FullImageRndSampler(slide, 1, ps, B, _mode(fs), seed=1000 + seed)
+            ratios = [fr for _c, fr in s.coords_generator()]
+            nb.append(len(ratios))
+            first.append(ratios[0])
+            macc.append(float(s._accum.mean()))
+        ref_nb, ref_first, ref_macc = np.array(case["n_batches"]), np.array(case["first_ratio"]), np.array(case["mean_accum"])
+        assert abs(np.mean(nb) - ref_nb.mean()) <= 0.75, (nb, ref_nb.tolist())
+        assert ref_nb.min() - 1 <= min(nb) and max(nb) <= ref_nb.max() + 1
+        assert abs(np.mean(first) - ref_first.mean()) <= 0.03
+        assert abs(np.mean(macc) / ref_macc.mean() - 1) <= 0.15
+
+
+def test_region_rnd_statistics_match_reference(api):
+    """RegionAnnotation._extract_patch_coords_rnd: accepted origins are uniform over the acceptable positions of the bbox in both
+    implementations; mean and spread of 6 000 draws agree with the reference's (region_samplers.py:82-143, np.random.seed(123))."""
+    from oracle.make_golden import region_polygons
+
+    _, _, rs = api
+    gold = _stats()
+    polys = region_polygons()
+    for r in gold["region"]:
+        reg = rs.RegionAnnotation("regions", 0, "X", polys[r["polygon"]].astype(np.float64), layer=1, layer_size=(2048, 2048), seed=77)
+        c = np.asarray(reg._extract_patch_coords_rnd(r["ps"], r["n"], r["ri"]), dtype=np.float64)
+        assert len(c) == r["n"]
+        se = np.array(r["std_yx"]) / np.sqrt(r["n"])
+        assert (np.abs(c.mean(0) - np.array(r["mean_yx"])) <= 6 * np.sqrt(2) * se).all(), (r["polygon"], c.mean(0), r["mean_yx"])
+        assert (np.abs(c.std(0) / np.array(r["std_yx"]) - 1) <= 0.05).all()
+        assert (c.min(0) >= np.array(r["min_yx"]) - 25).all() and (c.max(0) <= np.array(r["max_yx"]) + 25).all()
