@@ -315,7 +315,7 @@ def test_cover_sampler_statistics_match_reference(api):
         H, W, ps, B = case["H"], case["W"], case["ps"], case["batch"]
         slide = np.zeros((H, W, 3), np.uint8)
         nb, first, macc = [], [], []
-        for seed in gold["seeds"]:
+        for seed in range(4 * len(gold["seeds"])):                       # 48 runs here against the reference's 12
             s = fs.FullImageRndSampler(slide, 1, ps, B, _mode(fs), seed=1000 + seed)
             ratios = [fr for _c, fr in s.coords_generator()]
             nb.append(len(ratios))
@@ -324,7 +324,8 @@ def test_cover_sampler_statistics_match_reference(api):
         ref_nb, ref_first, ref_macc = np.array(case["n_batches"]), np.array(case["first_ratio"]), np.array(case["mean_accum"])
         assert abs(np.mean(nb) - ref_nb.mean()) <= 0.75, (nb, ref_nb.tolist())
         assert ref_nb.min() - 1 <= min(nb) and max(nb) <= ref_nb.max() + 1
-        assert abs(np.mean(first) - ref_first.mean()) <= 0.03
+        se = np.sqrt(ref_first.var(ddof=1) / len(ref_first) + np.var(first, ddof=1) / len(first))
+        assert abs(np.mean(first) - ref_first.mean()) <= 4 * se, (np.mean(first), ref_first.mean(), se)   # two-sample z-test, 4 sigma
         assert abs(np.mean(macc) / ref_macc.mean() - 1) <= 0.15
 
 
