@@ -308,10 +308,14 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(co
 }
 
 // ---- scatter (arbitrary coordinates) ------------------------------------------------------------
+// One block per patch, one warp per footprint row. A footprint row is a contiguous run of fw*n floats of the map; its 16-byte
+// aligned body is added with vector reductions (red.global.add.v4.f32: 4x fewer atomic operations than one per float), the
+// unaligned head and tail with scalar ones. Value of float f of the run = logit[(f) mod n].
 __global__ void __launch_bounds__(256) stitch_scatter_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords,
                                                              int64_t P, int ps, int d, int n, float* __restrict__ sum_map,
                                                              uint32_t* __restrict__ count_map, int64_t rows, int64_t dw,
-                                                             int64_t row_offset) {
+                                                             int64_t row_offset, int vec_ok) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int64_t patch = blockIdx.x; patch < P; patch += gridDim.x) {
         const int y = __ldg(coords + 2 * patch), x = __ldg(coords + 2 * patch + 1);
         // numpy slice semantics: start/stop clipped to [0, size]
@@ -323,17 +327,35 @@ __global__ void __launch_bounds__(256) stitch_scatter_kernel(const float* __rest
         int64_t hi = r1 < row_offset + rows ? r1 : row_offset + rows;
         if (hi <= lo || c1 <= c0) continue;
         const int fw = (int)(c1 - c0);
-        const int64_t cells = (hi - lo) * fw;
-        const int64_t total = cells * n;
+        const int len = fw * n;
         const float* lg = logits + patch * n;
-        for (int64_t f = threadIdx.x; f < total; f += blockDim.x) {
-            int64_t cell = f / n;
-            int c = (int)(f - cell * n);
-            int64_t rr = cell / fw;
-            int cc = (int)(cell - rr * fw);
-            int64_t idx = (lo - row_offset + rr) * dw + c0 + cc;
-            if (sum_map) atomicAdd(sum_map + idx * n + c, __ldg(lg + c));
-            if (count_map && c == 0) atomicAdd(count_map + idx, 1u);
+        for (int64_t rr = lo + warp; rr < hi; rr += nwarps) {
+            const int64_t cell0 = (rr - row_offset) * dw + c0;
+            if (sum_map) {
+                float* run = sum_map + cell0 * n;
+                int head = vec_ok ? (int)((4 - ((cell0 * n) & 3)) & 3) : len;   // floats before the first 16-byte boundary
+                if (head > len) head = len;
+                const int nvec = (len - head) >> 2;
+                const int tail0 = head + 4 * nvec;
+                if (lane < head) atomicAdd(run + lane, __ldg(lg + lane % n));
+                for (int q = lane; q < nvec; q += 32) {
+                    const int f = head + 4 * q;
+                    int c = f % n;
+                    float4 v;
+                    v.x = __ldg(lg + c); c = c + 1 == n ? 0 : c + 1;
+                    v.y = __ldg(lg + c); c = c + 1 == n ? 0 : c + 1;
+                    v.z = __ldg(lg + c); c = c + 1 == n ? 0 : c + 1;
+                    v.w = __ldg(lg + c);
+                    atomicAdd(reinterpret_cast<float4*>(run + f), v);
+                }
+                if (vec_ok) {
+                    if (lane < len - tail0) atomicAdd(run + tail0 + lane, __ldg(lg + (tail0 + lane) % n));
+                } else {
+                    for (int f = lane; f < len; f += 32) atomicAdd(run + f, __ldg(lg + f % n));
+                }
+            }
+            if (count_map)
+                for (int cc = lane; cc < fw; cc += 32) atomicAdd(count_map + cell0 + cc, 1u);
         }
     }
 }
@@ -537,7 +559,8 @@ extern "C" DH_API int dh_stitch_scatter(const float* logits, const int32_t* coor
     DH_REQUIRE(ps > 0 && d > 0 && n > 0 && rows >= 0 && dw >= 0 && P >= 0 && row_offset >= 0, "dh_stitch_scatter: bad sizes");
     if (P == 0 || rows == 0 || dw == 0) return DH_OK;
     int grid = (int)(P < (int64_t)kNumSMs * 8 ? P : (int64_t)kNumSMs * 8);
-    stitch_scatter_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, coords, P, ps, d, n, sum_map, count_map, rows, dw, row_offset);
+    const int vec_ok = sum_map && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 ? 1 : 0;  // float4 reductions need a 16-byte aligned map
+    stitch_scatter_kernel<<<grid, 256, 0, as_stream(stream)>>>(logits, coords, P, ps, d, n, sum_map, count_map, rows, dw, row_offset, vec_ok);
     DH_CHECK_LAUNCH("stitch_scatter_kernel");
     return DH_OK;
 }
