@@ -18,7 +18,10 @@
 // below 3*x (a = 3*x mod 16 extra leading bytes) and the consumers realign with a funnel shift of LDS words.
 // The copy never leaves the slide row: its end is roundup16(3*x + 3*ps) <= pitch when the patch is inside
 // the slide. Patches that are not entirely inside the slide (zero fill) and horizontally flipped patches take a
-// guarded byte path in the same kernel.
+// guarded byte path in the same kernel (NCHW output flips horizontally on the fast path: mirrored unit, reversed pixels).
+//
+// Concurrency is deliberately low: a 2-deep ring and at most 3 resident CTAs per SM. Deeper rings and higher occupancy were
+// measured slower (profiles/r01_gather.md): the kernel is HBM-bound and more reads in flight disturb the store stream.
 //
 // Tile = R consecutive output rows of one patch; persistent CTAs walk tiles round-robin (no division in the loop).
 // Unit = 16 bytes of output: NHWC 4 (f32) / 8 (bf16) consecutive elements of a patch row; NCHW 4 / 8 consecutive
