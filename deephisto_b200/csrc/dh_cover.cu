@@ -11,11 +11,15 @@
 // defined here (Philox4x32-10, counters below) is restated on the CPU in oracle/cover.py and the
 // coordinates are bit-identical to that restatement.
 //
-// One batch = 4 launches:
-//   A  eligibility bitmask + per-block eligible counts          (full coarse-grid pass, L2 resident)
+// The reference rescans the whole coarse grid three times per batch (probmap, choice, count_nonzero). Here the eligibility
+// bitmask, the per-block eligible counts and the non-zero count are STATE kept in the scratch buffer and maintained
+// incrementally by the accumulator update (a cell leaves the eligible set when its count reaches dense_level, joins the
+// non-zero set when it leaves 0), so a batch costs O(B * footprint + number of blocks), independent of the slide size:
+//   init (batch_index == 0, or dh_cover_init after restoring an accumulator): bitmask + block counts + non-zero count
 //   B  single block: exclusive scan of the block counts, top-up, partial Fisher-Yates of B ranks
-//   C  one warp per pick: rank -> k-th eligible cell -> jitter -> clamp -> coords; accumulator += footprint
-//   D  count of non-zero accumulator cells
+//   C  one warp per pick: rank -> k-th eligible cell -> jitter -> clamp -> coords                 (reads the state only)
+//   U  one warp per pick: accumulator += footprint, state transitions                              (after ALL picks are located)
+//   F  non-zero count -> nonzero_out
 #include "dh_common.cuh"
 
 namespace dh {
@@ -24,11 +28,12 @@ constexpr int kCellsPerBlock = 2048;
 constexpr int kMaxBatch = 2048;
 
 struct CoverScratch {
-    uint32_t* block_off;  // [nb + 1] counts -> exclusive offsets, [nb] = M
+    uint32_t* block_cnt;  // [nb] eligible cells per block (state)
+    uint32_t* block_off;  // [nb + 1] exclusive offsets of this batch, [nb] = M
     uint32_t* mask;       // [words] eligibility bits
     uint32_t* ranks;      // [B]
     uint32_t* extra;      // [B] top-up cells
-    uint32_t* meta;       // [0] = M (eligible), [1] = number of top-up cells
+    uint32_t* meta;       // [0] = M (eligible), [1] = number of top-up cells, [2] = non-zero accumulator cells (state)
 };
 
 __global__ void __launch_bounds__(256) cover_mask_kernel(const uint32_t* __restrict__ accum, int64_t cells, uint32_t dense_level,
@@ -50,7 +55,7 @@ __global__ void __launch_bounds__(256) cover_mask_kernel(const uint32_t* __restr
     if (threadIdx.x == 0) {
         uint32_t t = 0;
         for (int w = 0; w < 8; ++w) t += wsum[w];
-        s.block_off[blockIdx.x] = t;
+        s.block_cnt[blockIdx.x] = t;
     }
 }
 
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(1024) cover_pick_kernel(CoverScratch s, int nb
     // exclusive scan of block counts, 1024 at a time
     for (int b0 = 0; b0 < nb; b0 += 1024) {
         int b = b0 + threadIdx.x;
-        uint32_t v = b < nb ? s.block_off[b] : 0u;
+        uint32_t v = b < nb ? s.block_cnt[b] : 0u;
         uint32_t inc = v;
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -184,15 +189,35 @@ __global__ void __launch_bounds__(128) cover_place_kernel(uint32_t* __restrict__
     y = y > H - ps ? H - ps : y; y = y < 0 ? 0 : y;
     x = x > W - ps ? W - ps : x; x = x < 0 ? 0 : x;
     if (lane == 0) { coords[2 * slot] = (int32_t)y; coords[2 * slot + 1] = (int32_t)x; }
-    // full_samplers.py:86-92 accumulator footprint
+}
+
+// full_samplers.py:86-92 accumulator footprint, run after every pick of the batch has been located (the picks read the state).
+// State transitions: count reaches dense_level -> the cell leaves the eligible set; count leaves 0 -> one more non-zero cell.
+__global__ void __launch_bounds__(128) cover_update_kernel(uint32_t* __restrict__ accum, CoverScratch s, int64_t dw, int ps, int speedup,
+                                                           uint32_t dense_level, int B, const int32_t* __restrict__ coords) {
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (slot >= B) return;
+    const int64_t y = coords[2 * slot], x = coords[2 * slot + 1];
     const int64_t r0 = y / speedup, r1 = (y + ps) / speedup, c0 = x / speedup, c1 = (x + ps) / speedup;
     const int fw = (int)(c1 - c0);
     const int tot = (int)(r1 - r0) * fw;
+    uint32_t became_nonzero = 0;
     for (int f = lane; f < tot; f += 32) {
-        int rr = f / fw, cc = f - rr * fw;
-        atomicAdd(accum + (r0 + rr) * dw + c0 + cc, 1u);
+        const int rr = f / fw, cc = f - rr * fw;
+        const int64_t cell = (r0 + rr) * dw + c0 + cc;
+        const uint32_t old = atomicAdd(accum + cell, 1u);
+        became_nonzero += old == 0u;
+        if (old + 1u == dense_level) {
+            atomicAnd(s.mask + (cell >> 5), ~(1u << (cell & 31)));
+            atomicSub(s.block_cnt + cell / kCellsPerBlock, 1u);
+        }
     }
+    for (int o = 16; o; o >>= 1) became_nonzero += __shfl_xor_sync(0xffffffffu, became_nonzero, o);
+    if (lane == 0 && became_nonzero) atomicAdd(s.meta + 2, became_nonzero);
 }
+
+__global__ void cover_publish_kernel(CoverScratch s, uint32_t* __restrict__ nonzero_out) { *nonzero_out = s.meta[2]; }
 
 __global__ void __launch_bounds__(256) cover_nonzero_kernel(const uint32_t* __restrict__ accum, int64_t cells, uint32_t* __restrict__ out) {
     uint32_t cnt = 0;
@@ -205,10 +230,40 @@ __global__ void __launch_bounds__(256) cover_nonzero_kernel(const uint32_t* __re
 
 using namespace dh;
 
+static CoverScratch carve(uint32_t* scratch, int nb) {
+    CoverScratch s;
+    s.block_cnt = scratch;
+    s.block_off = s.block_cnt + nb;
+    s.mask = s.block_off + nb + 1;
+    s.ranks = s.mask + (int64_t)nb * (kCellsPerBlock / 32);
+    s.extra = s.ranks + kMaxBatch;
+    s.meta = s.extra + kMaxBatch;
+    return s;
+}
+
 extern "C" DH_API int64_t dh_cover_scratch_words(int64_t dh_, int64_t dw_) {
     int64_t cells = dh_ * dw_;
     int64_t nb = (cells + kCellsPerBlock - 1) / kCellsPerBlock;
-    return (nb + 1) + nb * (kCellsPerBlock / 32) + 2 * kMaxBatch + 8;
+    return nb + (nb + 1) + nb * (kCellsPerBlock / 32) + 2 * kMaxBatch + 8;
+}
+
+extern "C" DH_API int dh_cover_init(const uint32_t* accum, int64_t dh_, int64_t dw_, int dense_level, uint32_t* scratch, void* stream) {
+    DH_REQUIRE(accum && scratch, "dh_cover_init: null pointer");
+    DH_REQUIRE(dh_ > 0 && dw_ > 0 && dense_level > 0, "dh_cover_init: bad parameters");
+    const int64_t cells = dh_ * dw_;
+    DH_REQUIRE(cells < (1ll << 31), "dh_cover_init: coarse grid too large");
+    const int nb = (int)((cells + kCellsPerBlock - 1) / kCellsPerBlock);
+    CoverScratch s = carve(scratch, nb);
+    cudaStream_t st = as_stream(stream);
+    cover_mask_kernel<<<nb, 256, 0, st>>>(accum, cells, (uint32_t)dense_level, s);
+    DH_CHECK_LAUNCH("cover_mask_kernel");
+    cudaError_t e = cudaMemsetAsync(s.meta + 2, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    int64_t blocks = (cells + 255) / 256;
+    int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
+    cover_nonzero_kernel<<<grid, 256, 0, st>>>(accum, cells, s.meta + 2);
+    DH_CHECK_LAUNCH("cover_nonzero_kernel");
+    return DH_OK;
 }
 
 extern "C" DH_API int dh_cover_sample(uint32_t* accum, int64_t dh_, int64_t dw_, int64_t H, int64_t W, int ps, int speedup, int dense_level,
@@ -223,26 +278,21 @@ extern "C" DH_API int dh_cover_sample(uint32_t* accum, int64_t dh_, int64_t dw_,
     DH_REQUIRE(cells >= B, "dh_cover_sample: fewer coarse cells (%lld) than the batch size", (long long)cells);
     DH_REQUIRE(cells < (1ll << 31), "dh_cover_sample: coarse grid too large");
     const int nb = (int)((cells + kCellsPerBlock - 1) / kCellsPerBlock);
-    CoverScratch s;
-    s.block_off = scratch;
-    s.mask = s.block_off + nb + 1;
-    s.ranks = s.mask + (int64_t)nb * (kCellsPerBlock / 32);
-    s.extra = s.ranks + kMaxBatch;
-    s.meta = s.extra + kMaxBatch;
+    CoverScratch s = carve(scratch, nb);
     cudaStream_t st = as_stream(stream);
+    if (batch_index == 0) {  // first batch of a run: build the state from the accumulator as it is
+        int rc = dh_cover_init(accum, dh_, dw_, dense_level, scratch, stream);
+        if (rc != DH_OK) return rc;
+    }
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t b_lo = (uint32_t)batch_index, b_hi = (uint32_t)(batch_index >> 32);
-    cover_mask_kernel<<<nb, 256, 0, st>>>(accum, cells, (uint32_t)dense_level, s);
-    DH_CHECK_LAUNCH("cover_mask_kernel");
     cover_pick_kernel<<<1, 1024, 0, st>>>(s, nb, cells, B, k0, k1, b_lo, b_hi);
     DH_CHECK_LAUNCH("cover_pick_kernel");
     cover_place_kernel<<<(B + 3) / 4, 128, 0, st>>>(accum, s, nb, dh_, dw_, H, W, ps, speedup, B, k0, k1, b_lo, b_hi, coords_out);
     DH_CHECK_LAUNCH("cover_place_kernel");
-    cudaError_t e = cudaMemsetAsync(nonzero_out, 0, sizeof(uint32_t), st);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    int64_t blocks = (cells + 255) / 256;
-    int grid = (int)(blocks < (int64_t)kNumSMs * 8 ? blocks : (int64_t)kNumSMs * 8);
-    cover_nonzero_kernel<<<grid, 256, 0, st>>>(accum, cells, nonzero_out);
-    DH_CHECK_LAUNCH("cover_nonzero_kernel");
+    cover_update_kernel<<<(B + 3) / 4, 128, 0, st>>>(accum, s, dw_, ps, speedup, (uint32_t)dense_level, B, coords_out);
+    DH_CHECK_LAUNCH("cover_update_kernel");
+    cover_publish_kernel<<<1, 1, 0, st>>>(s, nonzero_out);
+    DH_CHECK_LAUNCH("cover_publish_kernel");
     return DH_OK;
 }

@@ -267,6 +267,15 @@ class CoverState:
         self.nonzero = torch.zeros(1, dtype=torch.int32, device=device)
         self.batch_index = 0
 
+    def restore(self, accum: torch.Tensor, batch_index: int) -> None:
+        """Resume a run: adopt a saved accumulator and batch counter and rebuild the sampler state (dh_cover_init). The Philox
+        stream is keyed by (seed, batch_index), so the continuation is identical to the uninterrupted run."""
+        lib = _lib.require_device()
+        self.accum.copy_(accum.to(self.accum.dtype))
+        self.batch_index = int(batch_index)
+        with torch.cuda.device(self.accum.device):
+            check(lib.dh_cover_init(self.accum.data_ptr(), self.dh, self.dw, self.dense_level, self.scratch.data_ptr(), _stream()), "dh_cover_init")
+
     def next_coords(self) -> tuple[torch.Tensor, torch.Tensor]:
         """One batch: int32 coords [B,2] and the device counter of non-zero accumulator cells."""
         lib = _lib.require_device()

@@ -158,14 +158,18 @@ DH_API int dh_colorize_overlay(const uint8_t* argmax_u8, const uint8_t* slide, i
 /* ------------------------------------------------------------------------------------------
  * B1-B3  FullImageRndSampler (full_samplers.py:81-94,105-114,125-162,263-274)
  * Coverage-driven random sampling on the 1/speedup coarse accumulator.
- * One call = one batch: eligible cells (accum < dense_level) are compacted in index order, topped
+ * One call = one batch: eligible cells (accum < dense_level) are taken in index order, topped
  * up with random non-eligible cells when fewer than B, B distinct cells are drawn (partial
  * Fisher-Yates, Philox4x32-10 keyed by seed, counters documented in oracle/cover.py), jittered,
  * clamped, written to coords_out, and the accumulator footprint of every patch is incremented.
- * scratch: uint32 [dh_cover_scratch_words(dh, dw)]; nonzero_out: device uint32 count of non-zero
- * accumulator cells after the update (filled_ratio = nonzero / (dh*dw)). B <= 2048.
+ * scratch: uint32 [dh_cover_scratch_words(dh, dw)] -- it holds STATE between calls (eligibility bitmask, per-block eligible
+ * counts, non-zero count), maintained incrementally by the accumulator update, so a batch does not rescan the coarse grid.
+ * The state is built from `accum` by the call with batch_index == 0, or explicitly by dh_cover_init (resuming a run from a
+ * restored accumulator). dense_level must not change between calls. nonzero_out: device uint32 count of non-zero accumulator
+ * cells after the update (filled_ratio = nonzero / (dh*dw)). B <= 2048.
  * ------------------------------------------------------------------------------------------ */
 DH_API int64_t dh_cover_scratch_words(int64_t dh, int64_t dw);
+DH_API int dh_cover_init(const uint32_t* accum, int64_t dh, int64_t dw, int dense_level, uint32_t* scratch, void* stream);
 DH_API int dh_cover_sample(uint32_t* accum, int64_t dh, int64_t dw, int64_t H, int64_t W, int ps, int speedup,
                     int dense_level, int B, uint64_t seed, uint64_t batch_index, int32_t* coords_out,
                     uint32_t* nonzero_out, uint32_t* scratch, void* stream);

@@ -483,3 +483,20 @@ def test_empty_inputs_and_error_reporting(ops):
         ops.gather_normalize(slide, torch.zeros((1, 2), dtype=torch.int32), 64)
     with pytest.raises(TypeError):
         ops.gather_normalize(slide, torch.zeros((1, 2), dtype=torch.int64, device="cuda"), 64)
+
+
+def test_cover_sampler_resume_from_saved_state(ops):
+    """(accumulator, batch_index) is the whole sampler state: a run restored from a snapshot continues with exactly the coordinates
+    of the uninterrupted run (the eligibility state is rebuilt by dh_cover_init)."""
+    H, W, ps, B = 1500, 1300, 224, 32
+    a = ops.CoverState(H, W, ps, 16, 2, B, seed=5)
+    for _ in range(3):
+        a.next_coords()
+    snap, idx = a.accum.clone(), a.batch_index
+    b = ops.CoverState(H, W, ps, 16, 2, B, seed=5)
+    b.restore(snap, idx)
+    for _ in range(6):
+        ca, na = a.next_coords()
+        cb, nb = b.next_coords()
+        assert torch.equal(ca, cb) and int(na.item()) == int(nb.item())
+    assert torch.equal(a.accum, b.accum)
