@@ -1,0 +1,448 @@
+// K5b: deterministic stitching for ARBITRARY patch coordinates (random samplers, any iterator of patches).
+//
+// Reference path replaced:
+//   examples/predict_full_patched.py:47-54   for each batch, for each patch in sampler order:
+//       prediction[y//d:(y+ps)//d, x//d:(x+ps)//d, :] += logits_i
+//
+// dh_stitch_scatter adds with atomics (order not preserved, 1e-5 parity, read-modify-write traffic). This file is the GATHER
+// formulation for a coordinate LIST: the map is cut into warp-sized tiles, every patch is binned into the tiles its footprint
+// touches, and one warp per tile adds the covering patches in ascending patch index -- the reference's order -- with plain
+// fp32 adds starting from 0. The result is bit-identical to the numpy loop, has no atomics on the map, and writes every
+// output exactly once (HBM write roofline: dh*dw*n*4 bytes for the sum map, dh*dw for the class map).
+//
+//   count  : one thread per patch, atomicAdd on the per-tile counters                  (P * tiles-per-patch integer atomics)
+//   alloc  : one thread per tile: list segment = warp-aggregated atomicAdd on one cursor (segment placement is arbitrary)
+//   fill   : one thread per patch, patch index into the tile's list segment           (arbitrary order inside a segment)
+//   tile   : one warp per tile: rank-sort the segment by patch index (shared memory), clip the footprints to tile-relative
+//            ranges, then walk the tile's rows. Rows between two footprint boundaries have identical values (run-length): the
+//            lane's values are recomputed only at a boundary and stored to every row of the run.
+// Two tile kernels share the binning: `sum` (a lane owns VEC consecutive floats of a map row; 16-byte stores) and `cell`
+// (a lane owns one cell: n <= 8 class sums in registers -> argmax byte and/or count).
+#include "dh_common.cuh"
+
+namespace dh {
+
+constexpr int kBinWarps = 8;    // warps per CTA, one tile each (no block-level synchronisation anywhere)
+constexpr int kBinCap = 128;    // patches per tile staged in shared memory; longer lists take the global-memory path
+constexpr int kBinMaxN = 8;     // classes the cell kernel keeps in registers
+
+static int g_bin_tile_rows = 0;  // 0 = heuristic; profiling override (dh_stitch_binned_set_tile_rows)
+
+struct BinGeom {
+    int64_t rows, row_offset, dw;
+    int64_t units_per_row;  // sum mode: dw * n floats; cell mode: dw cells
+    int64_t nty, ntx;
+    int ps, d, n;
+    int scale;              // units per cell: n (sum mode) or 1 (cell mode)
+    int TH, TW;             // tile = TH rows x TW units (TW = 32 * VEC)
+};
+
+struct BinRec {
+    int r0, r1;      // band-relative rows [r0, r1)
+    int u0, u1;      // units of the row [u0, u1)
+};
+
+// numpy slice semantics of prediction[y//d:(y+ps)//d, x//d:(x+ps)//d]: stops clipped to the array, empty when start >= stop
+__device__ __forceinline__ bool bin_footprint(const BinGeom& g, int y, int x, BinRec& f) {
+    // 32-bit unsigned divisions for the usual non-negative origins ((unsigned)y + ps cannot wrap: both < 2^31)
+    const unsigned ud = (unsigned)g.d, ups = (unsigned)g.ps;
+    int64_t r0, r1, c0, c1;
+    if (y >= 0) { r0 = (unsigned)y / ud; r1 = ((unsigned)y + ups) / ud; }
+    else { r0 = 0; const int64_t e = (int64_t)y + g.ps; r1 = e > 0 ? e / g.d : 0; }  // callers never pass negative origins: keep the footprint inside the map (same as dh_stitch_scatter)
+    if (x >= 0) { c0 = (unsigned)x / ud; c1 = ((unsigned)x + ups) / ud; }
+    else { c0 = 0; const int64_t e = (int64_t)x + g.ps; c1 = e > 0 ? e / g.d : 0; }
+    if (c1 > g.dw) c1 = g.dw;
+    r0 = r0 > g.row_offset ? r0 : g.row_offset;
+    r1 = r1 < g.row_offset + g.rows ? r1 : g.row_offset + g.rows;
+    if (r1 <= r0 || c1 <= c0) return false;
+    f.r0 = (int)(r0 - g.row_offset);
+    f.r1 = (int)(r1 - g.row_offset);
+    f.u0 = (int)(c0 * g.scale);
+    f.u1 = (int)(c1 * g.scale);
+    return true;
+}
+
+// cnt[ntiles] is followed by the list cursor cnt[ntiles] (zeroed together)
+__global__ void __launch_bounds__(256) bin_alloc_kernel(uint32_t* __restrict__ cnt, int64_t ntiles, uint32_t* __restrict__ off, uint32_t* __restrict__ len) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t c = t < ntiles ? cnt[t] : 0u;
+    uint32_t inc = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    uint32_t base = 0;
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 31 && total) base = atomicAdd(cnt + ntiles, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (t < ntiles) { off[t] = base + inc - c; len[t] = c; }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) bin_patches_kernel(const int32_t* __restrict__ coords, int64_t P, BinGeom g, uint32_t* __restrict__ cnt,
+                                                          const uint32_t* __restrict__ off, uint32_t* __restrict__ list) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        BinRec f;
+        if (!bin_footprint(g, __ldg(coords + 2 * p), __ldg(coords + 2 * p + 1), f)) continue;
+        const int ty0 = f.r0 / g.TH, ty1 = (f.r1 - 1) / g.TH, tx0 = f.u0 / g.TW, tx1 = (f.u1 - 1) / g.TW;
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const int64_t t = (int64_t)ty * g.ntx + tx;
+                if (FILL) list[off[t] + atomicSub(cnt + t, 1u) - 1u] = (uint32_t)p;  // the counters run back to zero
+                else atomicAdd(cnt + t, 1u);
+            }
+    }
+}
+
+// np.argmax: first maximum; NaN counts as the maximum (first NaN wins). Same rule as stitch_finalize_kernel.
+__device__ __forceinline__ uint8_t first_argmax(const float* v, int n) {
+    float best = v[0];
+    int best_c = 0;
+#pragma unroll
+    for (int c = 1; c < kBinMaxN; ++c)
+        if (c < n && (v[c] > best || (v[c] != v[c] && best == best))) { best = v[c]; best_c = c; }
+    return (uint8_t)best_c;
+}
+
+// ---- tile kernels ------------------------------------------------------------------------------------------------------
+// VEC units per lane. CELL = false: units are floats of a map row, output = sum map. CELL = true (VEC == 1): units are cells,
+// outputs = argmax byte and / or count. STAGED: the logits of the tile's patches sit in shared memory (n <= kBinMaxN).
+//
+// Rare path: more than kBinCap patches over one tile -> sorted list in global memory, footprints recomputed on the fly.
+template <int VEC, bool CELL>
+__device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, const int32_t* __restrict__ coords, const BinGeom& g, uint32_t beg, int L,
+                                           const uint32_t* __restrict__ list, uint32_t* __restrict__ sorted, float* __restrict__ sum_map,
+                                           uint32_t* __restrict__ count_map, uint8_t* __restrict__ argmax_map, int64_t ty, int64_t tx) {
+    const int lane = threadIdx.x & 31;
+    const int n = g.n;
+    for (int j = lane; j < L; j += 32) {
+        const uint32_t v = list[beg + j];
+        int rank = 0;
+        for (int i = 0; i < L; ++i) rank += list[beg + i] < v;
+        sorted[beg + rank] = v;
+    }
+    __syncwarp();
+    const int64_t ubase = tx * g.TW + (int64_t)lane * VEC;
+    const bool active = ubase < g.units_per_row;
+    int cls[VEC];
+    int c = (int)(ubase % n);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) { cls[k] = c; c = c + 1 == n ? 0 : c + 1; }
+    const int R0 = (int)(ty * g.TH);
+    const int R1 = (int)((int64_t)R0 + g.TH < g.rows ? R0 + g.TH : g.rows);
+    const bool want_vals = CELL ? argmax_map != nullptr : true;
+    int r = R0;
+    while (r < R1) {
+        float acc[CELL ? kBinMaxN : VEC];
+#pragma unroll
+        for (int k = 0; k < (CELL ? kBinMaxN : VEC); ++k) acc[k] = 0.f;
+        uint32_t hits = 0;
+        int next = R1;
+        for (int j = 0; j < L; ++j) {
+            const uint32_t id = sorted[beg + j];
+            BinRec f;
+            bin_footprint(g, __ldg(coords + 2 * (int64_t)id), __ldg(coords + 2 * (int64_t)id + 1), f);
+            if (f.r0 > r) { next = f.r0 < next ? f.r0 : next; continue; }  // starts below this row (warp-uniform)
+            if (f.r1 <= r) continue;                                        // ended above
+            next = f.r1 < next ? f.r1 : next;
+            const int64_t lo = f.u0 - ubase, hi = f.u1 - ubase;             // covered units relative to the lane's first unit
+            if (hi <= 0 || lo >= VEC) continue;
+            const float* lg = logits + (int64_t)id * n;
+            if constexpr (CELL) {
+                ++hits;
+                if (want_vals) {
+#pragma unroll
+                    for (int q = 0; q < kBinMaxN; ++q)
+                        if (q < n) acc[q] += __ldg(lg + q);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k)
+                    if (k >= lo && k < hi) acc[k] += __ldg(lg + cls[k]);
+            }
+        }
+        if (active) {
+            if constexpr (CELL) {
+                const uint8_t am = want_vals ? first_argmax(acc, n) : (uint8_t)0;
+                int64_t o = (int64_t)r * g.units_per_row + ubase;
+                for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
+                    if (argmax_map) argmax_map[o] = am;
+                    if (count_map) count_map[o] = hits;
+                }
+            } else {
+                float* o = sum_map + (int64_t)r * g.units_per_row + ubase;
+                for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) o[k] = acc[k];
+                }
+            }
+        }
+        r = next;
+    }
+}
+
+__host__ __device__ inline int bin_warp_smem_bytes(int n, bool staged) { return kBinCap * 20 + kBinCap * 4 * (staged ? n : 1); }
+
+template <int VEC, bool CELL, bool STAGED>
+__global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords, BinGeom g,
+                                                                  const uint32_t* __restrict__ off, const uint32_t* __restrict__ len,
+                                                                  const uint32_t* __restrict__ list, uint32_t* __restrict__ sorted, float* __restrict__ sum_map,
+                                                                  uint32_t* __restrict__ count_map, uint8_t* __restrict__ argmax_map) {
+    extern __shared__ __align__(16) unsigned char bin_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t ctas_x = (g.ntx + kBinWarps - 1) / kBinWarps;
+    const int64_t ty = blockIdx.x / ctas_x;
+    const int64_t tx = (blockIdx.x % ctas_x) * kBinWarps + w;
+    if (tx >= g.ntx) return;
+    const int64_t t = ty * g.ntx + tx;
+    const uint32_t beg = off[t];
+    const int L = (int)len[t];
+    const int n = g.n;
+    if (L > kBinCap) {
+        bin_tile_slow<VEC, CELL>(logits, coords, g, beg, L, list, sorted, sum_map, count_map, argmax_map, ty, tx);
+        return;
+    }
+    // per-warp staging: sorted patch ids, their row and unit ranges, their logits (the unsorted ids alias the logits area)
+    unsigned char* base = bin_smem + (size_t)w * bin_warp_smem_bytes(n, STAGED);
+    uint32_t* s_ids = reinterpret_cast<uint32_t*>(base);
+    int2* s_rows = reinterpret_cast<int2*>(base + kBinCap * 4);
+    int2* s_cols = reinterpret_cast<int2*>(base + kBinCap * 12);
+    float* s_lg = reinterpret_cast<float*>(base + kBinCap * 20);
+    uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_lg);
+
+    for (int j = lane; j < L; j += 32) s_raw[j] = list[beg + j];
+    __syncwarp();
+    for (int j = lane; j < L; j += 32) {  // rank sort: patch indices are distinct within a tile
+        const uint32_t v = s_raw[j];
+        int rank = 0;
+        for (int i = 0; i < L; ++i) rank += s_raw[i] < v;
+        s_ids[rank] = v;
+    }
+    __syncwarp();
+    for (int j = lane; j < L; j += 32) {
+        const uint32_t id = s_ids[j];
+        BinRec f;
+        bin_footprint(g, __ldg(coords + 2 * (int64_t)id), __ldg(coords + 2 * (int64_t)id + 1), f);
+        s_rows[j] = make_int2(f.r0, f.r1);
+        s_cols[j] = make_int2(f.u0, f.u1);
+    }
+    if (STAGED && (!CELL || argmax_map != nullptr)) {
+        for (int e = lane; e < L * n; e += 32) {
+            const int j = e / n;
+            s_lg[e] = __ldg(logits + (int64_t)s_ids[j] * n + (e - j * n));
+        }
+    }
+    __syncwarp();
+
+    const int ub = (int)(tx * g.TW) + lane * VEC;            // first unit owned by this lane (units_per_row + TW < 2^31, host check)
+    const bool active = ub < g.units_per_row;                // units_per_row % VEC == 0 (host check)
+    int cls[VEC];
+    if constexpr (!CELL) {
+        int c = ub % n;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { cls[k] = c; c = c + 1 == n ? 0 : c + 1; }
+    }
+    const int R0 = (int)(ty * g.TH);
+    const int R1 = (int)((int64_t)R0 + g.TH < g.rows ? R0 + g.TH : g.rows);
+    const bool want_vals = CELL ? argmax_map != nullptr : true;
+
+    int r = R0;
+    while (r < R1) {
+        float acc[CELL ? kBinMaxN : VEC];
+#pragma unroll
+        for (int k = 0; k < (CELL ? kBinMaxN : VEC); ++k) acc[k] = 0.f;
+        uint32_t hits = 0;
+        int next = R1;
+        for (int c0 = 0; c0 < L; c0 += 32) {
+            // lane j looks at patch c0 + j: does it cover row r, and where is its next row boundary? (ballot + warp minimum)
+            const int j = c0 + lane;
+            const int2 rw = j < L ? s_rows[j] : make_int2(0x7fffffff, 0x7fffffff);
+            const int cand = rw.x > r ? rw.x : (rw.y > r ? rw.y : 0x7fffffff);
+            const int nb = __reduce_min_sync(0xffffffffu, cand);
+            next = nb < next ? nb : next;
+            unsigned m = __ballot_sync(0xffffffffu, rw.x <= r && r < rw.y);
+            while (m) {  // covering patches in ascending list index = the reference's order; warp-uniform trip count
+                const int jj = c0 + __ffs(m) - 1;
+                m &= m - 1;
+                const int2 cu = s_cols[jj];
+                const int lo = cu.x - ub, hi = cu.y - ub;     // covered units relative to the lane's first unit
+                // adding +0.0f is the identity here: a sum that starts at +0.0f can never be -0.0f
+                if constexpr (CELL) {
+                    const bool cov = lo <= 0 && hi > 0;
+                    hits += cov;
+                    if (want_vals) {
+#pragma unroll
+                        for (int q = 0; q < kBinMaxN; ++q)
+                            if (q < n) acc[q] += cov ? s_lg[jj * n + q] : 0.f;
+                    }
+                } else {
+                    const float* lg = STAGED ? s_lg + jj * n : logits + (int64_t)s_ids[jj] * n;
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        const float v = STAGED ? lg[cls[k]] : __ldg(lg + cls[k]);
+                        acc[k] += (k >= lo && k < hi) ? v : 0.f;
+                    }
+                }
+            }
+        }
+        if (active) {
+            if constexpr (CELL) {
+                const uint8_t am = want_vals ? first_argmax(acc, n) : (uint8_t)0;
+                int64_t o = (int64_t)r * g.units_per_row + ub;
+                for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
+                    if (argmax_map) argmax_map[o] = am;
+                    if (count_map) count_map[o] = hits;
+                }
+            } else {
+                float* o = sum_map + (int64_t)r * g.units_per_row + ub;
+                for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
+                    if constexpr (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) o[k] = acc[k];
+                    }
+                }
+            }
+        }
+        r = next;
+    }
+}
+
+static int tile_rows_for(int ps, int d) {
+    if (g_bin_tile_rows > 0) return g_bin_tile_rows;
+    const int fh = ps / d;
+    return fh >= 48 ? 64 : fh >= 24 ? 32 : 16;
+}
+
+static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows, int64_t dw, int64_t row_offset) {
+    BinGeom g;
+    g.rows = rows; g.row_offset = row_offset; g.dw = dw;
+    g.ps = ps; g.d = d; g.n = n;
+    g.scale = cell ? 1 : n;
+    g.units_per_row = dw * g.scale;
+    g.TH = tile_rows_for(ps, d);
+    g.TW = 32 * vec;
+    g.nty = (rows + g.TH - 1) / g.TH;
+    g.ntx = (g.units_per_row + g.TW - 1) / g.TW;
+    return g;
+}
+
+static int64_t entries_cap(const BinGeom& g, int64_t P) {
+    const int64_t fh = g.ps / g.d + 1, fw = (int64_t)(g.ps / g.d + 1) * g.scale;  // largest footprint, rows / units
+    const int64_t tyx = (fh - 1 + g.TH - 1) / g.TH + 1, txx = (fw - 1 + g.TW - 1) / g.TW + 1;
+    return P * tyx * txx;
+}
+
+struct BinScratch {
+    uint32_t *cnt, *off, *len, *list, *sorted;
+    int64_t total_bytes;
+};
+
+static size_t roundup256(size_t v) { return (v + 255) / 256 * 256; }
+
+static void carve_bin(const BinGeom& g, int64_t P, void* base, BinScratch& s) {
+    const int64_t ntiles = g.nty * g.ntx, cap = entries_cap(g, P);
+    uintptr_t p = reinterpret_cast<uintptr_t>(base);
+    size_t o = 0;
+    s.cnt = reinterpret_cast<uint32_t*>(p + o); o += roundup256((ntiles + 1) * 4);  // [ntiles] counters + the list cursor
+    s.off = reinterpret_cast<uint32_t*>(p + o); o += roundup256(ntiles * 4);
+    s.len = reinterpret_cast<uint32_t*>(p + o); o += roundup256(ntiles * 4);
+    s.list = reinterpret_cast<uint32_t*>(p + o); o += roundup256(cap * 4);
+    s.sorted = reinterpret_cast<uint32_t*>(p + o); o += roundup256(cap * 4);
+    s.total_bytes = (int64_t)o;
+}
+
+static bool sum_vec4(const float* sum_map, int64_t dw, int n) { return (dw * n) % 4 == 0 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0; }
+
+template <int VEC, bool CELL, bool STAGED>
+static int run_binned(const float* logits, const int32_t* coords, int64_t P, const BinGeom& g, float* sum_map, uint32_t* count_map,
+                      uint8_t* argmax_u8, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
+    BinScratch s;
+    carve_bin(g, P, scratch, s);
+    DH_REQUIRE(s.total_bytes <= scratch_bytes, "dh_stitch_binned: scratch too small (%lld bytes, %lld needed)", (long long)scratch_bytes,
+               (long long)s.total_bytes);
+    const int64_t ntiles = g.nty * g.ntx;
+    DH_REQUIRE(ntiles < (1ll << 31) - 1 && entries_cap(g, P) < (1ll << 32), "dh_stitch_binned: map or patch list too large");
+    cudaError_t e = cudaMemsetAsync(s.cnt, 0, (ntiles + 1) * 4, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    const int64_t pb = (P + 255) / 256;
+    const int pgrid = (int)(pb < (int64_t)kNumSMs * 16 ? pb : (int64_t)kNumSMs * 16);
+    bin_patches_kernel<false><<<pgrid, 256, 0, st>>>(coords, P, g, s.cnt, nullptr, nullptr);
+    DH_CHECK_LAUNCH("bin_patches_kernel<count>");
+    bin_alloc_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(s.cnt, ntiles, s.off, s.len);
+    DH_CHECK_LAUNCH("bin_alloc_kernel");
+    bin_patches_kernel<true><<<pgrid, 256, 0, st>>>(coords, P, g, s.cnt, s.off, s.list);
+    DH_CHECK_LAUNCH("bin_patches_kernel<fill>");
+    const int64_t ctas = g.nty * ((g.ntx + kBinWarps - 1) / kBinWarps);
+    DH_REQUIRE(ctas < (1ll << 31), "dh_stitch_binned: too many tiles");
+    const int smem = kBinWarps * bin_warp_smem_bytes(g.n, STAGED);
+    auto kern = bin_tile_kernel<VEC, CELL, STAGED>;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_tile_kernel)");
+    }
+    kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map, count_map, argmax_u8);
+    DH_CHECK_LAUNCH("bin_tile_kernel");
+    return DH_OK;
+}
+
+}  // namespace dh
+
+using namespace dh;
+
+extern "C" DH_API int dh_stitch_binned_set_tile_rows(int rows) {
+    g_bin_tile_rows = rows > 0 ? rows : 0;
+    return DH_OK;
+}
+
+extern "C" DH_API int64_t dh_stitch_binned_scratch_bytes(int64_t P, int ps, int d, int n, int64_t rows, int64_t dw) {
+    if (P <= 0 || ps <= 0 || d <= 0 || n <= 0 || rows <= 0 || dw <= 0) return 256;
+    int64_t need = 0;
+    for (int mode = 0; mode < 3; ++mode) {  // sum (16-byte stores), sum (scalar stores), cell
+        BinGeom g = make_geom(mode == 2, mode == 0 ? 4 : 1, ps, d, n, rows, dw, 0);
+        BinScratch s;
+        carve_bin(g, P, nullptr, s);
+        need = s.total_bytes > need ? s.total_bytes : need;
+    }
+    return need;
+}
+
+extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coords, int64_t P, int ps, int d, int n, float* sum_map,
+                                       uint32_t* count_map, uint8_t* argmax_u8, int64_t rows, int64_t dw, int64_t row_offset, void* scratch,
+                                       int64_t scratch_bytes, void* stream) {
+    DH_REQUIRE(sum_map || count_map || argmax_u8, "dh_stitch_binned: no output requested");
+    DH_REQUIRE(ps > 0 && d > 0 && n > 0 && rows >= 0 && dw >= 0 && P >= 0 && row_offset >= 0, "dh_stitch_binned: bad sizes");
+    DH_REQUIRE(P < (1ll << 32) && rows < (1ll << 31) - 4096 && dw * (int64_t)n < (1ll << 31) - 4096, "dh_stitch_binned: sizes exceed 32-bit tile coordinates");
+    DH_REQUIRE(!(argmax_u8 && n > 256), "dh_stitch_binned: at most 256 classes fit the u8 class map");
+    DH_REQUIRE(!(argmax_u8 && n > kBinMaxN && !sum_map), "dh_stitch_binned: the class map of more than %d classes needs the sum map", kBinMaxN);
+    if (rows == 0 || dw == 0) return DH_OK;
+    cudaStream_t st = as_stream(stream);
+    if (P == 0) {  // no patches: the reference's map stays zero
+        cudaError_t e = cudaSuccess;
+        if (sum_map) e = cudaMemsetAsync(sum_map, 0, (size_t)rows * dw * n * 4, st);
+        if (e == cudaSuccess && count_map) e = cudaMemsetAsync(count_map, 0, (size_t)rows * dw * 4, st);
+        if (e == cudaSuccess && argmax_u8) e = cudaMemsetAsync(argmax_u8, 0, (size_t)rows * dw, st);
+        return e == cudaSuccess ? DH_OK : cuda_fail(e, "cudaMemsetAsync");
+    }
+    DH_REQUIRE(logits && coords && scratch, "dh_stitch_binned: null input");
+    int rc = DH_OK;
+    const bool staged = n <= kBinMaxN;
+    if (sum_map) {
+        const bool v4 = sum_vec4(sum_map, dw, n);
+        const BinGeom g = make_geom(false, v4 ? 4 : 1, ps, d, n, rows, dw, row_offset);
+        if (v4) rc = staged ? run_binned<4, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
+                            : run_binned<4, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        else rc = staged ? run_binned<1, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
+                         : run_binned<1, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        if (rc != DH_OK) return rc;
+    }
+    uint8_t* cell_argmax = argmax_u8 && staged ? argmax_u8 : nullptr;
+    if (count_map || cell_argmax) {
+        const BinGeom g = make_geom(true, 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
+        rc = run_binned<1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
+        if (rc != DH_OK) return rc;
+    }
+    if (argmax_u8 && !cell_argmax) rc = dh_stitch_finalize(sum_map, nullptr, rows * dw, n, nullptr, argmax_u8, stream);
+    return rc;
+}

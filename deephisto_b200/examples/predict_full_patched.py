@@ -129,7 +129,8 @@ _PREDICTORS: dict = {}
 
 class ImagePredictorPatched:
     def __init__(self, psim_path, patch_sampler, batch_predictor: Callable, anno: AnnoDescription, layer: int, downscale: int = 4,
-                 *, device="cuda", cnn_batch: Optional[int] = None, progress: bool = False):
+                 *, device="cuda", cnn_batch: Optional[int] = None, progress: bool = False, stream_bands: bool = True,
+                 stream_band_bytes: int = 1 << 30):
         self.patch_sampler = patch_sampler
         self.batch_predictor = batch_predictor
         self.anno = anno
@@ -138,6 +139,9 @@ class ImagePredictorPatched:
         self._device = torch.device(device)
         self._cnn_batch = cnn_batch
         self._progress = progress
+        self._stream_bands = stream_bands                      # lazy (non-resident) slides: upload row chunks behind the CNN
+        self._stream_band_bytes = stream_band_bytes
+        self._copy_stream = None
         if isinstance(patch_sampler, (FullImageDenseSampler, FullImageRndSampler)):
             self.h, self.w = patch_sampler.h, patch_sampler.w
         else:
@@ -160,6 +164,23 @@ class ImagePredictorPatched:
             a.record()
             yield
             b.record()
+
+        return ctx()
+
+    def _mark_on(self, stage: str, stream):
+        """_mark for work enqueued on another stream (the events are recorded there)."""
+        import contextlib
+
+        if self.stage_events is None:
+            return contextlib.nullcontext()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.stage_events.setdefault(stage, []).append((a, b))
+
+        @contextlib.contextmanager
+        def ctx():
+            a.record(stream)
+            yield
+            b.record(stream)
 
         return ctx()
 
@@ -202,11 +223,62 @@ class ImagePredictorPatched:
             with self._mark("cnn"):
                 logits[a : a + c] = pred.logits(feats)
 
+    def _logits_streamed(self, sampler: FullImageDenseSampler, logits: torch.Tensor, patch_ranges, max_band_bytes: Optional[int] = None):
+        """Logits of `patch_ranges` (as produced by bands.plan_band) for a slide that is NOT resident in HBM: the slide rows are
+        uploaded in row chunks on a copy stream, one chunk ahead of the chunk the CNN is working on, so the host->device traffic
+        hides behind the convolutions and at most three chunks (<= max_band_bytes each, default 1 GiB) live in HBM -- slides
+        larger than HBM (or than host RAM, through a memory-mapped .npy) are predicted the same way. Consecutive chunks re-upload
+        the ps - stride rows they share."""
+        from ..slide import band_to_device
+
+        g = bands.dense_grid(sampler.h, sampler.w, sampler.patch_size, sampler.stride, sampler.batch_size)
+        ps, stride = g.ps, g.stride
+        pitch = ops.DeviceSlide.pitch_for(sampler.w)
+        budget = int(max_band_bytes or self._stream_band_bytes)
+        per = max(1, (max(budget // pitch, ps) - ps) // stride + 1)          # main-grid rows per chunk
+        jobs = []                                                             # (slide_y0, slide_y1, [(first, count)])
+        for first, count in patch_ranges:
+            if first < g.main_n:                                              # whole main-grid rows [lo, hi]
+                lo, hi = first // g.nx, (first + count) // g.nx
+                for a in range(lo, hi, per):
+                    b = min(a + per, hi)
+                    jobs.append((a * stride, (b - 1) * stride + ps, [(a * g.nx, (b - a) * g.nx), (g.main_n + a, b - a)]))
+            elif first >= g.main_n + g.ny:                                     # last row, corner, padding copies
+                jobs.append((g.H - ps, g.H, [(first, count)]))
+            # the last-column entries [main_n + lo, main_n + hi] ride with their grid rows above
+        cur = torch.cuda.current_stream(self._device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self._device)
+        copy = self._copy_stream
+
+        def upload(job):
+            with torch.cuda.stream(copy), self._mark_on("upload", copy):
+                with sampler._src as psim:
+                    band = band_to_device(psim, sampler.layer, job[0], job[1], self._device)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            return band, ready
+
+        copy.wait_stream(cur)
+        nxt = upload(jobs[0]) if jobs else None
+        for i, job in enumerate(jobs):
+            band, ready = nxt
+            nxt = upload(jobs[i + 1]) if i + 1 < len(jobs) else None
+            cur.wait_event(ready)
+            band.storage.record_stream(cur)
+            for first, count in job[2]:
+                self._logits_for(sampler, band, logits, first, count, y_off=job[0])
+            del band
+
     def _dense_device(self, want_sum: bool, want_count: bool) -> dict:
         s: FullImageDenseSampler = self.patch_sampler
         n = len(self.anno.anno_classes)
         logits = torch.empty((s.n_padded, n), dtype=torch.float32, device=self._device)
-        self._logits_for(s, s._slide, logits, 0, s.n_padded)
+        if s._slide_dev is None:                                               # lazy_slide=True: stream the slide through HBM
+            g = bands.dense_grid(s.h, s.w, s.patch_size, s.stride, s.batch_size)
+            self._logits_streamed(s, logits, [(0, g.main_n), (g.main_n, g.ny), (g.main_n + g.ny, s.n_padded - g.main_n - g.ny)])
+        else:
+            self._logits_for(s, s._slide, logits, 0, s.n_padded)
         sum_map, cnt, amax = ops.stitch_dense(logits, s.h, s.w, s.patch_size, s.stride, self.downscale, s.batch_size,
                                               want_sum=want_sum, want_count=want_count, want_argmax=True)
         self.last_sum_map = sum_map
@@ -220,7 +292,9 @@ class ImagePredictorPatched:
         d = self.downscale
         plan = bands.plan_band(s.h, s.w, s.patch_size, s.stride, d, s.batch_size, rank, world)
         logits = torch.zeros((s.n_padded, n), dtype=torch.float32, device=self._device)
-        if plan.patch_ranges:
+        if plan.patch_ranges and s._slide_dev is None and self._stream_bands:
+            self._logits_streamed(s, logits, plan.patch_ranges)               # band rows streamed through HBM, upload hidden behind the CNN
+        elif plan.patch_ranges:
             slide, y_off = s.band_slide(plan.slide_y0, plan.slide_y1)
             for first, count in plan.patch_ranges:
                 self._logits_for(s, slide, logits, first, count, y_off)
@@ -284,24 +358,38 @@ class ImagePredictorPatched:
             yield lg, coords, patches[0].patch_size, progress
 
     def _scatter_device(self, batches, want_sum: bool, want_count: bool) -> dict:
+        """The reference's accumulation loop (:47-54) for arbitrary coordinates. The logits and coordinates of every batch stay
+        on the device (28 bytes per patch) and ONE dh_stitch_binned call at the end adds them per map cell in sampler order:
+        bit-identical to `prediction[...] += logits_i` patch by patch, no atomics, every map byte written once."""
         d = self.downscale
         dh, dw = self.h // d, self.w // d
         n = len(self.anno.anno_classes)
-        sum_map = torch.zeros((dh, dw, n), dtype=torch.float32, device=self._device)
-        cnt = torch.zeros((dh, dw), dtype=torch.int32, device=self._device) if want_count else None
         bar = None
         if self._progress:
             from tqdm import tqdm
 
             bar = tqdm(total=100, desc="Predicting", unit="step")
+        all_lg, all_coords, ps_seen = [], [], None
         for lg, coords, ps, progress in batches:
-            ops.stitch_scatter(lg.contiguous(), coords.contiguous(), ps, d, sum_map, cnt)
+            if ps_seen is not None and ps != ps_seen:
+                raise ValueError(f"patch size changed from {ps_seen} to {ps} between batches")
+            ps_seen = ps
+            all_lg.append(lg.reshape(-1, n))
+            all_coords.append(coords.reshape(-1, 2))
             if bar is not None:
                 bar.n = round(progress * 100, 2)
                 bar.refresh()
-        _, amax = ops.stitch_finalize(sum_map, None, want_norm=False, want_argmax=True)
+        if all_lg:
+            lg = all_lg[0].contiguous() if len(all_lg) == 1 else torch.cat(all_lg)
+            coords = all_coords[0].contiguous() if len(all_coords) == 1 else torch.cat(all_coords)
+        else:
+            lg = torch.zeros((0, n), dtype=torch.float32, device=self._device)
+            coords = torch.zeros((0, 2), dtype=torch.int32, device=self._device)
+        with self._mark("stitch"):
+            sum_map, cnt, amax = ops.stitch_binned(lg, coords, ps_seen or 1, d, dh, dw, want_sum=want_sum or n > 8, want_count=want_count,
+                                                   want_argmax=True)
         self.last_sum_map = sum_map
-        return {"argmax": amax, "sum": sum_map if want_sum else None, "count": cnt, "logits": None}
+        return {"argmax": amax, "sum": sum_map if want_sum else None, "count": cnt, "logits": lg, "coords": coords}
 
 
 def assemble_bands(band: torch.Tensor, dh: int, world: int, dist) -> torch.Tensor:

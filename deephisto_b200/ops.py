@@ -221,6 +221,29 @@ def stitch_scatter(logits: torch.Tensor, coords: torch.Tensor, ps: int, d: int, 
         )
 
 
+def stitch_binned(logits: torch.Tensor, coords: torch.Tensor, ps: int, d: int, rows: int, dw: int, *, row_offset: int = 0,
+                  want_sum: bool = True, want_count: bool = False, want_argmax: bool = False):
+    """Deterministic stitch of an arbitrary coordinate list: logits [P,n] f32 + int32 coords [P,2] -> (sum [rows,dw,n] f32,
+    count i32 [rows,dw], argmax u8 [rows,dw]), each None unless requested. Bit-identical to the reference's loop over the
+    patches in list order (predict_full_patched.py:47-54); the maps cover rows [row_offset, row_offset+rows)."""
+    lib = _lib.require_device()
+    _need_cuda(logits, "logits", torch.float32)
+    _need_cuda(coords, "coords", torch.int32)
+    if logits.dim() != 2 or coords.shape != (logits.shape[0], 2):
+        raise ValueError(f"logits [P,n] and coords [P,2] expected, got {tuple(logits.shape)} and {tuple(coords.shape)}")
+    P, n = logits.shape
+    dev = logits.device
+    sum_map = torch.empty((rows, dw, n), dtype=torch.float32, device=dev) if want_sum else None
+    cnt = torch.empty((rows, dw), dtype=torch.int32, device=dev) if want_count else None
+    amax = torch.empty((rows, dw), dtype=torch.uint8, device=dev) if want_argmax else None
+    nbytes = int(lib.dh_stitch_binned_scratch_bytes(P, ps, d, n, rows, dw))
+    scratch = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.dh_stitch_binned(logits.data_ptr(), coords.data_ptr(), P, ps, d, n, _ptr(sum_map), _ptr(cnt), _ptr(amax), rows, dw,
+                                   row_offset, scratch.data_ptr(), scratch.numel(), _stream()), "dh_stitch_binned")
+    return sum_map, cnt, amax
+
+
 def stitch_finalize(sum_map: torch.Tensor, count_map: Optional[torch.Tensor] = None, *, want_norm: bool = False,
                     want_argmax: bool = True):
     lib = _lib.require_device()

@@ -142,6 +142,18 @@ DH_API int dh_stitch_scatter(const float* logits, const int32_t* coords, int64_t
                       void* stream);
 DH_API int dh_stitch_finalize(const float* sum_map, const uint32_t* count_map, int64_t cells, int n,
                        float* norm_map, uint8_t* argmax_u8, void* stream);
+/* dh_stitch_binned: the same arbitrary coordinate list, DETERMINISTIC and bit-identical to the reference loop
+ * (predict_full_patched.py:47-54): patches are binned into warp-sized map tiles and every cell adds its covering
+ * patches in ascending list index with plain fp32 adds from 0 -- no atomics on the map, each output written once.
+ * The outputs are overwritten (not accumulated into): pass the whole list of a slide (all batches concatenated).
+ * Any of sum_map / count_map / argmax_u8 may be NULL (argmax of more than 8 classes needs sum_map). The maps hold
+ * rows [row_offset, row_offset+rows) of the full map. scratch: device bytes from dh_stitch_binned_scratch_bytes.
+ * dh_stitch_binned_set_tile_rows: profiling override of the tile height (0 = heuristic). */
+DH_API int64_t dh_stitch_binned_scratch_bytes(int64_t P, int ps, int d, int n, int64_t rows, int64_t dw);
+DH_API int dh_stitch_binned(const float* logits, const int32_t* coords, int64_t P, int ps, int d, int n,
+                     float* sum_map, uint32_t* count_map, uint8_t* argmax_u8, int64_t rows, int64_t dw,
+                     int64_t row_offset, void* scratch, int64_t scratch_bytes, void* stream);
+DH_API int dh_stitch_binned_set_tile_rows(int rows);
 
 /* ------------------------------------------------------------------------------------------
  * Prediction post-processing: perform_and_save_visualizations (examples/predict_full_patched.py:81-113).

@@ -211,6 +211,81 @@ def test_stitch_scatter_vs_oracle(ops):
     assert np.abs(sb.cpu().numpy() - want[20:60]).max() <= 1e-5 * scale
 
 
+@pytest.mark.parametrize("case", [
+    # H, W, ps, d, n, P, overhang
+    (1500, 1300, 224, 16, 5, 300, False),     # the reference's visualisation setting
+    (1500, 1300, 224, 4, 5, 200, False),      # dw * n % 4 == 0 -> 16-byte stores
+    (900, 1001, 224, 1, 5, 40, True),         # d = 1, dw * n % 4 != 0 -> scalar stores, patches overhanging the right/bottom edge
+    (1000, 777, 100, 7, 3, 150, True),        # ps % d != 0: footprints of 14 or 15 cells
+    (640, 640, 64, 2, 1, 500, False),         # one class
+    (800, 800, 224, 8, 8, 120, False),        # n = 8: the most the cell kernel keeps in registers
+    (800, 800, 224, 8, 11, 120, False),       # n > 8: class map through the sum map
+])
+def test_stitch_binned_bit_exact_vs_oracle(ops, case):
+    """dh_stitch_binned == the reference loop over an arbitrary coordinate list in list order: bit-identical sums, counts, argmax."""
+    H, W, ps, d, n, P, overhang = case
+    rng = np.random.default_rng(P + d)
+    ymax, xmax = (H - 1, W - 1) if overhang else (H - ps, W - ps)
+    coords = np.stack([rng.integers(0, ymax + 1, P), rng.integers(0, xmax + 1, P)], 1).astype(np.int32)
+    logits = (rng.standard_normal((P, n)) * 3).astype(np.float32)
+    want, wcnt, wam = ostitch.stitch(logits, coords, H, W, ps, d)
+    dh, dw = H // d, W // d
+    lg, cd = torch.from_numpy(logits).cuda(), torch.from_numpy(coords).cuda()
+    s, c, am = ops.stitch_binned(lg, cd, ps, d, dh, dw, want_count=True, want_argmax=True)
+    assert np.array_equal(bits(s), want.view(np.int32))
+    assert np.array_equal(c.cpu().numpy().astype(np.int64), wcnt)
+    assert np.array_equal(am.cpu().numpy().astype(np.int64), wam)
+    # outputs one at a time (different kernels / tile geometries) and a row band
+    _, _, am1 = ops.stitch_binned(lg, cd, ps, d, dh, dw, want_sum=n > 8, want_argmax=True)
+    _, c1, _ = ops.stitch_binned(lg, cd, ps, d, dh, dw, want_sum=False, want_count=True)
+    assert torch.equal(am1, am) and torch.equal(c1, c)
+    r0, r1 = dh // 3, dh // 3 + max(1, dh // 2)
+    sb, cb, ab = ops.stitch_binned(lg, cd, ps, d, r1 - r0, dw, row_offset=r0, want_count=True, want_argmax=True)
+    assert torch.equal(sb, s[r0:r1]) and torch.equal(cb, c[r0:r1]) and torch.equal(ab, am[r0:r1])
+    # the atomic scatter agrees to rounding
+    sc = torch.zeros_like(s)
+    ops.stitch_scatter(lg, cd, ps, d, sc, None)
+    assert float((sc - s).abs().max()) <= 1e-5 * float(np.abs(want).max())
+
+
+def test_stitch_binned_long_lists_and_tile_heights(ops):
+    """More patches over one tile than the shared-memory staging holds (global-memory path), duplicates of one origin included;
+    every tile height gives the same bits."""
+    H, W, ps, d, n = 1024, 1024, 224, 16, 5
+    rng = np.random.default_rng(7)
+    P = 900
+    coords = np.stack([rng.integers(300, 340, P), rng.integers(300, 340, P)], 1).astype(np.int32)   # ~900 patches over the same tiles
+    coords[100:200] = coords[100]
+    logits = rng.standard_normal((P, n)).astype(np.float32)
+    want, wcnt, wam = ostitch.stitch(logits, coords, H, W, ps, d)
+    lg, cd = torch.from_numpy(logits).cuda(), torch.from_numpy(coords).cuda()
+    from deephisto_b200 import _lib
+    lib = _lib.require_device()
+    try:
+        for th in (0, 1, 5, 16, 64, 1000):
+            lib.dh_stitch_binned_set_tile_rows(th)
+            s, c, am = ops.stitch_binned(lg, cd, ps, d, H // d, W // d, want_count=True, want_argmax=True)
+            assert np.array_equal(bits(s), want.view(np.int32)), th
+            assert np.array_equal(c.cpu().numpy().astype(np.int64), wcnt) and np.array_equal(am.cpu().numpy().astype(np.int64), wam), th
+    finally:
+        lib.dh_stitch_binned_set_tile_rows(0)
+
+
+def test_stitch_binned_equals_dense_stitch_on_the_dense_enumeration(ops):
+    """Fed with the dense sampler's own (padded) coordinate list, the binned stitch reproduces dh_stitch_dense bit for bit --
+    two independent implementations of the reference order (predict_full_patched.py:47-54 over full_samplers.py:374-404)."""
+    H, W, ps, stride, B, n = 6000, 5000, 224, 112, 64, 5
+    N, npad = ops.dense_count(H, W, ps, stride, B)
+    coords = ops.dense_coords(H, W, ps, stride, B)
+    lg = torch.randn((npad, n), generator=torch.Generator(device="cuda").manual_seed(1), device="cuda")
+    for d in (16, 4, 1):
+        s, c, am = ops.stitch_dense(lg, H, W, ps, stride, d, B, want_count=True, want_argmax=True)
+        s2, c2, am2 = ops.stitch_binned(lg, coords, ps, d, H // d, W // d, want_count=True, want_argmax=True)
+        assert torch.equal(s.view(torch.int32), s2.view(torch.int32)) and torch.equal(c, c2) and torch.equal(am, am2)
+        del s, s2
+        torch.cuda.empty_cache()
+
+
 # ---- B coverage sampler -----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("cfg", [(700, 900, 224, 16, 3), (2048, 2048, 224, 64, 0), (300, 5000, 224, 7, 11)])
 def test_cover_sampler_bit_exact_vs_oracle(ops, cfg):
@@ -470,6 +545,8 @@ def test_empty_inputs_and_error_reporting(ops):
     lg = torch.zeros((0, 5), device="cuda")
     sm = torch.zeros((10, 10, 5), device="cuda")
     ops.stitch_scatter(lg, empty, 64, 16, sm, None)                      # P = 0
+    z, zc, za = ops.stitch_binned(lg, empty, 64, 16, 8, 8, want_count=True, want_argmax=True)   # P = 0: the reference's map stays zero
+    assert int(z.abs().sum()) == 0 and int(zc.sum()) == 0 and int(za.sum()) == 0
     assert float(sm.abs().max()) == 0.0
     with pytest.raises(_lib.DeepHistoError, match="patch size"):
         ops.gather_normalize(slide, torch.zeros((1, 2), dtype=torch.int32, device="cuda"), 8200, dtype=torch.uint8)      # > 8192
