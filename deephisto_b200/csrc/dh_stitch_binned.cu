@@ -34,7 +34,8 @@ struct BinGeom {
     int64_t nty, ntx;
     int ps, d, n;
     int scale;              // units per cell: n (sum mode) or 1 (cell mode)
-    int TH, TW;             // tile = TH rows x TW units (TW = 32 * VEC)
+    int TH, TW;             // tile = TH rows x TW units (TW = 32 * VEC * G)
+    int G;                  // groups of 32 * VEC units per tile: a lane owns VEC consecutive units in each group
 };
 
 struct BinRec {
@@ -123,7 +124,8 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
         sorted[beg + rank] = v;
     }
     __syncwarp();
-    const int64_t ubase = tx * g.TW + (int64_t)lane * VEC;
+  for (int gi = 0; gi < g.G; ++gi) {
+    const int64_t ubase = tx * g.TW + (int64_t)gi * 32 * VEC + (int64_t)lane * VEC;
     const bool active = ubase < g.units_per_row;
     int cls[VEC];
     int c = (int)(ubase % n);
@@ -180,11 +182,12 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
         }
         r = next;
     }
+  }
 }
 
 __host__ __device__ inline int bin_warp_smem_bytes(int n, bool staged) { return kBinCap * 20 + kBinCap * 4 * (staged ? n : 1); }
 
-template <int VEC, bool CELL, bool STAGED>
+template <int VEC, int G, bool CELL, bool STAGED>
 __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords, BinGeom g,
                                                                   const uint32_t* __restrict__ off, const uint32_t* __restrict__ len,
                                                                   const uint32_t* __restrict__ list, uint32_t* __restrict__ sorted, float* __restrict__ sum_map,
@@ -235,13 +238,16 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
     }
     __syncwarp();
 
-    const int ub = (int)(tx * g.TW) + lane * VEC;            // first unit owned by this lane (units_per_row + TW < 2^31, host check)
-    const bool active = ub < g.units_per_row;                // units_per_row % VEC == 0 (host check)
-    int cls[VEC];
+    constexpr int GS = 32 * VEC;                             // units per group: group gi of the tile starts GS * gi units further right
+    const int ub = (int)(tx * g.TW) + lane * VEC;            // first unit owned by this lane in group 0 (units_per_row + TW < 2^31, host check)
+    int cls[G][VEC];                                         // units_per_row % VEC == 0 (host check): a lane's VEC units are all inside or all outside
     if constexpr (!CELL) {
-        int c = ub % n;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) { cls[k] = c; c = c + 1 == n ? 0 : c + 1; }
+        for (int gi = 0; gi < G; ++gi) {
+            int c = (ub + gi * GS) % n;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { cls[gi][k] = c; c = c + 1 == n ? 0 : c + 1; }
+        }
     }
     const int R0 = (int)(ty * g.TH);
     const int R1 = (int)((int64_t)R0 + g.TH < g.rows ? R0 + g.TH : g.rows);
@@ -249,9 +255,11 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
 
     int r = R0;
     while (r < R1) {
-        float acc[CELL ? kBinMaxN : VEC];
+        float acc[G][CELL ? kBinMaxN : VEC];
 #pragma unroll
-        for (int k = 0; k < (CELL ? kBinMaxN : VEC); ++k) acc[k] = 0.f;
+        for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+            for (int k = 0; k < (CELL ? kBinMaxN : VEC); ++k) acc[gi][k] = 0.f;
         uint32_t hits = 0;
         int next = R1;
         for (int c0 = 0; c0 < L; c0 += 32) {
@@ -274,33 +282,39 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
                     if (want_vals) {
 #pragma unroll
                         for (int q = 0; q < kBinMaxN; ++q)
-                            if (q < n) acc[q] += cov ? s_lg[jj * n + q] : 0.f;
+                            if (q < n) acc[0][q] += cov ? s_lg[jj * n + q] : 0.f;
                     }
                 } else {
                     const float* lg = STAGED ? s_lg + jj * n : logits + (int64_t)s_ids[jj] * n;
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) {
-                        const float v = STAGED ? lg[cls[k]] : __ldg(lg + cls[k]);
-                        acc[k] += (k >= lo && k < hi) ? v : 0.f;
-                    }
+                    for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) {
+                            const float v = STAGED ? lg[cls[gi][k]] : __ldg(lg + cls[gi][k]);
+                            acc[gi][k] += (k + gi * GS >= lo && k + gi * GS < hi) ? v : 0.f;
+                        }
                 }
             }
         }
-        if (active) {
-            if constexpr (CELL) {
-                const uint8_t am = want_vals ? first_argmax(acc, n) : (uint8_t)0;
+        if constexpr (CELL) {
+            if (ub < g.units_per_row) {
+                const uint8_t am = want_vals ? first_argmax(acc[0], n) : (uint8_t)0;
                 int64_t o = (int64_t)r * g.units_per_row + ub;
                 for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
                     if (argmax_map) argmax_map[o] = am;
                     if (count_map) count_map[o] = hits;
                 }
-            } else {
-                float* o = sum_map + (int64_t)r * g.units_per_row + ub;
-                for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
-                    if constexpr (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            }
+        } else {
+            float* o = sum_map + (int64_t)r * g.units_per_row + ub;
+            for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    if (ub + gi * GS >= g.units_per_row) continue;
+                    if constexpr (VEC == 4) *reinterpret_cast<float4*>(o + gi * GS) = make_float4(acc[gi][0], acc[gi][1], acc[gi][2], acc[gi][3]);
                     else {
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) o[k] = acc[k];
+                        for (int k = 0; k < VEC; ++k) o[gi * GS + k] = acc[gi][k];
                     }
                 }
             }
@@ -309,10 +323,18 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
     }
 }
 
+// profiling override: rows + 1000 * groups + 100000 * extra shared-memory KB per CTA (each field 0 = heuristic / none)
 static int tile_rows_for(int ps, int d) {
-    if (g_bin_tile_rows > 0) return g_bin_tile_rows;
+    if (g_bin_tile_rows % 1000 > 0) return g_bin_tile_rows % 1000;
     const int fh = ps / d;
     return fh >= 48 ? 64 : fh >= 24 ? 32 : 16;
+}
+
+static int groups_for(bool cell, int vec, int ps, int d, int n) {
+    if (cell || vec != 4) return 1;
+    const int ov = (g_bin_tile_rows / 1000) % 10;
+    if (ov > 0) return ov >= 2 ? 2 : 1;
+    return (int64_t)(ps / d) * n >= 512 ? 2 : 1;  // wide footprints: 256-float tiles halve the per-tile staging work (measured: profiles/r01_stitch.md)
 }
 
 static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows, int64_t dw, int64_t row_offset) {
@@ -322,7 +344,8 @@ static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows,
     g.scale = cell ? 1 : n;
     g.units_per_row = dw * g.scale;
     g.TH = tile_rows_for(ps, d);
-    g.TW = 32 * vec;
+    g.G = groups_for(cell, vec, ps, d, n);
+    g.TW = 32 * vec * g.G;
     g.nty = (rows + g.TH - 1) / g.TH;
     g.ntx = (g.units_per_row + g.TW - 1) / g.TW;
     return g;
@@ -355,7 +378,7 @@ static void carve_bin(const BinGeom& g, int64_t P, void* base, BinScratch& s) {
 
 static bool sum_vec4(const float* sum_map, int64_t dw, int n) { return (dw * n) % 4 == 0 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0; }
 
-template <int VEC, bool CELL, bool STAGED>
+template <int VEC, int G, bool CELL, bool STAGED>
 static int run_binned(const float* logits, const int32_t* coords, int64_t P, const BinGeom& g, float* sum_map, uint32_t* count_map,
                       uint8_t* argmax_u8, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
     BinScratch s;
@@ -376,8 +399,10 @@ static int run_binned(const float* logits, const int32_t* coords, int64_t P, con
     DH_CHECK_LAUNCH("bin_patches_kernel<fill>");
     const int64_t ctas = g.nty * ((g.ntx + kBinWarps - 1) / kBinWarps);
     DH_REQUIRE(ctas < (1ll << 31), "dh_stitch_binned: too many tiles");
-    const int smem = kBinWarps * bin_warp_smem_bytes(g.n, STAGED);
-    auto kern = bin_tile_kernel<VEC, CELL, STAGED>;
+    // at least 50 KB per CTA = at most 4 resident CTAs per SM: a fifth one only adds HBM write interleaving (measured 1.5-3 % slower)
+    int smem = kBinWarps * bin_warp_smem_bytes(g.n, STAGED) + (g_bin_tile_rows / 100000) * 1024;
+    if (!CELL && smem < 50 * 1024) smem = 50 * 1024;
+    auto kern = bin_tile_kernel<VEC, G, CELL, STAGED>;
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_tile_kernel)");
@@ -431,16 +456,18 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
     if (sum_map) {
         const bool v4 = sum_vec4(sum_map, dw, n);
         const BinGeom g = make_geom(false, v4 ? 4 : 1, ps, d, n, rows, dw, row_offset);
-        if (v4) rc = staged ? run_binned<4, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
-                            : run_binned<4, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
-        else rc = staged ? run_binned<1, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
-                         : run_binned<1, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        if (v4 && g.G == 2) rc = staged ? run_binned<4, 2, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
+                                        : run_binned<4, 2, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        else if (v4) rc = staged ? run_binned<4, 1, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
+                                 : run_binned<4, 1, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        else rc = staged ? run_binned<1, 1, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
+                         : run_binned<1, 1, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         if (rc != DH_OK) return rc;
     }
     uint8_t* cell_argmax = argmax_u8 && staged ? argmax_u8 : nullptr;
     if (count_map || cell_argmax) {
         const BinGeom g = make_geom(true, 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
-        rc = run_binned<1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
+        rc = run_binned<1, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
         if (rc != DH_OK) return rc;
     }
     if (argmax_u8 && !cell_argmax) rc = dh_stitch_finalize(sum_map, nullptr, rows * dw, n, nullptr, argmax_u8, stream);

@@ -119,13 +119,22 @@ class PinnedSlide:
     """A slide layer held in PINNED host memory with the device row pitch (uint8 [H, pitch], pitch % 16 == 0): the upload to
     HBM is one asynchronous cudaMemcpy at PCIe speed (a pageable numpy array goes through a staging copy first). Layer 1 only."""
 
-    def __init__(self, host, H: int, W: int, pitch: int):
+    def __init__(self, host, H: int, W: int, pitch: int, y_origin: int = 0, full_height: int = None):
+        """`y_origin` / `full_height`: the buffer holds rows [y_origin, y_origin + H) of a layer of `full_height` rows (one rank's
+        row band of a sharded slide); row arguments of every method stay in layer coordinates."""
         import torch
 
         if not (isinstance(host, torch.Tensor) and host.dtype == torch.uint8 and not host.is_cuda and host.numel() >= H * pitch):
             raise ValueError("PinnedSlide needs a host uint8 tensor of at least H * pitch bytes")
-        self.host, self.height, self.width, self.pitch = host, int(H), int(W), int(pitch)
+        self.host, self.rows, self.width, self.pitch = host, int(H), int(W), int(pitch)
+        self.y_origin = int(y_origin)
+        self.height = int(full_height) if full_height is not None else self.y_origin + self.rows
         self.pinned = host.is_pinned()      # False only when page-locking failed (_host_buffer): uploads then go through staging
+
+    def _rows(self, y0: int, y1: int):
+        if not (self.y_origin <= y0 <= y1 <= self.y_origin + self.rows):
+            raise ValueError(f"rows [{y0}, {y1}) are outside the band [{self.y_origin}, {self.y_origin + self.rows}) this buffer holds")
+        return y0 - self.y_origin, y1 - self.y_origin
 
     @staticmethod
     def _host_buffer(nbytes: int):
@@ -148,16 +157,16 @@ class PinnedSlide:
         return cls(host, H, W, pitch)
 
     @classmethod
-    def from_device(cls, dev: DeviceSlide) -> "PinnedSlide":
+    def from_device(cls, dev: DeviceSlide, y_origin: int = 0, full_height: int = None) -> "PinnedSlide":
         import torch
 
         host = cls._host_buffer(dev.H * dev.pitch)
         host.copy_(dev.storage[: dev.H * dev.pitch])
-        return cls(host, dev.H, dev.W, dev.pitch)
+        return cls(host, dev.H, dev.W, dev.pitch, y_origin, full_height)
 
     @property
     def nbytes(self) -> int:
-        return self.height * self.pitch
+        return self.rows * self.pitch
 
     def __enter__(self):
         return self
@@ -179,15 +188,19 @@ class PinnedSlide:
     def get_region_from_layer(self, layer: int, p0, p1) -> np.ndarray:
         self._assert_layer(layer)
         (y0, x0), (y1, x1) = p0, p1
-        return self.host.view(-1, self.pitch)[y0:y1, 3 * x0 : 3 * x1].numpy().reshape(y1 - y0, x1 - x0, 3)
+        a, b = self._rows(y0, y1)
+        return self.host.view(-1, self.pitch)[a:b, 3 * x0 : 3 * x1].numpy().reshape(y1 - y0, x1 - x0, 3)
 
-    def to_device(self, device="cuda", y0: int = 0, y1: int = None) -> DeviceSlide:
+    def to_device(self, device="cuda", y0: int = None, y1: int = None) -> DeviceSlide:
+        """Rows [y0, y1) (layer coordinates; default: everything this buffer holds) as a DeviceSlide whose row 0 is row y0."""
         import torch
 
-        y1 = self.height if y1 is None else y1
-        storage = torch.empty((y1 - y0) * self.pitch, dtype=torch.uint8, device=device)
-        storage.copy_(self.host[y0 * self.pitch : y1 * self.pitch], non_blocking=True)
-        return DeviceSlide(storage, y1 - y0, self.width, self.pitch)
+        y0 = self.y_origin if y0 is None else y0
+        y1 = self.y_origin + self.rows if y1 is None else y1
+        a, b = self._rows(y0, y1)
+        storage = torch.empty((b - a) * self.pitch, dtype=torch.uint8, device=device)
+        storage.copy_(self.host[a * self.pitch : b * self.pitch], non_blocking=True)
+        return DeviceSlide(storage, b - a, self.width, self.pitch)
 
 
 def open_slide(source):

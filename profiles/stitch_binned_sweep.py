@@ -18,6 +18,7 @@ peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROO
 lib = _lib.require_device()
 H = W = 40000
 PS, N = 224, 5
+CODES = [int(c) for c in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 16, 32, 64, 128]
 
 
 def timeit(fn, reps):
@@ -54,7 +55,8 @@ for name, coords in lists.items():
         cells = dh * dw
         reps = 10 if d >= 4 else 3
         for label, kw, out_bytes in (("sum", dict(want_sum=True), cells * N * 4), ("argmax", dict(want_sum=False, want_argmax=True), cells)):
-            for th in ((0,) if label == "argmax" else (0, 16, 32, 64, 128)):
+            # override code = tile rows + 1000 * groups + 100000 * extra smem KB per CTA (0 = the library's heuristic)
+            for th in ((0,) if label == "argmax" else CODES):
                 lib.dh_stitch_binned_set_tile_rows(th)
                 keep = {}
 
@@ -78,5 +80,5 @@ for name, coords in lists.items():
         torch.cuda.empty_cache()
 print(json.dumps({"peak_gbs": peak, "case": f"{H}x{W} ps{PS} n{N}", "rows": rows}, indent=1))
 for r in rows:
-    print(f'{r["kernel"]:15s} {r["list"]:18s} P={r["P"]:7d} d={r["d"]:2d} {r["outputs"]:14s} TH={r["tile_rows"]:3d} {r["ms"]:9.3f} ms {r["alg_MB"]:9.1f} MB '
+    print(f'{r["kernel"]:15s} {r["list"]:18s} P={r["P"]:7d} d={r["d"]:2d} {r["outputs"]:14s} code={r["tile_rows"]:7d} {r["ms"]:9.3f} ms {r["alg_MB"]:9.1f} MB '
           f'{r["GBs"]:7.0f} GB/s  {r["frac_of_measured"]:.3f}', file=sys.stderr)

@@ -100,3 +100,22 @@ def test_slide_sources_host_side():
     assert syn.layer_size(1) == (64, 48)
     with pytest.raises(ValueError):
         syn.layer_size(2)
+
+
+def test_pinned_slide_band_origin_host_side():
+    """PinnedSlide as one rank's row band of a sharded slide: row arguments stay in layer coordinates, rows outside the band raise."""
+    import numpy as np
+
+    from deephisto_b200 import slide as sl
+
+    a = np.arange(40 * 30 * 3, dtype=np.uint8).reshape(40, 30, 3)
+    whole = sl.PinnedSlide.from_numpy(a)
+    assert whole.layer_size(1) == (40, 30) and whole.nbytes == 40 * whole.pitch and whole.pitch % 16 == 0
+    assert np.array_equal(whole.get_region_from_layer(1, (3, 4), (10, 9)), a[3:10, 4:9])
+    band = sl.PinnedSlide(whole.host[12 * whole.pitch : 25 * whole.pitch], 13, 30, whole.pitch, y_origin=12, full_height=40)
+    assert band.layer_size(1) == (40, 30) and band.nbytes == 13 * whole.pitch
+    assert np.array_equal(band.get_region_from_layer(1, (14, 0), (20, 30)), a[14:20])
+    with pytest.raises(ValueError, match="outside the band"):
+        band.get_region_from_layer(1, (5, 0), (14, 30))
+    with pytest.raises(ValueError):
+        band.layer_size(2)
