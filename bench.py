@@ -297,14 +297,26 @@ def ours(args):
     fail = torch.zeros(1, dtype=torch.uint8, device=dev)
     launches = [0]
 
+    # the coordinate launch of chunk i+1 runs on a second stream next to the gather of chunk i, as in AnnoRegionRndSampler.torch_generator
+    # (DH_BENCH_OVERLAP=0 puts both on one stream: A/B in profiles/r01_gather.md)
+    overlap = os.environ.get("DH_BENCH_OVERLAP", "1") == "1"
+    side = torch.cuda.Stream(dev) if overlap else None
+    drawn = [torch.cuda.Event(), torch.cuda.Event()]
+    gathered = [torch.cuda.Event(), torch.cuda.Event()]
+
     def chunk(first_step, n_batches, ev=None):
         """Steps [first_step, first_step + n_batches): rank r draws from its own Philox slot range (rank << 40) -- disjoint
         streams, no data-path collective."""
         buf = (first_step // CHUNK) & 1
         n = n_batches * BATCH
         off = (rank << 40) + first_step * BATCH
+        if overlap:
+            side.wait_event(gathered[buf])                            # the coords buffer is free once its previous gather is done
         rc = sp(tstruct, n, K_PER_REGION, PS, thr, 500, 64, -1, 2 * BATCH, 0, off, coords[buf].data_ptr(), labels[buf].data_ptr(),
-                images[buf].data_ptr(), status[buf].data_ptr(), stream)
+                images[buf].data_ptr(), status[buf].data_ptr(), side.cuda_stream if overlap else stream)
+        if overlap:
+            drawn[buf].record(side)
+            torch.cuda.current_stream().wait_event(drawn[buf])
         if ev is not None:
             ev[0].record()
         fl = None if flip_bits is None else flip_bits.data_ptr() + first_step * BATCH
@@ -312,6 +324,8 @@ def ours(args):
                  stream)
         if ev is not None:
             ev[1].record()
+        if overlap:
+            gathered[buf].record()
         launches[0] += 2
         if rc:
             raise RuntimeError(_lib.last_error())
@@ -536,7 +550,8 @@ def ours_predict(args):
     # the band of the slide (with its patch-size halo) is made resident once, like the reference loads the layer in its constructor
     band, y_off = sampler.band_slide(plan.slide_y0, plan.slide_y1)
     sampler.band_slide = lambda y0, y1: (band, y_off)
-    ipp = pfp.ImagePredictorPatched(src, sampler, pred, anno, layer=1, downscale=16, device=dev, cnn_batch=args.cnn_batch)
+    ipp = pfp.ImagePredictorPatched(src, sampler, pred, anno, layer=1, downscale=16, device=dev, cnn_batch=args.cnn_batch,
+                                    stream_bands=False)           # `value`: the band stays resident in HBM across steps
     K, Wm = args.steps, max(1, min(args.warmup, 2))
 
     def step():

@@ -202,7 +202,8 @@ class AnnoRegionRndSampler:
         assert names == self.classes
         self._slides = [None] * len(img_anno_paths)
         self._slot_cursor = 0
-        self._producer = None          # CUDA stream the prefetch groups of torch_generator run on
+        self._producer = None          # CUDA stream the gathers of torch_generator's prefetch groups run on
+        self._drawer = None            # CUDA stream their coordinate draws run on
         self._slide_table = None       # ops.SlideTable over all images (multi-image datasets)
         self._fail = torch.zeros(1, dtype=torch.uint8, device=device) if torch.device(device).type == "cuda" else None
         if verbose:
@@ -310,18 +311,28 @@ class AnnoRegionRndSampler:
         cur = torch.cuda.current_stream(self._device) if on_gpu else None
         if on_gpu and self._producer is None:
             self._producer = torch.cuda.Stream(self._device)
+            self._drawer = torch.cuda.Stream(self._device)
             self._producer.wait_stream(cur)                 # tables (and anything else set up on the caller's stream) are complete
+            self._drawer.wait_stream(cur)
 
         def launch(nb):
-            """Enqueue one prefetch group on the producer stream; returns its tensors and the event that marks them ready."""
-            with torch.cuda.stream(self._producer):
+            """Enqueue one prefetch group; returns its tensors and the event that marks them ready. Coordinates are drawn on their
+            own stream: the draw of group g+1 does not depend on the gather of group g, so it runs next to it instead of
+            extending the producer stream's critical path (measured +4.6 % patches/s, profiles/r01_gather.md)."""
+            with torch.cuda.stream(self._drawer):
                 first_slot = self._slot_cursor
                 coords, labels, images, status = self._sample_raw(batch_size * nb, chunk, cls_idx)
+                group = {"labels": labels, "coords": coords.to(torch.float32), "fail": status.max()}
+                drawn = torch.cuda.Event()
+                drawn.record(self._drawer)
+            with torch.cuda.stream(self._producer):
+                self._producer.wait_event(drawn)
+                coords.record_stream(self._producer)
+                images.record_stream(self._producer)
                 flip = None
                 if self._flips:
                     flip = torch.cat([self._batch_flip(first_slot // max(batch_size, 1) + i, batch_size) for i in range(nb)])
-                features = self._gather(coords, images, self._out_dtype, self._out_layout, flip)
-                group = {"features": features, "labels": labels, "coords": coords.to(torch.float32), "fail": status.max()}
+                group["features"] = self._gather(coords, images, self._out_dtype, self._out_layout, flip)
                 ready = torch.cuda.Event()
                 ready.record(self._producer)
             return group, ready
