@@ -167,3 +167,20 @@ extern "C" DH_API int dh_synth_slide_rows(uint8_t* slide, int64_t H, int64_t W, 
 extern "C" DH_API int dh_synth_slide(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, uint64_t seed, void* stream) {
     return dh_synth_slide_rows(slide, H, W, pitch, 0, H, seed, stream);
 }
+
+extern "C" DH_API int dh_upload_rects(uint8_t* slide_dev, int64_t H, int64_t pitch, const uint8_t* slide_host, int64_t n_rects,
+                                      const int64_t* rects_host, void* stream) {
+    if (n_rects == 0) return DH_OK;
+    DH_REQUIRE(slide_dev && slide_host && rects_host, "dh_upload_rects: null pointer");
+    DH_REQUIRE(H > 0 && pitch > 0 && n_rects > 0, "dh_upload_rects: bad sizes");
+    for (int64_t i = 0; i < n_rects; ++i) {
+        const int64_t y0 = rects_host[4 * i], y1 = rects_host[4 * i + 1], b0 = rects_host[4 * i + 2], b1 = rects_host[4 * i + 3];
+        DH_REQUIRE(0 <= y0 && y0 <= y1 && y1 <= H && 0 <= b0 && b0 <= b1 && b1 <= pitch, "dh_upload_rects: rectangle %lld outside the slide",
+                   (long long)i);
+        if (y1 == y0 || b1 == b0) continue;
+        cudaError_t e = cudaMemcpy2DAsync(slide_dev + y0 * pitch + b0, (size_t)pitch, slide_host + y0 * pitch + b0, (size_t)pitch, (size_t)(b1 - b0),
+                                          (size_t)(y1 - y0), cudaMemcpyHostToDevice, as_stream(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy2DAsync");
+    }
+    return DH_OK;
+}

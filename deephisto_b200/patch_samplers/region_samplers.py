@@ -25,7 +25,7 @@ import torch
 from torch.utils.data import IterableDataset
 
 from .. import geometry, ops
-from ..slide import Patch, layer_to_device, open_slide
+from ..slide import Patch, PinnedSlide, layer_to_device, open_slide, upload_rects
 
 
 class RegionAnnotation:
@@ -178,7 +178,7 @@ class AnnoRegionRndSampler:
     def __init__(self, img_anno_paths, layer: int, patch_size: int, region_intersection: float = 0.75,
                  patches_from_one_region: int = 4, region_area_influence: float = 0.5, classes: list[str] = None,
                  one_image_for_batch: bool = False, *, seed: int = 0, device="cuda", out_dtype=torch.float32, out_layout: str = "NHWC",
-                 flips: bool = False, mean=None, std=None, verbose: bool = True):
+                 flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = True):
         self.img_anno_paths = img_anno_paths
         self.layer = layer
         self.patch_size = patch_size
@@ -201,6 +201,8 @@ class AnnoRegionRndSampler:
         self._tables, self._flat_regions, names = build_tables(images, layer, region_area_influence, None, one_image_for_batch, device)
         assert names == self.classes
         self._slides = [None] * len(img_anno_paths)
+        self._sparse_upload = sparse_upload    # PinnedSlide sources: upload only the tiles that intersect annotated regions
+        self.uploaded_bytes = 0                # bytes copied host -> device for pinned sources so far
         self._slot_cursor = 0
         self._producer = None          # CUDA stream the gathers of torch_generator's prefetch groups run on
         self._drawer = None            # CUDA stream their coordinate draws run on
@@ -231,10 +233,29 @@ class AnnoRegionRndSampler:
         return q
 
     # -- device pipeline --------------------------------------------------------------------------------
+    def _reachable_rects(self, j: int):
+        """Pixel rectangles (y0, y1, x0, x1) of image j that a patch of this sampler can touch: origins are drawn inside a region's
+        bounding box (region_samplers.py:123-124), so a patch stays within the box grown to at least patch_size + 1."""
+        ps, rects = self.patch_size, []
+        for regs in self.regions_per_image[j].values():
+            for r in regs:
+                v = np.asarray(r.vertices, dtype=np.float64)
+                x0, y0 = np.floor(v.min(axis=0)) - 1
+                x1, y1 = np.ceil(v.max(axis=0)) + 1
+                rects.append((y0, max(y1, y0 + ps + 2), x0, max(x1, x0 + ps + 2)))
+        return rects
+
     def _slide(self, j: int):
         if self._slides[j] is None:
             with self._sources[j] as psim:
-                self._slides[j] = layer_to_device(psim, self.layer, self._device)
+                if self._sparse_upload and isinstance(psim, PinnedSlide) and psim.y_origin == 0 and psim.rows == psim.height:
+                    # host-resident slide: only the tiles a region can reach travel over PCIe
+                    psim._assert_layer(self.layer)
+                    self._slides[j], n = upload_rects(psim, self._reachable_rects(j), self._device)
+                    self.uploaded_bytes += n
+                else:
+                    self._slides[j] = layer_to_device(psim, self.layer, self._device)
+                    self.uploaded_bytes += self._slides[j].H * self._slides[j].pitch if isinstance(psim, PinnedSlide) else 0
         return self._slides[j]
 
     def _check_failures(self):

@@ -228,6 +228,58 @@ def open_slide(source):
     raise TypeError(f"unsupported slide source {type(source)!r}")
 
 
+def tile_spans(rects, H: int, W: int, pitch: int, tile: int = 512):
+    """Cover pixel rectangles (y0, y1, x0, x1) with `tile` x `tile` tiles and return the covered area as an int64 array [n][4] =
+    {y0, y1, byte_x0, byte_x1} (byte columns 16-byte aligned, vertically adjacent identical runs merged) for dh_upload_rects."""
+    ty, tx = -(-H // tile), -(-W // tile)
+    occ = np.zeros((ty, tx), dtype=bool)
+    for y0, y1, x0, x1 in rects:
+        y0, y1, x0, x1 = max(0, int(y0)), min(H, int(y1)), max(0, int(x0)), min(W, int(x1))
+        if y1 > y0 and x1 > x0:
+            occ[y0 // tile : (y1 - 1) // tile + 1, x0 // tile : (x1 - 1) // tile + 1] = True
+    out, open_runs = [], {}                                    # open_runs: (b0, b1) -> first tile row of a vertical stack of equal runs
+    for i in range(ty + 1):
+        runs = set()
+        if i < ty:
+            row = occ[i]
+            j = 0
+            while j < tx:
+                if row[j]:
+                    k = j
+                    while k < tx and row[k]:
+                        k += 1
+                    runs.add(((j * tile * 3) // 16 * 16, min(pitch, -(-(min(W, k * tile) * 3) // 16) * 16)))
+                    j = k
+                else:
+                    j += 1
+        for key in [k for k in open_runs if k not in runs]:
+            out.append((open_runs.pop(key) * tile, min(H, i * tile), key[0], key[1]))
+        for key in runs:
+            open_runs.setdefault(key, i)
+    return np.asarray(sorted(out), dtype=np.int64).reshape(-1, 4)
+
+
+def upload_rects(host: "PinnedSlide", rects, device="cuda", tile: int = 512):
+    """DeviceSlide holding only the tiles of `host` that intersect `rects` (the rest is zero) and the number of bytes that
+    travelled: what an annotated sampler needs of a slide -- the reference reads just the patches it draws from storage
+    (region_samplers.py:513-520)."""
+    import torch
+
+    from . import _lib
+
+    if host.y_origin != 0 or host.rows != host.height:
+        raise ValueError("upload_rects needs a PinnedSlide holding the whole layer")
+    lib = _lib.require_device()
+    spans = np.ascontiguousarray(tile_spans(rects, host.height, host.width, host.pitch, tile))
+    dev = torch.device(device)
+    storage = torch.zeros(host.height * host.pitch, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dh_upload_rects(storage.data_ptr(), host.height, host.pitch, host.host.data_ptr(), len(spans), spans.ctypes.data,
+                                       torch.cuda.current_stream(dev).cuda_stream), "dh_upload_rects")
+    nbytes = int(((spans[:, 1] - spans[:, 0]) * (spans[:, 3] - spans[:, 2])).sum()) if len(spans) else 0
+    return DeviceSlide(storage, host.height, host.width, host.pitch), nbytes
+
+
 class DeviceSlideSource:
     """PSImage duck type over a slide that already lives in HBM (layer 1 only)."""
 

@@ -69,6 +69,13 @@ DH_API int dh_synth_slide(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, u
 DH_API int dh_synth_slide_rows(uint8_t* slide, int64_t H, int64_t W, int64_t pitch, int64_t y0, int64_t rows, uint64_t seed,
                                void* stream);
 
+/* Slide ingestion for the annotated samplers: the reference reads each patch from storage (region_samplers.py:513-520), so only
+ * pixels inside annotated regions ever travel. dh_upload_rects copies the listed rectangles of a HOST slide (same row pitch as the
+ * device slide; pinned memory makes the copies asynchronous) into the device slide: rects_host is a HOST array [n_rects][4] =
+ * {y0, y1, byte_x0, byte_x1}; one cudaMemcpy2DAsync per rectangle on `stream`. Bytes outside the rectangles are left untouched. */
+DH_API int dh_upload_rects(uint8_t* slide_dev, int64_t H, int64_t pitch, const uint8_t* slide_host, int64_t n_rects,
+                           const int64_t* rects_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * A1  FullImageDenseSampler._create_batched_coords (full_samplers.py:374-404)
  * Enumeration: main grid (y outer, x inner), last column, last row, corner, then the last batch

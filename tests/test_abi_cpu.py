@@ -119,3 +119,28 @@ def test_pinned_slide_band_origin_host_side():
         band.get_region_from_layer(1, (5, 0), (14, 30))
     with pytest.raises(ValueError):
         band.layer_size(2)
+
+
+def test_tile_spans_cover_the_rectangles_once():
+    """slide.tile_spans (input of dh_upload_rects): the spans cover every requested pixel, never overlap, stay 16-byte aligned."""
+    import numpy as np
+
+    from deephisto_b200 import ops, slide as sl
+
+    H, W = 2000, 3001
+    pitch = ops.DeviceSlide.pitch_for(W)
+    rng = np.random.default_rng(0)
+    rects = []
+    for _ in range(12):
+        y0, x0 = int(rng.integers(-50, H)), int(rng.integers(-50, W))
+        rects.append((y0, y0 + int(rng.integers(1, 900)), x0, x0 + int(rng.integers(1, 900))))
+    spans = sl.tile_spans(rects, H, W, pitch, tile=256)
+    cov = np.zeros((H, pitch), dtype=np.int32)
+    for y0, y1, b0, b1 in spans:
+        assert 0 <= y0 < y1 <= H and 0 <= b0 < b1 <= pitch and b0 % 16 == 0 and (b1 % 16 == 0 or b1 == pitch)
+        cov[y0:y1, b0:b1] += 1
+    assert cov.max() == 1
+    for y0, y1, x0, x1 in rects:
+        y0, y1, x0, x1 = max(0, y0), min(H, y1), max(0, x0), min(W, x1)
+        assert (cov[y0:y1, 3 * x0 : 3 * x1] == 1).all()
+    assert len(sl.tile_spans([], H, W, pitch)) == 0

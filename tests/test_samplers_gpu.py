@@ -170,6 +170,27 @@ def test_anno_region_rnd_sampler_torch_generator(api, tmp_path, one_image):
     assert not torch.equal(other[2], got[0][2])
 
 
+def test_anno_region_rnd_sampler_sparse_upload_from_pinned_slides(api, tmp_path):
+    """Slides that sit in pinned host memory: only the 512-px tiles a region can reach travel (dh_upload_rects); the batches are
+    bit-identical to those drawn from fully uploaded slides, and fewer bytes were copied."""
+    _, _, rs = api
+    from deephisto_b200.slide import PinnedSlide
+
+    hw, items, _ = _dataset(tmp_path)
+    pinned = [(PinnedSlide.from_numpy(np.asarray(img)), anno) for img, anno in items]
+    ps, B = 224, 24
+    full = rs.AnnoRegionRndSampler(items, layer=1, patch_size=ps, seed=9, verbose=False)
+    sparse = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False)
+    dense_up = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False, sparse_upload=False)
+    a = list(full.torch_generator(B, 6))
+    b = list(sparse.torch_generator(B, 6))
+    c = list(dense_up.torch_generator(B, 6))
+    for (fa, la, ca), (fb, lb, cb), (fc, lc, cc) in zip(a, b, c):
+        assert torch.equal(ca, cb) and torch.equal(la, lb) and torch.equal(fa, fb) and torch.equal(fa, fc)
+    total = sum(p.nbytes for p, _ in pinned)
+    assert 0 < sparse.uploaded_bytes <= total and dense_up.uploaded_bytes == total
+
+
 def test_anno_region_rnd_sampler_extras_and_structs(api, tmp_path):
     _, _, rs = api
     hw, items, polys_all = _dataset(tmp_path, 1)
