@@ -430,7 +430,7 @@ def ours(args):
     if tf.exists() and args.workload == "annotated_rnd":               # ncu capture of exactly this kernel / launch shape
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
     slide_bytes = host_slide.nbytes
-    uploaded = int(api.uploaded_bytes)                                # what actually travelled: the 512-px tiles a region can reach
+    uploaded = int(api.uploaded_bytes)                                # what actually travelled (the whole layer unless < 1/5 of it is annotated)
     line = {
         "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": mode["dtype"],
@@ -443,8 +443,7 @@ def ours(args):
                      "kernel_ms_per_batch": gather_total_ms / max(sum(nb for _, nb in gather_ms), 1), "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": uploaded / K, "d2h_bytes_per_step": d2h,
                 "api": f"AnnoRegionRndSampler.torch_generator(batch_size={BATCH}, n_batches=K) over a slide in pinned host memory: the timed region "
-                       "contains the one-time H2D upload of the slide tiles that annotated regions can reach (h2d_bytes_total of slide_bytes; the "
-                       "reference reads only the patches it draws, region_samplers.py:513-520), K batches, and per step the D2H read of labels+coords",
+                       "contains the one-time H2D upload of the slide (h2d_bytes_total), K batches, and per step the D2H read of labels+coords",
                 "h2d_bytes_total": uploaded, "slide_bytes": slide_bytes, "host_memory_pinned": bool(host_slide.pinned), "seconds": e2e_s,
                 "steady_state": {"value": steady_value, "unit": "patches/s", "note": "the same call repeated with the slide already resident"},
                 "features_to_host": {"value": kh * BATCH / e2e_host_s, "unit": "patches/s", "d2h_bytes_per_step": d2h + h_feats.numel() * mode["esize"]}},

@@ -25,7 +25,7 @@ import torch
 from torch.utils.data import IterableDataset
 
 from .. import geometry, ops
-from ..slide import Patch, PinnedSlide, layer_to_device, open_slide, upload_rects
+from ..slide import Patch, PinnedSlide, layer_to_device, open_slide, tile_spans, upload_rects
 
 
 class RegionAnnotation:
@@ -178,7 +178,8 @@ class AnnoRegionRndSampler:
     def __init__(self, img_anno_paths, layer: int, patch_size: int, region_intersection: float = 0.75,
                  patches_from_one_region: int = 4, region_area_influence: float = 0.5, classes: list[str] = None,
                  one_image_for_batch: bool = False, *, seed: int = 0, device="cuda", out_dtype=torch.float32, out_layout: str = "NHWC",
-                 flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = True):
+                 flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = None,
+                 prefetch_bytes: int = 5 << 29, prefetch_batches: int = 32):
         self.img_anno_paths = img_anno_paths
         self.layer = layer
         self.patch_size = patch_size
@@ -201,7 +202,8 @@ class AnnoRegionRndSampler:
         self._tables, self._flat_regions, names = build_tables(images, layer, region_area_influence, None, one_image_for_batch, device)
         assert names == self.classes
         self._slides = [None] * len(img_anno_paths)
-        self._sparse_upload = sparse_upload    # PinnedSlide sources: upload only the tiles that intersect annotated regions
+        self._prefetch_bytes, self._prefetch_batches = int(prefetch_bytes), int(prefetch_batches)   # torch_generator: features per prefetch group
+        self._sparse_upload = sparse_upload    # PinnedSlide sources: upload only the tiles annotated regions can reach (None = when < 1/5 of the layer)
         self.uploaded_bytes = 0                # bytes copied host -> device for pinned sources so far
         self._slot_cursor = 0
         self._producer = None          # CUDA stream the gathers of torch_generator's prefetch groups run on
@@ -248,10 +250,19 @@ class AnnoRegionRndSampler:
     def _slide(self, j: int):
         if self._slides[j] is None:
             with self._sources[j] as psim:
-                if self._sparse_upload and isinstance(psim, PinnedSlide) and psim.y_origin == 0 and psim.rows == psim.height:
+                sparse = self._sparse_upload
+                if sparse is not False and isinstance(psim, PinnedSlide) and psim.y_origin == 0 and psim.rows == psim.height:
+                    rects = self._reachable_rects(j)
+                    if sparse is None:
+                        # measured on a B200 box: the strided (2-D) copies of dh_upload_rects run at ~13 GB/s, one contiguous copy of
+                        # the layer at ~53 GB/s -> the sparse path pays off when less than ~1/5 of the layer is reachable
+                        spans = tile_spans(rects, psim.height, psim.width, psim.pitch)
+                        frac = float(((spans[:, 1] - spans[:, 0]) * (spans[:, 3] - spans[:, 2])).sum()) / max(psim.nbytes, 1) if len(spans) else 0.0
+                        sparse = frac < 0.2
+                if sparse is True and isinstance(psim, PinnedSlide) and psim.y_origin == 0 and psim.rows == psim.height:
                     # host-resident slide: only the tiles a region can reach travel over PCIe
                     psim._assert_layer(self.layer)
-                    self._slides[j], n = upload_rects(psim, self._reachable_rects(j), self._device)
+                    self._slides[j], n = upload_rects(psim, rects, self._device)
                     self.uploaded_bytes += n
                 else:
                     self._slides[j] = layer_to_device(psim, self.layer, self._device)
@@ -326,7 +337,7 @@ class AnnoRegionRndSampler:
         per_batch = batch_size * ps * ps * 3 * torch.empty((), dtype=self._out_dtype).element_size()
         ahead = batches_per_worker
         if chunk % self.patches_from_one_region == 0:
-            ahead = max(1, min(32, (5 << 29) // max(per_batch, 1)) // batches_per_worker) * batches_per_worker
+            ahead = max(1, min(self._prefetch_batches, self._prefetch_bytes // max(per_batch, 1)) // batches_per_worker) * batches_per_worker
         groups = self._split_chunks(n_batches, ahead)
         on_gpu = torch.device(self._device).type == "cuda"
         cur = torch.cuda.current_stream(self._device) if on_gpu else None
