@@ -4,9 +4,9 @@
 Default workload = BASELINE.json configs[1]: `examples.sample_annotated_rnd --torch` -- random 224x224 patches inside
 50 synthetic annotation polygons on a 32768 x 32768 synthetic slide, batch 256, fp32 NHWC features in [0,1] + int64
 labels + (y,x) coords, exactly what AnnoRegionRndSampler.torch_generator yields. One step = one batch of 256 patches.
-The device pipeline prefetches CHUNK (16) batches per pair of launches:
-    dh_region_sample (Philox draws + exact clip-area acceptance, 16 x 256 slots)  ->  dh_gather_normalize (16 x 256 patches)
-so a K-step run is ceil(K/16) chunk pairs (the last one partial) and every batch is a contiguous slice of the chunk buffer.
+The device pipeline prefetches CHUNK (32) batches per pair of launches, like AnnoRegionRndSampler.torch_generator:
+    dh_region_sample (Philox draws + exact clip-area acceptance, 32 x 256 slots)  ->  dh_gather_normalize (32 x 256 patches)
+so a K-step run is ceil(K/32) chunk pairs (the last one partial) and every batch is a contiguous slice of the chunk buffer.
 
   value     patches/s over all ranks, inputs (slide, polygon tables) resident in HBM, CUDA-event timed, max over ranks
   e2e       the same metric through the public Python API (AnnoRegionRndSampler.torch_generator) starting from a slide in
@@ -43,7 +43,7 @@ PATCH_IN = PS * PS * 3                 # 150 528 B uint8 read per patch
 SLIDE_HW = (32768, 32768)
 N_POLY = 50
 BATCH = 256
-CHUNK = 16                             # batches prefetched per (sample, gather) launch pair
+CHUNK = 32                             # batches prefetched per (sample, gather) launch pair
 K_PER_REGION = 4
 RI = 0.75
 
@@ -152,7 +152,7 @@ CONFIG = {
     "workload": "examples.sample_annotated_rnd --torch (BASELINE configs[1]): 224x224 random patches inside 50 synthetic polygons, "
                 "32768x32768 uint8 RGB slide, batch 256, patches_from_one_region 4, region_intersection 0.75, fp32 NHWC /255",
     "slide": list(SLIDE_HW), "patch": PS, "batch": BATCH, "polygons": N_POLY, "chunk_batches": CHUNK,
-    "l2_policy": "inputs larger than L2: random patches of a 3.2 GB slide; every gather launch writes a 2.5 GB chunk (16 batches of "
+    "l2_policy": "inputs larger than L2: random patches of a 3.2 GB slide; every gather launch writes a 4.9 GB chunk (32 batches of "
                  "154 MB) into one of two alternating buffers (126 MB L2)",
 }
 
@@ -237,7 +237,7 @@ def reference_arm(args):
 MODES = {
     # BASELINE configs[1]
     "annotated_rnd": dict(batch=BATCH, chunk=CHUNK, dtype="f32", torch_dtype="float32", layout="NHWC", dcode=0, lcode=0, esize=4, flips=False,
-                          config=CONFIG, kernel="gather_tma_kernel<float, NHWC, /255> (dh_gather_normalize), one launch per 16-batch chunk"),
+                          config=CONFIG, kernel="gather_tma_kernel<float, NHWC, /255> (dh_gather_normalize), one launch per 32-batch chunk"),
     # BASELINE configs[4]: the input pipeline of models.patch_cls_simple.train at 8k patches/step, bf16 NCHW with the batch-level
     # random H/V flips of train.py:71-81 fused into the gather
     "train_input": dict(batch=8192, chunk=1, dtype="bf16", torch_dtype="bfloat16", layout="NCHW", dcode=1, lcode=1, esize=2, flips=True,
@@ -428,7 +428,9 @@ def ours(args):
     traffic = None
     tf = ROOT / "profiles" / "gather_traffic.json"
     if tf.exists() and args.workload == "annotated_rnd":               # ncu capture of exactly this kernel / launch shape
-        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch")
+        cap = json.loads(tf.read_text())
+        if int(cap.get("algorithmic_bytes_per_launch", 0)) == alg_bytes_batch * CHUNK:      # same launch shape as the timed kernel
+            traffic = cap.get("dram_bytes_per_launch")
     slide_bytes = host_slide.nbytes
     uploaded = int(api.uploaded_bytes)                                # what actually travelled (the whole layer unless < 1/5 of it is annotated)
     line = {

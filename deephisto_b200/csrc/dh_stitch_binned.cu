@@ -107,8 +107,8 @@ __device__ __forceinline__ uint8_t first_argmax(const float* v, int n) {
 }
 
 // ---- tile kernels ------------------------------------------------------------------------------------------------------
-// VEC units per lane. CELL = false: units are floats of a map row, output = sum map. CELL = true (VEC == 1): units are cells,
-// outputs = argmax byte and / or count. STAGED: the logits of the tile's patches sit in shared memory (n <= kBinMaxN).
+// VEC units per lane. CELL = false: units are floats of a map row, output = sum map. CELL = true: units are cells (VEC = 1 or 4
+// cells per lane), outputs = argmax byte and / or count. STAGED: the logits of the tile's patches sit in shared memory (n <= kBinMaxN).
 //
 // Rare path: more than kBinCap patches over one tile -> sorted list in global memory, footprints recomputed on the fly.
 template <int VEC, bool CELL>
@@ -124,21 +124,22 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
         sorted[beg + rank] = v;
     }
     __syncwarp();
-  for (int gi = 0; gi < g.G; ++gi) {
-    const int64_t ubase = tx * g.TW + (int64_t)gi * 32 * VEC + (int64_t)lane * VEC;
+  constexpr int W1 = CELL ? 1 : VEC;                       // units a lane handles per pass (the fast kernel's lane-to-unit map does not matter here)
+  for (int gi = 0; gi < g.TW / (32 * W1); ++gi) {
+    const int64_t ubase = tx * g.TW + (int64_t)gi * 32 * W1 + (int64_t)lane * W1;
     const bool active = ubase < g.units_per_row;
-    int cls[VEC];
+    int cls[W1];
     int c = (int)(ubase % n);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) { cls[k] = c; c = c + 1 == n ? 0 : c + 1; }
+    for (int k = 0; k < W1; ++k) { cls[k] = c; c = c + 1 == n ? 0 : c + 1; }
     const int R0 = (int)(ty * g.TH);
     const int R1 = (int)((int64_t)R0 + g.TH < g.rows ? R0 + g.TH : g.rows);
     const bool want_vals = CELL ? argmax_map != nullptr : true;
     int r = R0;
     while (r < R1) {
-        float acc[CELL ? kBinMaxN : VEC];
+        float acc[CELL ? kBinMaxN : W1];
 #pragma unroll
-        for (int k = 0; k < (CELL ? kBinMaxN : VEC); ++k) acc[k] = 0.f;
+        for (int k = 0; k < (CELL ? kBinMaxN : W1); ++k) acc[k] = 0.f;
         uint32_t hits = 0;
         int next = R1;
         for (int j = 0; j < L; ++j) {
@@ -149,7 +150,7 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
             if (f.r1 <= r) continue;                                        // ended above
             next = f.r1 < next ? f.r1 : next;
             const int64_t lo = f.u0 - ubase, hi = f.u1 - ubase;             // covered units relative to the lane's first unit
-            if (hi <= 0 || lo >= VEC) continue;
+            if (hi <= 0 || lo >= W1) continue;
             const float* lg = logits + (int64_t)id * n;
             if constexpr (CELL) {
                 ++hits;
@@ -160,7 +161,7 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k)
+                for (int k = 0; k < W1; ++k)
                     if (k >= lo && k < hi) acc[k] += __ldg(lg + cls[k]);
             }
         }
@@ -176,7 +177,7 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
                 float* o = sum_map + (int64_t)r * g.units_per_row + ubase;
                 for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) o[k] = acc[k];
+                    for (int k = 0; k < W1; ++k) o[k] = acc[k];
                 }
             }
         }
@@ -255,12 +256,14 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
 
     int r = R0;
     while (r < R1) {
-        float acc[G][CELL ? kBinMaxN : VEC];
+        float acc[CELL ? VEC : G][CELL ? kBinMaxN : VEC];   // sum mode: [group][float]; cell mode: [cell][class]
 #pragma unroll
-        for (int gi = 0; gi < G; ++gi)
+        for (int gi = 0; gi < (CELL ? VEC : G); ++gi)
 #pragma unroll
             for (int k = 0; k < (CELL ? kBinMaxN : VEC); ++k) acc[gi][k] = 0.f;
-        uint32_t hits = 0;
+        uint32_t hits[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) hits[k] = 0;
         int next = R1;
         for (int c0 = 0; c0 < L; c0 += 32) {
             // lane j looks at patch c0 + j: does it cover row r, and where is its next row boundary? (ballot + warp minimum)
@@ -277,12 +280,17 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
                 const int lo = cu.x - ub, hi = cu.y - ub;     // covered units relative to the lane's first unit
                 // adding +0.0f is the identity here: a sum that starts at +0.0f can never be -0.0f
                 if constexpr (CELL) {
-                    const bool cov = lo <= 0 && hi > 0;
-                    hits += cov;
+                    bool cov[VEC];
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) { cov[k] = k >= lo && k < hi; hits[k] += cov[k]; }
                     if (want_vals) {
 #pragma unroll
                         for (int q = 0; q < kBinMaxN; ++q)
-                            if (q < n) acc[0][q] += cov ? s_lg[jj * n + q] : 0.f;
+                            if (q < n) {
+                                const float v = s_lg[jj * n + q];     // one broadcast read per class, used by all cells of the lane
+#pragma unroll
+                                for (int k = 0; k < VEC; ++k) acc[k][q] += cov[k] ? v : 0.f;
+                            }
                     }
                 } else {
                     const float* lg = STAGED ? s_lg + jj * n : logits + (int64_t)s_ids[jj] * n;
@@ -297,12 +305,19 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
             }
         }
         if constexpr (CELL) {
-            if (ub < g.units_per_row) {
-                const uint8_t am = want_vals ? first_argmax(acc[0], n) : (uint8_t)0;
+            if (ub < g.units_per_row) {                         // VEC == 4: dw % 4 == 0 and aligned maps (host check) -> one vector store per row
+                uint8_t am[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) am[k] = want_vals ? first_argmax(acc[k], n) : (uint8_t)0;
                 int64_t o = (int64_t)r * g.units_per_row + ub;
                 for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
-                    if (argmax_map) argmax_map[o] = am;
-                    if (count_map) count_map[o] = hits;
+                    if constexpr (VEC == 4) {
+                        if (argmax_map) *reinterpret_cast<uchar4*>(argmax_map + o) = make_uchar4(am[0], am[1], am[2], am[3]);
+                        if (count_map) *reinterpret_cast<uint4*>(count_map + o) = make_uint4(hits[0], hits[1], hits[2], hits[3]);
+                    } else {
+                        if (argmax_map) argmax_map[o] = am[0];
+                        if (count_map) count_map[o] = hits[0];
+                    }
                 }
             }
         } else {
@@ -424,8 +439,8 @@ extern "C" DH_API int dh_stitch_binned_set_tile_rows(int rows) {
 extern "C" DH_API int64_t dh_stitch_binned_scratch_bytes(int64_t P, int ps, int d, int n, int64_t rows, int64_t dw) {
     if (P <= 0 || ps <= 0 || d <= 0 || n <= 0 || rows <= 0 || dw <= 0) return 256;
     int64_t need = 0;
-    for (int mode = 0; mode < 3; ++mode) {  // sum (16-byte stores), sum (scalar stores), cell
-        BinGeom g = make_geom(mode == 2, mode == 0 ? 4 : 1, ps, d, n, rows, dw, 0);
+    for (int mode = 0; mode < 4; ++mode) {  // sum (16-byte stores), sum (scalar stores), cell, cell x 4
+        BinGeom g = make_geom(mode >= 2, mode == 0 || mode == 3 ? 4 : 1, ps, d, n, rows, dw, 0);
         BinScratch s;
         carve_bin(g, P, nullptr, s);
         need = s.total_bytes > need ? s.total_bytes : need;
@@ -466,8 +481,11 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
     }
     uint8_t* cell_argmax = argmax_u8 && staged ? argmax_u8 : nullptr;
     if (count_map || cell_argmax) {
-        const BinGeom g = make_geom(true, 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
-        rc = run_binned<1, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
+        // 4 cells per lane (uchar4 / uint4 stores) when the rows keep the vectors aligned
+        const bool c4 = dw % 4 == 0 && reinterpret_cast<uintptr_t>(cell_argmax) % 4 == 0 && reinterpret_cast<uintptr_t>(count_map) % 16 == 0;
+        const BinGeom g = make_geom(true, c4 ? 4 : 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
+        rc = c4 ? run_binned<4, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
+                : run_binned<1, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
         if (rc != DH_OK) return rc;
     }
     if (argmax_u8 && !cell_argmax) rc = dh_stitch_finalize(sum_map, nullptr, rows * dw, n, nullptr, argmax_u8, stream);

@@ -179,7 +179,7 @@ class AnnoRegionRndSampler:
                  patches_from_one_region: int = 4, region_area_influence: float = 0.5, classes: list[str] = None,
                  one_image_for_batch: bool = False, *, seed: int = 0, device="cuda", out_dtype=torch.float32, out_layout: str = "NHWC",
                  flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = None,
-                 prefetch_bytes: int = 5 << 29, prefetch_batches: int = 32):
+                 prefetch_bytes: int = 5 << 30, prefetch_batches: int = 32):
         self.img_anno_paths = img_anno_paths
         self.layer = layer
         self.patch_size = patch_size
@@ -329,7 +329,8 @@ class AnnoRegionRndSampler:
         # Coordinates are counter-based (Philox keyed by the global slot index), so several worker-sized chunks can be drawn by
         # ONE launch with identical results -- as long as the groups of k slots do not straddle a chunk boundary. The features of
         # all prefetched batches are then written by ONE gather launch (short launches cannot fill HBM: profiles/r01_gather.md);
-        # every yielded batch is a contiguous slice of that buffer. Prefetch depth: <= 32 batches and <= ~2.5 GB of features.
+        # every yielded batch is a contiguous slice of that buffer. Prefetch depth: <= 32 batches and <= ~5 GB of features
+        # (measured through the bench's consumer loop: 6.7-7.0 M patches/s with 16-batch groups, 7.55 M with 32; profiles/r01_gather.md).
         # The launches run on a PRODUCER STREAM, one prefetch group ahead of the batches being yielded: the consumer's own work on
         # the current stream (its CNN step, its read-back of labels) overlaps with the sampling of the next group instead of
         # queueing behind it -- the role the reference gives to its ProcessPoolExecutor workers (:721-738).
