@@ -482,7 +482,10 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
     uint8_t* cell_argmax = argmax_u8 && staged ? argmax_u8 : nullptr;
     if (count_map || cell_argmax) {
         // 4 cells per lane (uchar4 / uint4 stores) when the rows keep the vectors aligned
-        const bool c4 = dw % 4 == 0 && reinterpret_cast<uintptr_t>(cell_argmax) % 4 == 0 && reinterpret_cast<uintptr_t>(count_map) % 16 == 0;
+        // -- for footprints at least ~100 cells wide; narrower ones make a 128-cell tile mostly foreign patches (measured: d = 1 / 2 are
+        // 1.9x / 1.3x faster with 4 cells per lane, d = 4 / 16 1.3x / 1.7x slower; profiles/r01_stitch.md)
+        const bool c4 = ps / d >= 96 && dw % 4 == 0 && reinterpret_cast<uintptr_t>(cell_argmax) % 4 == 0 &&
+                        reinterpret_cast<uintptr_t>(count_map) % 16 == 0;
         const BinGeom g = make_geom(true, c4 ? 4 : 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
         rc = c4 ? run_binned<4, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
                 : run_binned<1, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
