@@ -555,7 +555,7 @@ def ours_predict(args):
     sampler.band_slide = lambda y0, y1: (band, y_off)
     ipp = pfp.ImagePredictorPatched(src, sampler, pred, anno, layer=1, downscale=16, device=dev, cnn_batch=args.cnn_batch,
                                     stream_bands=False)           # `value`: the band stays resident in HBM across steps
-    K, Wm = args.steps, max(1, min(args.warmup, 2))
+    K, Wm = args.steps, max(1, args.warmup)
 
     def step():
         return ipp.process_device(rank=rank, world=world)["argmax"] if world > 1 else ipp.dense_band_local(0, 1)["argmax_band"]
@@ -688,7 +688,7 @@ def main():
         # batch 64; train.py:142: 200 steps per epoch): the slide is uploaded once and stays resident for the whole job
         args.steps = {"predict": 3, "train_input": 40}.get(args.workload, 2500)
     if args.warmup is None:
-        args.warmup = {"predict": 1, "train_input": 4}.get(args.workload, 32)
+        args.warmup = {"predict": 3, "train_input": 4}.get(args.workload, 32)
     args.warmup = max(args.warmup, 3) if args.workload != "predict" else args.warmup
     if args.cpu_leg:
         emit(cpu_leg_bounded(args.cpu_budget))
