@@ -394,7 +394,8 @@ def ours(args):
 
     def new_api(src, seed):
         return AnnoRegionRndSampler([(src, polys)], layer=1, patch_size=PS, patches_from_one_region=K_PER_REGION, one_image_for_batch=True,
-                                    seed=seed, device=dev, verbose=False, out_dtype=out_dtype, out_layout=mode["layout"], flips=mode["flips"])
+                                    seed=seed, device=dev, verbose=False, out_dtype=out_dtype, out_layout=mode["layout"], flips=mode["flips"],
+                                    shard_upload=True if world > 1 and isinstance(src, PinnedSlide) else None)
 
     warm = new_api(source, 1 + rank)
     run_api(warm, max(Wm, CHUNK))                                    # warm-up of the API path (allocator, kernels), resident slide
@@ -445,7 +446,9 @@ def ours(args):
                      "kernel_ms_per_batch": gather_total_ms / max(sum(nb for _, nb in gather_ms), 1), "frac_of_nominal_8TBs": achieved / 8000.0},
         "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": uploaded / K, "d2h_bytes_per_step": d2h,
                 "api": f"AnnoRegionRndSampler.torch_generator(batch_size={BATCH}, n_batches=K) over a slide in pinned host memory: the timed region "
-                       "contains the one-time H2D upload of the slide (h2d_bytes_total), K batches, and per step the D2H read of labels+coords",
+                       "contains the one-time H2D upload of the slide (h2d_bytes_total per rank), K batches, and per step the D2H read of labels+coords"
+                       + ("; the ranks hold the same slide, so each uploads 1/world of its rows over its own PCIe link and one NCCL all-gather over "
+                          "NVLink replicates them (slide.sharded_upload)" if world > 1 else ""),
                 "h2d_bytes_total": uploaded, "slide_bytes": slide_bytes, "host_memory_pinned": bool(host_slide.pinned), "seconds": e2e_s,
                 "steady_state": {"value": steady_value, "unit": "patches/s", "note": "the same call repeated with the slide already resident"},
                 "features_to_host": {"value": kh * BATCH / e2e_host_s, "unit": "patches/s", "d2h_bytes_per_step": d2h + h_feats.numel() * mode["esize"]}},

@@ -75,7 +75,11 @@ class DeviceSlide:
         return s
 
     def to_numpy(self) -> np.ndarray:
-        return self.storage.view(self.H, self.pitch)[:, : 3 * self.W].cpu().numpy().reshape(self.H, self.W, 3)
+        return self.rows2d()[:, : 3 * self.W].cpu().numpy().reshape(self.H, self.W, 3)
+
+    def rows2d(self) -> torch.Tensor:
+        """uint8 [H, pitch] view of the rows (the storage may be longer than H * pitch: padded shards of a collective upload)."""
+        return self.storage[: self.H * self.pitch].view(self.H, self.pitch)
 
     @property
     def device(self):

@@ -25,7 +25,7 @@ import torch
 from torch.utils.data import IterableDataset
 
 from .. import geometry, ops
-from ..slide import Patch, PinnedSlide, layer_to_device, open_slide, tile_spans, upload_rects
+from ..slide import Patch, PinnedSlide, layer_to_device, open_slide, sharded_upload, tile_spans, upload_rects
 
 
 class RegionAnnotation:
@@ -178,7 +178,7 @@ class AnnoRegionRndSampler:
     def __init__(self, img_anno_paths, layer: int, patch_size: int, region_intersection: float = 0.75,
                  patches_from_one_region: int = 4, region_area_influence: float = 0.5, classes: list[str] = None,
                  one_image_for_batch: bool = False, *, seed: int = 0, device="cuda", out_dtype=torch.float32, out_layout: str = "NHWC",
-                 flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = None,
+                 flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = None, shard_upload=None,
                  prefetch_bytes: int = 5 << 30, prefetch_batches: int = 32):
         self.img_anno_paths = img_anno_paths
         self.layer = layer
@@ -204,6 +204,8 @@ class AnnoRegionRndSampler:
         self._slides = [None] * len(img_anno_paths)
         self._prefetch_bytes, self._prefetch_batches = int(prefetch_bytes), int(prefetch_batches)   # torch_generator: features per prefetch group
         self._sparse_upload = sparse_upload    # PinnedSlide sources: upload only the tiles annotated regions can reach (None = when < 1/5 of the layer)
+        self._shard_upload = shard_upload      # True / a process group: COLLECTIVE ingestion of pinned slides (slide.sharded_upload); every rank
+        #                                        of the group must then iterate the sampler (first use of an image is a collective call)
         self.uploaded_bytes = 0                # bytes copied host -> device for pinned sources so far
         self._slot_cursor = 0
         self._producer = None          # CUDA stream the gathers of torch_generator's prefetch groups run on
@@ -250,6 +252,14 @@ class AnnoRegionRndSampler:
     def _slide(self, j: int):
         if self._slides[j] is None:
             with self._sources[j] as psim:
+                whole_pinned = isinstance(psim, PinnedSlide) and psim.y_origin == 0 and psim.rows == psim.height
+                if self._shard_upload is not None and whole_pinned:
+                    # data-parallel ranks with the same host slide: 1/world of the rows over each rank's PCIe link + one NVLink all-gather
+                    psim._assert_layer(self.layer)
+                    group = None if self._shard_upload is True else self._shard_upload
+                    self._slides[j], n = sharded_upload(psim, self._device, group)
+                    self.uploaded_bytes += n
+                    return self._slides[j]
                 sparse = self._sparse_upload
                 if sparse is not False and isinstance(psim, PinnedSlide) and psim.y_origin == 0 and psim.rows == psim.height:
                     rects = self._reachable_rects(j)

@@ -112,7 +112,7 @@ class SyntheticSlide:
         self._assert_layer(layer)
         (y0, x0), (y1, x1) = p0, p1
         s = self.device_slide()
-        return s.storage.view(s.H, s.pitch)[y0:y1, 3 * x0 : 3 * x1].cpu().numpy().reshape(y1 - y0, x1 - x0, 3)
+        return s.rows2d()[y0:y1, 3 * x0 : 3 * x1].cpu().numpy().reshape(y1 - y0, x1 - x0, 3)
 
 
 class PinnedSlide:
@@ -280,6 +280,33 @@ def upload_rects(host: "PinnedSlide", rects, device="cuda", tile: int = 512):
     return DeviceSlide(storage, host.height, host.width, host.pitch), nbytes
 
 
+def sharded_upload(host: "PinnedSlide", device="cuda", group=None):
+    """Collective slide ingestion for data-parallel sampling: every rank of `group` holds the same layer in host memory and needs
+    it resident. Each rank copies only its 1/world share of the rows over ITS PCIe link and one all-gather over NVLink replicates
+    the shares (in place: a rank's share sits at its offset of the full buffer) -- instead of `world` full uploads competing for
+    the host's memory and PCIe bandwidth. Returns (DeviceSlide, bytes this rank copied from the host). Works with NCCL (CUDA) and
+    gloo (CPU tensors; used by the world_size-2 CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    if host.y_origin != 0 or host.rows != host.height:
+        raise ValueError("sharded_upload needs a PinnedSlide holding the whole layer")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = -(-host.rows // world)                                   # rows per rank; the last shares are padded
+    pitch = host.pitch
+    storage = torch.empty(per * world * pitch, dtype=torch.uint8, device=device)
+    a, b = min(host.rows, rank * per), min(host.rows, (rank + 1) * per)
+    mine = storage[rank * per * pitch : (rank + 1) * per * pitch]
+    if b > a:
+        mine[: (b - a) * pitch].copy_(host.host[a * pitch : b * pitch], non_blocking=True)
+    if (b - a) < per:
+        mine[(b - a) * pitch :].zero_()
+    dist.all_gather_into_tensor(storage, mine, group=group)
+    if storage.is_cuda:
+        return DeviceSlide(storage, host.rows, host.width, pitch), (b - a) * pitch
+    return storage[: host.rows * pitch], (b - a) * pitch          # CPU (gloo) callers get the assembled bytes
+
+
 class DeviceSlideSource:
     """PSImage duck type over a slide that already lives in HBM (layer 1 only)."""
 
@@ -308,7 +335,7 @@ class DeviceSlideSource:
         self._assert_layer(layer)
         (y0, x0), (y1, x1) = p0, p1
         s = self.dev
-        return s.storage.view(s.H, s.pitch)[y0:y1, 3 * x0 : 3 * x1].cpu().numpy().reshape(y1 - y0, x1 - x0, 3)
+        return s.rows2d()[y0:y1, 3 * x0 : 3 * x1].cpu().numpy().reshape(y1 - y0, x1 - x0, 3)
 
 
 def layer_to_device(src, layer: int, device="cuda") -> DeviceSlide:

@@ -134,3 +134,50 @@ def test_band_assembly_gloo_world2(tmp_path):
         outs.append(out)
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in out, out[-2000:]
+
+
+SHARD_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from deephisto_b200.slide import PinnedSlide, sharded_upload
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+for H, W in ((100, 37), (7, 5), (2, 64)):                     # ragged shares: 100 rows over 3 ranks, fewer rows than ranks
+    a = np.random.default_rng(H).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    host = PinnedSlide.from_numpy(a)
+    full, copied = sharded_upload(host, device="cpu")
+    per = -(-H // world)
+    assert copied == max(0, min(H, (rank + 1) * per) - min(H, rank * per)) * host.pitch
+    got = full.view(H, host.pitch)[:, : 3 * W].numpy().reshape(H, W, 3)
+    assert np.array_equal(got, a)
+    t = torch.tensor([copied]); dist.all_reduce(t)
+    assert int(t.item()) == host.nbytes                       # every byte travelled exactly once
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_sharded_slide_upload_gloo_world3(tmp_path):
+    """slide.sharded_upload: each rank copies 1/world of the rows from its host copy, one all-gather replicates them (the NCCL path
+    of the multi-GPU sampling e2e); here over gloo with CPU tensors, including shares that are ragged or empty."""
+    import subprocess
+
+    script = tmp_path / "shard_worker.py"
+    script.write_text(SHARD_WORKER)
+    port = _free_port()
+    procs = []
+    for r in range(3):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="3", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(ROOT)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        outs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in out, out[-2000:]
