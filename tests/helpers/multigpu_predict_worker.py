@@ -45,6 +45,19 @@ for (H, W, stride, d) in [(3000, 2100, 112, 16), (1777, 1300, 100, 4)]:
     a = pfp.ImagePredictorPatched(None, lazy, pred, anno, layer=1, downscale=d, device=dev, cnn_batch=64).process(rank=rank, world=world)
     b = pfp.ImagePredictorPatched(None, full_s, pred, anno, layer=1, downscale=d, device=dev, cnn_batch=64).process()
     assert a.shape == b.shape and (a != b).mean() < 0.01, (a != b).mean()
+# collective slide ingestion (slide.sharded_upload): 1/world of the rows per rank over PCIe, one NCCL all-gather; ragged shares
+import numpy as np  # noqa: E402
+
+from deephisto_b200.slide import PinnedSlide, sharded_upload  # noqa: E402
+
+for (H, W) in [(1000, 333), (world + 1, 40)]:
+    a = np.random.default_rng(H).integers(0, 256, (H, W, 3), dtype=np.uint8)
+    host = PinnedSlide.from_numpy(a)
+    dev_slide, copied = sharded_upload(host, dev)
+    assert np.array_equal(dev_slide.to_numpy(), a), f"rank {rank}: sharded upload differs from the host slide"
+    t = torch.tensor([copied], device=dev)
+    dist.all_reduce(t)
+    assert int(t.item()) == host.nbytes
 dist.barrier()
 dist.destroy_process_group()
 print(f"MULTIGPU OK rank {rank}/{world}")
