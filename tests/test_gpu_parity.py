@@ -577,3 +577,64 @@ def test_cover_sampler_resume_from_saved_state(ops):
         cb, nb = b.next_coords()
         assert torch.equal(ca, cb) and int(na.item()) == int(nb.item())
     assert torch.equal(a.accum, b.accum)
+
+
+def test_stitch_binned_random_shapes_vs_oracle(ops):
+    """Randomised shapes (slide size, patch size, downscale, class count, list length, overhanging and duplicated origins, row
+    bands): every output of dh_stitch_binned is bit-identical to the reference loop."""
+    rng = np.random.default_rng(2024)
+    for trial in range(24):
+        ps = int(rng.choice([32, 50, 64, 100, 224]))
+        d = int(rng.choice([1, 2, 3, 4, 7, 8, 16, 32]))
+        if d > ps:
+            d = ps
+        n = int(rng.choice([1, 2, 3, 5, 8, 9, 16]))
+        H, W = int(rng.integers(ps, 900)), int(rng.integers(ps, 900))
+        if (H // d) * (W // d) * n > 6_000_000:
+            H, W = max(ps, H // 3), max(ps, W // 3)
+        P = int(rng.choice([0, 1, 7, 60, 300]))
+        coords = np.stack([rng.integers(0, H, P), rng.integers(0, W, P)], 1).astype(np.int32)       # origins anywhere: footprints get clipped
+        if P > 10:
+            coords[3:6] = coords[2]                                                                # duplicated origins
+        logits = (rng.standard_normal((P, n)) * 2).astype(np.float32)
+        want, wcnt, wam = ostitch.stitch(logits, coords, H, W, ps, d)
+        dh, dw = H // d, W // d
+        if dh == 0 or dw == 0:
+            continue
+        lg, cd = torch.from_numpy(logits).cuda(), torch.from_numpy(coords).cuda()
+        s, c, am = ops.stitch_binned(lg, cd, ps, d, dh, dw, want_count=True, want_argmax=True)
+        tag = (trial, H, W, ps, d, n, P)
+        assert np.array_equal(bits(s), want.view(np.int32)), tag
+        assert np.array_equal(c.cpu().numpy().astype(np.int64), wcnt), tag
+        assert np.array_equal(am.cpu().numpy().astype(np.int64), wam), tag
+        r0 = int(rng.integers(0, dh))
+        r1 = int(rng.integers(r0, dh)) + 1
+        sb, cb, ab = ops.stitch_binned(lg, cd, ps, d, r1 - r0, dw, row_offset=r0, want_count=True, want_argmax=True)
+        assert torch.equal(sb, s[r0:r1]) and torch.equal(cb, c[r0:r1]) and torch.equal(ab, am[r0:r1]), tag
+
+
+def test_stitch_binned_and_upload_error_reporting(ops):
+    from deephisto_b200 import _lib
+    from deephisto_b200.slide import PinnedSlide, upload_rects
+
+    lib = _lib.require_device()
+    lg = torch.zeros((4, 11), device="cuda")
+    cd = torch.zeros((4, 2), dtype=torch.int32, device="cuda")
+    with pytest.raises(_lib.DeepHistoError, match="needs the sum map"):
+        ops.stitch_binned(lg, cd, 64, 16, 8, 8, want_sum=False, want_argmax=True)            # 11 classes: class map through the sum map only
+    out = torch.zeros((8, 8, 11), device="cuda")
+    tiny = torch.zeros(256, dtype=torch.uint8, device="cuda")
+    rc = lib.dh_stitch_binned(lg.data_ptr(), cd.data_ptr(), 4, 64, 16, 11, out.data_ptr(), None, None, 8, 8, 0, tiny.data_ptr(), 16,
+                              torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and "scratch too small" in _lib.last_error()
+    with pytest.raises(ValueError):
+        ops.stitch_binned(lg, cd[:3], 64, 16, 8, 8)
+    # dh_upload_rects: rectangles must lie inside the slide; an empty list is a no-op
+    host = PinnedSlide.from_numpy(synth.synth_slide(64, 48, 1))
+    dev, n = upload_rects(host, [])
+    assert n == 0 and int(dev.storage.sum()) == 0
+    dev, n = upload_rects(host, [(0, 64, 0, 48)], tile=16)
+    assert n == host.nbytes and np.array_equal(dev.to_numpy(), synth.synth_slide(64, 48, 1))
+    bad = np.asarray([[0, 65, 0, 16]], dtype=np.int64)
+    rc = lib.dh_upload_rects(dev.storage.data_ptr(), 64, host.pitch, host.host.data_ptr(), 1, bad.ctypes.data, torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and "outside the slide" in _lib.last_error()
