@@ -16,10 +16,7 @@
 // incrementally by the accumulator update (a cell leaves the eligible set when its count reaches dense_level, joins the
 // non-zero set when it leaves 0), so a batch costs O(B * footprint + number of blocks), independent of the slide size:
 //   init (batch_index == 0, or dh_cover_init after restoring an accumulator): bitmask + block counts + non-zero count
-//   B  single block: exclusive scan of the block counts, top-up, partial Fisher-Yates of B ranks
-//   C  one warp per pick: rank -> k-th eligible cell -> jitter -> clamp -> coords                 (reads the state only)
-//   U  one warp per pick: accumulator += footprint, state transitions                              (after ALL picks are located)
-//   F  non-zero count -> nonzero_out
+//   batch: ONE launch of one block (cover_batch_kernel below): scan, top-up, Fisher-Yates, placement, accumulator update, count
 #include "dh_common.cuh"
 
 namespace dh {
@@ -61,16 +58,36 @@ __global__ void __launch_bounds__(256) cover_mask_kernel(const uint32_t* __restr
 
 __device__ __forceinline__ bool mask_test(const uint32_t* mask, uint32_t cell) { return (mask[cell >> 5] >> (cell & 31)) & 1u; }
 
-__global__ void __launch_bounds__(1024) cover_pick_kernel(CoverScratch s, int nb, int64_t cells, int B, uint32_t key0, uint32_t key1,
-                                                          uint32_t batch_lo, uint32_t batch_hi) {
+// One batch in ONE launch of a single 1024-thread block (the serial part -- the hash-chained Fisher-Yates -- is the critical path
+// anyway; what can run in parallel around it does: scan of the block counts, Philox draws, placement and accumulator update by 32
+// warps). Phases, separated by block barriers:
+//   scan   exclusive scan of the per-block eligible counts -> block_off, M
+//   top-up (thread 0, rare) random non-eligible cells until M + extra >= B                      full_samplers.py:107-112
+//   draw   all B Fisher-Yates draws j_i = i + randint(Mt - i) in parallel                        (Philox is counter based)
+//   chain  (thread 0) the swaps, kept in a shared-memory hash map -> ranks                       full_samplers.py:135-143
+//   place  one warp per pick: rank -> k-th eligible cell -> jitter -> clamp -> coords            full_samplers.py:144-153
+//   update one warp per pick: accumulator += footprint, state transitions                        full_samplers.py:86-92
+//   publish non-zero count
+// stop_when_full: when every coarse cell is already covered the launch changes nothing and reports the count, so a host may enqueue
+// several batches ahead of reading the count back (the reference stops at filled_ratio >= 1, full_samplers.py:263-274).
+__global__ void __launch_bounds__(1024) cover_batch_kernel(uint32_t* __restrict__ accum, CoverScratch s, int nb, int64_t cells, int64_t dw,
+                                                           int64_t H, int64_t W, int ps, int speedup, uint32_t dense_level, int B, uint32_t key0,
+                                                           uint32_t key1, uint32_t batch_lo, uint32_t batch_hi, int32_t* __restrict__ coords,
+                                                           uint32_t* __restrict__ nonzero_out, int stop_when_full) {
     __shared__ uint32_t carry;
     __shared__ uint32_t wtot[32];
     __shared__ uint32_t hkey[2 * kMaxBatch];
     __shared__ uint32_t hval[2 * kMaxBatch];
+    __shared__ uint32_t s_rank[kMaxBatch];  // first the draws j_i, then (in place) the ranks
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (stop_when_full && s.meta[2] >= (uint32_t)cells) {  // uniform: the state is only written by earlier launches
+        if (threadIdx.x == 0) *nonzero_out = s.meta[2];
+        return;
+    }
     if (threadIdx.x == 0) carry = 0;
+    for (int i = threadIdx.x; i < 2 * kMaxBatch; i += blockDim.x) hkey[i] = 0xffffffffu;
     __syncthreads();
-    // exclusive scan of block counts, 1024 at a time
+    // ---- scan: exclusive scan of block counts, 1024 at a time
     for (int b0 = 0; b0 < nb; b0 += 1024) {
         int b = b0 + threadIdx.x;
         uint32_t v = b < nb ? s.block_cnt[b] : 0u;
@@ -89,135 +106,134 @@ __global__ void __launch_bounds__(1024) cover_pick_kernel(CoverScratch s, int nb
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x != 0) return;
     const uint32_t M = carry;
-    s.block_off[nb] = M;
-    // top-up (full_samplers.py:107-112): add distinct random non-eligible cells until M + extra >= B
-    uint32_t n_extra = 0;
-    if (M < (uint32_t)B) {
-        uint32_t need = (uint32_t)B - M;
-        uint32_t t = 0;
-        while (n_extra < need) {
-            Philox4 p = philox4x32_10(t, batch_lo, batch_hi, kStreamCoverTop, key0, key1);
-            ++t;
-            uint32_t cell = (uint32_t)(((uint64_t)p.v[0] * (uint64_t)cells) >> 32);
-            if (mask_test(s.mask, cell)) continue;
-            bool dup = false;
-            for (uint32_t q = 0; q < n_extra; ++q) dup |= (s.extra[q] == cell);
-            if (dup) continue;
-            s.extra[n_extra++] = cell;
+    // ---- top-up: add distinct random non-eligible cells until M + extra >= B
+    if (threadIdx.x == 0) {
+        s.block_off[nb] = M;
+        uint32_t n_extra = 0;
+        if (M < (uint32_t)B) {
+            uint32_t need = (uint32_t)B - M;
+            uint32_t t = 0;
+            while (n_extra < need) {
+                Philox4 p = philox4x32_10(t, batch_lo, batch_hi, kStreamCoverTop, key0, key1);
+                ++t;
+                uint32_t cell = (uint32_t)(((uint64_t)p.v[0] * (uint64_t)cells) >> 32);
+                if (mask_test(s.mask, cell)) continue;
+                bool dup = false;
+                for (uint32_t q = 0; q < n_extra; ++q) dup |= (s.extra[q] == cell);
+                if (dup) continue;
+                s.extra[n_extra++] = cell;
+            }
         }
+        s.meta[0] = M;
+        s.meta[1] = n_extra;
+        wtot[0] = n_extra;
     }
-    s.meta[0] = M;
-    s.meta[1] = n_extra;
-    // partial Fisher-Yates over the virtual array a[i] = i of length Mt (swaps kept in a hash map)
-    const uint32_t Mt = M + n_extra;
-    const uint32_t hmask = 2 * kMaxBatch - 1;
-    for (uint32_t i = 0; i < 2 * kMaxBatch; ++i) hkey[i] = 0xffffffffu;
-    auto hget = [&](uint32_t k) -> uint32_t {
-        uint32_t h = (k * 0x9E3779B1u) & hmask;
-        while (hkey[h] != 0xffffffffu) {
-            if (hkey[h] == k) return hval[h];
-            h = (h + 1) & hmask;
-        }
-        return k;
-    };
-    auto hset = [&](uint32_t k, uint32_t v) {
-        uint32_t h = (k * 0x9E3779B1u) & hmask;
-        while (hkey[h] != 0xffffffffu && hkey[h] != k) h = (h + 1) & hmask;
-        hkey[h] = k;
-        hval[h] = v;
-    };
-    for (uint32_t i = 0; i < (uint32_t)B; ++i) {
+    __syncthreads();
+    const uint32_t Mt = M + wtot[0];
+    // ---- draw: j_i = i + randint(Mt - i) for every step of the partial Fisher-Yates over the virtual array a[i] = i
+    for (uint32_t i = threadIdx.x; i < (uint32_t)B; i += blockDim.x) {
         Philox4 p = philox4x32_10(i, batch_lo, batch_hi, kStreamCoverPick, key0, key1);
-        uint32_t j = i + bounded_u32(p.v[0], Mt - i);
-        uint32_t aj = hget(j), ai = hget(i);
-        s.ranks[i] = aj;
-        hset(j, ai);
+        s_rank[i] = i + bounded_u32(p.v[0], Mt - i);
     }
-}
-
-__global__ void __launch_bounds__(128) cover_place_kernel(uint32_t* __restrict__ accum, CoverScratch s, int nb, int64_t dh, int64_t dw,
-                                                          int64_t H, int64_t W, int ps, int speedup, int B, uint32_t key0, uint32_t key1,
-                                                          uint32_t batch_lo, uint32_t batch_hi, int32_t* __restrict__ coords) {
-    const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (slot >= B) return;
-    const uint32_t M = s.meta[0];
-    const uint32_t rank = s.ranks[slot];
-    uint32_t cell;
-    if (rank >= M) {
-        cell = s.extra[rank - M];
-    } else {
-        // block containing the rank: last b with block_off[b] <= rank
-        int lo = 0, hi = nb - 1;
-        while (lo < hi) {
-            int mid = (lo + hi + 1) >> 1;
-            if (s.block_off[mid] <= rank) lo = mid; else hi = mid - 1;
-        }
-        uint32_t local = rank - s.block_off[lo];
-        const uint32_t w0 = (uint32_t)lo * (kCellsPerBlock / 32);
-        // each lane owns 2 mask words of the block's 64; warp prefix over popcounts
-        uint32_t m0 = s.mask[w0 + 2 * lane], m1 = s.mask[w0 + 2 * lane + 1];
-        uint32_t pc = __popc(m0) + __popc(m1);
-        uint32_t inc = pc;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        uint32_t excl = inc - pc;
-        bool mine = (local >= excl) && (local < inc);
-        unsigned bal = __ballot_sync(0xffffffffu, mine);
-        int src = __ffs(bal) - 1;
-        uint32_t found = 0;
-        if (lane == src) {
-            uint32_t r = local - excl;
-            uint32_t word = m0, widx = w0 + 2 * lane;
-            if (r >= (uint32_t)__popc(m0)) { r -= __popc(m0); word = m1; widx += 1; }
-            // r-th set bit of word
-            for (uint32_t q = 0; q < r; ++q) word &= word - 1;
-            found = widx * 32 + (__ffs(word) - 1);
-        }
-        cell = __shfl_sync(0xffffffffu, found, src);
-    }
-    // full_samplers.py:144-153 jitter + clamp
-    Philox4 pj = philox4x32_10((uint32_t)slot, batch_lo, batch_hi, kStreamCoverJit, key0, key1);
-    const int64_t pd2 = ps / speedup / 2;
-    int64_t cy = cell / dw, cx = cell - cy * dw;
-    int64_t y = (cy - pd2) * speedup + (int64_t)bounded_u32(pj.v[0], (uint32_t)speedup);
-    int64_t x = (cx - pd2) * speedup + (int64_t)bounded_u32(pj.v[1], (uint32_t)speedup);
-    y = y > H - ps ? H - ps : y; y = y < 0 ? 0 : y;
-    x = x > W - ps ? W - ps : x; x = x < 0 ? 0 : x;
-    if (lane == 0) { coords[2 * slot] = (int32_t)y; coords[2 * slot + 1] = (int32_t)x; }
-}
-
-// full_samplers.py:86-92 accumulator footprint, run after every pick of the batch has been located (the picks read the state).
-// State transitions: count reaches dense_level -> the cell leaves the eligible set; count leaves 0 -> one more non-zero cell.
-__global__ void __launch_bounds__(128) cover_update_kernel(uint32_t* __restrict__ accum, CoverScratch s, int64_t dw, int ps, int speedup,
-                                                           uint32_t dense_level, int B, const int32_t* __restrict__ coords) {
-    const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (slot >= B) return;
-    const int64_t y = coords[2 * slot], x = coords[2 * slot + 1];
-    const int64_t r0 = y / speedup, r1 = (y + ps) / speedup, c0 = x / speedup, c1 = (x + ps) / speedup;
-    const int fw = (int)(c1 - c0);
-    const int tot = (int)(r1 - r0) * fw;
-    uint32_t became_nonzero = 0;
-    for (int f = lane; f < tot; f += 32) {
-        const int rr = f / fw, cc = f - rr * fw;
-        const int64_t cell = (r0 + rr) * dw + c0 + cc;
-        const uint32_t old = atomicAdd(accum + cell, 1u);
-        became_nonzero += old == 0u;
-        if (old + 1u == dense_level) {
-            atomicAnd(s.mask + (cell >> 5), ~(1u << (cell & 31)));
-            atomicSub(s.block_cnt + cell / kCellsPerBlock, 1u);
+    __syncthreads();
+    // ---- chain: the swaps depend on each other (hash map of the touched entries)
+    if (threadIdx.x == 0) {
+        const uint32_t hmask = 2 * kMaxBatch - 1;
+        auto hget = [&](uint32_t k) -> uint32_t {
+            uint32_t h = (k * 0x9E3779B1u) & hmask;
+            while (hkey[h] != 0xffffffffu) {
+                if (hkey[h] == k) return hval[h];
+                h = (h + 1) & hmask;
+            }
+            return k;
+        };
+        auto hset = [&](uint32_t k, uint32_t v) {
+            uint32_t h = (k * 0x9E3779B1u) & hmask;
+            while (hkey[h] != 0xffffffffu && hkey[h] != k) h = (h + 1) & hmask;
+            hkey[h] = k;
+            hval[h] = v;
+        };
+        for (uint32_t i = 0; i < (uint32_t)B; ++i) {
+            const uint32_t j = s_rank[i];
+            const uint32_t aj = hget(j), ai = hget(i);
+            s_rank[i] = aj;
+            hset(j, ai);
         }
     }
-    for (int o = 16; o; o >>= 1) became_nonzero += __shfl_xor_sync(0xffffffffu, became_nonzero, o);
-    if (lane == 0 && became_nonzero) atomicAdd(s.meta + 2, became_nonzero);
+    __syncthreads();
+    // ---- place: one warp per pick
+    for (int slot = wid; slot < B; slot += 32) {
+        const uint32_t rank = s_rank[slot];
+        uint32_t cell;
+        if (rank >= M) {
+            cell = s.extra[rank - M];
+        } else {
+            // block containing the rank: last b with block_off[b] <= rank
+            int lo = 0, hi = nb - 1;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (s.block_off[mid] <= rank) lo = mid; else hi = mid - 1;
+            }
+            uint32_t local = rank - s.block_off[lo];
+            const uint32_t w0 = (uint32_t)lo * (kCellsPerBlock / 32);
+            // each lane owns 2 mask words of the block's 64; warp prefix over popcounts
+            uint32_t m0 = s.mask[w0 + 2 * lane], m1 = s.mask[w0 + 2 * lane + 1];
+            uint32_t pc = __popc(m0) + __popc(m1);
+            uint32_t inc = pc;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            uint32_t excl = inc - pc;
+            bool mine = (local >= excl) && (local < inc);
+            unsigned bal = __ballot_sync(0xffffffffu, mine);
+            int src = __ffs(bal) - 1;
+            uint32_t found = 0;
+            if (lane == src) {
+                uint32_t r = local - excl;
+                uint32_t word = m0, widx = w0 + 2 * lane;
+                if (r >= (uint32_t)__popc(m0)) { r -= __popc(m0); word = m1; widx += 1; }
+                for (uint32_t q = 0; q < r; ++q) word &= word - 1;  // r-th set bit of word
+                found = widx * 32 + (__ffs(word) - 1);
+            }
+            cell = __shfl_sync(0xffffffffu, found, src);
+        }
+        // full_samplers.py:144-153 jitter + clamp
+        Philox4 pj = philox4x32_10((uint32_t)slot, batch_lo, batch_hi, kStreamCoverJit, key0, key1);
+        const int64_t pd2 = ps / speedup / 2;
+        int64_t cy = cell / dw, cx = cell - cy * dw;
+        int64_t y = (cy - pd2) * speedup + (int64_t)bounded_u32(pj.v[0], (uint32_t)speedup);
+        int64_t x = (cx - pd2) * speedup + (int64_t)bounded_u32(pj.v[1], (uint32_t)speedup);
+        y = y > H - ps ? H - ps : y; y = y < 0 ? 0 : y;
+        x = x > W - ps ? W - ps : x; x = x < 0 ? 0 : x;
+        if (lane == 0) { coords[2 * slot] = (int32_t)y; coords[2 * slot + 1] = (int32_t)x; }
+    }
+    __syncthreads();  // every pick has been located against the state of the PREVIOUS batch before the state changes
+    // ---- update: accumulator footprint (full_samplers.py:86-92). State transitions: count reaches dense_level -> the cell leaves
+    // the eligible set; count leaves 0 -> one more non-zero cell.
+    for (int slot = wid; slot < B; slot += 32) {
+        const int64_t y = coords[2 * slot], x = coords[2 * slot + 1];
+        const int64_t r0 = y / speedup, r1 = (y + ps) / speedup, c0 = x / speedup, c1 = (x + ps) / speedup;
+        const int fw = (int)(c1 - c0);
+        const int tot = (int)(r1 - r0) * fw;
+        uint32_t became_nonzero = 0;
+        for (int f = lane; f < tot; f += 32) {
+            const int rr = f / fw, cc = f - rr * fw;
+            const int64_t cell = (r0 + rr) * dw + c0 + cc;
+            const uint32_t old = atomicAdd(accum + cell, 1u);
+            became_nonzero += old == 0u;
+            if (old + 1u == dense_level) {
+                atomicAnd(s.mask + (cell >> 5), ~(1u << (cell & 31)));
+                atomicSub(s.block_cnt + cell / kCellsPerBlock, 1u);
+            }
+        }
+        for (int o = 16; o; o >>= 1) became_nonzero += __shfl_xor_sync(0xffffffffu, became_nonzero, o);
+        if (lane == 0 && became_nonzero) atomicAdd(s.meta + 2, became_nonzero);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *nonzero_out = atomicAdd(s.meta + 2, 0u);
 }
-
-__global__ void cover_publish_kernel(CoverScratch s, uint32_t* __restrict__ nonzero_out) { *nonzero_out = s.meta[2]; }
 
 __global__ void __launch_bounds__(256) cover_nonzero_kernel(const uint32_t* __restrict__ accum, int64_t cells, uint32_t* __restrict__ out) {
     uint32_t cnt = 0;
@@ -268,7 +284,7 @@ extern "C" DH_API int dh_cover_init(const uint32_t* accum, int64_t dh_, int64_t 
 
 extern "C" DH_API int dh_cover_sample(uint32_t* accum, int64_t dh_, int64_t dw_, int64_t H, int64_t W, int ps, int speedup, int dense_level,
                                int B, uint64_t seed, uint64_t batch_index, int32_t* coords_out, uint32_t* nonzero_out,
-                               uint32_t* scratch, void* stream) {
+                               uint32_t* scratch, int stop_when_full, void* stream) {
     DH_REQUIRE(accum && coords_out && nonzero_out && scratch, "dh_cover_sample: null pointer");
     DH_REQUIRE(ps > 0 && speedup > 0 && dense_level > 0, "dh_cover_sample: bad parameters");
     DH_REQUIRE(dh_ == H / speedup && dw_ == W / speedup && dh_ > 0 && dw_ > 0, "dh_cover_sample: coarse grid must be (H//speedup, W//speedup)");
@@ -286,13 +302,8 @@ extern "C" DH_API int dh_cover_sample(uint32_t* accum, int64_t dh_, int64_t dw_,
     }
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t b_lo = (uint32_t)batch_index, b_hi = (uint32_t)(batch_index >> 32);
-    cover_pick_kernel<<<1, 1024, 0, st>>>(s, nb, cells, B, k0, k1, b_lo, b_hi);
-    DH_CHECK_LAUNCH("cover_pick_kernel");
-    cover_place_kernel<<<(B + 3) / 4, 128, 0, st>>>(accum, s, nb, dh_, dw_, H, W, ps, speedup, B, k0, k1, b_lo, b_hi, coords_out);
-    DH_CHECK_LAUNCH("cover_place_kernel");
-    cover_update_kernel<<<(B + 3) / 4, 128, 0, st>>>(accum, s, dw_, ps, speedup, (uint32_t)dense_level, B, coords_out);
-    DH_CHECK_LAUNCH("cover_update_kernel");
-    cover_publish_kernel<<<1, 1, 0, st>>>(s, nonzero_out);
-    DH_CHECK_LAUNCH("cover_publish_kernel");
+    cover_batch_kernel<<<1, 1024, 0, st>>>(accum, s, nb, cells, dw_, H, W, ps, speedup, (uint32_t)dense_level, B, k0, k1, b_lo, b_hi, coords_out,
+                                           nonzero_out, stop_when_full);
+    DH_CHECK_LAUNCH("cover_batch_kernel");
     return DH_OK;
 }

@@ -303,19 +303,33 @@ class CoverState:
         with torch.cuda.device(self.accum.device):
             check(lib.dh_cover_init(self.accum.data_ptr(), self.dh, self.dw, self.dense_level, self.scratch.data_ptr(), _stream()), "dh_cover_init")
 
-    def next_coords(self) -> tuple[torch.Tensor, torch.Tensor]:
-        """One batch: int32 coords [B,2] and the device counter of non-zero accumulator cells."""
+    def next_coords(self, *, stop_when_full: bool = False, coords_out: Optional[torch.Tensor] = None,
+                    nonzero_out: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """One batch (one launch): int32 coords [B,2] and the device counter of non-zero accumulator cells. With stop_when_full a call
+        after coverage is complete leaves the accumulator and `coords_out` untouched (batches can then be enqueued ahead of the
+        read-back of the counter)."""
         lib = _lib.require_device()
-        coords = torch.empty((self.B, 2), dtype=torch.int32, device=self.accum.device)
+        coords = torch.empty((self.B, 2), dtype=torch.int32, device=self.accum.device) if coords_out is None else coords_out
+        nonzero = self.nonzero if nonzero_out is None else nonzero_out
         with torch.cuda.device(self.accum.device):
             check(
                 lib.dh_cover_sample(self.accum.data_ptr(), self.dh, self.dw, self.H, self.W, self.ps, self.speedup, self.dense_level, self.B,
-                                    self.seed, self.batch_index, coords.data_ptr(), self.nonzero.data_ptr(), self.scratch.data_ptr(),
-                                    _stream()),
+                                    self.seed, self.batch_index, coords.data_ptr(), nonzero.data_ptr(), self.scratch.data_ptr(),
+                                    1 if stop_when_full else 0, _stream()),
                 "dh_cover_sample",
             )
         self.batch_index += 1
-        return coords, self.nonzero
+        return coords, nonzero
+
+    def next_group(self, n_batches: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """`n_batches` consecutive batches enqueued without a host synchronisation: coords int32 [n, B, 2] (zeros for batches after
+        coverage completed) and their non-zero counters int32 [n] -- one read-back serves the whole group."""
+        dev = self.accum.device
+        coords = torch.zeros((n_batches, self.B, 2), dtype=torch.int32, device=dev)
+        counts = torch.zeros(n_batches, dtype=torch.int32, device=dev)
+        for g in range(n_batches):
+            self.next_coords(stop_when_full=True, coords_out=coords[g], nonzero_out=counts[g : g + 1])
+        return coords, counts
 
 
 def region_accept_dense(edges: torch.Tensor, edge_begin: int, edge_end: int, y0: int, x0: int, ny: int, nx: int, stride: int,

@@ -66,17 +66,31 @@ class FullImageRndSampler:
         self._state: ops.CoverState | None = None
 
     # -- device-side iteration ------------------------------------------------------------------------
-    def coords_generator(self) -> Iterator[tuple[torch.Tensor, float]]:
-        """(int32 device coords [B,2], filled_ratio) per batch until filled_ratio >= 1 (:263-274)."""
+    def _group_generator(self, group: int = 8) -> Iterator[tuple[torch.Tensor, list[float]]]:
+        """Groups of up to `group` batches: (int32 device coords [g, B, 2], their filled ratios), ending with the batch that reaches
+        filled_ratio >= 1 (:263-274). The batches of a group are enqueued back to back (one launch each) and ONE read-back of their
+        non-zero counters serves the group; launches that find the slide already covered are no-ops (dh_cover_sample,
+        stop_when_full), so the accumulator is exactly the footprint histogram of the yielded batches."""
         self._state = ops.CoverState(self.h, self.w, self.patch_size, self._downscale, self.dense_level, self.batch_size,
                                      self._seed, self._device)
         cells = self.dh * self.dw
-        filled_ratio = 0.0
-        while filled_ratio < 1:
-            coords, nonzero = self._state.next_coords()
-            filled_ratio = int(nonzero.item()) / cells
-            self._filled_ratio.append(filled_ratio)
-            yield coords, filled_ratio
+        done = False
+        while not done:
+            coords, counts = self._state.next_group(group)
+            ratios = [c / cells for c in counts.tolist()]
+            keep = len(ratios)
+            for i, r in enumerate(ratios):
+                if r >= 1:
+                    keep, done = i + 1, True
+                    break
+            self._filled_ratio.extend(ratios[:keep])
+            yield coords[:keep], ratios[:keep]
+
+    def coords_generator(self) -> Iterator[tuple[torch.Tensor, float]]:
+        """(int32 device coords [B,2], filled_ratio) per batch until filled_ratio >= 1 (:263-274)."""
+        for coords, ratios in self._group_generator():
+            for g, r in enumerate(ratios):
+                yield coords[g], r
 
     def generator(self) -> Iterator[tuple[list[Patch], float]]:
         for coords, filled_ratio in self.coords_generator():
@@ -89,9 +103,14 @@ class FullImageRndSampler:
                         layout: str = "NHWC") -> Iterator[tuple[torch.Tensor, torch.Tensor, float]]:
         """features [B,ps,ps,3] float32 with values 0..255 -- the reference does NOT divide by 255 here
         (:286); pass normalize=True for [0,1]. coords float32 [B,2] (y, x)."""
-        for coords, filled_ratio in self.coords_generator():
-            features = ops.gather_normalize(self._slide, coords, self.patch_size, dtype=dtype, layout=layout, scale255=normalize)
-            yield features, coords.to(torch.float32), filled_ratio
+        for coords, ratios in self._group_generator():                       # one gather launch per group of batches
+            g = len(ratios)
+            features = ops.gather_normalize(self._slide, coords.reshape(g * self.batch_size, 2), self.patch_size, dtype=dtype, layout=layout,
+                                            scale255=normalize)
+            features = features.view((g, self.batch_size) + tuple(features.shape[1:]))
+            coords_f = coords.to(torch.float32)
+            for i, r in enumerate(ratios):
+                yield features[i], coords_f[i], r
 
     # -- reporting helpers of the reference -------------------------------------------------------------
     @property

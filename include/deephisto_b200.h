@@ -189,9 +189,12 @@ DH_API int dh_colorize_overlay(const uint8_t* argmax_u8, const uint8_t* slide, i
  * ------------------------------------------------------------------------------------------ */
 DH_API int64_t dh_cover_scratch_words(int64_t dh, int64_t dw);
 DH_API int dh_cover_init(const uint32_t* accum, int64_t dh, int64_t dw, int dense_level, uint32_t* scratch, void* stream);
+/* One batch = ONE launch. stop_when_full != 0: a call made when every coarse cell is already covered changes nothing (coords_out
+ * untouched) and only reports the count -- the reference's loop ends at filled_ratio >= 1 (full_samplers.py:263-274), so a host
+ * can enqueue several batches before it reads a count back. */
 DH_API int dh_cover_sample(uint32_t* accum, int64_t dh, int64_t dw, int64_t H, int64_t W, int ps, int speedup,
                     int dense_level, int B, uint64_t seed, uint64_t batch_index, int32_t* coords_out,
-                    uint32_t* nonzero_out, uint32_t* scratch, void* stream);
+                    uint32_t* nonzero_out, uint32_t* scratch, int stop_when_full, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * C/D  RegionAnnotation._extract_patch_coords_dense / _rnd (region_samplers.py:82-191)
