@@ -73,19 +73,22 @@ __device__ __forceinline__ bool mask_test(const uint32_t* mask, uint32_t cell) {
 __global__ void __launch_bounds__(1024) cover_batch_kernel(uint32_t* __restrict__ accum, CoverScratch s, int nb, int64_t cells, int64_t dw,
                                                            int64_t H, int64_t W, int ps, int speedup, uint32_t dense_level, int B, uint32_t key0,
                                                            uint32_t key1, uint32_t batch_lo, uint32_t batch_hi, int32_t* __restrict__ coords,
-                                                           uint32_t* __restrict__ nonzero_out, int stop_when_full) {
+                                                           uint32_t* __restrict__ nonzero_out, int stop_when_full, int hsize, int off_in_smem) {
     __shared__ uint32_t carry;
     __shared__ uint32_t wtot[32];
-    __shared__ uint32_t hkey[2 * kMaxBatch];
-    __shared__ uint32_t hval[2 * kMaxBatch];
-    __shared__ uint32_t s_rank[kMaxBatch];  // first the draws j_i, then (in place) the ranks
+    extern __shared__ uint32_t cover_smem[];
+    uint32_t* hkey = cover_smem;               // [hsize] open-addressing hash of the Fisher-Yates swaps, hsize = pow2 >= 2 B
+    uint32_t* hval = hkey + hsize;             // [hsize]
+    uint32_t* s_rank = hval + hsize;           // [B] first the draws j_i, then (in place) the ranks
+    uint32_t* s_off = s_rank + B;              // [nb + 1] copy of block_off for the placement's binary search (when off_in_smem)
+    const uint32_t* boff = off_in_smem ? s_off : s.block_off;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (stop_when_full && s.meta[2] >= (uint32_t)cells) {  // uniform: the state is only written by earlier launches
         if (threadIdx.x == 0) *nonzero_out = s.meta[2];
         return;
     }
     if (threadIdx.x == 0) carry = 0;
-    for (int i = threadIdx.x; i < 2 * kMaxBatch; i += blockDim.x) hkey[i] = 0xffffffffu;
+    for (int i = threadIdx.x; i < hsize; i += blockDim.x) hkey[i] = 0xffffffffu;
     __syncthreads();
     // ---- scan: exclusive scan of block counts, 1024 at a time
     for (int b0 = 0; b0 < nb; b0 += 1024) {
@@ -102,7 +105,10 @@ __global__ void __launch_bounds__(1024) cover_batch_kernel(uint32_t* __restrict_
         for (int w = 0; w < wid; ++w) woff += wtot[w];
         uint32_t excl = carry + woff + inc - v;
         __syncthreads();
-        if (b < nb) s.block_off[b] = excl;
+        if (b < nb) {
+            s.block_off[b] = excl;
+            if (off_in_smem) s_off[b] = excl;
+        }
         if (threadIdx.x == 1023) carry = excl + v;
         __syncthreads();
     }
@@ -110,6 +116,7 @@ __global__ void __launch_bounds__(1024) cover_batch_kernel(uint32_t* __restrict_
     // ---- top-up: add distinct random non-eligible cells until M + extra >= B
     if (threadIdx.x == 0) {
         s.block_off[nb] = M;
+        if (off_in_smem) s_off[nb] = M;
         uint32_t n_extra = 0;
         if (M < (uint32_t)B) {
             uint32_t need = (uint32_t)B - M;
@@ -139,7 +146,7 @@ __global__ void __launch_bounds__(1024) cover_batch_kernel(uint32_t* __restrict_
     __syncthreads();
     // ---- chain: the swaps depend on each other (hash map of the touched entries)
     if (threadIdx.x == 0) {
-        const uint32_t hmask = 2 * kMaxBatch - 1;
+        const uint32_t hmask = (uint32_t)hsize - 1;
         auto hget = [&](uint32_t k) -> uint32_t {
             uint32_t h = (k * 0x9E3779B1u) & hmask;
             while (hkey[h] != 0xffffffffu) {
@@ -173,9 +180,9 @@ __global__ void __launch_bounds__(1024) cover_batch_kernel(uint32_t* __restrict_
             int lo = 0, hi = nb - 1;
             while (lo < hi) {
                 int mid = (lo + hi + 1) >> 1;
-                if (s.block_off[mid] <= rank) lo = mid; else hi = mid - 1;
+                if (boff[mid] <= rank) lo = mid; else hi = mid - 1;
             }
-            uint32_t local = rank - s.block_off[lo];
+            uint32_t local = rank - boff[lo];
             const uint32_t w0 = (uint32_t)lo * (kCellsPerBlock / 32);
             // each lane owns 2 mask words of the block's 64; warp prefix over popcounts
             uint32_t m0 = s.mask[w0 + 2 * lane], m1 = s.mask[w0 + 2 * lane + 1];
@@ -218,14 +225,25 @@ __global__ void __launch_bounds__(1024) cover_batch_kernel(uint32_t* __restrict_
         const int fw = (int)(c1 - c0);
         const int tot = (int)(r1 - r0) * fw;
         uint32_t became_nonzero = 0;
-        for (int f = lane; f < tot; f += 32) {
-            const int rr = f / fw, cc = f - rr * fw;
-            const int64_t cell = (r0 + rr) * dw + c0 + cc;
-            const uint32_t old = atomicAdd(accum + cell, 1u);
-            became_nonzero += old == 0u;
-            if (old + 1u == dense_level) {
-                atomicAnd(s.mask + (cell >> 5), ~(1u << (cell & 31)));
-                atomicSub(s.block_cnt + cell / kCellsPerBlock, 1u);
+        for (int f0 = lane; f0 < tot; f0 += 32 * 8) {  // 8 independent atomics in flight per lane (a 14 x 14 footprint is 7 per lane)
+            int64_t cell[8];
+            uint32_t old[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int f = f0 + 32 * u;
+                const int rr = f / fw, cc = f - rr * fw;
+                cell[u] = f < tot ? (r0 + rr) * dw + c0 + cc : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) old[u] = cell[u] >= 0 ? atomicAdd(accum + cell[u], 1u) : 1u;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (cell[u] < 0) continue;
+                became_nonzero += old[u] == 0u;
+                if (old[u] + 1u == dense_level) {
+                    atomicAnd(s.mask + (cell[u] >> 5), ~(1u << (cell[u] & 31)));
+                    atomicSub(s.block_cnt + cell[u] / kCellsPerBlock, 1u);
+                }
             }
         }
         for (int o = 16; o; o >>= 1) became_nonzero += __shfl_xor_sync(0xffffffffu, became_nonzero, o);
@@ -302,8 +320,16 @@ extern "C" DH_API int dh_cover_sample(uint32_t* accum, int64_t dh_, int64_t dw_,
     }
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t b_lo = (uint32_t)batch_index, b_hi = (uint32_t)(batch_index >> 32);
-    cover_batch_kernel<<<1, 1024, 0, st>>>(accum, s, nb, cells, dw_, H, W, ps, speedup, (uint32_t)dense_level, B, k0, k1, b_lo, b_hi, coords_out,
-                                           nonzero_out, stop_when_full);
+    int hsize = 64;
+    while (hsize < 2 * B) hsize *= 2;
+    const int off_in_smem = nb + 1 <= 24 * 1024 ? 1 : 0;  // up to 96 KB of block offsets (a 112k x 112k slide at speedup 16)
+    const size_t smem = (size_t)(2 * hsize + B + (off_in_smem ? nb + 1 : 0)) * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(cover_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(cover_batch_kernel)");
+    }
+    cover_batch_kernel<<<1, 1024, smem, st>>>(accum, s, nb, cells, dw_, H, W, ps, speedup, (uint32_t)dense_level, B, k0, k1, b_lo, b_hi, coords_out,
+                                              nonzero_out, stop_when_full, hsize, off_in_smem);
     DH_CHECK_LAUNCH("cover_batch_kernel");
     return DH_OK;
 }

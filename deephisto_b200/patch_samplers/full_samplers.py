@@ -70,13 +70,15 @@ class FullImageRndSampler:
         """Groups of up to `group` batches: (int32 device coords [g, B, 2], their filled ratios), ending with the batch that reaches
         filled_ratio >= 1 (:263-274). The batches of a group are enqueued back to back (one launch each) and ONE read-back of their
         non-zero counters serves the group; launches that find the slide already covered are no-ops (dh_cover_sample,
-        stop_when_full), so the accumulator is exactly the footprint histogram of the yielded batches."""
+        stop_when_full), so after a complete run the accumulator is exactly the footprint histogram of the yielded batches. The
+        device runs up to two groups ahead of the batch being consumed (the reference's worker pool runs ahead as well)."""
         self._state = ops.CoverState(self.h, self.w, self.patch_size, self._downscale, self.dense_level, self.batch_size,
                                      self._seed, self._device)
         cells = self.dh * self.dw
         done = False
+        ahead = self._state.next_group(group)
         while not done:
-            coords, counts = self._state.next_group(group)
+            (coords, counts), ahead = ahead, self._state.next_group(group)   # the next group is enqueued before this one is read back
             ratios = [c / cells for c in counts.tolist()]
             keep = len(ratios)
             for i, r in enumerate(ratios):
