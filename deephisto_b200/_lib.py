@@ -78,6 +78,7 @@ SIGNATURES = {
     "dh_cover_scratch_words": (_i64, [_i64, _i64]),
     "dh_cover_init": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "dh_cover_sample": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _i32, _vp]),
+    "dh_cover_sample_group": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _u64, _u64, _i32, _vp, _vp, _vp, _vp]),
     "dh_region_accept_dense": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _f64, _vp, _vp, _vp]),
     "dh_compact_coords": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "dh_region_sample": (

@@ -333,3 +333,15 @@ extern "C" DH_API int dh_cover_sample(uint32_t* accum, int64_t dh_, int64_t dw_,
     DH_CHECK_LAUNCH("cover_batch_kernel");
     return DH_OK;
 }
+
+extern "C" DH_API int dh_cover_sample_group(uint32_t* accum, int64_t dh_, int64_t dw_, int64_t H, int64_t W, int ps, int speedup, int dense_level,
+                                            int B, uint64_t seed, uint64_t first_batch_index, int n_batches, int32_t* coords_out,
+                                            uint32_t* nonzero_out, uint32_t* scratch, void* stream) {
+    DH_REQUIRE(n_batches >= 0, "dh_cover_sample_group: negative batch count");
+    for (int g = 0; g < n_batches; ++g) {
+        int rc = dh_cover_sample(accum, dh_, dw_, H, W, ps, speedup, dense_level, B, seed, first_batch_index + (uint64_t)g,
+                                 coords_out + (int64_t)g * B * 2, nonzero_out + g, scratch, 1, stream);
+        if (rc != DH_OK) return rc;
+    }
+    return DH_OK;
+}

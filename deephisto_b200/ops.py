@@ -324,11 +324,15 @@ class CoverState:
     def next_group(self, n_batches: int) -> tuple[torch.Tensor, torch.Tensor]:
         """`n_batches` consecutive batches enqueued without a host synchronisation: coords int32 [n, B, 2] (zeros for batches after
         coverage completed) and their non-zero counters int32 [n] -- one read-back serves the whole group."""
+        lib = _lib.require_device()
         dev = self.accum.device
         coords = torch.zeros((n_batches, self.B, 2), dtype=torch.int32, device=dev)
         counts = torch.zeros(n_batches, dtype=torch.int32, device=dev)
-        for g in range(n_batches):
-            self.next_coords(stop_when_full=True, coords_out=coords[g], nonzero_out=counts[g : g + 1])
+        with torch.cuda.device(dev):
+            check(lib.dh_cover_sample_group(self.accum.data_ptr(), self.dh, self.dw, self.H, self.W, self.ps, self.speedup, self.dense_level,
+                                            self.B, self.seed, self.batch_index, n_batches, coords.data_ptr(), counts.data_ptr(),
+                                            self.scratch.data_ptr(), _stream()), "dh_cover_sample_group")
+        self.batch_index += n_batches
         return coords, counts
 
 

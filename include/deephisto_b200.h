@@ -195,6 +195,11 @@ DH_API int dh_cover_init(const uint32_t* accum, int64_t dh, int64_t dw, int dens
 DH_API int dh_cover_sample(uint32_t* accum, int64_t dh, int64_t dw, int64_t H, int64_t W, int ps, int speedup,
                     int dense_level, int B, uint64_t seed, uint64_t batch_index, int32_t* coords_out,
                     uint32_t* nonzero_out, uint32_t* scratch, int stop_when_full, void* stream);
+/* n_batches consecutive batches (batch_index = first_batch_index + g) enqueued by one call, each with stop_when_full semantics:
+ * coords_out [n_batches][B][2] (pre-zeroed by the caller: batches after full coverage are left untouched), nonzero_out [n_batches]. */
+DH_API int dh_cover_sample_group(uint32_t* accum, int64_t dh, int64_t dw, int64_t H, int64_t W, int ps, int speedup,
+                          int dense_level, int B, uint64_t seed, uint64_t first_batch_index, int n_batches,
+                          int32_t* coords_out, uint32_t* nonzero_out, uint32_t* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * C/D  RegionAnnotation._extract_patch_coords_dense / _rnd (region_samplers.py:82-191)
