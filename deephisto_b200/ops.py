@@ -321,9 +321,10 @@ class CoverState:
         self.batch_index += 1
         return coords, nonzero
 
-    def next_group(self, n_batches: int) -> tuple[torch.Tensor, torch.Tensor]:
+    def next_group(self, n_batches: int, read_back: bool = False):
         """`n_batches` consecutive batches enqueued without a host synchronisation: coords int32 [n, B, 2] (zeros for batches after
-        coverage completed) and their non-zero counters int32 [n] -- one read-back serves the whole group."""
+        coverage completed) and their non-zero counters int32 [n] -- one read-back serves the whole group. With read_back the
+        second value is (pinned host int32 [n], event): the asynchronous copy of the counters and the event that marks it done."""
         lib = _lib.require_device()
         dev = self.accum.device
         coords = torch.zeros((n_batches, self.B, 2), dtype=torch.int32, device=dev)
@@ -333,7 +334,14 @@ class CoverState:
                                             self.B, self.seed, self.batch_index, n_batches, coords.data_ptr(), counts.data_ptr(),
                                             self.scratch.data_ptr(), _stream()), "dh_cover_sample_group")
         self.batch_index += n_batches
-        return coords, counts
+        if not read_back:
+            return coords, counts
+        # the counters travel right behind the group's own launches: a group enqueued later does not delay their read-back
+        host = torch.empty(n_batches, dtype=torch.int32, pin_memory=True)
+        host.copy_(counts, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        return coords, (host, ready)
 
 
 def region_accept_dense(edges: torch.Tensor, edge_begin: int, edge_end: int, y0: int, x0: int, ny: int, nx: int, stride: int,

@@ -66,7 +66,7 @@ class FullImageRndSampler:
         self._state: ops.CoverState | None = None
 
     # -- device-side iteration ------------------------------------------------------------------------
-    def _group_generator(self, group: int = 8) -> Iterator[tuple[torch.Tensor, list[float]]]:
+    def _group_generator(self, group: int = 16) -> Iterator[tuple[torch.Tensor, list[float]]]:
         """Groups of up to `group` batches: (int32 device coords [g, B, 2], their filled ratios), ending with the batch that reaches
         filled_ratio >= 1 (:263-274). The batches of a group are enqueued back to back (one launch each) and ONE read-back of their
         non-zero counters serves the group; launches that find the slide already covered are no-ops (dh_cover_sample,
@@ -76,9 +76,10 @@ class FullImageRndSampler:
                                      self._seed, self._device)
         cells = self.dh * self.dw
         done = False
-        ahead = self._state.next_group(group)
+        ahead = self._state.next_group(group, read_back=True)
         while not done:
-            (coords, counts), ahead = ahead, self._state.next_group(group)   # the next group is enqueued before this one is read back
+            (coords, (counts, ready)), ahead = ahead, self._state.next_group(group, read_back=True)   # next group enqueued before this one is read
+            ready.synchronize()
             ratios = [c / cells for c in counts.tolist()]
             keep = len(ratios)
             for i, r in enumerate(ratios):
