@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_kernel(const floa
 // in the row loop (the first version of this kernel spent its time on two 64-bit divisions per row per thread:
 // profiles/r01_stitch.md).
 constexpr int kStitchV = 2;  // float4 per thread per row
+constexpr int kStitchNC = 8; // classes summed in registers by the pipelined per-cell loop (more classes: one class at a time)
 
 struct RowClass {
     int64_t lo_raw, hi_raw;  // unclamped main-grid row range covering the current map row
@@ -212,6 +213,49 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(co
                 const int64_t main_n = g.ny * g.nx;
                 float best = 0.f;
                 int best_c = 0;
+                if (n <= kStitchNC) {
+                    // Patches outer, classes inner: per class the adds keep the reference's order, but the n loads of a patch are
+                    // independent and the loads of patch p+1 are issued before the adds of patch p -- the covering patches cost about
+                    // one L2 round trip instead of one per (patch, class) (the d = 16 map is latency-bound: profiles/r01_stitch.md).
+                    float acc[kStitchNC], cur[kStitchNC];
+#pragma unroll
+                    for (int c = 0; c < kStitchNC; ++c) { acc[c] = 0.f; cur[c] = 0.f; }
+                    bool have = false;
+                    auto visit = [&](int64_t idx) {
+                        const float* lg = logits + idx * n;
+                        float nxt[kStitchNC];
+#pragma unroll
+                        for (int c = 0; c < kStitchNC; ++c) nxt[c] = c < n ? __ldg(lg + c) : 0.f;
+                        if (have) {
+#pragma unroll
+                            for (int c = 0; c < kStitchNC; ++c) acc[c] = __fadd_rn(acc[c], cur[c]);
+                        }
+#pragma unroll
+                        for (int c = 0; c < kStitchNC; ++c) cur[c] = nxt[c];
+                        have = true;
+                    };
+                    for (int64_t gy = cy.lo; gy <= cy.hi; ++gy)
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) visit(gy * g.nx + gx);
+                    if (cx.last)
+                        for (int64_t gy = cy.lo; gy <= cy.hi; ++gy) visit(main_n + gy);
+                    if (cy.last)
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) visit(main_n + g.ny + gx);
+                    if (cx.last && cy.last)
+                        for (int64_t k = 0; k <= g.pads; ++k) visit(g.N - 1 + k);
+                    if (have) {
+#pragma unroll
+                        for (int c = 0; c < kStitchNC; ++c) acc[c] = __fadd_rn(acc[c], cur[c]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < kStitchNC; ++c) {
+                        if (c < n) {
+                            if (WITH_SUM) vals[t * n + c] = acc[c];
+                            if (WITH_ARGMAX) {
+                                if (c == 0 || acc[c] > best || (acc[c] != acc[c] && best == best)) { best = acc[c]; best_c = c; }  // np.argmax: first maximum; NaN wins
+                            }
+                        }
+                    }
+                } else {
                 for (int c = 0; c < n; ++c) {
                     float acc = 0.f;
                     for (int64_t gy = cy.lo; gy <= cy.hi; ++gy)
@@ -226,6 +270,7 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(co
                     if (WITH_ARGMAX) {
                         if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; best_c = c; }  // np.argmax: first maximum; NaN wins
                     }
+                }
                 }
                 if (WITH_COUNT) {
                     int64_t ry = cy.hi >= cy.lo ? cy.hi - cy.lo + 1 : 0;
