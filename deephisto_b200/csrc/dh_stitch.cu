@@ -515,6 +515,87 @@ __global__ void __launch_bounds__(256) colorize_overlay_vec_kernel(const uint8_t
     }
 }
 
+// d = 4 or 8: one thread per 16-PIXEL column block (48 bytes per slide row = three 128-bit loads = CP = 16 / d cells), so loads and
+// stores are vectors instead of the 12-byte segments / single bytes of the per-cell kernel. The last block of a map row may hold
+// fewer than CP cells: those are read with 32-bit loads like the per-cell kernel.
+template <int CP>
+__global__ void __launch_bounds__(256) colorize_overlay_cols_kernel(const uint8_t* __restrict__ argmax_map, const uint8_t* __restrict__ slide,
+                                                                    int64_t pitch, int64_t dh, int64_t dw, const uint8_t* __restrict__ lut,
+                                                                    double alpha, uint8_t* __restrict__ mask_out, uint8_t* __restrict__ thumb_out,
+                                                                    uint8_t* __restrict__ overlay_out) {
+    constexpr int d = 16 / CP;
+    constexpr uint32_t area = d * d;
+    const int64_t blocks_per_row = (dw + CP - 1) / CP;
+    const int64_t total = dh * blocks_per_row;
+    const double beta = __dsub_rn(1.0, alpha);
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / blocks_per_row, jb = t - i * blocks_per_row;
+        const int64_t j0 = jb * CP;
+        const int ncell = (int)(dw - j0 < CP ? dw - j0 : CP);
+        const uint8_t* src = slide + (i * d) * pitch + 48 * jb;
+        uint32_t sums[CP][3];
+#pragma unroll
+        for (int k = 0; k < CP; ++k) sums[k][0] = sums[k][1] = sums[k][2] = 0;
+        if (ncell == CP) {
+#pragma unroll
+            for (int r = 0; r < d; ++r) {
+                const uint4* q = reinterpret_cast<const uint4*>(src + (int64_t)r * pitch);
+                const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+                rgb_sums3(a.x, a.y, a.z, sums[0][0], sums[0][1], sums[0][2]);                                  // pixels 0-3
+                rgb_sums3(a.w, b.x, b.y, sums[4 / d][0], sums[4 / d][1], sums[4 / d][2]);                      // pixels 4-7
+                rgb_sums3(b.z, b.w, c.x, sums[8 / d][0], sums[8 / d][1], sums[8 / d][2]);                      // pixels 8-11
+                rgb_sums3(c.y, c.z, c.w, sums[12 / d][0], sums[12 / d][1], sums[12 / d][2]);                   // pixels 12-15
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < CP; ++k) {
+                if (k >= ncell) continue;
+                for (int r = 0; r < d; ++r) {
+                    const uint32_t* q = reinterpret_cast<const uint32_t*>(src + (int64_t)r * pitch + 3 * d * k);
+#pragma unroll
+                    for (int gq = 0; gq < d / 4; ++gq) rgb_sums3(__ldg(q + 3 * gq), __ldg(q + 3 * gq + 1), __ldg(q + 3 * gq + 2), sums[k][0], sums[k][1], sums[k][2]);
+                }
+            }
+        }
+        uint8_t om[3 * CP], ot[3 * CP], oo[3 * CP];
+#pragma unroll
+        for (int k = 0; k < CP; ++k) {
+            const uint32_t cls = k < ncell ? argmax_map[i * dw + j0 + k] : 0u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const uint32_t col = lut[3 * cls + c];
+                const uint32_t img = (sums[k][c] + area / 2) / area;
+                om[3 * k + c] = (uint8_t)col;
+                ot[3 * k + c] = (uint8_t)img;
+                oo[3 * k + c] = (uint8_t)(int)__dadd_rn(__dmul_rn((double)img, alpha), __dmul_rn((double)col, beta));
+            }
+        }
+        const int64_t o = 3 * (i * dw + j0);
+        auto put = [&](uint8_t* out, const uint8_t* v) {
+            if (!out) return;
+            // full blocks: 3 * CP bytes at a (3 * CP)-byte multiple offset from the row start; rows start 2-byte aligned only when
+            // 3 * dw is even, so vector stores are used when the absolute address allows it
+            const uintptr_t addr = reinterpret_cast<uintptr_t>(out + o);
+            if (ncell == CP && CP == 4 && addr % 4 == 0) {
+                uint32_t* w = reinterpret_cast<uint32_t*>(out + o);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) w[q] = (uint32_t)v[4 * q] | ((uint32_t)v[4 * q + 1] << 8) | ((uint32_t)v[4 * q + 2] << 16) | ((uint32_t)v[4 * q + 3] << 24);
+            } else if (ncell == CP && CP == 2 && addr % 2 == 0) {
+                uint16_t* w = reinterpret_cast<uint16_t*>(out + o);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) w[q] = (uint16_t)((uint32_t)v[2 * q] | ((uint32_t)v[2 * q + 1] << 8));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 3 * CP; ++q)
+                    if (q < 3 * ncell) out[o + q] = v[q];
+            }
+        };
+        put(mask_out, om);
+        put(thumb_out, ot);
+        put(overlay_out, oo);
+    }
+}
+
 static int make_stitch_grid(int64_t H, int64_t W, int ps, int stride, int d, int n, int batch_size, StitchGrid* g) {
     DH_REQUIRE(ps > 0 && stride > 0 && d > 0, "stitch: ps, stride and downscale must be positive");
     DH_REQUIRE(n > 0 && n <= 64, "stitch: n classes %d outside 1..64", n);
@@ -639,6 +720,16 @@ extern "C" DH_API int dh_colorize_overlay(const uint8_t* argmax_u8, const uint8_
         const int64_t cells = dh_ * dw_;  // d <= 256: the per-channel sums (255 * d * d) fit 32 bits
         const int64_t blocks = (cells + 255) / 256;
         const int grid = (int)(blocks < (int64_t)kNumSMs * 32 ? blocks : (int64_t)kNumSMs * 32);
+        if (d == 4 || d == 8) {  // 16-pixel column blocks: 128-bit loads, word / half-word stores
+            const int cp = 16 / d;
+            const int64_t items = dh_ * ((dw_ + cp - 1) / cp);
+            const int64_t bl = (items + 255) / 256;
+            const int gr = (int)(bl < (int64_t)kNumSMs * 32 ? bl : (int64_t)kNumSMs * 32);
+            if (d == 4) colorize_overlay_cols_kernel<4><<<gr, 256, 0, as_stream(stream)>>>(argmax_u8, slide, pitch, dh_, dw_, lut_rgb, alpha, mask_out, thumb_out, overlay_out);
+            else colorize_overlay_cols_kernel<2><<<gr, 256, 0, as_stream(stream)>>>(argmax_u8, slide, pitch, dh_, dw_, lut_rgb, alpha, mask_out, thumb_out, overlay_out);
+            DH_CHECK_LAUNCH("colorize_overlay_cols_kernel");
+            return DH_OK;
+        }
         if (d % 16 == 0)
             colorize_overlay_vec_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(argmax_u8, slide, pitch, dh_, dw_, d, lut_rgb, alpha, mask_out,
                                                                              thumb_out, overlay_out);
