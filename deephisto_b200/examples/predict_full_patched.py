@@ -149,13 +149,14 @@ class ImagePredictorPatched:
                 self.h, self.w = psim.layer_size(self.layer)
         self.last_sum_map: Optional[torch.Tensor] = None      # kept when process_device(want_sum=True)
         self.stage_events: Optional[dict] = None              # set to {} to collect CUDA events per stage (bench breakdown)
+        self.nvtx = False                                     # True: NVTX ranges "deephisto/<stage>" around the stages (Nsight timelines)
 
     def _mark(self, stage: str):
         """(start, end) CUDA events appended to stage_events[stage]; a no-op context when profiling is off."""
         import contextlib
 
         if self.stage_events is None:
-            return contextlib.nullcontext()
+            return torch.cuda.nvtx.range(f"deephisto/{stage}") if self.nvtx else contextlib.nullcontext()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.stage_events.setdefault(stage, []).append((a, b))
 

@@ -64,6 +64,22 @@ class FullImageRndSampler:
         self._seed = seed
         self._device = device
         self._state: ops.CoverState | None = None
+        self._resume = None
+
+    # -- resume: (accumulator, batch counter) is the whole state of a run (the Philox draws are keyed by seed and batch index) --
+    def state_dict(self) -> dict:
+        if self._state is None:
+            return {"seed": int(self._seed), "batch_index": 0, "accum": None, "filled_ratio": []}
+        torch.cuda.synchronize(self._state.accum.device)
+        return {"seed": int(self._seed), "batch_index": int(self._state.batch_index), "accum": self._state.accum.cpu().clone(),
+                "filled_ratio": list(self._filled_ratio)}
+
+    def load_state_dict(self, state: dict) -> None:
+        """The next `generator*()` call continues the saved run instead of starting from an empty accumulator. A state taken in
+        the middle of an iteration includes the batches the device had already enqueued ahead of the consumer."""
+        if int(state["seed"]) != int(self._seed):
+            raise ValueError(f"state was saved with seed {state['seed']}, this sampler uses seed {self._seed}")
+        self._resume = state if state.get("accum") is not None else None
 
     # -- device-side iteration ------------------------------------------------------------------------
     def _group_generator(self, group: int = 16) -> Iterator[tuple[torch.Tensor, list[float]]]:
@@ -75,6 +91,12 @@ class FullImageRndSampler:
         self._state = ops.CoverState(self.h, self.w, self.patch_size, self._downscale, self.dense_level, self.batch_size,
                                      self._seed, self._device)
         cells = self.dh * self.dw
+        if self._resume is not None:
+            self._state.restore(self._resume["accum"].to(self._device), self._resume["batch_index"])
+            self._filled_ratio = list(self._resume["filled_ratio"])
+            self._resume = None
+            if self._filled_ratio and self._filled_ratio[-1] >= 1:
+                return
         done = False
         ahead = self._state.next_group(group, read_back=True)
         while not done:

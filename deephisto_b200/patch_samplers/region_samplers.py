@@ -215,6 +215,16 @@ class AnnoRegionRndSampler:
         if verbose:
             self._print_anno_stats(self.regions)
 
+    # -- resume: the Philox draws are keyed by (seed, global slot index), so two integers are the whole sampler state ---------
+    def state_dict(self) -> dict:
+        return {"seed": int(self._seed), "slot_cursor": int(self._slot_cursor)}
+
+    def load_state_dict(self, state: dict) -> None:
+        """Continue a run: the batches drawn after this call are bit-identical to those the saved sampler would have drawn next."""
+        if int(state["seed"]) != int(self._seed):
+            raise ValueError(f"state was saved with seed {state['seed']}, this sampler uses seed {self._seed}")
+        self._slot_cursor = int(state["slot_cursor"])
+
     # -- bookkeeping identical to the reference -------------------------------------------------------
     def _print_anno_stats(self, regions):
         areas = {cls: sum(i.area for i in regs) for cls, regs in regions.items()}

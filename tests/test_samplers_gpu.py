@@ -367,3 +367,37 @@ def test_region_rnd_statistics_match_reference(api):
         assert (np.abs(c.mean(0) - np.array(r["mean_yx"])) <= 6 * np.sqrt(2) * se).all(), (r["polygon"], c.mean(0), r["mean_yx"])
         assert (np.abs(c.std(0) / np.array(r["std_yx"]) - 1) <= 0.05).all()
         assert (c.min(0) >= np.array(r["min_yx"]) - 25).all() and (c.max(0) <= np.array(r["max_yx"]) + 25).all()
+
+
+def test_sampler_state_dicts_resume_bit_identically(api, tmp_path):
+    """Checkpoint / resume of the random samplers: AnnoRegionRndSampler's state is (seed, slot cursor), FullImageRndSampler's
+    is (accumulator, batch counter); a restored sampler continues with exactly the batches of the uninterrupted run."""
+    fs, _, rs = api
+    hw, items, _ = _dataset(tmp_path, n_images=1)
+    a = rs.AnnoRegionRndSampler(items, layer=1, patch_size=224, seed=4, verbose=False)
+    first = list(a.torch_generator(16, 3))
+    state = a.state_dict()
+    rest = list(a.torch_generator(16, 4))
+    b = rs.AnnoRegionRndSampler(items, layer=1, patch_size=224, seed=4, verbose=False)
+    b.load_state_dict(state)
+    again = list(b.torch_generator(16, 4))
+    assert len(first) == 3 and all(torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2]) for x, y in zip(rest, again))
+    with pytest.raises(ValueError, match="seed"):
+        rs.AnnoRegionRndSampler(items, layer=1, patch_size=224, seed=5, verbose=False).load_state_dict(state)
+    # coverage sampler: run to the end, and resume a copy from a mid-run snapshot of the device state
+    host = synth.synth_slide(1500, 1300, 3)
+    full = fs.FullImageRndSampler(host, 1, 224, 2, _mode(fs), seed=2)
+    ref = [(c.cpu(), r) for c, r in full.coords_generator()]
+    assert len(ref) > 40                                      # the snapshot below (<= 32 batches in) is taken mid-run
+    part = fs.FullImageRndSampler(host, 1, 224, 2, _mode(fs), seed=2)
+    it = part.coords_generator()
+    for _ in range(5):
+        next(it)
+    snap = part.state_dict()                                  # includes the groups the device has enqueued ahead of the consumer
+    k = snap["batch_index"]
+    assert 5 <= k <= len(ref) + 32 and len(snap["filled_ratio"]) <= k
+    resumed = fs.FullImageRndSampler(host, 1, 224, 2, _mode(fs), seed=2)
+    resumed.load_state_dict(dict(snap, filled_ratio=[r for _, r in ref[:k]]))
+    tail = [(c.cpu(), r) for c, r in resumed.coords_generator()]
+    assert len(tail) == max(0, len(ref) - k)
+    assert all(torch.equal(x[0], y[0]) and x[1] == y[1] for x, y in zip(tail, ref[k:]))
