@@ -372,7 +372,7 @@ def test_region_rnd_statistics_match_reference(api):
 def test_sampler_state_dicts_resume_bit_identically(api, tmp_path):
     """Checkpoint / resume of the random samplers: AnnoRegionRndSampler's state is (seed, slot cursor), FullImageRndSampler's
     is (accumulator, batch counter); a restored sampler continues with exactly the batches of the uninterrupted run."""
-    fs, _, rs = api
+    _, fs, rs = api
     hw, items, _ = _dataset(tmp_path, n_images=1)
     a = rs.AnnoRegionRndSampler(items, layer=1, patch_size=224, seed=4, verbose=False)
     first = list(a.torch_generator(16, 3))
