@@ -41,102 +41,10 @@ __host__ __device__ __forceinline__ Cover cover_1d(int64_t i, int64_t cnt, int p
 
 constexpr int kStitchThreads = 256;
 
-// smem: 4 copies of the tile values, copy s stored at float offset s (so that a row whose global
-// float offset is == s mod 4 can be streamed out with aligned 16-byte loads and stores).
-template <bool WITH_SUM, bool WITH_ARGMAX, bool WITH_COUNT>
-__global__ void __launch_bounds__(kStitchThreads) stitch_dense_kernel(const float* __restrict__ logits, StitchGrid g,
-                                                                      float* __restrict__ sum_map,
-                                                                      uint32_t* __restrict__ count_map,
-                                                                      uint8_t* __restrict__ argmax_map,
-                                                                      int64_t row_begin, int64_t row_end, int tj_max,
-                                                                      int rows_per_block) {
-    extern __shared__ __align__(16) float smem[];
-    const int n = g.n;
-    const int copy_stride = tj_max * n + 4;             // floats per shifted copy (multiple of 4: tj_max % 4 == 0)
-    float* vals = smem;                                  // [4][copy_stride]
-    uint32_t* cnts = reinterpret_cast<uint32_t*>(smem + 4 * copy_stride);  // [tj_max]
-    uint8_t* amax = reinterpret_cast<uint8_t*>(cnts + tj_max);             // [tj_max]
-
-    const int64_t j0 = (int64_t)blockIdx.x * tj_max;
-    const int tj = (int)((g.dw - j0) < tj_max ? (g.dw - j0) : tj_max);
-    const int64_t i0 = row_begin + (int64_t)blockIdx.y * rows_per_block;
-    const int64_t i1 = (i0 + rows_per_block) < row_end ? (i0 + rows_per_block) : row_end;
-
-    int64_t sig_lo = -2, sig_hi = -2;
-    int sig_last = -1;
-    for (int64_t i = i0; i < i1; ++i) {
-        Cover cy = cover_1d(i, g.ny, g.ps, g.stride, g.d, g.lastrow_cell);
-        if (cy.lo != sig_lo || cy.hi != sig_hi || (int)cy.last != sig_last) {
-            sig_lo = cy.lo; sig_hi = cy.hi; sig_last = (int)cy.last;
-            __syncthreads();  // previous row's readers are done with vals
-            for (int t = threadIdx.x; t < tj; t += blockDim.x) {
-                const int64_t j = j0 + t;
-                Cover cx = cover_1d(j, g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
-                const int64_t main_n = g.ny * g.nx;
-                uint32_t cnt = 0;
-                float best = 0.f;
-                int best_c = 0;
-                for (int c = 0; c < n; ++c) {
-                    float acc = 0.f;
-                    for (int64_t gy = cy.lo; gy <= cy.hi; ++gy)
-                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, __ldg(logits + (gy * g.nx + gx) * n + c));
-                    if (cx.last)
-                        for (int64_t gy = cy.lo; gy <= cy.hi; ++gy) acc = __fadd_rn(acc, __ldg(logits + (main_n + gy) * n + c));
-                    if (cy.last)
-                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, __ldg(logits + (main_n + g.ny + gx) * n + c));
-                    if (cx.last && cy.last)
-                        for (int64_t k = 0; k <= g.pads; ++k) acc = __fadd_rn(acc, __ldg(logits + (g.N - 1 + k) * n + c));
-                    if (WITH_SUM) {
-#pragma unroll
-                        for (int s = 0; s < 4; ++s) vals[s * copy_stride + s + t * n + c] = acc;
-                    }
-                    if (WITH_ARGMAX) {
-                        // np.argmax: first maximum; a NaN is a maximum
-                        if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; best_c = c; }
-                    }
-                }
-                if (WITH_COUNT) {
-                    int64_t ry = cy.hi >= cy.lo ? cy.hi - cy.lo + 1 : 0;
-                    int64_t rx = cx.hi >= cx.lo ? cx.hi - cx.lo + 1 : 0;
-                    cnt = (uint32_t)(ry * rx + (cx.last ? ry : 0) + (cy.last ? rx : 0) + ((cx.last && cy.last) ? 1 + g.pads : 0));
-                    cnts[t] = cnt;
-                }
-                if (WITH_ARGMAX) amax[t] = (uint8_t)best_c;
-            }
-            __syncthreads();
-        }
-        const int64_t lrow = i - row_begin;  // output pointers start at row_begin
-        if (WITH_SUM) {
-            const int64_t base = (lrow * g.dw + j0) * n;  // float offset of the segment
-            const int len = tj * n;
-            const int s = (int)(base & 3);
-            const float* v = vals + s * copy_stride + s;  // v[f] = value f of the tile, (v + f) 16B-aligned iff (base+f)%4==0
-            int head = (4 - s) & 3;
-            if (head > len) head = len;
-            const int nvec = (len - head) >> 2;
-            float* out = sum_map + base;
-            if ((int)threadIdx.x < head) __stcs(out + threadIdx.x, v[threadIdx.x]);
-            for (int q = threadIdx.x; q < nvec; q += blockDim.x) {
-                const int f = head + 4 * q;
-                float4 val = *reinterpret_cast<const float4*>(v + f);
-                __stcs(reinterpret_cast<float4*>(out + f), val);
-            }
-            const int tail0 = head + 4 * nvec;
-            if ((int)threadIdx.x < len - tail0) __stcs(out + tail0 + threadIdx.x, v[tail0 + threadIdx.x]);
-        }
-        if (WITH_COUNT) {
-            for (int t = threadIdx.x; t < tj; t += blockDim.x) count_map[lrow * g.dw + j0 + t] = cnts[t];
-        }
-        if (WITH_ARGMAX) {
-            for (int t = threadIdx.x; t < tj; t += blockDim.x) argmax_map[lrow * g.dw + j0 + t] = amax[t];
-        }
-    }
-}
-
-// ---- aligned fast path ------------------------------------------------------------------------------
+// ---- register-resident row classes ----------------------------------------------------------------------
 // When dw*n is a multiple of 4 floats and the column tile is a multiple of 4 cells, every row segment of a tile starts on
 // a 16-byte boundary: a thread keeps its float4s (and count / argmax words) of the current row class IN REGISTERS and the
-// per-row work is just the stores. The row class (which patch rows cover map row i) is advanced incrementally -- no division
+// per-row work is just the stores (other widths: PHASED below). The row class (which patch rows cover map row i) is advanced incrementally -- no division
 // in the row loop (the first version of this kernel spent its time on two 64-bit divisions per row per thread:
 // profiles/r01_stitch.md).
 constexpr int kStitchV = 2;  // float4 per thread per row
@@ -167,7 +75,11 @@ struct RowClass {
     }
 };
 
-template <bool WITH_SUM, bool WITH_ARGMAX, bool WITH_COUNT>
+// PHASED: dw * n is not a multiple of 4, so the 16-byte phase of a row segment changes from row to row (p = row * dw * n mod 4).
+// A thread then keeps one register set per phase -- the same class values cut into vectors at the four possible offsets -- and the
+// row loop picks the set of the row's phase; the <= 3 floats before the first and after the last aligned vector of a row are
+// stored as scalars from shared memory.
+template <bool WITH_SUM, bool WITH_ARGMAX, bool WITH_COUNT, bool PHASED>
 __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(const float* __restrict__ logits, StitchGrid g,
                                                                               float* __restrict__ sum_map,
                                                                               uint32_t* __restrict__ count_map,
@@ -184,12 +96,13 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(co
     const int tj = (int)((g.dw - j0) < tj_max ? (g.dw - j0) : tj_max);
     const int64_t i0 = row_begin + (int64_t)blockIdx.y * rows_per_block;
     const int64_t i1 = (i0 + rows_per_block) < row_end ? (i0 + rows_per_block) : row_end;
-    const int nvec = (tj * n) >> 2;  // (tj * n) % 4 == 0 by construction
+    const int tile_floats = tj * n;
+    const int nvec = tile_floats >> 2;  // !PHASED: (tj * n) % 4 == 0 by construction
     const int tid = threadIdx.x;
 
     RowClass rc;
     rc.init(i0, g.ps, g.stride, g.d);
-    float4 vreg[kStitchV];
+    float4 vreg[PHASED ? 4 : 1][kStitchV];
     uint32_t creg[2] = {0, 0};
     uint32_t areg[2] = {0, 0};
     float* out_row = WITH_SUM ? sum_map + ((i0 - row_begin) * g.dw + j0) * n : nullptr;
@@ -281,10 +194,22 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(co
             }
             __syncthreads();
             if (WITH_SUM) {
+                if constexpr (PHASED) {
 #pragma unroll
-                for (int v = 0; v < kStitchV; ++v) {
-                    const int q = tid + v * kStitchThreads;
-                    if (q < nvec) vreg[v] = reinterpret_cast<const float4*>(vals)[q];
+                    for (int p = 0; p < 4; ++p) {
+                        const int head = (4 - p) & 3;
+#pragma unroll
+                        for (int v = 0; v < kStitchV; ++v) {
+                            const int b = head + 4 * (tid + v * kStitchThreads);
+                            if (b + 3 < tile_floats) vreg[p][v] = make_float4(vals[b], vals[b + 1], vals[b + 2], vals[b + 3]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < kStitchV; ++v) {
+                        const int q = tid + v * kStitchThreads;
+                        if (q < nvec) vreg[0][v] = reinterpret_cast<const float4*>(vals)[q];
+                    }
                 }
             }
             if (WITH_COUNT) {
@@ -308,12 +233,36 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(co
         }
         // stream the class out: nothing but stores and pointer increments per row
         if (WITH_SUM) {
-            float4* o0 = reinterpret_cast<float4*>(out_row) + tid;
-            const bool h0 = tid < nvec, h1 = tid + kStitchThreads < nvec;
-            for (int64_t r = 0; r < run; ++r) {
-                if (h0) __stcs(o0, vreg[0]);
-                if (h1) __stcs(o0 + kStitchThreads, vreg[1]);
-                o0 = reinterpret_cast<float4*>(reinterpret_cast<float*>(o0) + row_floats);
+            if constexpr (PHASED) {
+                float* rowp = out_row;
+                int p = (int)(((i - row_begin) * row_floats + j0 * n) & 3);   // sum_map is 16-byte aligned (host check)
+                const int pstep = (int)(row_floats & 3);
+                for (int64_t r = 0; r < run; ++r) {
+                    int head = (4 - p) & 3;
+                    if (head > tile_floats) head = tile_floats;            // a last tile of one or two floats
+                    const int nv = (tile_floats - head) >> 2;
+                    const int tail0 = head + 4 * nv;
+                    float4* o = reinterpret_cast<float4*>(rowp + head) + tid;
+                    const bool h0 = tid < nv, h1 = tid + kStitchThreads < nv;
+                    switch (p) {
+                        case 0: if (h0) __stcs(o, vreg[0][0]); if (h1) __stcs(o + kStitchThreads, vreg[0][1]); break;
+                        case 1: if (h0) __stcs(o, vreg[1][0]); if (h1) __stcs(o + kStitchThreads, vreg[1][1]); break;
+                        case 2: if (h0) __stcs(o, vreg[2][0]); if (h1) __stcs(o + kStitchThreads, vreg[2][1]); break;
+                        default: if (h0) __stcs(o, vreg[3][0]); if (h1) __stcs(o + kStitchThreads, vreg[3][1]); break;
+                    }
+                    if (tid < head) rowp[tid] = vals[tid];
+                    else if (tid >= 32 && tid - 32 < tile_floats - tail0) rowp[tail0 + tid - 32] = vals[tail0 + tid - 32];
+                    rowp += row_floats;
+                    p = (p + pstep) & 3;
+                }
+            } else {
+                float4* o0 = reinterpret_cast<float4*>(out_row) + tid;
+                const bool h0 = tid < nvec, h1 = tid + kStitchThreads < nvec;
+                for (int64_t r = 0; r < run; ++r) {
+                    if (h0) __stcs(o0, vreg[0][0]);
+                    if (h1) __stcs(o0 + kStitchThreads, vreg[0][1]);
+                    o0 = reinterpret_cast<float4*>(reinterpret_cast<float*>(o0) + row_floats);
+                }
             }
             out_row += run * row_floats;
         }
@@ -632,7 +581,8 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
     const int64_t rows = row_end - row_begin;
     cudaStream_t st = as_stream(stream);
     const bool s = sum_map != nullptr, a = argmax_u8 != nullptr, c = count_map != nullptr;
-    if (!s || (g.dw * n) % 4 == 0) {
+    {
+        const bool phased = s && (g.dw * n) % 4 != 0;
         // aligned fast path: column tile = multiple of 16 cells with at most kStitchV float4 per thread per row
         int tj = (kStitchThreads * 4 * kStitchV / n) & ~15;
         if (tj > 2 * kStitchThreads) tj = 2 * kStitchThreads;
@@ -645,31 +595,14 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
         const int amax_vec = (a && g.dw % 4 == 0 && reinterpret_cast<uintptr_t>(argmax_u8) % 4 == 0) ? 1 : 0;
         dim3 grid((unsigned)col_tiles, (unsigned)row_groups);
         size_t smem = (size_t)tj * n * sizeof(float) + (size_t)tj * sizeof(uint32_t) + (size_t)tj;
-#define DH_STA(S, A, C) stitch_dense_aligned_kernel<S, A, C><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, (int)rpb, amax_vec)
-        if (s) { if (a) { if (c) DH_STA(true, true, true); else DH_STA(true, true, false); } else { if (c) DH_STA(true, false, true); else DH_STA(true, false, false); } }
-        else   { if (a) { if (c) DH_STA(false, true, true); else DH_STA(false, true, false); } else { DH_STA(false, false, true); } }
+#define DH_STA(S, A, C, P) stitch_dense_aligned_kernel<S, A, C, P><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, (int)rpb, amax_vec)
+        if (s && phased) { if (a) { if (c) DH_STA(true, true, true, true); else DH_STA(true, true, false, true); } else { if (c) DH_STA(true, false, true, true); else DH_STA(true, false, false, true); } }
+        else if (s) { if (a) { if (c) DH_STA(true, true, true, false); else DH_STA(true, true, false, false); } else { if (c) DH_STA(true, false, true, false); else DH_STA(true, false, false, false); } }
+        else   { if (a) { if (c) DH_STA(false, true, true, false); else DH_STA(false, true, false, false); } else { DH_STA(false, false, true, false); } }
 #undef DH_STA
         DH_CHECK_LAUNCH("stitch_dense_aligned_kernel");
         return DH_OK;
     }
-    int tj = 2048 / n;
-    tj = tj / 32 * 32;
-    if (tj > 256) tj = 256;
-    if (tj < 32) tj = 32;
-    const int64_t col_tiles = (g.dw + tj - 1) / tj;
-    // enough row groups to fill the machine a few times over, but long enough to reuse a row class
-    int rpb = 32;
-    while (rpb > 4 && col_tiles * ((rows + rpb - 1) / rpb) < (int64_t)kNumSMs * 8) rpb >>= 1;
-    const int64_t row_groups = (rows + rpb - 1) / rpb;
-    DH_REQUIRE(row_groups <= 65535, "dh_stitch_dense: too many row groups (%lld); stitch in bands", (long long)row_groups);
-    dim3 grid((unsigned)col_tiles, (unsigned)row_groups);
-    size_t smem = (size_t)(4 * (tj * n + 4)) * sizeof(float) + (size_t)tj * sizeof(uint32_t) + (size_t)tj;
-#define DH_ST(S, A, C) stitch_dense_kernel<S, A, C><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, rpb)
-    if (s) { if (a) { if (c) DH_ST(true, true, true); else DH_ST(true, true, false); } else { if (c) DH_ST(true, false, true); else DH_ST(true, false, false); } }
-    else   { if (a) { if (c) DH_ST(false, true, true); else DH_ST(false, true, false); } else { DH_ST(false, false, true); } }
-#undef DH_ST
-    DH_CHECK_LAUNCH("stitch_dense_kernel");
-    return DH_OK;
 }
 
 extern "C" DH_API int dh_stitch_dense(const float* logits, int64_t H, int64_t W, int ps, int stride, int d, int n, int batch_size,

@@ -13,7 +13,7 @@ sys.path.insert(0, str(ROOT))
 from deephisto_b200 import ops  # noqa: E402
 
 peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
-H = W = 40000
+H = W = int(sys.argv[1]) if len(sys.argv) > 1 else 40000     # e.g. 39999: dw * n is not a multiple of 4 floats -> the PHASED store path
 PS, STRIDE, B, N = 224, 112, 64, 5
 n, npad = ops.dense_count(H, W, PS, STRIDE, B)
 g = torch.Generator(device="cuda").manual_seed(0)
