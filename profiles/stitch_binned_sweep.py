@@ -16,9 +16,9 @@ from deephisto_b200 import _lib, ops  # noqa: E402
 
 peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 lib = _lib.require_device()
-H = W = 40000
 PS, N = 224, 5
 CODES = [int(c) for c in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 16, 32, 64, 128]
+H = W = int(sys.argv[2]) if len(sys.argv) > 2 else 40000     # e.g. 39999: rows not 16-byte aligned -> scalar-store tile kernel
 
 
 def timeit(fn, reps):
