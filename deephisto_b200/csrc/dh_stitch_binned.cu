@@ -36,6 +36,8 @@ struct BinGeom {
     int scale;              // units per cell: n (sum mode) or 1 (cell mode)
     int TH, TW;             // tile = TH rows x TW units (TW = 32 * VEC * G)
     int G;                  // groups of 32 * VEC units per tile: a lane owns VEC consecutive units in each group
+    int phased;             // sum map rows not 16-byte aligned (dw * n % 4 != 0): in row r a tile covers units [t*TW + s_r, (t+1)*TW + s_r),
+                            // s_r = (4 - r * dw * n) mod 4, so that every 4-unit vector is aligned; lists are binned 3 units wider
 };
 
 struct BinRec {
@@ -86,7 +88,8 @@ __global__ void __launch_bounds__(256) bin_patches_kernel(const int32_t* __restr
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
         BinRec f;
         if (!bin_footprint(g, __ldg(coords + 2 * p), __ldg(coords + 2 * p + 1), f)) continue;
-        const int ty0 = f.r0 / g.TH, ty1 = (f.r1 - 1) / g.TH, tx0 = f.u0 / g.TW, tx1 = (f.u1 - 1) / g.TW;
+        const int ty0 = f.r0 / g.TH, ty1 = (f.r1 - 1) / g.TH, tx1 = (f.u1 - 1) / g.TW;
+        const int tx0 = g.phased ? (f.u0 >= 3 ? (f.u0 - 3) / g.TW : 0) : f.u0 / g.TW;   // phased tiles reach 3 units to the right
         for (int ty = ty0; ty <= ty1; ++ty)
             for (int tx = tx0; tx <= tx1; ++tx) {
                 const int64_t t = (int64_t)ty * g.ntx + tx;
@@ -125,9 +128,13 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
     }
     __syncwarp();
   constexpr int W1 = CELL ? 1 : VEC;                       // units a lane handles per pass (the fast kernel's lane-to-unit map does not matter here)
-  for (int gi = 0; gi < g.TW / (32 * W1); ++gi) {
+  const int npass = g.TW / (32 * W1);
+  // phased tiles also own the 3 units right of the tile (a neighbour's vectors start 0..3 units late); writing them from both sides
+  // stores identical values
+  const int64_t ulimit = g.phased ? ((tx + 1) * g.TW + 3 < g.units_per_row ? (tx + 1) * g.TW + 3 : g.units_per_row) : g.units_per_row;
+  for (int gi = 0; gi < npass + (g.phased ? 1 : 0); ++gi) {
     const int64_t ubase = tx * g.TW + (int64_t)gi * 32 * W1 + (int64_t)lane * W1;
-    const bool active = ubase < g.units_per_row;
+    const bool active = ubase < ulimit;
     int cls[W1];
     int c = (int)(ubase % n);
 #pragma unroll
@@ -177,7 +184,8 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
                 float* o = sum_map + (int64_t)r * g.units_per_row + ubase;
                 for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
 #pragma unroll
-                    for (int k = 0; k < W1; ++k) o[k] = acc[k];
+                    for (int k = 0; k < W1; ++k)
+                        if (ubase + k < ulimit) o[k] = acc[k];
                 }
             }
         }
@@ -187,6 +195,51 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
 }
 
 __host__ __device__ inline int bin_warp_smem_bytes(int n, bool staged) { return kBinCap * 20 + kBinCap * 4 * (staged ? n : 1); }
+
+struct BinStage {
+    uint32_t* ids;   // [L] patch indices, ascending
+    int2* rows;      // [L] band-relative rows [r0, r1)
+    int2* cols;      // [L] units [u0, u1)
+    float* lg;       // [L * n] logits (STAGED)
+};
+
+// per-warp staging: sorted patch ids, their row and unit ranges, their logits (the unsorted ids alias the logits area)
+template <bool STAGED>
+__device__ __forceinline__ BinStage bin_stage(unsigned char* base, const float* __restrict__ logits, const int32_t* __restrict__ coords,
+                                              const BinGeom& g, const uint32_t* __restrict__ list, uint32_t beg, int L, int lane, bool load_logits) {
+    BinStage st;
+    const int n = g.n;
+    st.ids = reinterpret_cast<uint32_t*>(base);
+    st.rows = reinterpret_cast<int2*>(base + kBinCap * 4);
+    st.cols = reinterpret_cast<int2*>(base + kBinCap * 12);
+    st.lg = reinterpret_cast<float*>(base + kBinCap * 20);
+    uint32_t* s_raw = reinterpret_cast<uint32_t*>(st.lg);
+    for (int j = lane; j < L; j += 32) s_raw[j] = list[beg + j];
+    __syncwarp();
+    for (int j = lane; j < L; j += 32) {  // rank sort: patch indices are distinct within a tile
+        const uint32_t v = s_raw[j];
+        int rank = 0;
+        for (int i = 0; i < L; ++i) rank += s_raw[i] < v;
+        st.ids[rank] = v;
+    }
+    __syncwarp();
+    for (int j = lane; j < L; j += 32) {
+        const uint32_t id = st.ids[j];
+        BinRec f;
+        bin_footprint(g, __ldg(coords + 2 * (int64_t)id), __ldg(coords + 2 * (int64_t)id + 1), f);
+        st.rows[j] = make_int2(f.r0, f.r1);
+        st.cols[j] = make_int2(f.u0, f.u1);
+    }
+    if (STAGED && load_logits) {
+        for (int e = lane; e < L * n; e += 32) {
+            const int j = e / n;
+            st.lg[e] = __ldg(logits + (int64_t)st.ids[j] * n + (e - j * n));
+        }
+    }
+    __syncwarp();
+    return st;
+}
+
 
 template <int VEC, int G, bool CELL, bool STAGED>
 __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords, BinGeom g,
@@ -207,37 +260,12 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
         bin_tile_slow<VEC, CELL>(logits, coords, g, beg, L, list, sorted, sum_map, count_map, argmax_map, ty, tx);
         return;
     }
-    // per-warp staging: sorted patch ids, their row and unit ranges, their logits (the unsorted ids alias the logits area)
-    unsigned char* base = bin_smem + (size_t)w * bin_warp_smem_bytes(n, STAGED);
-    uint32_t* s_ids = reinterpret_cast<uint32_t*>(base);
-    int2* s_rows = reinterpret_cast<int2*>(base + kBinCap * 4);
-    int2* s_cols = reinterpret_cast<int2*>(base + kBinCap * 12);
-    float* s_lg = reinterpret_cast<float*>(base + kBinCap * 20);
-    uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_lg);
-
-    for (int j = lane; j < L; j += 32) s_raw[j] = list[beg + j];
-    __syncwarp();
-    for (int j = lane; j < L; j += 32) {  // rank sort: patch indices are distinct within a tile
-        const uint32_t v = s_raw[j];
-        int rank = 0;
-        for (int i = 0; i < L; ++i) rank += s_raw[i] < v;
-        s_ids[rank] = v;
-    }
-    __syncwarp();
-    for (int j = lane; j < L; j += 32) {
-        const uint32_t id = s_ids[j];
-        BinRec f;
-        bin_footprint(g, __ldg(coords + 2 * (int64_t)id), __ldg(coords + 2 * (int64_t)id + 1), f);
-        s_rows[j] = make_int2(f.r0, f.r1);
-        s_cols[j] = make_int2(f.u0, f.u1);
-    }
-    if (STAGED && (!CELL || argmax_map != nullptr)) {
-        for (int e = lane; e < L * n; e += 32) {
-            const int j = e / n;
-            s_lg[e] = __ldg(logits + (int64_t)s_ids[j] * n + (e - j * n));
-        }
-    }
-    __syncwarp();
+    const BinStage stg = bin_stage<STAGED>(bin_smem + (size_t)w * bin_warp_smem_bytes(n, STAGED), logits, coords, g, list, beg, L, lane,
+                                           !CELL || argmax_map != nullptr);
+    uint32_t* s_ids = stg.ids;
+    int2* s_rows = stg.rows;
+    int2* s_cols = stg.cols;
+    float* s_lg = stg.lg;
 
     constexpr int GS = 32 * VEC;                             // units per group: group gi of the tile starts GS * gi units further right
     const int ub = (int)(tx * g.TW) + lane * VEC;            // first unit owned by this lane in group 0 (units_per_row + TW < 2^31, host check)
@@ -338,6 +366,99 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
     }
 }
 
+// Sum map whose rows are NOT 16-byte aligned (dw * n % 4 != 0; BinGeom::phased): in row r every lane's vector starts s_r units
+// later, s_r = (4 - r * dw * n) mod 4, which makes its address a multiple of 16 bytes. A lane therefore sums the 7 units
+// [ub, ub + 7) of a row run once and stores the window [ub + s_r, ub + s_r + 4) of each row; the first s_r units of a row are
+// scalar stores of tile 0, the last vector of a row is clipped to the row end.
+template <bool STAGED>
+__global__ void __launch_bounds__(kBinWarps * 32) bin_tile_phased_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords, BinGeom g,
+                                                                         const uint32_t* __restrict__ off, const uint32_t* __restrict__ len,
+                                                                         const uint32_t* __restrict__ list, uint32_t* __restrict__ sorted,
+                                                                         float* __restrict__ sum_map) {
+    extern __shared__ __align__(16) unsigned char bin_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t ctas_x = (g.ntx + kBinWarps - 1) / kBinWarps;
+    const int64_t ty = blockIdx.x / ctas_x;
+    const int64_t tx = (blockIdx.x % ctas_x) * kBinWarps + w;
+    if (tx >= g.ntx) return;
+    const int64_t t = ty * g.ntx + tx;
+    const uint32_t beg = off[t];
+    const int L = (int)len[t];
+    const int n = g.n;
+    if (L > kBinCap) {
+        bin_tile_slow<4, false>(logits, coords, g, beg, L, list, sorted, sum_map, nullptr, nullptr, ty, tx);
+        return;
+    }
+    const BinStage stg = bin_stage<STAGED>(bin_smem + (size_t)w * bin_warp_smem_bytes(n, STAGED), logits, coords, g, list, beg, L, lane, true);
+    constexpr int NU = 7;                                    // units summed per lane: a 4-unit window at shift 0..3
+    const int RF = (int)g.units_per_row;
+    const int ub = (int)(tx * g.TW) + lane * 4;
+    int cls[NU];
+    {
+        int c = ub % n;
+#pragma unroll
+        for (int k = 0; k < NU; ++k) { cls[k] = c; c = c + 1 == n ? 0 : c + 1; }
+    }
+    const int R0 = (int)(ty * g.TH);
+    const int R1 = (int)((int64_t)R0 + g.TH < g.rows ? R0 + g.TH : g.rows);
+    const int pstep = RF & 3;
+    int r = R0;
+    while (r < R1) {
+        float acc[NU];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) acc[k] = 0.f;
+        int next = R1;
+        for (int c0 = 0; c0 < L; c0 += 32) {
+            const int j = c0 + lane;
+            const int2 rw = j < L ? stg.rows[j] : make_int2(0x7fffffff, 0x7fffffff);
+            const int cand = rw.x > r ? rw.x : (rw.y > r ? rw.y : 0x7fffffff);
+            const int nb = __reduce_min_sync(0xffffffffu, cand);
+            next = nb < next ? nb : next;
+            unsigned m = __ballot_sync(0xffffffffu, rw.x <= r && r < rw.y);
+            while (m) {  // covering patches in ascending list index = the reference's order
+                const int jj = c0 + __ffs(m) - 1;
+                m &= m - 1;
+                const int2 cu = stg.cols[jj];
+                const int lo = cu.x - ub, hi = cu.y - ub;
+                const float* lg = STAGED ? stg.lg + jj * n : logits + (int64_t)stg.ids[jj] * n;
+#pragma unroll
+                for (int k = 0; k < NU; ++k) {
+                    const float v = STAGED ? lg[cls[k]] : __ldg(lg + cls[k]);
+                    acc[k] += (k >= lo && k < hi) ? v : 0.f;   // adding +0.0f is the identity: a sum that starts at +0.0f is never -0.0f
+                }
+            }
+        }
+        float* rowp = sum_map + (int64_t)r * RF;
+        int p = (int)(((int64_t)r * RF) & 3);                 // sum_map is 16-byte aligned (host check)
+        for (int rr = r; rr < next; ++rr) {
+            const int s = (4 - p) & 3;
+            float w0, w1, w2, w3;
+            switch (s) {
+                case 0: w0 = acc[0]; w1 = acc[1]; w2 = acc[2]; w3 = acc[3]; break;
+                case 1: w0 = acc[1]; w1 = acc[2]; w2 = acc[3]; w3 = acc[4]; break;
+                case 2: w0 = acc[2]; w1 = acc[3]; w2 = acc[4]; w3 = acc[5]; break;
+                default: w0 = acc[3]; w1 = acc[4]; w2 = acc[5]; w3 = acc[6]; break;
+            }
+            const int u = ub + s;
+            if (u + 4 <= RF) {
+                *reinterpret_cast<float4*>(rowp + u) = make_float4(w0, w1, w2, w3);
+            } else if (u < RF) {                                 // the last vector of the row, clipped
+                rowp[u] = w0;
+                if (u + 1 < RF) rowp[u + 1] = w1;
+                if (u + 2 < RF) rowp[u + 2] = w2;
+            }
+            if (tx == 0 && lane == 0) {                          // the s units before the row's first aligned vector
+                if (s > 0) rowp[0] = acc[0];
+                if (s > 1) rowp[1] = acc[1];
+                if (s > 2) rowp[2] = acc[2];
+            }
+            rowp += RF;
+            p = (p + pstep) & 3;
+        }
+        r = next;
+    }
+}
+
 // profiling override: rows + 1000 * groups + 100000 * extra shared-memory KB per CTA (each field 0 = heuristic / none)
 static int tile_rows_for(int ps, int d) {
     if (g_bin_tile_rows % 1000 > 0) return g_bin_tile_rows % 1000;
@@ -352,14 +473,15 @@ static int groups_for(bool cell, int vec, int ps, int d, int n) {
     return (int64_t)(ps / d) * n >= 512 ? 2 : 1;  // wide footprints: 256-float tiles halve the per-tile staging work (measured: profiles/r01_stitch.md)
 }
 
-static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows, int64_t dw, int64_t row_offset) {
+static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows, int64_t dw, int64_t row_offset, bool phased = false) {
     BinGeom g;
+    g.phased = phased ? 1 : 0;
     g.rows = rows; g.row_offset = row_offset; g.dw = dw;
     g.ps = ps; g.d = d; g.n = n;
     g.scale = cell ? 1 : n;
     g.units_per_row = dw * g.scale;
     g.TH = tile_rows_for(ps, d);
-    g.G = groups_for(cell, vec, ps, d, n);
+    g.G = phased ? 1 : groups_for(cell, vec, ps, d, n);
     g.TW = 32 * vec * g.G;
     g.nty = (rows + g.TH - 1) / g.TH;
     g.ntx = (g.units_per_row + g.TW - 1) / g.TW;
@@ -367,7 +489,7 @@ static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows,
 }
 
 static int64_t entries_cap(const BinGeom& g, int64_t P) {
-    const int64_t fh = g.ps / g.d + 1, fw = (int64_t)(g.ps / g.d + 1) * g.scale;  // largest footprint, rows / units
+    const int64_t fh = g.ps / g.d + 1, fw = (int64_t)(g.ps / g.d + 1) * g.scale + (g.phased ? 3 : 0);  // largest footprint, rows / units
     const int64_t tyx = (fh - 1 + g.TH - 1) / g.TH + 1, txx = (fw - 1 + g.TW - 1) / g.TW + 1;
     return P * tyx * txx;
 }
@@ -393,7 +515,7 @@ static void carve_bin(const BinGeom& g, int64_t P, void* base, BinScratch& s) {
 
 static bool sum_vec4(const float* sum_map, int64_t dw, int n) { return (dw * n) % 4 == 0 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0; }
 
-template <int VEC, int G, bool CELL, bool STAGED>
+template <int VEC, int G, bool CELL, bool STAGED, bool PHASED = false>
 static int run_binned(const float* logits, const int32_t* coords, int64_t P, const BinGeom& g, float* sum_map, uint32_t* count_map,
                       uint8_t* argmax_u8, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
     BinScratch s;
@@ -417,12 +539,21 @@ static int run_binned(const float* logits, const int32_t* coords, int64_t P, con
     // at least 50 KB per CTA = at most 4 resident CTAs per SM: a fifth one only adds HBM write interleaving (measured 1.5-3 % slower)
     int smem = kBinWarps * bin_warp_smem_bytes(g.n, STAGED) + (g_bin_tile_rows / 100000) * 1024;
     if (!CELL && smem < 50 * 1024) smem = 50 * 1024;
-    auto kern = bin_tile_kernel<VEC, G, CELL, STAGED>;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_tile_kernel)");
+    if constexpr (PHASED) {
+        auto kern = bin_tile_phased_kernel<STAGED>;
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_tile_phased_kernel)");
+        }
+        kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map);
+    } else {
+        auto kern = bin_tile_kernel<VEC, G, CELL, STAGED>;
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_tile_kernel)");
+        }
+        kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map, count_map, argmax_u8);
     }
-    kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map, count_map, argmax_u8);
     DH_CHECK_LAUNCH("bin_tile_kernel");
     return DH_OK;
 }
@@ -439,8 +570,8 @@ extern "C" DH_API int dh_stitch_binned_set_tile_rows(int rows) {
 extern "C" DH_API int64_t dh_stitch_binned_scratch_bytes(int64_t P, int ps, int d, int n, int64_t rows, int64_t dw) {
     if (P <= 0 || ps <= 0 || d <= 0 || n <= 0 || rows <= 0 || dw <= 0) return 256;
     int64_t need = 0;
-    for (int mode = 0; mode < 4; ++mode) {  // sum (16-byte stores), sum (scalar stores), cell, cell x 4
-        BinGeom g = make_geom(mode >= 2, mode == 0 || mode == 3 ? 4 : 1, ps, d, n, rows, dw, 0);
+    for (int mode = 0; mode < 5; ++mode) {  // sum (16-byte stores), sum (scalar stores), cell, cell x 4, sum (phased 16-byte stores)
+        BinGeom g = make_geom(mode == 2 || mode == 3, mode == 1 || mode == 2 ? 1 : 4, ps, d, n, rows, dw, 0, mode == 4);
         BinScratch s;
         carve_bin(g, P, nullptr, s);
         need = s.total_bytes > need ? s.total_bytes : need;
@@ -470,9 +601,13 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
     const bool staged = n <= kBinMaxN;
     if (sum_map) {
         const bool v4 = sum_vec4(sum_map, dw, n);
-        const BinGeom g = make_geom(false, v4 ? 4 : 1, ps, d, n, rows, dw, row_offset);
-        if (v4 && g.G == 2) rc = staged ? run_binned<4, 2, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
-                                        : run_binned<4, 2, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        // rows not 16-byte aligned (dw * n % 4 != 0) but an aligned base: 16-byte stores at a per-row shift (bin_tile_phased_kernel)
+        const bool phased = !v4 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 && dw * (int64_t)n >= 8;
+        const BinGeom g = make_geom(false, v4 || phased ? 4 : 1, ps, d, n, rows, dw, row_offset, phased);
+        if (phased) rc = staged ? run_binned<4, 1, false, true, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
+                                : run_binned<4, 1, false, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        else if (v4 && g.G == 2) rc = staged ? run_binned<4, 2, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
+                                             : run_binned<4, 2, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (v4) rc = staged ? run_binned<4, 1, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
                                  : run_binned<4, 1, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else rc = staged ? run_binned<1, 1, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
