@@ -602,7 +602,8 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
     if (sum_map) {
         const bool v4 = sum_vec4(sum_map, dw, n);
         // rows not 16-byte aligned (dw * n % 4 != 0) but an aligned base: 16-byte stores at a per-row shift (bin_tile_phased_kernel)
-        const bool phased = !v4 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 && dw * (int64_t)n >= 8;
+        // (not for small footprints: 7 instead of 4 sums per lane cost more than the vector stores save -- measured at d = 16)
+        const bool phased = !v4 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 && dw * (int64_t)n >= 8 && ps / d >= 24;
         const BinGeom g = make_geom(false, v4 || phased ? 4 : 1, ps, d, n, rows, dw, row_offset, phased);
         if (phased) rc = staged ? run_binned<4, 1, false, true, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
                                 : run_binned<4, 1, false, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
