@@ -124,3 +124,28 @@ def patch_origin(g: DenseGrid, i: int) -> tuple[int, int]:
     if i < g.main_n + g.ny + g.nx:
         return g.H - g.ps, (i - g.main_n - g.ny) * g.stride
     return g.H - g.ps, g.W - g.ps
+
+
+def stream_jobs(g: DenseGrid, patch_ranges, row_bytes: int, budget_bytes: int) -> list[tuple[int, int, list[tuple[int, int]]]]:
+    """Row chunks for predicting a slide that is NOT resident in HBM: [(slide_y0, slide_y1, [(first, count)])] -- each job uploads
+    slide rows [slide_y0, slide_y1) (at most ~budget_bytes of `row_bytes`-wide rows, never less than one patch row) and computes
+    the listed entries of the padded dense enumeration. `patch_ranges` is what plan_band produces: whole main-grid rows, their
+    last-column entries (these ride with their grid rows) and optionally the tail (last row, corner, padding copies). Consecutive
+    chunks re-upload the ps - stride rows they share."""
+    ps, stride = g.ps, g.stride
+    per = max(1, (max(budget_bytes // max(row_bytes, 1), ps) - ps) // stride + 1)   # main-grid rows per chunk
+    jobs = []
+    for first, count in patch_ranges:
+        if count <= 0:
+            continue
+        if first < g.main_n:                                              # whole main-grid rows [lo, hi)
+            if first % g.nx or count % g.nx:
+                raise ValueError("main-grid patch ranges must cover whole grid rows")
+            lo, hi = first // g.nx, (first + count) // g.nx
+            for a in range(lo, hi, per):
+                b = min(a + per, hi)
+                jobs.append((a * stride, (b - 1) * stride + ps, [(a * g.nx, (b - a) * g.nx), (g.main_n + a, b - a)]))
+        elif first >= g.main_n + g.ny:                                     # last row, corner, padding copies
+            jobs.append((g.H - ps, g.H, [(first, count)]))
+        # entries [main_n + lo, main_n + hi) (last column) ride with their grid rows above
+    return jobs

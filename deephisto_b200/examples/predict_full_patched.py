@@ -233,20 +233,7 @@ class ImagePredictorPatched:
         from ..slide import band_to_device
 
         g = bands.dense_grid(sampler.h, sampler.w, sampler.patch_size, sampler.stride, sampler.batch_size)
-        ps, stride = g.ps, g.stride
-        pitch = ops.DeviceSlide.pitch_for(sampler.w)
-        budget = int(max_band_bytes or self._stream_band_bytes)
-        per = max(1, (max(budget // pitch, ps) - ps) // stride + 1)          # main-grid rows per chunk
-        jobs = []                                                             # (slide_y0, slide_y1, [(first, count)])
-        for first, count in patch_ranges:
-            if first < g.main_n:                                              # whole main-grid rows [lo, hi]
-                lo, hi = first // g.nx, (first + count) // g.nx
-                for a in range(lo, hi, per):
-                    b = min(a + per, hi)
-                    jobs.append((a * stride, (b - 1) * stride + ps, [(a * g.nx, (b - a) * g.nx), (g.main_n + a, b - a)]))
-            elif first >= g.main_n + g.ny:                                     # last row, corner, padding copies
-                jobs.append((g.H - ps, g.H, [(first, count)]))
-            # the last-column entries [main_n + lo, main_n + hi] ride with their grid rows above
+        jobs = bands.stream_jobs(g, patch_ranges, ops.DeviceSlide.pitch_for(sampler.w), int(max_band_bytes or self._stream_band_bytes))
         cur = torch.cuda.current_stream(self._device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self._device)

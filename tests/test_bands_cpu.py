@@ -181,3 +181,31 @@ def test_sharded_slide_upload_gloo_world3(tmp_path):
         outs.append(out)
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"OK {r}" in out, out[-2000:]
+
+
+@pytest.mark.parametrize("case", [(1500, 1000, 224, 112, 16), (8192, 8192, 224, 224, 16), (1000, 777, 224, 100, 7), (448, 448, 224, 224, 4),
+                                  (224, 900, 224, 112, 8)])
+@pytest.mark.parametrize("world", [1, 3])
+def test_stream_jobs_cover_every_patch_once_with_its_rows(case, world):
+    """bands.stream_jobs (row chunks of a slide streamed through HBM): over all ranks' bands every entry of the padded enumeration a
+    band needs appears in exactly one job of that band, and the job's slide rows contain the patch; chunks respect the byte budget."""
+    H, W, ps, stride, B = case
+    g = bands.dense_grid(H, W, ps, stride, B)
+    row_bytes = (3 * W + 15) // 16 * 16
+    for budget_rows in (ps, ps + 2 * stride, 10 * ps):
+        for rank in range(world):
+            plan = bands.plan_band(H, W, ps, stride, 8, B, rank, world)
+            jobs = bands.stream_jobs(g, plan.patch_ranges, row_bytes, budget_rows * row_bytes)
+            seen = []
+            for y0, y1, ranges in jobs:
+                assert 0 <= y0 < y1 <= H
+                assert y1 - y0 <= max(budget_rows, ps) or len(jobs) == 1 or y0 == H - ps
+                for first, count in ranges:
+                    for i in range(first, first + count):
+                        y, _ = bands.patch_origin(g, i)
+                        assert y0 <= y and y + ps <= y1, (i, y, y0, y1)
+                        seen.append(i)
+            assert sorted(seen) == sorted(bands.patch_indices(plan))
+    if g.ny > 0 and g.nx > 1:
+        with pytest.raises(ValueError):
+            bands.stream_jobs(g, [(1, g.nx)], row_bytes, 1 << 30)          # main-grid ranges must be whole grid rows
