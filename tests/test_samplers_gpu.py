@@ -307,14 +307,16 @@ def test_install_dropin_registers_reference_module_names(api):
     ("sample_annotated_rnd", ["--synthetic", "6000", "6000", "-n", "4", "--quiet"]),
     ("sample_annotated_dense", ["--synthetic", "6000", "6000", "--polygons", "3", "--stride", "200"]),
     ("predict_full_patched", ["--synthetic", "1500", "1300", "--downscale", "16"]),
+    ("extract_patches_for_test_set", ["--synthetic", "6000", "6000", "--polygons", "5", "--patches-per-class", "8", "--out", "{tmp}"]),
 ])
-def test_example_entry_points_run(script, extra):
+def test_example_entry_points_run(script, extra, tmp_path):
     """The reference's `python -m examples.<name>` entry points (README.md:19-32) run end to end on synthetic inputs."""
     import subprocess
     import sys
     from pathlib import Path
 
     root = Path(__file__).resolve().parent.parent
+    extra = [str(tmp_path / "out") if a == "{tmp}" else a for a in extra]
     out = subprocess.run([sys.executable, "-m", f"deephisto_b200.examples.{script}", *extra], cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert ("items/s" in out.stdout) or ("Gpx/s" in out.stdout)
