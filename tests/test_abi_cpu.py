@@ -144,3 +144,43 @@ def test_tile_spans_cover_the_rectangles_once():
         y0, y1, x0, x1 = max(0, y0), min(H, y1), max(0, x0), min(W, x1)
         assert (cov[y0:y1, 3 * x0 : 3 * x1] == 1).all()
     assert len(sl.tile_spans([], H, W, pitch)) == 0
+
+
+def test_dense_count_and_band_plans_property():
+    """Host-only arithmetic against the oracle's restatement of the reference enumeration (full_samplers.py:374-404) on random
+    shapes: dh_dense_count (C), bands.dense_grid (Python) and the oracle agree; every rank's band plan lists exactly the patches
+    whose footprint touches its rows; dh_stitch_binned_scratch_bytes is monotone in the list length."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from deephisto_b200 import bands, ops
+    from oracle import dense as odense
+
+    lib = _lib.load()
+
+    @settings(max_examples=60, deadline=None)
+    @given(ps=st.sampled_from([32, 64, 100, 224]), extra_h=st.integers(0, 700), extra_w=st.integers(0, 700), stride=st.integers(8, 300),
+           B=st.integers(1, 70), d=st.sampled_from([1, 3, 4, 16]), world=st.integers(1, 5))
+    def check(ps, extra_h, extra_w, stride, B, d, world):
+        H, W = ps + extra_h, ps + extra_w
+        coords, n = odense.dense_coords(H, W, ps, stride, B)
+        N, npad = ops.dense_count(H, W, ps, stride, B)
+        g = bands.dense_grid(H, W, ps, stride, B)
+        assert (N, npad) == (n, len(coords)) == (g.N, g.n_padded)
+        for i in (0, N - 1, npad - 1, N // 2):
+            assert bands.patch_origin(g, i) == tuple(int(v) for v in coords[i])
+        dh = H // d
+        covered = set()
+        for rank in range(world):
+            plan = bands.plan_band(H, W, ps, stride, d, B, rank, world)
+            idx = set(bands.patch_indices(plan))
+            touching = {i for i, (y, _x) in enumerate(coords.tolist()) if y // d < plan.row_end and min((y + ps) // d, dh) > plan.row_begin}
+            assert touching <= idx, (rank, sorted(touching - idx)[:5])
+            covered |= idx
+        if dh > 0:
+            assert {i for i, (y, _x) in enumerate(coords.tolist()) if min((y + ps) // d, dh) > y // d} <= covered
+        a = lib.dh_stitch_binned_scratch_bytes(npad, ps, d, 5, max(dh, 1), max(W // d, 1))
+        b = lib.dh_stitch_binned_scratch_bytes(2 * npad, ps, d, 5, max(dh, 1), max(W // d, 1))
+        assert 0 < a <= b
+
+    check()
