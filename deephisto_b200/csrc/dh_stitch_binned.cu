@@ -16,8 +16,9 @@
 //   tile   : one warp per tile: rank-sort the segment by patch index (shared memory), clip the footprints to tile-relative
 //            ranges, then walk the tile's rows. Rows between two footprint boundaries have identical values (run-length): the
 //            lane's values are recomputed only at a boundary and stored to every row of the run.
-// Two tile kernels share the binning: `sum` (a lane owns VEC consecutive floats of a map row; 16-byte stores) and `cell`
-// (a lane owns one cell: n <= 8 class sums in registers -> argmax byte and/or count).
+// Three tile kernels share the binning: `sum` (bin_tile_kernel<VEC, G, false>: a lane owns G groups of VEC consecutive floats of a map
+// row; 16-byte stores), `cell` (bin_tile_kernel<VEC, 1, true>: a lane owns 1 or 4 cells, n <= 8 class sums in registers -> argmax byte
+// and / or count) and `phased sum` (bin_tile_phased_kernel: map rows that are not 16-byte aligned, 16-byte stores at a per-row shift).
 #include "dh_common.cuh"
 
 namespace dh {
