@@ -72,6 +72,13 @@ class DeviceBatchPredictor:
             model = model.to(memory_format=torch.channels_last)
         self.model = model
 
+    def gather(self, slide, coords: torch.Tensor, ps: int) -> torch.Tensor:
+        """[B,3,ps,ps] model input for patches at `coords`, written by dh_gather_normalize in the memory format the model runs in:
+        channels_last models get an NHWC buffer viewed as NCHW (no layout pass between the gather and the first convolution)."""
+        if self.channels_last:
+            return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True).permute(0, 3, 1, 2)
+        return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NCHW", scale255=True)
+
     @torch.no_grad()
     def logits(self, features: torch.Tensor) -> torch.Tensor:
         if self.channels_last:
@@ -220,7 +227,7 @@ class ImagePredictorPatched:
                 coords = ops.dense_coords(sampler.h, sampler.w, ps, sampler.stride, sampler.batch_size, first=a, count=c, device=self._device)
                 if y_off:
                     coords[:, 0] -= y_off
-                feats = ops.gather_normalize(slide, coords, ps, dtype=pred.dtype, layout="NCHW", scale255=True)
+                feats = pred.gather(slide, coords, ps)
             with self._mark("cnn"):
                 logits[a : a + c] = pred.logits(feats)
 
@@ -325,7 +332,7 @@ class ImagePredictorPatched:
 
         def flush():
             coords = pending[0] if len(pending) == 1 else torch.cat(pending)
-            feats = ops.gather_normalize(s._slide, coords, s.patch_size, dtype=pred.dtype, layout="NCHW", scale255=True)
+            feats = pred.gather(s._slide, coords, s.patch_size)
             return pred.logits(feats), coords, s.patch_size, progress
 
         for coords, progress in s.coords_generator():
