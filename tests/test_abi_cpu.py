@@ -184,3 +184,36 @@ def test_dense_count_and_band_plans_property():
         assert 0 < a <= b
 
     check()
+
+
+def test_anno_utils_host_side():
+    """anno.utils pieces that need no GPU (reference anno/utils.py:19-246, 371-408): class descriptions, visualiser parameters,
+    patch-accent parsing, preview sizing, legend drawing."""
+    from PIL import Image
+
+    from deephisto_b200.anno import utils as au
+
+    d = au.AnnoDescription.with_known_colors({"AT": (245, 119, 34), "BG": (153, 255, 255)})
+    assert [c.id for c in d.anno_classes] == [0, 1] and d.color_by_label("BG") == (153, 255, 255)
+    auto = au.AnnoDescription.with_auto_colors(["a", "b", "c"])
+    assert len({c.color for c in auto.anno_classes}) == 3 and all(0 <= v <= 255 for c in auto.anno_classes for v in c.color)
+    c = au.AnnoClass(3, "TUM", alternate_labels=("tumor",), description="x", color=(1, 2, 3))
+    assert c.label_full == "TUM (tumor)" and "TUM (tumor)" in str(c)
+    p = au.AnnoVisualizerParams.default()
+    assert (p.fill, p.fill_transparency, p.line_width, p.show_legend, p.legend_placement, p.legend_size) == (True, 0.3, 2, True, "TR", 20)
+    assert au.AnnoVisualizerParams.no_legend().show_legend is False
+    acc = au.PatchVisAccent.parse("r28_LP_7_x17311_y14066", layer=2, patch_s=224)
+    assert (acc.layer, acc.size, acc.x, acc.y, acc.label) == (2, 224, 17311, 14066, "LP")
+    v = au.AnnoVisualizer(d)
+    assert v._downscale(40000, 30000, None, 2000, False) == 20 and v._downscale(1000, 1000, 0.25, None, False) == 4
+    assert v._downscale(500, 400, None, None, False) == 1
+    with pytest.raises(RuntimeError, match="too big"):
+        v._downscale(100000, 100000, None, None, False)
+    assert v._downscale(100000, 100000, None, None, True) == 7
+    with pytest.raises(ValueError):
+        v._downscale(100, 100, 1.5, None, False)
+    img = Image.new("RGB", (320, 200), (10, 10, 10))
+    for place in ("TL", "TR", "BL", "BR"):
+        v.vis_params = au.AnnoVisualizerParams(True, 0.3, 2, True, place, 12)
+        out = v._add_legend(img.copy())
+        assert out.size == (320, 200) and out.getcolors(maxcolors=1 << 16) is not None and len(out.getcolors(maxcolors=1 << 16)) > 2
