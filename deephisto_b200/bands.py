@@ -147,5 +147,14 @@ def stream_jobs(g: DenseGrid, patch_ranges, row_bytes: int, budget_bytes: int) -
                 jobs.append((a * stride, (b - 1) * stride + ps, [(a * g.nx, (b - a) * g.nx), (g.main_n + a, b - a)]))
         elif first >= g.main_n + g.ny:                                     # last row, corner, padding copies
             jobs.append((g.H - ps, g.H, [(first, count)]))
-        # entries [main_n + lo, main_n + hi) (last column) ride with their grid rows above
+        elif g.nx == 0:                                                    # W == ps: the last column IS the grid, nothing to ride with
+            lo, hi = first - g.main_n, first - g.main_n + count
+            for a in range(lo, hi, per):
+                b = min(a + per, hi)
+                jobs.append((a * stride, (b - 1) * stride + ps, [(g.main_n + a, b - a)]))
+        # otherwise entries [main_n + lo, main_n + hi) (last column) ride with their grid rows above
+    covered = sum(c for _, _, rs in jobs for _, c in rs)
+    wanted = sum(c for _, c in patch_ranges if c > 0)
+    if covered != wanted:
+        raise ValueError(f"stream_jobs covers {covered} of {wanted} patch entries (last-column ranges must match their grid rows)")
     return jobs

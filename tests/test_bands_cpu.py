@@ -23,6 +23,9 @@ CASES = [  # (H, W, ps, stride, d, batch)
     (300, 260, 32, 48, 4, 5),      # stride > ps: gaps between patches
     (224, 500, 224, 64, 8, 3),     # h == ps: no main-grid rows
     (448, 448, 224, 224, 1, 4),
+    (32, 32, 32, 8, 16, 1),        # one patch, dh = 2: with world 3 / 8 some ranks own no map rows
+    (40, 64, 32, 8, 32, 3),        # dh = 1
+    (500, 224, 224, 64, 8, 3),     # w == ps: the last column is the whole grid
 ]
 
 
@@ -53,6 +56,8 @@ def test_band_plan_reproduces_full_map(case, world):
         assert (plan.row_begin, plan.row_end) == bands.band_rows(dh, rank, world)
         idx = bands.patch_indices(plan)
         assert len(idx) == len(set(idx)) == plan.n_patches
+        if plan.row_end == plan.row_begin:                       # world > dh: an empty band computes nothing
+            assert plan.n_patches == 0 and plan.patch_ranges == []
         masked = np.zeros_like(logits)
         masked[idx] = logits[idx]
         # zeroed logits still ADD 0.0 in the oracle loop; a patch outside the plan must not touch the band at all
@@ -88,11 +93,13 @@ from deephisto_b200.examples.predict_full_patched import assemble_bands
 from oracle import dense as odense, stitch as ostitch
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
-for (H, W, ps, stride, d, B) in [(1000, 777, 224, 100, 3, 7), (2048, 2048, 224, 112, 16, 64)]:
+for (H, W, ps, stride, d, B) in [(1000, 777, 224, 100, 3, 7), (2048, 2048, 224, 112, 16, 64), (40, 64, 32, 8, 32, 3)]:  # last: dh = 1 < world
     coords, _ = odense.dense_coords(H, W, ps, stride, B)
     logits = np.random.default_rng(9).standard_normal((len(coords), 5)).astype(np.float32)
     full, _, famax = ostitch.stitch(logits, coords, H, W, ps, d)
     plan = bands.plan_band(H, W, ps, stride, d, B, rank, world)
+    if H // d < world and plan.row_end == plan.row_begin:
+        assert plan.n_patches == 0 and plan.rows_max == 1
     keep = np.zeros(len(coords), bool); keep[bands.patch_indices(plan)] = True
     band, _, bamax = ostitch.stitch(logits[keep], coords[keep], H, W, ps, d, plan.row_begin, plan.row_end)
     pad = torch.zeros((plan.rows_max,) + band.shape[1:]); pad[: len(band)] = torch.from_numpy(band)
@@ -184,7 +191,7 @@ def test_sharded_slide_upload_gloo_world3(tmp_path):
 
 
 @pytest.mark.parametrize("case", [(1500, 1000, 224, 112, 16), (8192, 8192, 224, 224, 16), (1000, 777, 224, 100, 7), (448, 448, 224, 224, 4),
-                                  (224, 900, 224, 112, 8)])
+                                  (224, 900, 224, 112, 8), (900, 224, 224, 112, 8), (224, 224, 224, 112, 8)])
 @pytest.mark.parametrize("world", [1, 3])
 def test_stream_jobs_cover_every_patch_once_with_its_rows(case, world):
     """bands.stream_jobs (row chunks of a slide streamed through HBM): over all ranks' bands every entry of the padded enumeration a
