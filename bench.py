@@ -1,26 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the deephisto_b200 hot path (contract: one JSON line on stdout from rank 0).
 
-Default workload = BASELINE.json configs[1]: `examples.sample_annotated_rnd --torch` -- random 224x224 patches inside
+Primary workload = BASELINE.json configs[1]: `examples.sample_annotated_rnd --torch` -- random 224x224 patches inside
 50 synthetic annotation polygons on a 32768 x 32768 synthetic slide, batch 256, fp32 NHWC features in [0,1] + int64
 labels + (y,x) coords, exactly what AnnoRegionRndSampler.torch_generator yields. One step = one batch of 256 patches.
 The device pipeline prefetches CHUNK (32) batches per pair of launches, like AnnoRegionRndSampler.torch_generator:
     dh_region_sample (Philox draws + exact clip-area acceptance, 32 x 256 slots)  ->  dh_gather_normalize (32 x 256 patches)
-so a K-step run is ceil(K/32) chunk pairs (the last one partial) and every batch is a contiguous slice of the chunk buffer.
+so a K-step region is ceil(K/32) chunk pairs (the last one partial) and every batch is a contiguous slice of the chunk buffer.
+The K-step region is timed REGIONS (5) times back to back, each bracketed by barrier + synchronize; `value` is the median region.
 
   value     patches/s over all ranks, inputs (slide, polygon tables) resident in HBM, CUDA-event timed, max over ranks
   e2e       the same metric through the public Python API (AnnoRegionRndSampler.torch_generator) starting from a slide in
-            PINNED HOST memory: its upload to HBM is inside the timed region (once per run -- the slide then stays resident,
-            which is the product's design), and every step ends with the device->host read of the step's labels and
-            coordinates; features stay in HBM for the consumer CNN (`features_to_host` also reports the PCIe-bound variant)
-  roofline  dominant kernel (gather+normalise): algorithmic bytes / CUDA-event time of that kernel vs measured HBM peak
+            PINNED HOST memory, every step ending with the device->host read of the step's labels and coordinates. A K-step job
+            that needs fewer pixel bytes than half the slide gathers them IN PLACE from the pinned buffer (zero-copy: the gather's
+            bulk row copies read host memory over PCIe; the layer becomes resident in the background, after the job's last
+            gather); a longer job uploads the layer first (once) and then runs from HBM. e2e.* flat keys attribute the time.
+  roofline  dominant kernel (gather+normalise): algorithmic bytes of the launches ACTUALLY TIMED / their CUDA-event time vs the
+            measured HBM peak; at N = 1 also roofline.stitch_* = the stitch kernels on the 40k x 40k case (BASELINE configs[2])
+  e2e.predict_*  BASELINE's second metric in the same line: whole-slide patched prediction of a 100 000 x 100 000 synthetic
+            slide (configs[3]; ResNet18 bf16 channels_last via torch/cuDNN), row bands over the N ranks + NCCL all-gather,
+            Gpx/s with the band resident and end to end from pinned host memory, our kernels' and the CNN's share, band parity
   cpu_baseline / --impl reference: the reference's CPU path (oracle/cpu_pipeline.py restates
             AnnoRegionRndSampler.torch_generator; the reference itself needs psimage + shapely, which do not exist)
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload annotated_rnd|predict]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload annotated_rnd|train_input|predict]
 
-`--workload predict` (BASELINE configs[2]/[3]): whole-slide patched prediction, ResNet18 (torch/cuDNN) on a synthetic
-40k x 40k slide (1 GPU) or 100k x 100k slide row-band sharded over N GPUs; metric = gigapixels/s; one step = one slide.
+`--workload predict` runs only the prediction part (any slide size / CNN options) as its own line; one step = one slide.
 """
 
 from __future__ import annotations
@@ -148,13 +153,32 @@ def init_nccl(dev):
 # --------------------------------------------------------------------------------------------------------------------
 # CPU legs (run in a process that never touched CUDA: they start worker pools)
 METRIC = "patches/sec sampled+normalised"
-CONFIG = {
-    "workload": "examples.sample_annotated_rnd --torch (BASELINE configs[1]): 224x224 random patches inside 50 synthetic polygons, "
-                "32768x32768 uint8 RGB slide, batch 256, patches_from_one_region 4, region_intersection 0.75, fp32 NHWC /255",
-    "slide": list(SLIDE_HW), "patch": PS, "batch": BATCH, "polygons": N_POLY, "chunk_batches": CHUNK,
-    "l2_policy": "inputs larger than L2: random patches of a 3.2 GB slide; every gather launch writes a 4.9 GB chunk (32 batches of "
-                 "154 MB) into one of two alternating buffers (126 MB L2)",
-}
+REGIONS = 5                            # the K-step region is timed this many times; `value` is the median
+PREDICT_HW = (100000, 100000)          # BASELINE configs[3]; the same slide for every N (strong scaling)
+PREDICT_STEPS = 2                      # timed slides of the prediction part (1 warm-up slide before them)
+STITCH_HW = (40000, 40000)             # BASELINE configs[2]: the stitch roofline case
+
+
+def make_config(world: int) -> dict:
+    """`config` of BOTH arms (identical dicts, so the driver's same_config check holds)."""
+    return {
+        "workload": "examples.sample_annotated_rnd --torch (BASELINE configs[1]): 224x224 random patches inside 50 synthetic polygons, "
+                    "32768x32768 uint8 RGB slide, batch 256, patches_from_one_region 4, region_intersection 0.75, fp32 NHWC /255",
+        "slide": list(SLIDE_HW), "patch": PS, "batch": BATCH, "polygons": N_POLY, "chunk_batches": CHUNK, "timed_regions": REGIONS,
+        "l2_policy": "inputs larger than L2: random patches of a 3.2 GB slide; every gather launch writes >= 3.8 GB of features into one "
+                     "of two alternating buffers (126 MB L2)",
+        "parallelism": f"replicated slide, batches sharded by rank (x{world}), no data-path collective",
+        "predict_workload": f"examples.predict_full_patched (BASELINE configs[3]) in the same line as e2e.predict_*: patch_cls_simple ResNet18 "
+                            f"(random init, seed 0) on a synthetic {PREDICT_HW[0]}x{PREDICT_HW[1]} slide, 224x224 patches at stride 112, dense "
+                            f"sampler batch 64, stitch downscale 16, argmax map; row bands x{world} with patch-size halo + NCCL all-gather of "
+                            f"the u8 class-map bands; 1 warm-up + {PREDICT_STEPS} timed slides (strong scaling: the slide is the same for every N)",
+        "stitch_workload": f"roofline.stitch_*: dh_stitch_dense / dh_stitch_binned sum maps of the {STITCH_HW[0]}x{STITCH_HW[1]} stride-112 case "
+                           "(BASELINE configs[2]), n = 5 classes; binned = the coverage sampler's own coordinate list; unaligned = 39999x39999 "
+                           "(map rows not 16-byte aligned); N = 1 only",
+    }
+
+
+CONFIG = make_config(1)
 
 
 def cpu_pipe(cores):
@@ -220,12 +244,25 @@ def reference_arm(args):
     desc = (f"{args.steps} steps x {sample} patches (bounded sample of the 256-patch batch) of the same workload ({H}x{W} slide in host RAM, "
             f"{N_POLY} polygons), {cores} worker processes, {bpw} sampled batches (= {bpw * sample} patches, the reference's 2 x 256) per job like the "
             f"reference's spawn ProcessPoolExecutor (pool start-up excluded); {dt:.2f} s")
+    e2e = {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if not args.no_predict:
+        # BASELINE's second metric on the host cores: the oracle port of examples.predict_full_patched on a 2048 x 2048 crop (324 patches,
+        # CPU ResNet18 fp32); seconds per 100k x 100k slide = crop time x (795 712 / 384 padded patches), linear in the patch count
+        crop = cpu_predict_crop(steps=1)
+        from deephisto_b200 import bands
+
+        full = bands.dense_grid(PREDICT_HW[0], PREDICT_HW[1], PS, 112, 64).n_padded
+        s_full = crop["s_per_crop"] * full / crop["patches"]
+        e2e.update({"predict_gpx_per_s": PREDICT_HW[0] * PREDICT_HW[1] / 1e9 / s_full, "predict_e2e_gpx_per_s": PREDICT_HW[0] * PREDICT_HW[1] / 1e9 / s_full,
+                    "predict_s_per_slide": s_full, "predict_ms_ours": None, "predict_ms_cnn": 1e3 * crop["cnn_s"] * full / crop["patches"],
+                    "predict_halo_frac": 0.0, "predict_band_parity": None, "predict_patches_per_s": crop["patches"] / crop["s_per_crop"],
+                    "predict_crop_gpx_per_s": crop["gpx_per_s"], "predict_extrapolated_from": "2048x2048 crop, linear in padded patch count"})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": make_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "patches/s", "cores": cores, "kind": "port", "sample": desc},
-        "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": e2e,
         "gpu_launches": 0,
         "note": "oracle port of AnnoRegionRndSampler.torch_generator (region_samplers.py:685-738): the reference itself cannot run "
                 "(psimage and shapely are neither vendored nor installable); CPU tensors are left on the host as the reference yields them",
@@ -233,20 +270,60 @@ def reference_arm(args):
     emit(line)
 
 
+def cpu_predict_crop(steps=1, hw=2048):
+    """ImagePredictorPatched.process + batch_predictor restated on the CPU (oracle), hw x hw crop, ResNet18 on the host cores."""
+    import numpy as np
+    import torch
+
+    from deephisto_b200.examples.predict_full_patched import get_model
+    from oracle import cpu_pipeline, stitch as ostitch, synth
+
+    H = W = hw
+    slide = synth.synth_slide(H, W, 0)
+    torch.manual_seed(0)
+    model = get_model(5).eval()
+    n, cnn_s, patches = 0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(max(1, steps)):
+        logits, coords = [], []
+        for feats, c, _ in cpu_pipeline.dense_batches(slide, PS, 112, 64):
+            c0 = time.perf_counter()
+            with torch.no_grad():
+                logits.append(model(feats.permute(0, 3, 1, 2).contiguous()).numpy())
+            cnn_s += time.perf_counter() - c0
+            coords.append(c.numpy().astype(np.int64))
+        ostitch.stitch(np.concatenate(logits), np.concatenate(coords), H, W, PS, 16)
+        patches = sum(len(c) for c in coords)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"s_per_crop": dt / n, "cnn_s": cnn_s / n, "patches": patches, "gpx_per_s": n * H * W / 1e9 / dt, "n": n, "threads": torch.get_num_threads()}
+
+
 # --------------------------------------------------------------------------------------------------------------------
 MODES = {
     # BASELINE configs[1]
     "annotated_rnd": dict(batch=BATCH, chunk=CHUNK, dtype="f32", torch_dtype="float32", layout="NHWC", dcode=0, lcode=0, esize=4, flips=False,
-                          config=CONFIG, kernel="gather_tma_kernel<float, NHWC, /255> (dh_gather_normalize), one launch per 32-batch chunk"),
+                          kernel="gather_tma_kernel<float, NHWC, /255> (dh_gather_normalize), one launch per chunk of <= 32 batches"),
     # BASELINE configs[4]: the input pipeline of models.patch_cls_simple.train at 8k patches/step, bf16 NCHW with the batch-level
     # random H/V flips of train.py:71-81 fused into the gather
     "train_input": dict(batch=8192, chunk=1, dtype="bf16", torch_dtype="bfloat16", layout="NCHW", dcode=1, lcode=1, esize=2, flips=True,
-                        config=dict(CONFIG, workload="models.patch_cls_simple.train input pipeline (BASELINE configs[4]): on-device annotated random sampling, "
-                                    "8192 patches per step, bf16 NCHW /255 with batch-level random H/V flips (train.py:71-81), same slide and polygons "
-                                    "as configs[1]", batch=8192, chunk_batches=1,
-                                    l2_policy="inputs larger than L2: random patches of a 3.2 GB slide; every step writes a 2.5 GB batch"),
                         kernel="gather_tma_kernel<bf16, NCHW, /255> with flips (dh_gather_normalize), one launch per 8192-patch step"),
 }
+
+
+def mode_config(workload: str, world: int) -> dict:
+    cfg = make_config(world)
+    if workload == "train_input":
+        cfg.update(workload="models.patch_cls_simple.train input pipeline (BASELINE configs[4]): on-device annotated random sampling, "
+                            "8192 patches per step, bf16 NCHW /255 with batch-level random H/V flips (train.py:71-81), same slide and polygons "
+                            "as configs[1]", batch=8192, chunk_batches=1,
+                   l2_policy="inputs larger than L2: random patches of a 3.2 GB slide; every step writes a 2.5 GB batch")
+    return cfg
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
 
 
 def ours(args):
@@ -285,15 +362,19 @@ def ours(args):
     images = torch.empty((2, n_slots), dtype=torch.int32, device=dev)
     status = torch.zeros((2, n_slots), dtype=torch.uint8, device=dev)
     feats = torch.empty((2, n_slots, PS, PS, 3) if mode["layout"] == "NHWC" else (2, n_slots, 3, PS, PS), dtype=out_dtype, device=dev)
+    Wm = max(Wm, 3)
+    chunks_per_region = (K + CHUNK - 1) // CHUNK
+    first_timed = (Wm + CHUNK - 1) // CHUNK * CHUNK                 # keep chunk boundaries aligned with the buffers
+    region_stride = chunks_per_region * CHUNK                       # steps between the starts of consecutive timed regions
     # one H and one V coin per batch, like torchvision's flips of the whole [B,3,H,W] tensor (train.py:71-81)
     flip_bits = None
     if mode["flips"]:
-        n_coins = (max(Wm, 3) + CHUNK + K) * 2 + 4 * CHUNK
+        n_coins = first_timed + REGIONS * region_stride + CHUNK
         coins = torch.randint(0, 4, (n_coins,), generator=torch.Generator().manual_seed(7 + rank), dtype=torch.uint8)
         flip_bits = coins.repeat_interleave(BATCH).to(dev)
     tstruct = C.byref(tables.struct)
     sp, gp = lib.dh_region_sample, lib.dh_gather_normalize
-    sl_ptr, pitch = slide.storage.data_ptr(), slide.pitch
+    sl_ptr, pitch = slide.ptr, slide.pitch
     fail = torch.zeros(1, dtype=torch.uint8, device=dev)
     launches = [0]
 
@@ -344,33 +425,33 @@ def ours(args):
 
     clocks = ClockSampler(local)
     clocks.start()
-    Wm = max(Wm, 3)
     run_steps(0, Wm)
     torch.maximum(fail, status.max().reshape(1), out=fail)
     torch.cuda.synchronize()
-    launches[0] = 0
-    first_timed = (Wm + CHUNK - 1) // CHUNK * CHUNK                 # keep chunk boundaries aligned with the buffers
-    if world > 1:
-        dist.barrier()
-    evs = []
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    t_start.record()
-    run_steps(first_timed, K, evs)
-    t_end.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms_total = t_start.elapsed_time(t_end)
+    # ---- REGIONS timed regions of exactly K steps each, every one bracketed by barrier + synchronize, time = max over ranks ------------
+    evs, region_ms = [], []
+    for r in range(REGIONS):
+        launches[0] = 0
+        if world > 1:
+            dist.barrier()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t_start.record()
+        run_steps(first_timed + r * region_stride, K, evs)
+        t_end.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([t_start.elapsed_time(t_end)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        region_ms.append(float(t.item()))
+    launches_per_region = launches[0]
+    ms_total = median(region_ms)
     gather_ms = [(a.elapsed_time(b), nb) for a, b, nb in evs]
-    gather_total_ms = sum(m for m, _ in gather_ms)
     torch.maximum(fail, status.max().reshape(1), out=fail)
     if int(fail.item()) != 0:
         raise RuntimeError("region sampling reported failed slots")
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     value = world * K * BATCH / (ms_total / 1e3)
     del feats, coords, labels, images, status
     torch.cuda.empty_cache()
@@ -384,13 +465,16 @@ def ours(args):
     def run_api(api, n_batches, to_host=False, h_feats=None):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        first = None
         for f, l, c in api.torch_generator(batch_size=BATCH, n_batches=n_batches, batches_per_worker=2):
             h_labels.copy_(l, non_blocking=True)
             h_coords.copy_(c, non_blocking=True)
             if to_host:
                 h_feats.copy_(f, non_blocking=True)
             torch.cuda.current_stream().synchronize()                 # the consumer reads this step's result
-        return time.perf_counter() - t0
+            if first is None:
+                first = time.perf_counter() - t0
+        return time.perf_counter() - t0, first
 
     def new_api(src, seed):
         return AnnoRegionRndSampler([(src, polys)], layer=1, patch_size=PS, patches_from_one_region=K_PER_REGION, one_image_for_batch=True,
@@ -404,16 +488,32 @@ def ours(args):
     api = new_api(host_slide, 101 + rank)                              # polygon parsing / table build: constructor, not timed (as in the reference)
     if world > 1:
         dist.barrier()
-    e2e_s = run_api(api, K)                                          # includes the one-time H2D upload of the 3.2 GB slide
-    steady_s = run_api(api, K)                                       # same call again: slide already resident
-    t = torch.tensor([e2e_s, steady_s], dtype=torch.float64, device=dev)
+    e2e_s, first_s = run_api(api, K)                                 # K batches from the pinned host slide (in place, or upload first: cost rule)
+    in_flight = int(api.upload_in_flight_bytes())                    # background upload not finished when the timed region ended
+    zero_copy = int(api.zero_copy_bytes)
+    uploaded_in_region = int(api.uploaded_bytes) if zero_copy == 0 else 0
+    steady_s, _ = run_api(api, K)                                    # same call again: slide already resident (run_api synchronises first)
+    ingest = api.ingest_stats()
+    t = torch.tensor([e2e_s, steady_s, first_s or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value, steady_value = (world * K * BATCH / float(x) for x in t.tolist())
+    e2e_s, steady_s, first_s = (float(x) for x in t.tolist())
+    e2e_value, steady_value = world * K * BATCH / e2e_s, world * K * BATCH / steady_s
     h_feats = torch.empty((BATCH, PS, PS, 3) if mode["layout"] == "NHWC" else (BATCH, 3, PS, PS), dtype=out_dtype).pin_memory()
     kh = max(2, min(K, 32 if BATCH <= 256 else 4))
     run_api(api, 2, True, h_feats)
-    e2e_host_s = run_api(api, kh, True, h_feats)
+    e2e_host_s, _ = run_api(api, kh, True, h_feats)
+    slide_bytes = int(host_slide.nbytes)
+    del api, host_slide, h_feats
+    torch.cuda.empty_cache()
+
+    # ---- the stitch kernels against the same roofline (N = 1), and BASELINE's second metric: whole-slide prediction -----------------
+    stitch = stitch_rooflines(torch) if (world == 1 and args.workload == "annotated_rnd" and not args.no_stitch) else {}
+    predict = {}
+    if args.workload == "annotated_rnd" and not args.no_predict:
+        pargs = argparse.Namespace(slide=list(PREDICT_HW), bf16=True, fold_bn=True, cudnn_benchmark=True, cnn_batch=1024,
+                                   steps=PREDICT_STEPS, warmup=1)
+        predict = predict_measure(pargs, dev, world, rank, e2e_steps=1)["flat"]
     clk = clocks.finish()
 
     if rank != 0:
@@ -421,41 +521,57 @@ def ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
-    alg_bytes_batch = BATCH * (PATCH_IN + PATCH_IN * mode["esize"])
-    alg_total = alg_bytes_batch * sum(nb for _, nb in gather_ms)
-    achieved = alg_total / (gather_total_ms / 1e3) / 1e9
-    full = [m for m, nb in gather_ms if nb == CHUNK]
-    traffic = None
+    per_patch = PATCH_IN * (1 + mode["esize"])
+    patches_timed = sum(nb for _, nb in gather_ms) * BATCH
+    gather_total_ms = sum(m for m, _ in gather_ms)
+    achieved = per_patch * patches_timed / (gather_total_ms / 1e3) / 1e9
+    launch_patches = sorted({nb * BATCH for _, nb in gather_ms})
+    traffic, traffic_src = None, None
     tf = ROOT / "profiles" / "gather_traffic.json"
-    if tf.exists() and args.workload == "annotated_rnd":               # ncu capture of exactly this kernel / launch shape
+    if tf.exists() and args.workload == "annotated_rnd":
         cap = json.loads(tf.read_text())
-        if int(cap.get("algorithmic_bytes_per_launch", 0)) == alg_bytes_batch * CHUNK:      # same launch shape as the timed kernel
-            traffic = cap.get("dram_bytes_per_launch")
-    slide_bytes = host_slide.nbytes
-    uploaded = int(api.uploaded_bytes)                                # what actually travelled (the whole layer unless < 1/5 of it is annotated)
+        cap_patches = int(cap.get("algorithmic_bytes_per_launch", 0)) // per_patch
+        if launch_patches == [cap_patches]:                             # the ncu capture has exactly the launch shape timed here
+            traffic, traffic_src = cap.get("dram_bytes_per_launch"), "profiles/gather_traffic.json (ncu --set full of this launch shape)"
+        else:
+            traffic_src = (f"not reported: the committed ncu capture (profiles/gather_traffic.json) is of a {cap_patches}-patch launch "
+                           f"({cap.get('dram_bytes_per_launch')} DRAM bytes vs {cap.get('algorithmic_bytes_per_launch')} algorithmic), the launches timed here hold "
+                           f"{launch_patches} patches")
     line = {
         "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": mode["dtype"],
-        "data": "synthetic", "config": dict(mode["config"], parallelism=f"replicated slide, batches sharded by rank (x{world}), no data-path collective"),
+        "data": "synthetic", "config": mode_config(args.workload, world),
         "gigapixels_per_s": value * PS * PS / 1e9,
-        "roofline": {"bound": "hbm", "kernel": mode["kernel"],
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes_batch * CHUNK, "algorithmic_bytes_per_patch": PATCH_IN * (1 + mode["esize"]),
-                     "kernel_ms_avg_full_chunk": (sum(full) / len(full)) if full else None, "launches_timed": len(gather_ms),
-                     "kernel_ms_per_batch": gather_total_ms / max(sum(nb for _, nb in gather_ms), 1), "frac_of_nominal_8TBs": achieved / 8000.0},
-        "e2e": {"value": e2e_value, "unit": "patches/s", "h2d_bytes_per_step": uploaded / K, "d2h_bytes_per_step": d2h,
-                "api": f"AnnoRegionRndSampler.torch_generator(batch_size={BATCH}, n_batches=K) over a slide in pinned host memory: the timed region "
-                       "contains the one-time H2D upload of the slide (h2d_bytes_total per rank), K batches, and per step the D2H read of labels+coords"
-                       + ("; the ranks hold the same slide, so each uploads 1/world of its rows over its own PCIe link and one NCCL all-gather over "
-                          "NVLink replicates them (slide.sharded_upload)" if world > 1 else ""),
-                "h2d_bytes_total": uploaded, "slide_bytes": slide_bytes, "host_memory_pinned": bool(host_slide.pinned), "seconds": e2e_s,
-                "steady_state": {"value": steady_value, "unit": "patches/s", "note": "the same call repeated with the slide already resident"},
-                "features_to_host": {"value": kh * BATCH / e2e_host_s, "unit": "patches/s", "d2h_bytes_per_step": d2h + h_feats.numel() * mode["esize"]}},
-        "gpu_launches": launches[0],
+        "timed_regions": REGIONS, "region_ms_min": min(region_ms), "region_ms_median": ms_total, "region_ms_max": max(region_ms),
+        "roofline": dict({"bound": "hbm", "kernel": mode["kernel"],
+                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                          "peak_source": peak_src, "algorithmic_bytes_per_launch": per_patch * patches_timed / len(gather_ms),
+                          "algorithmic_bytes_per_patch": per_patch, "patches_per_launch": patches_timed / len(gather_ms),
+                          "launches_timed": len(gather_ms), "kernel_ms_avg": gather_total_ms / len(gather_ms),
+                          "kernel_ms_median": median([m for m, _ in gather_ms]),
+                          "kernel_ms_per_batch": gather_total_ms / max(sum(nb for _, nb in gather_ms), 1), "frac_of_nominal_8TBs": achieved / 8000.0},
+                         **stitch),
+        "e2e": dict({"value": e2e_value, "unit": "patches/s",
+                     "h2d_bytes_per_step": (zero_copy + uploaded_in_region) / K, "d2h_bytes_per_step": d2h,
+                     "api": f"AnnoRegionRndSampler.torch_generator(batch_size={BATCH}, n_batches=K) over a slide in pinned host memory, per step the D2H "
+                            "read of labels+coords. Cost rule of the sampler: a job whose patches need fewer bytes than half the slide reads them IN "
+                            "PLACE from the pinned buffer (the gather kernel's bulk row copies go over PCIe: zero_copy_bytes, counted as patch "
+                            "bytes ps*ps*3; row alignment adds <= 5 %) and the layer is uploaded in the background AFTER the job's last gather "
+                            "(upload_bytes_in_flight_at_end); a longer job uploads the layer first"
+                            + ("; the ranks hold the same slide, so a rank uploads 1/world of its rows over its own PCIe link and one NCCL "
+                               "all-gather over NVLink replicates them (slide.sharded_upload)" if world > 1 else ""),
+                     "seconds": e2e_s, "ms_first_batch": 1e3 * first_s, "zero_copy_bytes": zero_copy, "uploaded_bytes_in_region": uploaded_in_region,
+                     "upload_bytes_in_flight_at_end": in_flight, "ms_alloc": ingest["alloc_ms"], "ms_upload": ingest["upload_ms"],
+                     "ms_allgather": ingest["allgather_ms"], "upload_bytes": ingest["bytes"], "slide_bytes": slide_bytes,
+                     "steady_value": steady_value, "steady_seconds": steady_s,
+                     "features_to_host_value": kh * BATCH / e2e_host_s, "features_to_host_d2h_bytes_per_step": d2h + BATCH * PS * PS * 3 * mode["esize"]},
+                    **predict),
+        "gpu_launches": launches_per_region,
         "clocks": clk,
     }
     if args.with_training and args.workload == "train_input":
-        line["training_consumer"] = training_consumer(api, dev, BATCH, torch)
+        api2 = new_api(source, 55 + rank)
+        line["training_consumer"] = training_consumer(api2, dev, BATCH, torch)
     if world == 1 and not args.no_cpu_baseline and args.workload == "annotated_rnd":
         out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--cpu-leg", "--cpu-budget", str(args.cpu_budget)],
                              capture_output=True, text=True)
@@ -466,6 +582,73 @@ def ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stitch_rooflines(torch, reps=5) -> dict:
+    """roofline.stitch_*: CUDA-event median of `reps` launches of the stitch kernels on the 40k x 40k stride-112 case, sum map, n = 5.
+    Algorithmic bytes = dh*dw*n*4 (every output written once) + P*n*4 (logits read once); frac = that / time / hbm peak."""
+    from deephisto_b200 import ops
+
+    peak, _ = measured_peaks()
+    out = {}
+    n = 5
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return median(ts)
+
+    def cover_list(H, W):
+        st = ops.CoverState(H, W, PS, 16, 2, 1024, seed=0)
+        cells = (H // 16) * (W // 16)
+        parts = []
+        while True:
+            c, counts = st.next_group(16)
+            parts.append(c.reshape(-1, 2))
+            if int(counts[-1].item()) >= cells:
+                keep = int((counts < cells).sum().item()) + 1           # batches up to and including the one that completes coverage
+                parts[-1] = parts[-1][: keep * 1024]
+                break
+        return torch.cat(parts).contiguous()
+
+    keep = {}
+    H, W = STITCH_HW
+    npad = ops.dense_count(H, W, PS, 112, 64)[1]
+    g = torch.Generator(device="cuda").manual_seed(0)
+    dense_lg = torch.randn((npad, n), generator=g, device="cuda")
+    for d in (1, 2, 4, 16):
+        def run():
+            keep["o"] = None                                            # free the previous map first (d = 1: 32 GB)
+            keep["o"] = ops.stitch_dense(dense_lg, H, W, PS, 112, d, 64, want_sum=True)
+        ms = timed(run)
+        alg = (H // d) * (W // d) * n * 4 + npad * n * 4
+        out[f"stitch_dense_d{d}_frac"] = alg / ms / 1e6 / peak
+        out[f"stitch_dense_d{d}_ms"] = ms
+    keep.clear()
+    for tag, (h, w), ds in (("", (H, W), (1, 2, 4, 16)), ("unaligned_", (H - 1, W - 1), (4,))):
+        coords = cover_list(h, w)
+        lg = torch.randn((coords.shape[0], n), generator=g, device="cuda")
+        for d in ds:
+            def run():
+                keep["o"] = None
+                keep["o"] = ops.stitch_binned(lg, coords, PS, d, h // d, w // d, want_sum=True)
+            ms = timed(run)
+            alg = (h // d) * (w // d) * n * 4 + coords.shape[0] * n * 4
+            out[f"stitch_binned_{tag}d{d}_frac"] = alg / ms / 1e6 / peak
+            out[f"stitch_binned_{tag}d{d}_ms"] = ms
+        out[f"stitch_binned_{tag}patches"] = int(coords.shape[0])
+        keep.clear()
+    del dense_lg
+    torch.cuda.empty_cache()
+    return out
 
 
 def training_consumer(api, dev, batch, torch, steps=3, micro=1024):
@@ -517,7 +700,7 @@ def training_consumer(api, dev, batch, torch, steps=3, micro=1024):
 def predict_config(world, args):
     hw = tuple(args.slide) if args.slide else ((40000, 40000) if world == 1 else (100000, 100000))
     return hw, {
-        "workload": f"examples.predict_full_patched (BASELINE configs[{2 if world == 1 else 3}]): patch_cls_simple ResNet18 (random init, seed 0, "
+        "workload": f"examples.predict_full_patched (BASELINE configs[{2 if hw[0] <= 40000 else 3}]): patch_cls_simple ResNet18 (random init, seed 0, "
                     f"{'bf16 channels_last' if args.bf16 else 'fp32, torch defaults (TF32 convolutions)'}{', BatchNorm folded' if args.fold_bn else ''}"
                     f"{', cudnn.benchmark' if args.cudnn_benchmark else ''}) on a synthetic {hw[0]}x{hw[1]} slide, "
                     f"224x224 patches at stride 112, dense sampler batch 64 (CNN batch {args.cnn_batch}), stitch downscale 16, argmax map",
@@ -526,22 +709,52 @@ def predict_config(world, args):
     }
 
 
-def ours_predict(args):
-    import torch
-    import torch.distributed as dist
-
-    from deephisto_b200 import _lib, bands
+def band_parity_check(torch, dist, dev, rank, world) -> int:
+    """Small banded-vs-single self-check inside the bench run (N > 1): with logits that are a fixed function of the patch pixels the
+    NCCL-assembled sum map and class map must equal the single-GPU ones bit for bit (the FixedLogits case of tests/test_multigpu.py)."""
     from deephisto_b200.anno.utils import AnnoDescription
     from deephisto_b200.examples import predict_full_patched as pfp
     from deephisto_b200.patch_samplers import full_samplers as fs
     from deephisto_b200.slide import SyntheticSlide
 
-    world, rank, local = dist_env()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        init_nccl(dev)
-    _lib.require_device()
+    class FixedLogits(pfp.DeviceBatchPredictor):
+        def logits(self, features):
+            f = features.float()
+            return torch.stack([f[:, 0, 3, 7], f[:, 1, 100, 50], f[:, 2, 223, 223], f[:, 0, 0, 0] * 2, f[:, 1, 17, 200] - f[:, 2, 5, 5]], 1).contiguous()
+
+    anno = AnnoDescription.with_auto_colors([f"c{i}" for i in range(5)])
+    mode = fs.SamplerExecutionMode.INMEMORY_SINGLEPROC
+    model = torch.nn.Identity()
+    H, W, stride, d = 3000, 2100, 112, 16
+    ok = 1
+    try:
+        lazy = fs.FullImageDenseSampler(SyntheticSlide(H, W, seed=5), 1, PS, 64, mode, stride=stride, device=dev, lazy_slide=True)
+        out = pfp.ImagePredictorPatched(None, lazy, FixedLogits(model, dev), anno, layer=1, downscale=d, device=dev, cnn_batch=96).process_device(
+            want_sum=True, rank=rank, world=world)
+        full_s = fs.FullImageDenseSampler(SyntheticSlide(H, W, seed=5), 1, PS, 64, mode, stride=stride, device=dev)
+        full = pfp.ImagePredictorPatched(None, full_s, FixedLogits(model, dev), anno, layer=1, downscale=d, device=dev, cnn_batch=128).process_device(want_sum=True)
+        ok = int(torch.equal(out["sum"], full["sum"]) and torch.equal(out["argmax"], full["argmax"]) and out["argmax"].shape == (H // d, W // d))
+    except Exception as e:                                              # a failed self-check must not hide the measured numbers
+        print(f"band parity self-check raised: {e!r}", file=sys.stderr)
+        ok = 0
+    t = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item())
+
+
+def predict_measure(args, dev, world, rank, e2e_steps=None) -> dict:
+    """Whole-slide patched prediction on `world` ranks (process group already initialised when world > 1): args.warmup warm-up slides,
+    args.steps timed slides with this rank's slide band resident (CUDA events, max over ranks), then e2e slides starting from the band in
+    pinned host memory. Returns {"flat": the e2e.predict_* keys, "line": pieces of the standalone --workload predict line}."""
+    import torch
+    import torch.distributed as dist
+
+    from deephisto_b200 import bands
+    from deephisto_b200.anno.utils import AnnoDescription
+    from deephisto_b200.examples import predict_full_patched as pfp
+    from deephisto_b200.patch_samplers import full_samplers as fs
+    from deephisto_b200.slide import PinnedSlide, SyntheticSlide
+
     (H, W), cfg = predict_config(world, args)
     torch.manual_seed(0)
     model = pfp.get_model(5)
@@ -562,8 +775,6 @@ def ours_predict(args):
     def step():
         return ipp.process_device(rank=rank, world=world)["argmax"] if world > 1 else ipp.dense_band_local(0, 1)["argmax_band"]
 
-    clocks = ClockSampler(local)
-    clocks.start()
     for _ in range(Wm):
         out = step()
     torch.cuda.synchronize()
@@ -587,8 +798,6 @@ def ours_predict(args):
     # e2e: every step starts from this rank's slide band in PINNED HOST memory: the public call streams it through HBM in row chunks
     # on a copy stream, one chunk ahead of the CNN (ImagePredictorPatched._logits_streamed), and the class map is read back (what
     # process() returns) -- the reference likewise reads the layer from storage in its constructor (full_samplers.py:53-55)
-    from deephisto_b200.slide import PinnedSlide
-
     host_band = PinnedSlide.from_device(band, y_origin=y_off, full_height=H)     # setup, not timed
     h_map = torch.empty(out.shape, dtype=torch.uint8).pin_memory()
     del band, sampler, ipp
@@ -599,12 +808,14 @@ def ours_predict(args):
     def step2():
         return ipp2.process_device(rank=rank, world=world)["argmax"] if world > 1 else ipp2.dense_band_local(0, 1)["argmax_band"]
 
-    h_map.copy_(step2())                                               # warm-up of the streamed path (allocator)
+    Ke = K if e2e_steps is None else e2e_steps
+    if e2e_steps is None:
+        h_map.copy_(step2())                                           # warm-up of the streamed path (allocator)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     w0 = time.perf_counter()
-    for _ in range(K):
+    for _ in range(Ke):
         h_map.copy_(step2(), non_blocking=True)
         torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
@@ -612,21 +823,58 @@ def ours_predict(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
+    h2d, d2h = int(host_band.nbytes), int(h_map.numel())
+    del host_band, sampler2, ipp2, h_map
+    torch.cuda.empty_cache()
+    parity = band_parity_check(torch, dist, dev, rank, world) if world > 1 else None
+    gpx = H * W / 1e9
+    g = bands.dense_grid(H, W, PS, 112, 64)
+    halo = sum(bands.plan_band(H, W, PS, 112, 16, 64, r, world).n_patches for r in range(world)) / g.n_padded - 1.0
+    ours_ms = sum(v for k, v in stage_ms.items() if k != "cnn")
+    flat = {
+        "predict_gpx_per_s": K * gpx / (ms_total / 1e3), "predict_e2e_gpx_per_s": Ke * gpx / e2e_s, "predict_s_per_slide": ms_total / K / 1e3,
+        "predict_ms_ours": ours_ms, "predict_ms_cnn": stage_ms.get("cnn", 0.0), "predict_ms_gather": stage_ms.get("coords+gather", 0.0),
+        "predict_ms_stitch": stage_ms.get("stitch", 0.0), "predict_ms_assemble": stage_ms.get("assemble (NCCL all-gather)", 0.0),
+        "predict_halo_frac": halo, "predict_band_parity": parity, "predict_patches_per_s": K * g.n_padded / (ms_total / 1e3),
+        "predict_slide_px": H * W, "predict_steps": K, "predict_e2e_steps": Ke, "predict_h2d_bytes_per_slide_per_rank": h2d,
+        "predict_d2h_bytes_per_slide": d2h,
+        "predict_cnn": ("bf16 channels_last" if args.bf16 else "fp32 (TF32 convolutions)") + (", BatchNorm folded" if args.fold_bn else "")
+                       + (", cudnn.benchmark" if args.cudnn_benchmark else "") + f", CNN batch {args.cnn_batch} (torch/cuDNN: not part of the rebuilt path)",
+    }
+    return {"flat": flat, "cfg": cfg, "ms_total": ms_total, "e2e_s": e2e_s, "Ke": Ke, "stage_ms": stage_ms, "grid": g, "plan": plan, "hw": (H, W),
+            "h2d": h2d, "d2h": d2h}
+
+
+def ours_predict(args):
+    import torch
+    import torch.distributed as dist
+
+    from deephisto_b200 import _lib
+
+    world, rank, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        init_nccl(dev)
+    _lib.require_device()
+    clocks = ClockSampler(local)
+    clocks.start()
+    m = predict_measure(args, dev, world, rank)
     clk = clocks.finish()
     if rank == 0:
+        (H, W), K, g = m["hw"], args.steps, m["grid"]
         gpx = H * W / 1e9
-        g = bands.dense_grid(H, W, PS, 112, 64)
         line = {
-            "metric": "WSI gigapixels/sec patched predict", "value": K * gpx / (ms_total / 1e3), "unit": "Gpx/s", "n_gpus": world, "steps": K,
-            "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": "WSI gigapixels/sec patched predict", "value": K * gpx / (m["ms_total"] / 1e3), "unit": "Gpx/s", "n_gpus": world, "steps": K,
+            "warmup": max(1, args.warmup), "ms_per_step": m["ms_total"] / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16" if args.bf16 else "f32", "data": "synthetic",
-            "config": dict(cfg, parallelism=f"row bands x{world} with patch-size halo (recomputed halo patch rows), NCCL all-gather of the u8 class-map bands"),
-            "patches_per_s": K * g.n_padded / (ms_total / 1e3), "patches_per_slide": g.n_padded, "patches_this_rank": plan.n_patches,
-            "e2e": {"value": K * gpx / e2e_s, "unit": "Gpx/s", "h2d_bytes_per_step": int(host_band.nbytes), "d2h_bytes_per_step": int(h_map.numel()),
-                    "api": "per step: ImagePredictorPatched.process_device on a lazy sampler over this rank's slide band in pinned host memory (row "
-                           "chunks of <= 1 GiB uploaded on a copy stream one chunk ahead of the CNN), class map copied to pinned host memory "
-                           "(h2d/d2h bytes are per rank)"},
-            "stage_ms_per_step_rank0": stage_ms,
+            "config": dict(m["cfg"], parallelism=f"row bands x{world} with patch-size halo (recomputed halo patch rows), NCCL all-gather of the u8 class-map bands"),
+            "patches_per_s": K * g.n_padded / (m["ms_total"] / 1e3), "patches_per_slide": g.n_padded, "patches_this_rank": m["plan"].n_patches,
+            "e2e": dict({"value": m["Ke"] * gpx / m["e2e_s"], "unit": "Gpx/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                         "api": "per step: ImagePredictorPatched.process_device on a lazy sampler over this rank's slide band in pinned host memory (row "
+                                "chunks of <= 1 GiB uploaded on a copy stream one chunk ahead of the CNN), class map copied to pinned host memory "
+                                "(h2d/d2h bytes are per rank)"}, **m["flat"]),
+            "stage_ms_per_step_rank0": m["stage_ms"],
             "roofline": None, "gpu_launches": None, "clocks": clk,
             "note": "CNN-bound (torch/cuDNN ResNet18, not part of the rebuilt path): stage_ms_per_step_rank0 separates this repo's kernels "
                     "(coords+gather, stitch, assemble) from the CNN",
@@ -638,33 +886,13 @@ def ours_predict(args):
 
 def reference_arm_predict(args):
     """ImagePredictorPatched.process + batch_predictor restated on the CPU (oracle), 2048 x 2048 crop, model on the host cores."""
-    import numpy as np
-    import torch
-
-    from deephisto_b200.examples.predict_full_patched import get_model
-    from oracle import cpu_pipeline, stitch as ostitch, synth
-
-    H = W = 2048
-    slide = synth.synth_slide(H, W, 0)
-    torch.manual_seed(0)
-    model = get_model(5).eval()
-    t0 = time.perf_counter()
-    n = 0
-    for _ in range(max(1, min(args.steps, 2))):
-        logits, coords = [], []
-        for feats, c, _ in cpu_pipeline.dense_batches(slide, PS, 112, 64):
-            with torch.no_grad():
-                logits.append(model(feats.permute(0, 3, 1, 2).contiguous()).numpy())
-            coords.append(c.numpy().astype(np.int64))
-        ostitch.stitch(np.concatenate(logits), np.concatenate(coords), H, W, PS, 16)
-        n += 1
-    dt = time.perf_counter() - t0
-    val = n * H * W / 1e9 / dt
+    crop = cpu_predict_crop(steps=max(1, min(args.steps, 2)))
+    val = crop["gpx_per_s"]
     emit({"impl": "reference", "metric": "WSI gigapixels/sec patched predict", "value": val, "unit": "Gpx/s", "n_gpus": args.gpus,
-                      "steps": n, "warmup": 0, "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                      "dtype": "f32", "data": "synthetic", "config": {"workload": "oracle port of examples.predict_full_patched on a 2048x2048 crop, CPU ResNet18"},
-                      "cpu_baseline": {"value": val, "unit": "Gpx/s", "cores": torch.get_num_threads(), "kind": "port", "sample": f"{n} x 2048x2048 crop"},
-                      "e2e": {"value": val, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+          "steps": crop["n"], "warmup": 0, "ms_per_step": 1e3 * crop["s_per_crop"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+          "dtype": "f32", "data": "synthetic", "config": {"workload": "oracle port of examples.predict_full_patched on a 2048x2048 crop, CPU ResNet18"},
+          "cpu_baseline": {"value": val, "unit": "Gpx/s", "cores": crop["threads"], "kind": "port", "sample": f"{crop['n']} x 2048x2048 crop"},
+          "e2e": {"value": val, "unit": "Gpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def main():
@@ -681,6 +909,8 @@ def main():
     ap.add_argument("--cudnn-benchmark", action="store_true", help="predict workload: torch.backends.cudnn.benchmark = True")
     ap.add_argument("--with-training", action="store_true", help="train_input workload: also time a ResNet18 bf16 training step fed by the sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-predict", action="store_true", help="default workload: skip the e2e.predict_* part (100k x 100k whole-slide prediction)")
+    ap.add_argument("--no-stitch", action="store_true", help="default workload: skip the roofline.stitch_* part")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the bounded cpu_baseline sample")
     ap.add_argument("--ref-budget", type=float, default=60.0, help="--impl reference: target seconds for the K timed steps")
     ap.add_argument("--cpu-leg", action="store_true", help=argparse.SUPPRESS)

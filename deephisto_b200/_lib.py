@@ -71,6 +71,7 @@ SIGNATURES = {
     "dh_stitch_scatter": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i64, _i64, _vp]),
     "dh_stitch_finalize": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "dh_upload_rects": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "dh_host_device_pointer": (C.c_int, [_vp, C.POINTER(_u64)]),
     "dh_stitch_binned_scratch_bytes": (_i64, [_i64, _i32, _i32, _i32, _i64, _i64]),
     "dh_stitch_binned": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "dh_stitch_binned_set_tile_rows": (C.c_int, [_i32]),

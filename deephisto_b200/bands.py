@@ -107,6 +107,33 @@ def plan_band(H: int, W: int, ps: int, stride: int, d: int, batch_size: int, ran
     return plan
 
 
+def rnd_band(H: int, ps: int, d: int, speedup: int, rank: int, world: int) -> BandPlan:
+    """Row band of rank `rank` for prediction with the coverage-driven RANDOM sampler (the reference's default sampler,
+    examples/predict_full_patched.py:156-163): map rows as in plan_band; slide rows [slide_y0, slide_y1) = the band's pixel rows
+    widened to whole coarse cells of the sampler's 1/speedup accumulator (full_samplers.py:81-94), and to at least one patch.
+    The rank runs its own coverage sampler over exactly these rows, so every coarse cell of the band gets covered by the rank that
+    owns it; patches never leave [slide_y0, slide_y1), and where neighbouring bands had to be widened into each other the stitch
+    still sees every patch (the ranks exchange their (coords, logits) lists, 28 bytes per patch). patch_ranges stays empty: the
+    patches are drawn, not enumerated."""
+    if H < ps:
+        raise ValueError(f"slide height {H} smaller than patch {ps}")
+    dh = H // d
+    r0, r1 = band_rows(dh, rank, world)
+    rows_max = max(band_rows(dh, r, world)[1] - band_rows(dh, r, world)[0] for r in range(world))
+    plan = BandPlan(rank, world, r0, r1, rows_max)
+    if r1 <= r0:
+        return plan
+    y0 = (r0 * d) // speedup * speedup
+    y1 = min(H, -(-(r1 * d) // speedup) * speedup)
+    if r1 == dh:
+        y1 = H                                       # the last band also owns the slide rows below the last whole map row
+    if y1 - y0 < ps:                                 # thin band: widen (downwards first) to hold one patch
+        y1 = min(H, y0 + ps)
+        y0 = max(0, y1 - ps) // speedup * speedup
+    plan.slide_y0, plan.slide_y1 = y0, y1
+    return plan
+
+
 def patch_indices(plan: BandPlan) -> list[int]:
     out: list[int] = []
     for first, count in plan.patch_ranges:

@@ -184,3 +184,16 @@ extern "C" DH_API int dh_upload_rects(uint8_t* slide_dev, int64_t H, int64_t pit
     }
     return DH_OK;
 }
+
+extern "C" DH_API int dh_host_device_pointer(const void* host_ptr, uint64_t* device_ptr_out_host) {
+    DH_REQUIRE(host_ptr && device_ptr_out_host, "dh_host_device_pointer: null pointer");
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, host_ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return cuda_fail(e, "cudaPointerGetAttributes"); }
+    if (attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) {
+        set_error("dh_host_device_pointer: %p is not page-locked host memory mapped into the device address space", host_ptr);
+        return DH_ERR_UNSUPPORTED;
+    }
+    *device_ptr_out_host = (uint64_t)reinterpret_cast<uintptr_t>(attr.devicePointer);
+    return DH_OK;
+}

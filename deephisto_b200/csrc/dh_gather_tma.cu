@@ -149,6 +149,22 @@ __device__ __forceinline__ float norm_f(float f, int c, const TmaGatherParams& p
     return f;
 }
 
+// byte k of `word` -> normalised value, for the fast path.
+// bf16 output with plain /255: ONE FMA on the magic float m = 2^23 + v (exact): fma(m, c, -2^23 * c) = RN(v * c), c = RN(1/255) -- the
+// 2^23 * c term is a power-of-two multiple of c, so it cancels exactly inside the FMA. RN(v * c) differs from the IEEE quotient
+// float(v) / 255 on 126 of the 256 bytes (last fp32 bit), but its bf16 rounding is the same for ALL 256 (exhaustive check in
+// tests/test_oracle_cpu.py::test_bf16_div255_shortcut), so bf16 batches stay bit-identical to bf16(float32(v) / 255): 2.5 instead of
+// 4.5 instructions per element on the output mode that is closest to the issue limit (2 bytes written per input byte).
+template <typename OutT, bool SCALE, bool AFFINE>
+__device__ __forceinline__ float conv_byte(uint32_t word, int k, uint32_t magic, int c, const TmaGatherParams& p) {
+    if constexpr (SCALE && !AFFINE && sizeof(OutT) == 2) {
+        const float m = __uint_as_float(__byte_perm(word, magic, 0x7440u + (uint32_t)k));
+        return __fmaf_rn(m, 0x1.010102p-8f, -0x1.010102p+15f);
+    } else {
+        return norm_f<SCALE, AFFINE>(byte_f(word, k, magic), c, p);
+    }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -305,7 +321,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                         int c = cph[k];
 #pragma unroll
                         for (int j = 0; j < E; ++j) {
-                            f[j] = norm_f<SCALE, AFFINE>(byte_f(w[j >> 2], j & 3, magic), c, p);
+                            f[j] = conv_byte<OutT, SCALE, AFFINE>(w[j >> 2], j & 3, magic, c, p);
                             if (AFFINE) c = c == 2 ? 0 : c + 1;
                         }
                         DH_STORE(ok, f);
@@ -316,7 +332,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
 #pragma unroll
                             for (int j = 0; j < E; ++j) {
                                 const int b = 3 * j + ch;  // byte of pixel j, channel ch
-                                f[j] = norm_f<SCALE, AFFINE>(byte_f(w[b >> 2], b & 3, magic), ch, p);
+                                f[j] = conv_byte<OutT, SCALE, AFFINE>(w[b >> 2], b & 3, magic, ch, p);
                             }
                             DH_STORE(ok + ch * plane, f);
                         }
@@ -327,7 +343,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
 #pragma unroll
                             for (int j = 0; j < E; ++j) {
                                 const int b = 3 * (E - 1 - j) + ch;  // output pixel j = source pixel E-1-j of the mirrored unit
-                                f[j] = norm_f<SCALE, AFFINE>(byte_f(w[b >> 2], b & 3, magic), ch, p);
+                                f[j] = conv_byte<OutT, SCALE, AFFINE>(w[b >> 2], b & 3, magic, ch, p);
                             }
                             DH_STORE(ok + ch * plane, f);
                         }

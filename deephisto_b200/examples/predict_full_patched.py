@@ -19,6 +19,7 @@ assembles the bands with an NCCL all-gather (`torch.distributed` must be initial
 
 from __future__ import annotations
 
+import weakref
 from pathlib import Path
 from typing import Callable, Optional
 
@@ -71,6 +72,10 @@ class DeviceBatchPredictor:
         if self.channels_last:
             model = model.to(memory_format=torch.channels_last)
         self.model = model
+        self._source_model = None                              # weak reference to the caller's module (batch_predictor's cache check)
+
+    def source_model(self):
+        return None if self._source_model is None else self._source_model()
 
     def gather(self, slide, coords: torch.Tensor, ps: int) -> torch.Tensor:
         """[B,3,ps,ps] model input for patches at `coords`, written by dh_gather_normalize in the memory format the model runs in:
@@ -124,14 +129,15 @@ def fold_batchnorm(model: torch.nn.Module) -> torch.nn.Module:
 
 def batch_predictor(patches: list[Patch], model, device) -> np.ndarray:
     """Reference :66-78 (same signature and return type); the /255, NHWC->NCHW and float conversion run in the gather kernel."""
-    key = (id(model), str(device))
-    pred = _PREDICTORS.get(key)
-    if pred is None:
-        pred = _PREDICTORS[key] = DeviceBatchPredictor(model, device)
+    per_model = _PREDICTORS.setdefault(model, {})        # keyed by the model OBJECT (weakly): a collected model takes its predictors along
+    pred = per_model.get(str(device))
+    if pred is None or pred.source_model() is not model:
+        pred = per_model[str(device)] = DeviceBatchPredictor(model, device)
+        pred._source_model = weakref.ref(model)
     return pred(patches)
 
 
-_PREDICTORS: dict = {}
+_PREDICTORS: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
 class ImagePredictorPatched:
@@ -209,10 +215,12 @@ class ImagePredictorPatched:
             if world is not None and world > 1:
                 return self._dense_banded(rank, world, want_sum)
             return self._dense_device(want_sum, want_count)
-        if world is not None and world > 1:
-            raise ValueError("row-band sharding needs a FullImageDenseSampler object and a DeviceBatchPredictor")
         if fast and isinstance(self.patch_sampler, FullImageRndSampler):
+            if world is not None and world > 1:
+                return self._rnd_banded(rank, world, want_sum, want_count)
             return self._scatter_device(self._rnd_batches(), want_sum, want_count)
+        if world is not None and world > 1:
+            raise ValueError("row-band sharding needs a FullImageDenseSampler / FullImageRndSampler object and a DeviceBatchPredictor")
         return self._scatter_device(self._host_batches(), want_sum, want_count)
 
     # ---- dense, device resident, bit-exact sums -----------------------------------------------------------------------
@@ -321,19 +329,22 @@ class ImagePredictorPatched:
         return out
 
     # ---- arbitrary coordinates: scatter-accumulate ------------------------------------------------------------------------
-    def _rnd_batches(self):
+    def _rnd_batches(self, sampler: Optional[FullImageRndSampler] = None):
         """Coverage-driven random sampling (the reference's default, :156-163). The sampler's batches depend on each other through
         the coverage accumulator, the CNN does not feed back into them: coordinates of several sampler batches are collected
         and sent through gather + CNN together (the reference's batch of 64 leaves the tensor cores mostly idle)."""
-        s: FullImageRndSampler = self.patch_sampler
+        s: FullImageRndSampler = self.patch_sampler if sampler is None else sampler
         pred: DeviceBatchPredictor = self.batch_predictor
         target = self._cnn_batch or max(s.batch_size, 1024)
         pending, n_pending, progress = [], 0, 0.0
 
         def flush():
             coords = pending[0] if len(pending) == 1 else torch.cat(pending)
-            feats = pred.gather(s._slide, coords, s.patch_size)
-            return pred.logits(feats), coords, s.patch_size, progress
+            with self._mark("coords+gather"):
+                feats = pred.gather(s._slide, coords, s.patch_size)
+            with self._mark("cnn"):
+                lg = pred.logits(feats)
+            return lg, coords, s.patch_size, progress
 
         for coords, progress in s.coords_generator():
             pending.append(coords)
@@ -343,6 +354,54 @@ class ImagePredictorPatched:
                 pending, n_pending = [], 0
         if pending:
             yield flush()
+
+    def _rnd_banded(self, rank: int, world: int, want_sum: bool, want_count: bool = False) -> dict:
+        """Row-band sharded prediction with the coverage-driven random sampler (the reference's default sampler, :156-163). Rank r
+        owns the map rows of bands.rnd_band and runs ITS OWN coverage sampler (Philox substream r) over the slide rows of that band
+        only, so the CNN work splits evenly and no rank holds more than its band of the slide. Exchange steps (NCCL): (1) the ranks
+        all-gather their (coords, logits) lists -- 28 bytes per patch -- so that every rank stitches ALL patches that touch its rows,
+        in rank-major list order, with dh_stitch_binned: the assembled map is bit-identical to a single-GPU stitch of the concatenated
+        list; (2) the all-gather of the band maps, as for the dense sampler."""
+        import torch.distributed as dist
+
+        s: FullImageRndSampler = self.patch_sampler
+        d, n, ps = self.downscale, len(self.anno.anno_classes), s.patch_size
+        dh, dw = s.h // d, s.w // d
+        plan = bands.rnd_band(s.h, ps, d, s._downscale, rank, world)
+        lgs, cos = [], []
+        if plan.row_end > plan.row_begin:
+            sub = s.band_sampler(plan.slide_y0, plan.slide_y1, rank)
+            for lg, coords, _, _ in self._rnd_batches(sub):
+                lgs.append(lg.reshape(-1, n))
+                c = coords.reshape(-1, 2).clone()
+                c[:, 0] += plan.slide_y0                                           # band-relative -> layer coordinates
+                cos.append(c)
+        lg = torch.cat(lgs) if lgs else torch.zeros((0, n), dtype=torch.float32, device=self._device)
+        co = torch.cat(cos) if cos else torch.zeros((0, 2), dtype=torch.int32, device=self._device)
+        with self._mark("assemble (NCCL all-gather)"):
+            lg_all, co_all, counts = gather_patch_lists(lg, co, world, dist)
+        rows = plan.row_end - plan.row_begin
+        amax_band = torch.zeros((plan.rows_max, dw), dtype=torch.uint8, device=self._device)
+        sum_band = torch.zeros((plan.rows_max, dw, n), dtype=torch.float32, device=self._device) if want_sum else None
+        cnt_band = torch.zeros((plan.rows_max, dw), dtype=torch.int32, device=self._device) if want_count else None
+        if rows > 0:
+            with self._mark("stitch"):
+                sm, cn, am = ops.stitch_binned(lg_all, co_all, ps, d, rows, dw, row_offset=plan.row_begin, want_sum=want_sum or n > 8,
+                                               want_count=want_count, want_argmax=True)
+            amax_band[:rows] = am
+            if want_sum:
+                sum_band[:rows] = sm
+            if want_count:
+                cnt_band[:rows] = cn
+        with self._mark("assemble (NCCL all-gather)"):
+            out = {"argmax": assemble_bands(amax_band, dh, world, dist), "sum": None, "count": None, "logits": lg_all, "coords": co_all,
+                   "plan": plan, "patches_per_rank": counts}
+            if want_sum:
+                out["sum"] = assemble_bands(sum_band, dh, world, dist)
+            if want_count:
+                out["count"] = assemble_bands(cnt_band, dh, world, dist)
+        self.last_sum_map = out["sum"]
+        return out
 
     def _host_batches(self):
         """The reference's loop (:47-54): any iterator of (list[Patch], progress) and any callable list[Patch] -> [B, n]."""
@@ -385,6 +444,27 @@ class ImagePredictorPatched:
                                                    want_argmax=True)
         self.last_sum_map = sum_map
         return {"argmax": amax, "sum": sum_map if want_sum else None, "count": cnt, "logits": lg, "coords": coords}
+
+
+def gather_patch_lists(logits: torch.Tensor, coords: torch.Tensor, world: int, dist):
+    """All-gather per-rank patch lists of different lengths: (logits [sum P_r, n], coords [sum P_r, 2], [P_0 .. P_{world-1}]),
+    concatenated in rank order. Lists are padded to the longest one for the collective (NCCL or gloo)."""
+    n = logits.shape[1]
+    cnt = torch.tensor([logits.shape[0]], dtype=torch.int64, device=logits.device)
+    cnts = torch.empty(world, dtype=torch.int64, device=logits.device)
+    dist.all_gather_into_tensor(cnts, cnt)
+    counts = [int(v) for v in cnts.tolist()]
+    pmax = max(max(counts), 1)
+    # one int32 buffer per rank: [pmax][n] logits bit patterns, then [pmax][2] coordinates
+    mine = torch.zeros(pmax * (n + 2), dtype=torch.int32, device=logits.device)
+    mine[: logits.shape[0] * n] = logits.contiguous().view(torch.int32).reshape(-1)
+    mine[pmax * n : pmax * n + coords.shape[0] * 2] = coords.contiguous().reshape(-1)
+    everything = torch.empty(world * pmax * (n + 2), dtype=torch.int32, device=logits.device)
+    dist.all_gather_into_tensor(everything, mine)
+    everything = everything.view(world, pmax * (n + 2))
+    lg = torch.cat([everything[r, : counts[r] * n].view(torch.float32).reshape(counts[r], n) for r in range(world)])
+    co = torch.cat([everything[r, pmax * n : pmax * n + counts[r] * 2].reshape(counts[r], 2) for r in range(world)])
+    return lg.contiguous(), co.contiguous(), counts
 
 
 def assemble_bands(band: torch.Tensor, dh: int, world: int, dist) -> torch.Tensor:

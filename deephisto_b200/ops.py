@@ -85,6 +85,35 @@ class DeviceSlide:
     def device(self):
         return self.storage.device
 
+    @property
+    def ptr(self) -> int:
+        """Address the kernels read the slide from."""
+        return self.storage.data_ptr()
+
+
+class MappedHostSlide:
+    """A slide layer that stays in PAGE-LOCKED HOST memory and is read by the gather kernels in place, through its device-visible
+    address (dh_host_device_pointer): every bulk row copy of the gather then travels over PCIe, and only the rows of the patches
+    actually drawn do. Same attributes as DeviceSlide where the gather needs them (ptr, H, W, pitch); `device` is the GPU that reads."""
+
+    def __init__(self, host: torch.Tensor, H: int, W: int, pitch: int, device="cuda"):
+        if host.is_cuda or host.dtype != torch.uint8 or not host.is_pinned() or host.numel() < H * pitch:
+            raise ValueError("MappedHostSlide needs a pinned host uint8 tensor of at least H * pitch bytes")
+        lib = _lib.require_device()
+        out = C.c_uint64(0)
+        with torch.cuda.device(device):
+            check(lib.dh_host_device_pointer(host.data_ptr(), C.byref(out)), "dh_host_device_pointer")
+        self.host, self.H, self.W, self.pitch = host, int(H), int(W), int(pitch)
+        self._ptr, self._device = int(out.value), torch.device(device)
+
+    @property
+    def ptr(self) -> int:
+        return self._ptr
+
+    @property
+    def device(self):
+        return self._device
+
 
 def dense_count(H: int, W: int, ps: int, stride: int, batch_size: int) -> tuple[int, int]:
     """(N, N padded to a multiple of batch_size) of full_samplers.py:374-404."""
@@ -109,7 +138,7 @@ def dense_coords(H: int, W: int, ps: int, stride: int, batch_size: int, first: i
     return out
 
 
-def gather_normalize(slide: DeviceSlide, coords: torch.Tensor, ps: int, *, dtype=torch.float32, layout: str = "NHWC",
+def gather_normalize(slide: "DeviceSlide | MappedHostSlide", coords: torch.Tensor, ps: int, *, dtype=torch.float32, layout: str = "NHWC",
                      scale255: bool = True, mean: Optional[Sequence[float]] = None, std: Optional[Sequence[float]] = None,
                      flip: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                      out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -137,7 +166,7 @@ def gather_normalize(slide: DeviceSlide, coords: torch.Tensor, ps: int, *, dtype
         s = (C.c_float * 3)(*(std if std is not None else (1.0, 1.0, 1.0)))
     with torch.cuda.device(coords.device):
         check(
-            lib.dh_gather_normalize(slide.storage.data_ptr(), slide.H, slide.W, slide.pitch, coords.data_ptr(), _ptr(out_index), B,
+            lib.dh_gather_normalize(slide.ptr, slide.H, slide.W, slide.pitch, coords.data_ptr(), _ptr(out_index), B,
                                     ps, out.data_ptr(), _DTYPES[dtype], lay, int(bool(scale255)), m, s, _ptr(flip), _stream()),
             "dh_gather_normalize",
         )
@@ -147,11 +176,11 @@ def gather_normalize(slide: DeviceSlide, coords: torch.Tensor, ps: int, *, dtype
 class SlideTable:
     """Descriptor table of several resident slides for gather_normalize_multi (one launch over a multi-image dataset)."""
 
-    def __init__(self, slides: Sequence[DeviceSlide]):
+    def __init__(self, slides: Sequence[DeviceSlide], device=None):
         self.slides = list(slides)
-        rows = [[s.storage.data_ptr(), s.H, s.W, s.pitch] for s in self.slides]
+        rows = [[s.ptr, s.H, s.W, s.pitch] for s in self.slides]
         self.host = np.ascontiguousarray(np.asarray(rows, dtype=np.int64))
-        self.dev = torch.from_numpy(self.host).to(self.slides[0].device)
+        self.dev = torch.from_numpy(self.host).to(self.slides[0].device if device is None else device)
 
 
 def gather_normalize_multi(table: SlideTable, images: torch.Tensor, coords: torch.Tensor, ps: int, *, dtype=torch.float32, layout: str = "NHWC",

@@ -41,21 +41,26 @@ class FullImageRndSampler:
     """Coverage-driven random sampling until every coarse (1/speedup) cell is covered (full_samplers.py:21-299).
 
     Extra keyword-only arguments (not in the reference): `seed` (Philox key; the reference uses the unseeded
-    global numpy RNG), `device`."""
+    global numpy RNG), `device`, `lazy_slide` (row-band sharded prediction: the layer is not uploaded by the constructor, every
+    rank makes only its band resident through `band_sampler`)."""
 
     def __init__(self, psimage_path: Path, layer: int, patch_size: int, batch_size: int, mode: SamplerExecutionMode,
-                 dense_level: int = 2, speedup: int = 16, *, seed: int = 0, device="cuda"):
+                 dense_level: int = 2, speedup: int = 16, *, seed: int = 0, device="cuda", lazy_slide: bool = False, quiet: bool = False):
         self.mode = mode
         self._psim_path = psimage_path
-        src = open_slide(psimage_path)
-        with src as psim:
+        self._src = open_slide(psimage_path)
+        self._slide_dev = None
+        self._device = device
+        with self._src as psim:
             self.layer = layer
             psim._assert_layer(layer)
             self.h, self.w = psim.layer_size(self.layer)
-            self._slide = layer_to_device(psim, layer, device)
+            if not lazy_slide:
+                self._slide_dev = layer_to_device(psim, layer, device)
         self.dh = self.h // speedup
         self.dw = self.w // speedup
-        print(f"Image {self.h} x {self.w} at {speedup}x -> {self.dh} x {self.dw}")
+        if not quiet:
+            print(f"Image {self.h} x {self.w} at {speedup}x -> {self.dh} x {self.dw}")
         self.patch_size = patch_size
         self.batch_size = batch_size
         self._downscale = speedup
@@ -65,21 +70,46 @@ class FullImageRndSampler:
         self._device = device
         self._state: ops.CoverState | None = None
         self._resume = None
+        self._consumed = 0             # batches handed to the consumer by the running / last iteration
 
-    # -- resume: (accumulator, batch counter) is the whole state of a run (the Philox draws are keyed by seed and batch index) --
+    @property
+    def _slide(self):
+        if self._slide_dev is None:
+            with self._src as psim:
+                self._slide_dev = layer_to_device(psim, self.layer, self._device)
+        return self._slide_dev
+
+    def band_sampler(self, y0: int, y1: int, stream_index: int) -> "FullImageRndSampler":
+        """A coverage sampler over slide rows [y0, y1) only (one rank's row band of a sharded prediction): same parameters, its own
+        accumulator, Philox key = (seed, stream_index) so that the bands draw from disjoint substreams. Coordinates it yields are
+        relative to row y0. A resident slide is viewed in place, a lazy one uploads / generates just these rows."""
+        if not (0 <= y0 < y1 <= self.h) or y1 - y0 < self.patch_size:
+            raise ValueError(f"band [{y0}, {y1}) must lie inside the {self.h}-row layer and hold at least one patch")
+        if self._slide_dev is not None:
+            s = self._slide_dev
+            band = ops.DeviceSlide(s.storage[y0 * s.pitch : y1 * s.pitch], y1 - y0, s.W, s.pitch)
+        else:
+            with self._src as psim:
+                band = band_to_device(psim, self.layer, y0, y1, self._device)
+        seed = (int(self._seed) & 0xFFFFFFFF) | ((int(stream_index) + 1) << 32)
+        return FullImageRndSampler(band, 1, self.patch_size, self.batch_size, self.mode, self.dense_level, self._downscale, seed=seed,
+                                   device=self._device, quiet=True)
+
+    # -- resume: the Philox draws are keyed by (seed, batch index) and the accumulator is a pure function of the batches drawn, so
+    #    (seed, number of batches handed to the consumer) is the whole state of a run
     def state_dict(self) -> dict:
-        if self._state is None:
-            return {"seed": int(self._seed), "batch_index": 0, "accum": None, "filled_ratio": []}
-        torch.cuda.synchronize(self._state.accum.device)
-        return {"seed": int(self._seed), "batch_index": int(self._state.batch_index), "accum": self._state.accum.cpu().clone(),
-                "filled_ratio": list(self._filled_ratio)}
+        """State as of the LAST BATCH HANDED TO THE CONSUMER. The device runs up to two groups ahead of the consumer; those batches are
+        not part of the state -- a restored sampler draws them again (bit-identically) instead of counting their footprints as covered."""
+        k = int(self._consumed)
+        return {"seed": int(self._seed), "batch_index": k, "accum": None, "filled_ratio": list(self._filled_ratio[:k])}
 
     def load_state_dict(self, state: dict) -> None:
-        """The next `generator*()` call continues the saved run instead of starting from an empty accumulator. A state taken in
-        the middle of an iteration includes the batches the device had already enqueued ahead of the consumer."""
+        """The next `generator*()` call continues the saved run: the first `batch_index` batches are replayed on the device (their
+        coordinates discarded; ~40 us each) to rebuild the accumulator, then iteration continues with batch `batch_index`. States that
+        carry an accumulator (saved by an earlier version after a complete iteration) are adopted directly (dh_cover_init)."""
         if int(state["seed"]) != int(self._seed):
             raise ValueError(f"state was saved with seed {state['seed']}, this sampler uses seed {self._seed}")
-        self._resume = state if state.get("accum") is not None else None
+        self._resume = state if (state.get("accum") is not None or int(state.get("batch_index", 0)) > 0) else None
 
     # -- device-side iteration ------------------------------------------------------------------------
     def _group_generator(self, group: int = 16) -> Iterator[tuple[torch.Tensor, list[float]]]:
@@ -91,10 +121,18 @@ class FullImageRndSampler:
         self._state = ops.CoverState(self.h, self.w, self.patch_size, self._downscale, self.dense_level, self.batch_size,
                                      self._seed, self._device)
         cells = self.dh * self.dw
+        self._consumed = 0
+        self._filled_ratio = []
         if self._resume is not None:
-            self._state.restore(self._resume["accum"].to(self._device), self._resume["batch_index"])
-            self._filled_ratio = list(self._resume["filled_ratio"])
-            self._resume = None
+            res, self._resume = self._resume, None
+            k = int(res["batch_index"])
+            if res.get("accum") is not None:
+                self._state.restore(res["accum"].to(self._device), k)
+            else:
+                for a in range(0, k, 256):                                       # replay: same launches, coordinates discarded
+                    self._state.next_group(min(256, k - a))
+            self._filled_ratio = list(res["filled_ratio"])
+            self._consumed = k
             if self._filled_ratio and self._filled_ratio[-1] >= 1:
                 return
         done = False
@@ -115,6 +153,7 @@ class FullImageRndSampler:
         """(int32 device coords [B,2], filled_ratio) per batch until filled_ratio >= 1 (:263-274)."""
         for coords, ratios in self._group_generator():
             for g, r in enumerate(ratios):
+                self._consumed += 1                                              # state_dict(): resume behind the batch being handed out
                 yield coords[g], r
 
     def generator(self) -> Iterator[tuple[list[Patch], float]]:
@@ -135,6 +174,7 @@ class FullImageRndSampler:
             features = features.view((g, self.batch_size) + tuple(features.shape[1:]))
             coords_f = coords.to(torch.float32)
             for i, r in enumerate(ratios):
+                self._consumed += 1
                 yield features[i], coords_f[i], r
 
     # -- reporting helpers of the reference -------------------------------------------------------------

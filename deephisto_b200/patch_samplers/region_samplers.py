@@ -179,7 +179,7 @@ class AnnoRegionRndSampler:
                  patches_from_one_region: int = 4, region_area_influence: float = 0.5, classes: list[str] = None,
                  one_image_for_batch: bool = False, *, seed: int = 0, device="cuda", out_dtype=torch.float32, out_layout: str = "NHWC",
                  flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = None, shard_upload=None,
-                 prefetch_bytes: int = 5 << 30, prefetch_batches: int = 32):
+                 prefetch_bytes: int = 5 << 30, prefetch_batches: int = 32, zero_copy: bool = None, zero_copy_fraction: float = 0.5):
         self.img_anno_paths = img_anno_paths
         self.layer = layer
         self.patch_size = patch_size
@@ -207,7 +207,19 @@ class AnnoRegionRndSampler:
         self._shard_upload = shard_upload      # True / a process group: COLLECTIVE ingestion of pinned slides (slide.sharded_upload); every rank
         #                                        of the group must then iterate the sampler (first use of an image is a collective call)
         self.uploaded_bytes = 0                # bytes copied host -> device for pinned sources so far
+        # Zero-copy ingestion of PINNED host slides (torch_generator): a job whose patches add up to less than `zero_copy_fraction`
+        # of the slide bytes gathers them straight from host memory (the gather's bulk row copies read the mapped pinned buffer over
+        # PCIe) instead of waiting for the whole layer to be uploaded; the layer is then made resident in the background, behind the
+        # job's last gather. None = that cost rule, True = always while a slide is not resident, False = never.
+        self._zero_copy, self._zero_copy_fraction = zero_copy, float(zero_copy_fraction)
+        self.zero_copy_bytes = 0               # patch bytes (ps * ps * 3 each) read in place from pinned host memory so far
+        self._mapped = [None] * len(img_anno_paths)        # ops.MappedHostSlide views of pinned sources
+        self._mapped_table = None
+        self._upload_done = [None] * len(img_anno_paths)   # event of a background upload still in flight (resident slides wait on it)
+        self._copy_stream = None
+        self.ingest_events: list[dict] = []    # one record per upload: host ms of the allocation, CUDA events of copy / all-gather
         self._slot_cursor = 0
+        self._yield_cursor = None      # slot cursor behind the last batch a running torch_generator has handed out
         self._producer = None          # CUDA stream the gathers of torch_generator's prefetch groups run on
         self._drawer = None            # CUDA stream their coordinate draws run on
         self._slide_table = None       # ops.SlideTable over all images (multi-image datasets)
@@ -217,13 +229,17 @@ class AnnoRegionRndSampler:
 
     # -- resume: the Philox draws are keyed by (seed, global slot index), so two integers are the whole sampler state ---------
     def state_dict(self) -> dict:
-        return {"seed": int(self._seed), "slot_cursor": int(self._slot_cursor)}
+        """Taken while a torch_generator is running, the state is that of the last batch handed to the consumer: the batches the
+        device has prefetched beyond it are drawn again after a restore (the draw is a pure function of the slot index)."""
+        cur = self._slot_cursor if self._yield_cursor is None else self._yield_cursor
+        return {"seed": int(self._seed), "slot_cursor": int(cur)}
 
     def load_state_dict(self, state: dict) -> None:
         """Continue a run: the batches drawn after this call are bit-identical to those the saved sampler would have drawn next."""
         if int(state["seed"]) != int(self._seed):
             raise ValueError(f"state was saved with seed {state['seed']}, this sampler uses seed {self._seed}")
         self._slot_cursor = int(state["slot_cursor"])
+        self._yield_cursor = None
 
     # -- bookkeeping identical to the reference -------------------------------------------------------
     def _print_anno_stats(self, regions):
@@ -259,7 +275,46 @@ class AnnoRegionRndSampler:
                 rects.append((y0, max(y1, y0 + ps + 2), x0, max(x1, x0 + ps + 2)))
         return rects
 
+    def _whole_pinned(self, j: int) -> bool:
+        src = self._sources[j]
+        return isinstance(src, PinnedSlide) and src.pinned and src.y_origin == 0 and src.rows == src.height
+
+    def _mapped_slide(self, j: int):
+        """Image j read in place from its pinned host buffer (zero-copy ingestion)."""
+        if self._mapped[j] is None:
+            src = self._sources[j]
+            src._assert_layer(self.layer)
+            self._mapped[j] = ops.MappedHostSlide(src.host, src.rows, src.width, src.pitch, self._device)
+        return self._mapped[j]
+
+    def ingest_stats(self) -> dict:
+        """Milliseconds spent making slides resident so far: {"alloc_ms" (host time of the device allocations), "upload_ms" (host ->
+        device copies, CUDA events), "allgather_ms" (NVLink replication of sharded uploads), "bytes"}. Synchronises on the events."""
+        out = {"alloc_ms": 0.0, "upload_ms": 0.0, "allgather_ms": 0.0, "bytes": 0}
+        for rec in self.ingest_events:
+            out["alloc_ms"] += rec.get("alloc_ms", 0.0)
+            out["bytes"] += rec.get("bytes", 0)
+            for key in ("upload", "allgather"):
+                if key in rec:
+                    a, b = rec[key]
+                    b.synchronize()
+                    out[key + "_ms"] += a.elapsed_time(b)
+        return out
+
+    def upload_in_flight_bytes(self) -> int:
+        """Bytes of background uploads (behind a zero-copy job) that have not completed yet."""
+        n = 0
+        for j, ev in enumerate(self._upload_done):
+            if ev is not None and not ev.query():
+                n += self._sources[j].nbytes
+        return n
+
     def _slide(self, j: int):
+        if self._slides[j] is not None and self._upload_done[j] is not None:
+            if self._upload_done[j].query():
+                self._upload_done[j] = None
+            else:
+                torch.cuda.current_stream(self._device).wait_event(self._upload_done[j])   # background upload still in flight
         if self._slides[j] is None:
             with self._sources[j] as psim:
                 whole_pinned = isinstance(psim, PinnedSlide) and psim.y_origin == 0 and psim.rows == psim.height
@@ -267,7 +322,10 @@ class AnnoRegionRndSampler:
                     # data-parallel ranks with the same host slide: 1/world of the rows over each rank's PCIe link + one NVLink all-gather
                     psim._assert_layer(self.layer)
                     group = None if self._shard_upload is True else self._shard_upload
-                    self._slides[j], n = sharded_upload(psim, self._device, group)
+                    rec = {}
+                    self._slides[j], n = sharded_upload(psim, self._device, group, stats=rec)
+                    rec["bytes"] = n
+                    self.ingest_events.append(rec)
                     self.uploaded_bytes += n
                     return self._slides[j]
                 sparse = self._sparse_upload
@@ -284,10 +342,41 @@ class AnnoRegionRndSampler:
                     psim._assert_layer(self.layer)
                     self._slides[j], n = upload_rects(psim, rects, self._device)
                     self.uploaded_bytes += n
+                elif isinstance(psim, PinnedSlide):
+                    import time
+
+                    psim._assert_layer(self.layer)
+                    rec = {}
+                    t0 = time.perf_counter()
+                    storage = torch.empty(psim.rows * psim.pitch, dtype=torch.uint8, device=self._device)
+                    rec["alloc_ms"] = 1e3 * (time.perf_counter() - t0)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    storage.copy_(psim.host[: psim.rows * psim.pitch], non_blocking=True)
+                    b.record()
+                    rec["upload"], rec["bytes"] = (a, b), psim.rows * psim.pitch
+                    self.ingest_events.append(rec)
+                    self._slides[j] = ops.DeviceSlide(storage, psim.rows, psim.width, psim.pitch)
+                    self.uploaded_bytes += psim.rows * psim.pitch
                 else:
                     self._slides[j] = layer_to_device(psim, self.layer, self._device)
-                    self.uploaded_bytes += self._slides[j].H * self._slides[j].pitch if isinstance(psim, PinnedSlide) else 0
         return self._slides[j]
+
+    def _background_upload(self, after_event=None):
+        """Make every pinned slide that is not resident yet resident on the copy stream, behind `after_event` (the last gather that
+        reads host memory in place, so the two do not share the PCIe link); later gathers wait on the upload's event (_slide)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self._device)
+        with torch.cuda.stream(self._copy_stream):
+            if after_event is not None:
+                self._copy_stream.wait_event(after_event)
+            for j in range(len(self._slides)):
+                if self._slides[j] is None and self._whole_pinned(j):
+                    sl = self._slide(j)
+                    sl.storage.record_stream(self._copy_stream)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                    self._upload_done[j] = ev
 
     def _check_failures(self):
         if self._fail is not None and int(self._fail.item()) != 0:
@@ -312,22 +401,34 @@ class AnnoRegionRndSampler:
         torch.maximum(self._fail, status.max().reshape(1), out=self._fail)
         return coords, labels, images
 
-    def _gather(self, coords, images, dtype, layout, flip=None, scale255=True):
+    def _gather(self, coords, images, dtype, layout, flip=None, scale255=True, mapped: bool = False):
+        """`mapped`: read the patches in place from the pinned host slides (zero-copy ingestion) instead of the resident copies."""
         ps = self.patch_size
+        get = self._mapped_slide if mapped else self._slide
+        if mapped:
+            self.zero_copy_bytes += int(coords.shape[0]) * ps * ps * 3
         if len(self._slides) == 1:
-            return ops.gather_normalize(self._slide(0), coords, ps, dtype=dtype, layout=layout, scale255=scale255, mean=self._mean,
+            return ops.gather_normalize(get(0), coords, ps, dtype=dtype, layout=layout, scale255=scale255, mean=self._mean,
                                         std=self._std, flip=flip)
         if dtype != torch.uint8 and ps % (4 if dtype == torch.float32 else 8) == 0:
             # one launch over all source slides (descriptor table in HBM); every image of the dataset is made resident on first use
-            if self._slide_table is None:
-                self._slide_table = ops.SlideTable([self._slide(j) for j in range(len(self._slides))])
-            return ops.gather_normalize_multi(self._slide_table, images, coords, ps, dtype=dtype, layout=layout, scale255=scale255,
+            if mapped:
+                if self._mapped_table is None:
+                    self._mapped_table = ops.SlideTable([get(j) for j in range(len(self._slides))], device=self._device)
+                table = self._mapped_table
+            else:
+                if self._slide_table is None or any(e is not None for e in self._upload_done):
+                    slides = [self._slide(j) for j in range(len(self._slides))]      # waits on background uploads still in flight
+                    if self._slide_table is None:
+                        self._slide_table = ops.SlideTable(slides)
+                table = self._slide_table
+            return ops.gather_normalize_multi(table, images, coords, ps, dtype=dtype, layout=layout, scale255=scale255,
                                               mean=self._mean, std=self._std, flip=flip)
         shape = (len(coords), ps, ps, 3) if layout == "NHWC" else (len(coords), 3, ps, ps)
         out = torch.empty(shape, dtype=dtype, device=coords.device)
         for j in torch.unique(images).tolist():                                                  # one gather per source slide
             idx = torch.nonzero(images == j).reshape(-1).to(torch.int32)
-            ops.gather_normalize(self._slide(j), coords[idx.long()].contiguous(), ps, dtype=dtype, layout=layout, scale255=scale255,
+            ops.gather_normalize(get(j), coords[idx.long()].contiguous(), ps, dtype=dtype, layout=layout, scale255=scale255,
                                  mean=self._mean, std=self._std, flip=None if flip is None else flip[idx.long()].contiguous(), out=out,
                                  out_index=idx)
         return out
@@ -362,6 +463,15 @@ class AnnoRegionRndSampler:
         groups = self._split_chunks(n_batches, ahead)
         on_gpu = torch.device(self._device).type == "cuda"
         cur = torch.cuda.current_stream(self._device) if on_gpu else None
+        # zero-copy ingestion: slides that are still only in pinned host memory are read in place when this job touches less of them
+        # than an upload would move (cost rule above); the upload then runs in the background behind the job's last gather
+        pending_up = [j for j in range(len(self._slides)) if self._slides[j] is None]
+        mapped = bool(on_gpu and pending_up and self._zero_copy is not False and all(self._whole_pinned(j) for j in pending_up)
+                      and (len(pending_up) == len(self._slides) or len(self._slides) == 1)
+                      and (self._sparse_upload is not True or self._zero_copy is True))
+        if mapped and self._zero_copy is None:
+            job = n_batches * batch_size * ps * ps * 3
+            mapped = job <= self._zero_copy_fraction * sum(self._sources[j].nbytes for j in pending_up)
         if on_gpu and self._producer is None:
             self._producer = torch.cuda.Stream(self._device)
             self._drawer = torch.cuda.Stream(self._device)
@@ -385,17 +495,27 @@ class AnnoRegionRndSampler:
                 flip = None
                 if self._flips:
                     flip = torch.cat([self._batch_flip(first_slot // max(batch_size, 1) + i, batch_size) for i in range(nb)])
-                group["features"] = self._gather(coords, images, self._out_dtype, self._out_layout, flip)
+                group["features"] = self._gather(coords, images, self._out_dtype, self._out_layout, flip, mapped=mapped)
+                group["first_slot"] = first_slot
                 ready = torch.cuda.Event()
                 ready.record(self._producer)
             return group, ready
 
-        pending = launch(groups[0]) if groups else None
+        def launch_next(gi):
+            if gi >= len(groups):
+                return None
+            out = launch(groups[gi])
+            if mapped and gi == len(groups) - 1:
+                self._background_upload(after_event=out[1])
+            return out
+
+        pending = launch_next(0)
         for gi, nb in enumerate(groups):
             group, ready = pending
-            pending = launch(groups[gi + 1]) if gi + 1 < len(groups) else None
+            pending = launch_next(gi + 1)
             cur = torch.cuda.current_stream(self._device)    # the stream the caller consumes this group on
             cur.wait_event(ready)
+            first_slot = group.pop("first_slot")
             for t in group.values():
                 t.record_stream(cur)                         # allocated on the producer stream, used on the caller's
             if int(group["fail"].item()) != 0:
@@ -405,10 +525,12 @@ class AnnoRegionRndSampler:
             fv = feats.view((nb, batch_size) + tuple(feats.shape[1:])).unbind(0)
             lv = group["labels"].view(nb, batch_size).unbind(0)
             cv = group["coords"].view(nb, batch_size, 2).unbind(0)
-            for f, l, c in zip(fv, lv, cv):
+            for i, (f, l, c) in enumerate(zip(fv, lv, cv)):
                 if transforms is not None:
                     f = transforms(f)
+                self._yield_cursor = first_slot + (i + 1) * batch_size     # state_dict(): resume behind the batch being handed out
                 yield f, l, c
+        self._yield_cursor = None
 
     def structs_generator(self, batch_size: int, n_batches: int, batches_per_worker: int = 2, max_workers: int = None,
                           cls_idx: int = None) -> Iterator[list[tuple[Patch, int]]]:

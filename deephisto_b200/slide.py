@@ -140,11 +140,10 @@ class PinnedSlide:
     def _host_buffer(nbytes: int):
         import torch
 
-        buf = torch.empty(nbytes, dtype=torch.uint8)
         try:
-            return buf.pin_memory()
-        except RuntimeError:               # page-locking refused (ulimit / small host): keep a pageable buffer
-            return buf
+            return torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)     # page-locked at allocation: no pageable staging copy
+        except RuntimeError:               # page-locking refused (ulimit / small host, or no CUDA runtime): a pageable buffer
+            return torch.empty(nbytes, dtype=torch.uint8)
 
     @classmethod
     def from_numpy(cls, arr: np.ndarray) -> "PinnedSlide":
@@ -280,12 +279,15 @@ def upload_rects(host: "PinnedSlide", rects, device="cuda", tile: int = 512):
     return DeviceSlide(storage, host.height, host.width, host.pitch), nbytes
 
 
-def sharded_upload(host: "PinnedSlide", device="cuda", group=None):
+def sharded_upload(host: "PinnedSlide", device="cuda", group=None, stats: dict = None):
     """Collective slide ingestion for data-parallel sampling: every rank of `group` holds the same layer in host memory and needs
     it resident. Each rank copies only its 1/world share of the rows over ITS PCIe link and one all-gather over NVLink replicates
     the shares (in place: a rank's share sits at its offset of the full buffer) -- instead of `world` full uploads competing for
     the host's memory and PCIe bandwidth. Returns (DeviceSlide, bytes this rank copied from the host). Works with NCCL (CUDA) and
-    gloo (CPU tensors; used by the world_size-2 CPU tests)."""
+    gloo (CPU tensors; used by the world_size-2 CPU tests). `stats` (optional dict) receives "alloc_ms" (host time of the device
+    allocation) and, on CUDA, the event pairs "upload" and "allgather" for the two phases."""
+    import time
+
     import torch
     import torch.distributed as dist
 
@@ -294,14 +296,26 @@ def sharded_upload(host: "PinnedSlide", device="cuda", group=None):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     per = -(-host.rows // world)                                   # rows per rank; the last shares are padded
     pitch = host.pitch
+    t0 = time.perf_counter()
     storage = torch.empty(per * world * pitch, dtype=torch.uint8, device=device)
+    timed = stats is not None and storage.is_cuda
+    if stats is not None:
+        stats["alloc_ms"] = 1e3 * (time.perf_counter() - t0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timed else None
     a, b = min(host.rows, rank * per), min(host.rows, (rank + 1) * per)
     mine = storage[rank * per * pitch : (rank + 1) * per * pitch]
+    if timed:
+        ev[0].record()
     if b > a:
         mine[: (b - a) * pitch].copy_(host.host[a * pitch : b * pitch], non_blocking=True)
     if (b - a) < per:
         mine[(b - a) * pitch :].zero_()
+    if timed:
+        ev[1].record()
     dist.all_gather_into_tensor(storage, mine, group=group)
+    if timed:
+        ev[2].record()
+        stats["upload"], stats["allgather"] = (ev[0], ev[1]), (ev[1], ev[2])
     if storage.is_cuda:
         return DeviceSlide(storage, host.rows, host.width, pitch), (b - a) * pitch
     return storage[: host.rows * pitch], (b - a) * pitch          # CPU (gloo) callers get the assembled bytes

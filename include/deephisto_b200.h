@@ -76,6 +76,13 @@ DH_API int dh_synth_slide_rows(uint8_t* slide, int64_t H, int64_t W, int64_t pit
 DH_API int dh_upload_rects(uint8_t* slide_dev, int64_t H, int64_t pitch, const uint8_t* slide_host, int64_t n_rects,
                            const int64_t* rects_host, void* stream);
 
+/* Zero-copy ingestion: the device-visible address of a PAGE-LOCKED host buffer (cudaHostAlloc / cudaHostRegister under unified
+ * addressing). The gather kernels accept it as `slide`: their bulk copies then read the patch rows straight from host memory over
+ * PCIe -- the reference reads a patch from storage at the moment it is drawn (region_samplers.py:513-520), and a short job that
+ * touches a fraction of the slide should not wait for the whole layer to be uploaded (full_samplers.py:53-55). Host-only call:
+ * writes the address to *device_ptr_out_host; DH_ERR_UNSUPPORTED when the pointer is not mapped page-locked host memory. */
+DH_API int dh_host_device_pointer(const void* host_ptr, uint64_t* device_ptr_out_host);
+
 /* ------------------------------------------------------------------------------------------
  * A1  FullImageDenseSampler._create_batched_coords (full_samplers.py:374-404)
  * Enumeration: main grid (y outer, x inner), last column, last row, corner, then the last batch

@@ -4,6 +4,7 @@ import os
 import sys
 from pathlib import Path
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -45,8 +46,31 @@ for (H, W, stride, d) in [(3000, 2100, 112, 16), (1777, 1300, 100, 4)]:
     a = pfp.ImagePredictorPatched(None, lazy, pred, anno, layer=1, downscale=d, device=dev, cnn_batch=64).process(rank=rank, world=world)
     b = pfp.ImagePredictorPatched(None, full_s, pred, anno, layer=1, downscale=d, device=dev, cnn_batch=64).process()
     assert a.shape == b.shape and (a != b).mean() < 0.01, (a != b).mean()
+# the reference's DEFAULT predict sampler (coverage-driven random sampling, predict_full_patched.py:156-163) through process(rank, world):
+# per-rank band samplers, all-gather of the (coords, logits) lists, binned stitch per band, all-gather of the band maps. The assembled
+# maps equal a single-GPU stitch of the concatenated list bit for bit, and every map cell is covered (d = speedup = 16).
+from deephisto_b200 import ops  # noqa: E402
+
+for (H, W, d) in [(2100, 1500, 16), (1333, 1000, 4)]:
+    rs = fs.FullImageRndSampler(SyntheticSlide(H, W, seed=7), 1, 224, 16, mode, seed=3, device=dev, lazy_slide=True)
+    ipp = pfp.ImagePredictorPatched(None, rs, FixedLogits(model, dev), anno, layer=1, downscale=d, device=dev, cnn_batch=96)
+    out = ipp.process_device(want_sum=True, want_count=True, rank=rank, world=world)
+    assert rs._slide_dev is None and out["argmax"].shape == (H // d, W // d) and sum(out["patches_per_rank"]) == len(out["coords"])
+    assert min(out["patches_per_rank"]) > 0
+    s1, c1, a1 = ops.stitch_binned(out["logits"], out["coords"], 224, d, H // d, W // d, want_count=True, want_argmax=True)
+    assert torch.equal(out["sum"].view(torch.int32), s1.view(torch.int32)), f"rank {rank}: banded random-sampler sum map differs"
+    assert torch.equal(out["argmax"], a1) and torch.equal(out["count"], c1)
+    if d == 16:
+        assert int(c1.min()) >= 1, "uncovered map cells"
+    # FixedLogits are a function of the patch pixels: recompute them from the full slide at the gathered coordinates
+    full = SyntheticSlide(H, W, seed=7).device_slide(dev)
+    chk = FixedLogits(model, dev)
+    idx = torch.arange(0, len(out["coords"]), max(1, len(out["coords"]) // 64), device=dev)
+    again = chk.logits(chk.gather(full, out["coords"][idx].contiguous(), 224))
+    assert torch.equal(again, out["logits"][idx]), f"rank {rank}: logits of the gathered list do not match the slide"
+    b = pfp.ImagePredictorPatched(None, rs, FixedLogits(model, dev), anno, layer=1, downscale=d, device=dev).process(rank=rank, world=world)
+    assert np.array_equal(b, a1.cpu().numpy().astype(np.int64))
 # collective slide ingestion (slide.sharded_upload): 1/world of the rows per rank over PCIe, one NCCL all-gather; ragged shares
-import numpy as np  # noqa: E402
 
 from deephisto_b200.slide import PinnedSlide, sharded_upload  # noqa: E402
 

@@ -216,3 +216,74 @@ def test_stream_jobs_cover_every_patch_once_with_its_rows(case, world):
     if g.ny > 0 and g.nx > 1:
         with pytest.raises(ValueError):
             bands.stream_jobs(g, [(1, g.nx)], row_bytes, 1 << 30)          # main-grid ranges must be whole grid rows
+
+
+@pytest.mark.parametrize("case", [(3000, 224, 16, 16), (100000, 224, 16, 16), (1777, 224, 4, 16), (1000, 224, 3, 16), (500, 224, 16, 16),
+                                  (224, 224, 16, 16), (4096, 64, 8, 16)])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_rnd_band_rows(case, world):
+    """bands.rnd_band (row bands of the coverage-driven random sampler): map rows partition [0, dh); every band's slide rows hold
+    at least one patch, start on a coarse-cell boundary, contain the band's own pixel rows, and together cover the slide."""
+    H, ps, d, sp = case
+    dh = H // d
+    rows, covered = 0, np.zeros(H, bool)
+    for rank in range(world):
+        p = bands.rnd_band(H, ps, d, sp, rank, world)
+        assert (p.row_begin, p.row_end) == bands.band_rows(dh, rank, world) and p.rows_max >= p.row_end - p.row_begin
+        rows += p.row_end - p.row_begin
+        if p.row_end == p.row_begin:
+            assert (p.slide_y0, p.slide_y1) == (0, 0)
+            continue
+        assert 0 <= p.slide_y0 < p.slide_y1 <= H and p.slide_y1 - p.slide_y0 >= ps and p.slide_y0 % sp == 0
+        assert p.slide_y0 <= p.row_begin * d and p.row_end * d <= p.slide_y1
+        assert p.patch_ranges == []
+        covered[p.slide_y0 : p.slide_y1] = True
+    assert rows == dh and covered.all()
+
+
+LIST_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from deephisto_b200.examples.predict_full_patched import gather_patch_lists
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+for lens in ([5, 0, 3], [0, 0, 0], [1, 7, 2]):
+    n = 5
+    def mk(r):
+        g = torch.Generator().manual_seed(100 + r)
+        return torch.randn((lens[r], n), generator=g), torch.randint(0, 1 << 20, (lens[r], 2), generator=g, dtype=torch.int32)
+    lg, co = mk(rank)
+    lg_all, co_all, counts = gather_patch_lists(lg, co, world, dist)
+    assert counts == lens
+    want_lg = torch.cat([mk(r)[0] for r in range(world)]); want_co = torch.cat([mk(r)[1] for r in range(world)])
+    assert lg_all.dtype == torch.float32 and co_all.dtype == torch.int32
+    assert torch.equal(lg_all.view(torch.int32), want_lg.view(torch.int32)) and torch.equal(co_all, want_co)
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_gather_patch_lists_gloo_world3(tmp_path):
+    """The exchange step of the random sampler's banded prediction: ragged per-rank (logits, coords) lists all-gathered in rank
+    order, bit patterns preserved, empty lists included."""
+    import subprocess
+
+    script = tmp_path / "list_worker.py"
+    script.write_text(LIST_WORKER)
+    port = _free_port()
+    procs = []
+    for r in range(3):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="3", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script), str(ROOT)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        outs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"OK {r}" in out, out[-2000:]

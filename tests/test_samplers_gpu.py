@@ -181,8 +181,8 @@ def test_anno_region_rnd_sampler_sparse_upload_from_pinned_slides(api, tmp_path)
     pinned = [(PinnedSlide.from_numpy(np.asarray(img)), anno) for img, anno in items]
     ps, B = 224, 24
     full = rs.AnnoRegionRndSampler(items, layer=1, patch_size=ps, seed=9, verbose=False)
-    sparse = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False, sparse_upload=True)
-    dense_up = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False, sparse_upload=False)
+    sparse = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False, sparse_upload=True, zero_copy=False)
+    dense_up = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False, sparse_upload=False, zero_copy=False)
     a = list(full.torch_generator(B, 6))
     b = list(sparse.torch_generator(B, 6))
     c = list(dense_up.torch_generator(B, 6))
@@ -190,6 +190,31 @@ def test_anno_region_rnd_sampler_sparse_upload_from_pinned_slides(api, tmp_path)
         assert torch.equal(ca, cb) and torch.equal(la, lb) and torch.equal(fa, fb) and torch.equal(fa, fc)
     total = sum(p.nbytes for p, _ in pinned)
     assert 0 < sparse.uploaded_bytes <= total and dense_up.uploaded_bytes == total
+    # zero-copy ingestion: the first job gathers straight from the pinned host buffers (dh_host_device_pointer; nothing is uploaded
+    # before its last gather), the slides become resident behind it, and the following job reads the resident copies -- all batches
+    # bit-identical to the fully uploaded sampler's
+    zero = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False, sparse_upload=False, zero_copy=True)
+    z = list(zero.torch_generator(B, 6))
+    assert zero.zero_copy_bytes == 6 * B * ps * ps * 3
+    for (fa, la, ca), (fz, lz, cz) in zip(a, z):
+        assert torch.equal(ca, cz) and torch.equal(la, lz) and torch.equal(fa, fz)
+    a2 = list(full.torch_generator(B, 3))
+    z2 = list(zero.torch_generator(B, 3))
+    torch.cuda.synchronize()
+    assert zero.zero_copy_bytes == 6 * B * ps * ps * 3 and zero.uploaded_bytes == total and zero.upload_in_flight_bytes() == 0
+    for (fa, la, ca), (fz, lz, cz) in zip(a2, z2):
+        assert torch.equal(ca, cz) and torch.equal(la, lz) and torch.equal(fa, fz)
+    st = zero.ingest_stats()
+    assert st["bytes"] == total and st["upload_ms"] > 0
+    # the cost rule (zero_copy=None): a job that touches less than half of the slide bytes reads in place, a larger one uploads first
+    auto = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False, sparse_upload=False)
+    small = int(0.4 * total / (ps * ps * 3)) // B
+    if small >= 1:
+        list(auto.torch_generator(B, small))
+        assert auto.zero_copy_bytes == small * B * ps * ps * 3
+    big = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=9, verbose=False, sparse_upload=False)
+    list(big.torch_generator(B, int(0.6 * total / (ps * ps * 3)) // B + 1))
+    assert big.zero_copy_bytes == 0 and big.uploaded_bytes == total
 
 
 def test_anno_region_rnd_sampler_extras_and_structs(api, tmp_path):
@@ -386,20 +411,52 @@ def test_sampler_state_dicts_resume_bit_identically(api, tmp_path):
     assert len(first) == 3 and all(torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2]) for x, y in zip(rest, again))
     with pytest.raises(ValueError, match="seed"):
         rs.AnnoRegionRndSampler(items, layer=1, patch_size=224, seed=5, verbose=False).load_state_dict(state)
-    # coverage sampler: run to the end, and resume a copy from a mid-run snapshot of the device state
+    # mid-generator snapshot: the sampler has prefetched a whole group, the state is that of the last batch handed out
+    c = rs.AnnoRegionRndSampler(items, layer=1, patch_size=224, seed=4, verbose=False)
+    ref = list(c.torch_generator(16, 9))
+    d = rs.AnnoRegionRndSampler(items, layer=1, patch_size=224, seed=4, verbose=False)
+    it = d.torch_generator(16, 9)
+    for _ in range(4):
+        next(it)
+    mid = d.state_dict()
+    assert mid["slot_cursor"] == 4 * 16
+    e = rs.AnnoRegionRndSampler(items, layer=1, patch_size=224, seed=4, verbose=False)
+    e.load_state_dict(mid)
+    tail = list(e.torch_generator(16, 5))
+    assert all(torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) and torch.equal(x[2], y[2]) for x, y in zip(ref[4:], tail))
+    # coverage sampler: run to the end, and resume a copy from a snapshot taken in the MIDDLE of an iteration -- the device has
+    # enqueued up to two groups (32 batches) beyond the batch the consumer holds; those must be drawn again, not counted as covered
     host = synth.synth_slide(1500, 1300, 3)
     full = fs.FullImageRndSampler(host, 1, 224, 2, _mode(fs), seed=2)
     ref = [(c.cpu(), r) for c, r in full.coords_generator()]
-    assert len(ref) > 40                                      # the snapshot below (<= 32 batches in) is taken mid-run
+    assert len(ref) > 40
+    done_state = full.state_dict()
+    assert done_state["batch_index"] == len(ref) and done_state["filled_ratio"][-1] >= 1
     part = fs.FullImageRndSampler(host, 1, 224, 2, _mode(fs), seed=2)
     it = part.coords_generator()
     for _ in range(5):
         next(it)
-    snap = part.state_dict()                                  # includes the groups the device has enqueued ahead of the consumer
-    k = snap["batch_index"]
-    assert 5 <= k <= len(ref) + 32 and len(snap["filled_ratio"]) <= k
+    snap = part.state_dict()
+    assert snap["batch_index"] == 5 and snap["filled_ratio"] == [r for _, r in ref[:5]]
     resumed = fs.FullImageRndSampler(host, 1, 224, 2, _mode(fs), seed=2)
-    resumed.load_state_dict(dict(snap, filled_ratio=[r for _, r in ref[:k]]))
+    resumed.load_state_dict(snap)
     tail = [(c.cpu(), r) for c, r in resumed.coords_generator()]
-    assert len(tail) == max(0, len(ref) - k)
-    assert all(torch.equal(x[0], y[0]) and x[1] == y[1] for x, y in zip(tail, ref[k:]))
+    assert len(tail) == len(ref) - 5
+    assert all(torch.equal(x[0], y[0]) and x[1] == y[1] for x, y in zip(tail, ref[5:]))
+    assert resumed._filled_ratio == [r for _, r in ref]
+    # the stitched prediction of a resumed run has no holes: the accumulator equals the footprint histogram of ALL batches
+    acc = np.zeros((1500 // 16, 1300 // 16), np.int64)
+    for cc, _ in ref:
+        for y, x in cc.numpy().tolist():
+            acc[y // 16:(y + 224) // 16, x // 16:(x + 224) // 16] += 1
+    assert np.array_equal(resumed._accum.astype(np.int64), acc) and acc.min() >= 1
+    # generator_torch counts consumed batches the same way
+    gt = fs.FullImageRndSampler(host, 1, 224, 2, _mode(fs), seed=2)
+    g = gt.generator_torch()
+    for _ in range(19):
+        next(g)
+    assert gt.state_dict()["batch_index"] == 19
+    # a finished run resumes to an empty iteration
+    fin = fs.FullImageRndSampler(host, 1, 224, 2, _mode(fs), seed=2)
+    fin.load_state_dict(done_state)
+    assert list(fin.coords_generator()) == []
