@@ -75,11 +75,13 @@ SIGNATURES = {
     "dh_stitch_binned_scratch_bytes": (_i64, [_i64, _i32, _i32, _i32, _i64, _i64]),
     "dh_stitch_binned": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "dh_stitch_binned_set_tile_rows": (C.c_int, [_i32]),
+    "dh_stitch_binned_set_variant": (C.c_int, [_i32]),
     "dh_colorize_overlay": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _f64, _vp, _vp, _vp, _vp]),
     "dh_cover_scratch_words": (_i64, [_i64, _i64]),
     "dh_cover_init": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp]),
     "dh_cover_sample": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _u64, _u64, _vp, _vp, _vp, _i32, _vp]),
     "dh_cover_sample_group": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _i32, _u64, _u64, _i32, _vp, _vp, _vp, _vp]),
+    "dh_cover_set_variant": (C.c_int, [_i32]),
     "dh_region_accept_dense": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _f64, _vp, _vp, _vp]),
     "dh_compact_coords": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "dh_region_sample": (

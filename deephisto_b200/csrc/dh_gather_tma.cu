@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
 
 // persistent grid = SMs x resident CTAs of this instantiation, so every CTA is co-resident
 template <typename K>
-static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_t smem, cudaStream_t st) {
+static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_t smem, cudaStream_t st, int occ_override) {
     static int occ_cache[64] = {0};  // per instantiation, indexed by shared-memory size in KB
     int& occ = occ_cache[(smem >> 10) & 63];
     if (occ == 0) {
@@ -409,7 +409,7 @@ static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_
         if (occ < 1) occ = 1;
         if (occ > 3) occ = 3;  // measured (profiles/r01_gather.md): 3 resident CTAs per SM beat 4 (and 5, 6) -- less concurrency, less HBM read/write interference
     }
-    const int64_t want = (int64_t)kNumSMs * occ;
+    const int64_t want = (int64_t)kNumSMs * (occ_override > 0 ? occ_override : occ);   // profiling: DH_GATHER_OCC resident CTAs per SM
     const int grid = (int)(n_tiles < want ? n_tiles : want);
     kernel<<<grid, kTmaThreads, smem, st>>>(p);
     return DH_OK;
@@ -452,8 +452,10 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     int rc_launch = DH_OK;
     // every consumer thread owns exactly KU units (see the kernel): true for ps = 224 in all four output modes
     const bool full_units = R * units_per_row == kConsumers * (nchw ? (E == 4 ? 4 : 2) : 6);
-#define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st) \
-                                            : launch_one(gather_tma_kernel<T, N, S, A, false>, p, n_tiles, smem, st)
+    const char* env_occ = getenv("DH_GATHER_OCC");  // profiling override of the resident CTAs per SM (grid size), 0 = default
+    const int occ_o = env_occ ? atoi(env_occ) : 0;
+#define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st, occ_o) \
+                                            : launch_one(gather_tma_kernel<T, N, S, A, false>, p, n_tiles, smem, st, occ_o)
 #define DH_TMA_SA(T, N)                                                                  \
     do {                                                                                 \
         if (scale255) { if (affine) DH_TMA(T, N, true, true); else DH_TMA(T, N, true, false); } \
@@ -461,7 +463,7 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     } while (0)
     if (debug) {  // profiling switches exist for one instantiation only
         if (!(out_dtype == DH_F32 && !nchw && scale255 && !affine && full_units)) return DH_ERR_UNSUPPORTED;
-        rc_launch = launch_one(gather_tma_kernel<float, false, true, false, true, true>, p, n_tiles, smem, st);
+        rc_launch = launch_one(gather_tma_kernel<float, false, true, false, true, true>, p, n_tiles, smem, st, occ_o);
     } else if (out_dtype == DH_F32) { if (nchw) DH_TMA_SA(float, true); else DH_TMA_SA(float, false); }
     else                     { if (nchw) DH_TMA_SA(__nv_bfloat16, true); else DH_TMA_SA(__nv_bfloat16, false); }
 #undef DH_TMA_SA

@@ -16,9 +16,15 @@
 //   tile   : one warp per tile: rank-sort the segment by patch index (shared memory), clip the footprints to tile-relative
 //            ranges, then walk the tile's rows. Rows between two footprint boundaries have identical values (run-length): the
 //            lane's values are recomputed only at a boundary and stored to every row of the run.
-// Three tile kernels share the binning: `sum` (bin_tile_kernel<VEC, G, false>: a lane owns G groups of VEC consecutive floats of a map
-// row; 16-byte stores), `cell` (bin_tile_kernel<VEC, 1, true>: a lane owns 1 or 4 cells, n <= 8 class sums in registers -> argmax byte
-// and / or count) and `phased sum` (bin_tile_phased_kernel: map rows that are not 16-byte aligned, 16-byte stores at a per-row shift).
+// Tile kernels (they share the binning):
+//   bin_seg_kernel (n <= 8 classes, the product path): inside a row run the tile's columns fall into SEGMENTS of cells with the same
+//       covering patches (boundaries = the column edges of the tile's patches, found once per tile). Per run one lane per segment adds
+//       the covering patches' logits (n adds per patch and SEGMENT instead of per patch and output float), the sums go to shared memory,
+//       every lane fetches the values of its output units from its precomputed segment slots and streams them to all rows of the run.
+//       Store flavours: 16-byte stores (aligned rows), 16-byte stores at a per-row shift (rows not 16-byte aligned), scalar, and the
+//       class-map / count outputs (1 or 4 cells per lane).
+//   bin_tile_kernel / bin_tile_phased_kernel (any n; round-1 formulation: every lane re-sums its own floats per run): more than 8
+//       classes, and the A/B reference for the segment kernel (dh_stitch_binned_set_variant(1)).
 #include "dh_common.cuh"
 
 namespace dh {
@@ -28,6 +34,7 @@ constexpr int kBinCap = 128;    // patches per tile staged in shared memory; lon
 constexpr int kBinMaxN = 8;     // classes the cell kernel keeps in registers
 
 static int g_bin_tile_rows = 0;  // 0 = heuristic; profiling override (dh_stitch_binned_set_tile_rows)
+static int g_bin_variant = 0;    // 0 = segment kernel whenever n <= 8; 1 = round-1 row-run kernels (A/B, dh_stitch_binned_set_variant)
 
 struct BinGeom {
     int64_t rows, row_offset, dw;
@@ -460,6 +467,254 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_phased_kernel(const f
     }
 }
 
+// ---- segment formulation ---------------------------------------------------------------------------------------------------
+// KIND: 0 = sum map, 16-byte stores, G groups of 128 floats per tile; 1 = sum map, rows not 16-byte aligned (per-row shift, 7 units
+// gathered, 4 stored); 2 = sum map, scalar stores (32 floats per tile); 3 / 4 = class map and / or count, 1 / 4 cells per lane.
+constexpr int kSegCap = 264;        // segments per tile: <= cells of the tile + 1
+constexpr int kSegVals = 288;       // floats per value buffer: segments * n <= tile units + 3 n
+constexpr int kSegWords = 16;       // boundary bitmap words (<= 512 tile cells)
+
+__host__ __device__ inline int seg_warp_smem_bytes() {
+    return kBinCap * 8 /* r0 r1 c0 c1 (u16) */ + kBinCap * 32 /* logits, stride 8 */ + 2 * kSegWords * 4 + kSegCap * 2 + 2 * kSegVals * 4;
+}
+
+template <int KIND, int G>
+__global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords, BinGeom g,
+                                                                 const uint32_t* __restrict__ off, const uint32_t* __restrict__ len,
+                                                                 const uint32_t* __restrict__ list, uint32_t* __restrict__ sorted,
+                                                                 float* __restrict__ sum_map, uint32_t* __restrict__ count_map,
+                                                                 uint8_t* __restrict__ argmax_map) {
+    constexpr bool CELL = KIND >= 3;
+    constexpr int VEC = (KIND == 0 || KIND == 1 || KIND == 4) ? 4 : 1;
+    constexpr int K = KIND == 0 ? 4 * G : (KIND == 1 ? 7 : (KIND == 4 ? 4 : 1));   // units a lane fetches per run
+    extern __shared__ __align__(16) unsigned char bin_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t ctas_x = (g.ntx + kBinWarps - 1) / kBinWarps;
+    const int64_t ty = blockIdx.x / ctas_x;
+    const int64_t tx = (blockIdx.x % ctas_x) * kBinWarps + w;
+    if (tx >= g.ntx) return;
+    const int64_t t = ty * g.ntx + tx;
+    const uint32_t beg = off[t];
+    const int L = (int)len[t];
+    const int n = g.n;
+    if (L > kBinCap) {
+        bin_tile_slow<VEC, CELL>(logits, coords, g, beg, L, list, sorted, sum_map, count_map, argmax_map, ty, tx);
+        return;
+    }
+    unsigned char* base = bin_smem + (size_t)w * seg_warp_smem_bytes();
+    uint16_t* s_r0 = reinterpret_cast<uint16_t*>(base);
+    uint16_t* s_r1 = s_r0 + kBinCap;
+    uint16_t* s_c0 = s_r1 + kBinCap;
+    uint16_t* s_c1 = s_c0 + kBinCap;
+    float* s_lg = reinterpret_cast<float*>(base + kBinCap * 8);                      // [L][8]
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(base + kBinCap * 40);            // [kSegWords] segment-start bitmap over the tile's cells
+    uint32_t* s_wpre = s_bits + kSegWords;                                          // [kSegWords] set bits before each word
+    uint16_t* s_segc = reinterpret_cast<uint16_t*>(s_wpre + kSegWords);             // [S] first cell of each segment (tile relative)
+    float* s_val = reinterpret_cast<float*>(base + kBinCap * 40 + 2 * kSegWords * 4 + kSegCap * 2);   // [2][kSegVals] double-buffered
+    uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_val);                            // staging only: unsorted / sorted ids alias the values
+    uint32_t* s_ids = s_raw + kBinCap;
+
+    const int R0 = (int)(ty * g.TH);
+    const int TH = (int)((int64_t)R0 + g.TH < g.rows ? g.TH : g.rows - R0);         // rows of this tile
+    const int RF = (int)g.units_per_row;
+    const int U0 = (int)(tx * g.TW);
+    const int U1 = (KIND == 1) ? (U0 + g.TW + 3 < RF ? U0 + g.TW + 3 : RF) : (U0 + g.TW < RF ? U0 + g.TW : RF);   // phased tiles reach 3 units further
+    const int scale = g.scale;                                                      // units per cell: n (sum) or 1 (cell)
+    const int C0 = U0 / scale;
+    const int ncells = (U1 + scale - 1) / scale - C0;
+
+    // ---- stage: ids in ascending order, footprints clipped to the tile (rows / cells relative to the tile), logits
+    for (int j = lane; j < L; j += 32) s_raw[j] = list[beg + j];
+    if (lane < kSegWords) s_bits[lane] = lane == 0 ? 1u : 0u;                       // cell 0 starts segment 0
+    __syncwarp();
+    for (int j = lane; j < L; j += 32) {  // rank sort: patch indices are distinct within a tile
+        const uint32_t v = s_raw[j];
+        int rank = 0;
+        for (int i = 0; i < L; ++i) rank += s_raw[i] < v;
+        s_ids[rank] = v;
+    }
+    __syncwarp();
+    for (int j = lane; j < L; j += 32) {
+        const uint32_t id = s_ids[j];
+        BinRec f;
+        bin_footprint(g, __ldg(coords + 2 * (int64_t)id), __ldg(coords + 2 * (int64_t)id + 1), f);
+        const int a = f.r0 - R0, b = f.r1 - R0;
+        s_r0[j] = (uint16_t)(a < 0 ? 0 : a);
+        s_r1[j] = (uint16_t)(b > TH ? TH : (b < 0 ? 0 : b));
+        int c0 = f.u0 / scale - C0, c1 = f.u1 / scale - C0;                          // footprints are whole cells: u0, u1 are multiples of scale
+        c0 = c0 < 0 ? 0 : (c0 > ncells ? ncells : c0);
+        c1 = c1 < 0 ? 0 : (c1 > ncells ? ncells : c1);
+        s_c0[j] = (uint16_t)c0;
+        s_c1[j] = (uint16_t)c1;
+        if (c0 > 0 && c0 < ncells) atomicOr(s_bits + (c0 >> 5), 1u << (c0 & 31));
+        if (c1 > 0 && c1 < ncells) atomicOr(s_bits + (c1 >> 5), 1u << (c1 & 31));
+    }
+    if (!CELL || argmax_map != nullptr) {
+        for (int e = lane; e < L * 8; e += 32) {                                   // rows of 8 floats, zero padded: the adds below are unconditional in q
+            const int j = e >> 3, q = e & 7;
+            s_lg[e] = q < n ? __ldg(logits + (int64_t)s_ids[j] * n + q) : 0.f;
+        }
+    }
+    __syncwarp();
+    // ---- segments: prefix popcounts of the bitmap words, first cell of every segment
+    int S;
+    {
+        const uint32_t word = lane < kSegWords ? s_bits[lane] : 0u;
+        const uint32_t pc = __popc(word);
+        uint32_t inc = pc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        S = (int)__shfl_sync(0xffffffffu, inc, 31);
+        if (lane < kSegWords) {
+            s_wpre[lane] = inc - pc;
+            uint32_t rest = word;
+            int k = (int)(inc - pc);
+            while (rest) {
+                s_segc[k++] = (uint16_t)(lane * 32 + __ffs(rest) - 1);
+                rest &= rest - 1;
+            }
+        }
+    }
+    __syncwarp();   // also: every lane is done with s_ids before the value buffers (which alias it) are written
+    // ---- the lane's output units and their slots in the value buffer
+    const int ub = U0 + lane * VEC;
+    int slot[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int u = ub + (KIND == 0 ? (k >> 2) * (32 * VEC) + (k & 3) : k);
+        int sl = 0;
+        if (u < U1) {
+            const int c = u / scale, rel = c - C0;
+            const int seg = (int)s_wpre[rel >> 5] + __popc(s_bits[rel >> 5] & (0xffffffffu >> (31 - (rel & 31)))) - 1;
+            sl = CELL ? seg : seg * n + (u - c * scale);
+        }
+        slot[k] = sl;
+    }
+    const bool want_vals = CELL ? argmax_map != nullptr : true;
+    const int pstep = RF & 3;
+
+    int r = 0, buf = 0;
+    while (r < TH) {
+        float* const val = s_val + buf * kSegVals;
+        int next = TH;
+        // ---- one lane per segment: the covering patches' logits in ascending list index = the reference's order
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            const int sg = s0 + lane;
+            const int sc = sg < S ? (int)s_segc[sg] : 0xffff;
+            float acc[kBinMaxN];
+#pragma unroll
+            for (int q = 0; q < kBinMaxN; ++q) acc[q] = 0.f;
+            uint32_t hits = 0;
+            for (int j0 = 0; j0 < L; j0 += 32) {
+                const int j = j0 + lane;
+                const int a = j < L ? (int)s_r0[j] : 0x7fff, b = j < L ? (int)s_r1[j] : 0x7fff;
+                if (s0 == 0) {
+                    const int cand = a > r ? a : (b > r ? b : 0x7fff);
+                    const int nbound = __reduce_min_sync(0xffffffffu, cand);
+                    next = nbound < next ? nbound : next;
+                }
+                unsigned m = __ballot_sync(0xffffffffu, a <= r && r < b);
+                while (m) {  // warp-uniform trip count
+                    const int jj = j0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const bool cov = (int)s_c0[jj] <= sc && sc < (int)s_c1[jj];
+                    hits += cov;
+                    if (want_vals) {
+                        const float4 lo = *reinterpret_cast<const float4*>(s_lg + jj * 8);
+                        // adding under the predicate only: a sum that starts at +0.0f and adds v is the reference's 0.0 + v
+                        // (classes q >= n add the +0.0f padding to sums nobody reads)
+                        if (cov) { acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w; }
+                        if (n > 4) {
+                            const float4 hi = *reinterpret_cast<const float4*>(s_lg + jj * 8 + 4);
+                            if (cov) { acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w; }
+                        }
+                    }
+                }
+            }
+            if (sg < S) {
+                if constexpr (CELL) {
+                    const uint32_t am = want_vals ? (uint32_t)first_argmax(acc, n) : 0u;
+                    reinterpret_cast<uint32_t*>(val)[sg] = am | (hits << 8);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < kBinMaxN; ++q)
+                        if (q < n) val[sg * n + q] = acc[q];
+                }
+            }
+        }
+        __syncwarp();
+        // ---- fetch this lane's units, stream them to every row of the run
+        if constexpr (CELL) {
+            uint32_t pk[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) pk[k] = reinterpret_cast<const uint32_t*>(val)[slot[k]];
+            if (ub < U1) {                                          // VEC == 4: dw % 4 == 0 and aligned maps (host check)
+                int64_t o = (int64_t)(R0 + r) * RF + ub;
+                for (int rr = r; rr < next; ++rr, o += RF) {
+                    if constexpr (KIND == 4) {
+                        if (argmax_map) *reinterpret_cast<uchar4*>(argmax_map + o) = make_uchar4(pk[0] & 255u, pk[1] & 255u, pk[2] & 255u, pk[3] & 255u);
+                        if (count_map) *reinterpret_cast<uint4*>(count_map + o) = make_uint4(pk[0] >> 8, pk[1] >> 8, pk[2] >> 8, pk[3] >> 8);
+                    } else {
+                        if (argmax_map) argmax_map[o] = (uint8_t)(pk[0] & 255u);
+                        if (count_map) count_map[o] = pk[0] >> 8;
+                    }
+                }
+            }
+        } else {
+            float v[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) v[k] = val[slot[k]];
+            if constexpr (KIND == 0) {
+                float* o = sum_map + (int64_t)(R0 + r) * RF + ub;
+                for (int rr = r; rr < next; ++rr, o += RF) {
+#pragma unroll
+                    for (int gi = 0; gi < G; ++gi)
+                        if (ub + gi * 128 < U1) *reinterpret_cast<float4*>(o + gi * 128) = make_float4(v[4 * gi], v[4 * gi + 1], v[4 * gi + 2], v[4 * gi + 3]);
+                }
+            } else if constexpr (KIND == 2) {
+                float* o = sum_map + (int64_t)(R0 + r) * RF + ub;
+                if (ub < U1)
+                    for (int rr = r; rr < next; ++rr, o += RF) *o = v[0];
+            } else {
+                // rows not 16-byte aligned: in row rr the lane's vector starts sft = (4 - rr * RF) mod 4 units later (then 16-byte aligned);
+                // the first sft units of a row are scalar stores of tile 0, the last vector of a row is clipped
+                float* rowp = sum_map + (int64_t)(R0 + r) * RF;
+                int p = (int)(((int64_t)(R0 + r) * RF) & 3);         // sum_map is 16-byte aligned (host check)
+                for (int rr = r; rr < next; ++rr) {
+                    const int sft = (4 - p) & 3;
+                    float w0, w1, w2, w3;
+                    switch (sft) {
+                        case 0: w0 = v[0]; w1 = v[1]; w2 = v[2]; w3 = v[3]; break;
+                        case 1: w0 = v[1]; w1 = v[2]; w2 = v[3]; w3 = v[4]; break;
+                        case 2: w0 = v[2]; w1 = v[3]; w2 = v[4]; w3 = v[5]; break;
+                        default: w0 = v[3]; w1 = v[4]; w2 = v[5]; w3 = v[6]; break;
+                    }
+                    const int u = ub + sft;
+                    if (u + 4 <= RF) {
+                        *reinterpret_cast<float4*>(rowp + u) = make_float4(w0, w1, w2, w3);
+                    } else if (u < RF) {
+                        rowp[u] = w0;
+                        if (u + 1 < RF) rowp[u + 1] = w1;
+                        if (u + 2 < RF) rowp[u + 2] = w2;
+                    }
+                    if (tx == 0 && lane == 0) {
+                        if (sft > 0) rowp[0] = v[0];
+                        if (sft > 1) rowp[1] = v[1];
+                        if (sft > 2) rowp[2] = v[2];
+                    }
+                    rowp += RF;
+                    p = (p + pstep) & 3;
+                }
+            }
+        }
+        r = next;
+        buf ^= 1;   // the next run writes the other buffer: one warp barrier per run is enough
+    }
+}
+
 // profiling override: rows + 1000 * groups + 100000 * extra shared-memory KB per CTA (each field 0 = heuristic / none)
 static int tile_rows_for(int ps, int d) {
     if (g_bin_tile_rows % 1000 > 0) return g_bin_tile_rows % 1000;
@@ -516,7 +771,8 @@ static void carve_bin(const BinGeom& g, int64_t P, void* base, BinScratch& s) {
 
 static bool sum_vec4(const float* sum_map, int64_t dw, int n) { return (dw * n) % 4 == 0 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0; }
 
-template <int VEC, int G, bool CELL, bool STAGED, bool PHASED = false>
+// SEGK >= 0: bin_seg_kernel<SEGK, G> (n <= kBinMaxN); -1: the row-run kernels
+template <int VEC, int G, bool CELL, bool STAGED, bool PHASED = false, int SEGK = -1>
 static int run_binned(const float* logits, const int32_t* coords, int64_t P, const BinGeom& g, float* sum_map, uint32_t* count_map,
                       uint8_t* argmax_u8, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
     BinScratch s;
@@ -540,7 +796,13 @@ static int run_binned(const float* logits, const int32_t* coords, int64_t P, con
     // at least 50 KB per CTA = at most 4 resident CTAs per SM: a fifth one only adds HBM write interleaving (measured 1.5-3 % slower)
     int smem = kBinWarps * bin_warp_smem_bytes(g.n, STAGED) + (g_bin_tile_rows / 100000) * 1024;
     if (!CELL && smem < 50 * 1024) smem = 50 * 1024;
-    if constexpr (PHASED) {
+    if constexpr (SEGK >= 0) {
+        auto kern = bin_seg_kernel<SEGK, G>;
+        smem = kBinWarps * seg_warp_smem_bytes() + (g_bin_tile_rows / 100000) * 1024;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_seg_kernel)");
+        kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map, count_map, argmax_u8);
+    } else if constexpr (PHASED) {
         auto kern = bin_tile_phased_kernel<STAGED>;
         if (smem > 48 * 1024) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -565,6 +827,12 @@ using namespace dh;
 
 extern "C" DH_API int dh_stitch_binned_set_tile_rows(int rows) {
     g_bin_tile_rows = rows > 0 ? rows : 0;
+    return DH_OK;
+}
+
+extern "C" DH_API int dh_stitch_binned_set_variant(int variant) {
+    if (variant < 0 || variant > 1) { set_error("dh_stitch_binned_set_variant: variant must be 0 (segment kernel) or 1 (row-run kernels)"); return DH_ERR_INVALID; }
+    g_bin_variant = variant;
     return DH_OK;
 }
 
@@ -606,7 +874,12 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         // (not for small footprints: 7 instead of 4 sums per lane cost more than the vector stores save -- measured at d = 16)
         const bool phased = !v4 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 && dw * (int64_t)n >= 8 && ps / d >= 24;
         const BinGeom g = make_geom(false, v4 || phased ? 4 : 1, ps, d, n, rows, dw, row_offset, phased);
-        if (phased) rc = staged ? run_binned<4, 1, false, true, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
+        const bool seg = staged && g_bin_variant == 0 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
+        if (seg && phased) rc = run_binned<4, 1, false, true, true, 1>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        else if (seg && v4 && g.G == 2) rc = run_binned<4, 2, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        else if (seg && v4) rc = run_binned<4, 1, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        else if (seg) rc = run_binned<1, 1, false, true, false, 2>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        else if (phased) rc = staged ? run_binned<4, 1, false, true, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
                                 : run_binned<4, 1, false, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (v4 && g.G == 2) rc = staged ? run_binned<4, 2, false, true>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)
                                              : run_binned<4, 2, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
@@ -624,8 +897,12 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         const bool c4 = ps / d >= 96 && dw % 4 == 0 && reinterpret_cast<uintptr_t>(cell_argmax) % 4 == 0 &&
                         reinterpret_cast<uintptr_t>(count_map) % 16 == 0;
         const BinGeom g = make_geom(true, c4 ? 4 : 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
-        rc = c4 ? run_binned<4, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
-                : run_binned<1, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
+        if (g_bin_variant == 0)
+            rc = c4 ? run_binned<4, 1, true, true, false, 4>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
+                    : run_binned<1, 1, true, true, false, 3>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
+        else
+            rc = c4 ? run_binned<4, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
+                    : run_binned<1, 1, true, true>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
         if (rc != DH_OK) return rc;
     }
     if (argmax_u8 && !cell_argmax) rc = dh_stitch_finalize(sum_map, nullptr, rows * dw, n, nullptr, argmax_u8, stream);

@@ -168,6 +168,8 @@ DH_API int dh_stitch_binned(const float* logits, const int32_t* coords, int64_t 
                      float* sum_map, uint32_t* count_map, uint8_t* argmax_u8, int64_t rows, int64_t dw,
                      int64_t row_offset, void* scratch, int64_t scratch_bytes, void* stream);
 DH_API int dh_stitch_binned_set_tile_rows(int rows);
+/* Profiling / tests: 0 = auto (segment kernel for n <= 8 classes), 1 = the row-run tile kernels of round 1. Same bits either way. */
+DH_API int dh_stitch_binned_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------
  * Prediction post-processing: perform_and_save_visualizations (examples/predict_full_patched.py:81-113).
@@ -207,6 +209,9 @@ DH_API int dh_cover_sample(uint32_t* accum, int64_t dh, int64_t dw, int64_t H, i
 DH_API int dh_cover_sample_group(uint32_t* accum, int64_t dh, int64_t dw, int64_t H, int64_t W, int ps, int speedup,
                           int dense_level, int B, uint64_t seed, uint64_t first_batch_index, int n_batches,
                           int32_t* coords_out, uint32_t* nonzero_out, uint32_t* scratch, void* stream);
+/* Profiling / tests: 0 = auto (one persistent launch per group, state as a count tree in shared memory), 1 = one launch per batch
+ * with a full scan of the block counts (the only variant for coarse grids beyond 67 M cells). Same coordinates either way. */
+DH_API int dh_cover_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------
  * C/D  RegionAnnotation._extract_patch_coords_dense / _rnd (region_samplers.py:82-191)

@@ -1,0 +1,252 @@
+"""Round-2 measurement probes (not a product path). CUDA-event medians, printed as text on stderr and JSON on stdout.
+    python profiles/r02_probe.py cover      coverage sampler: persistent group kernel vs one launch per batch
+    python profiles/r02_probe.py binned     dh_stitch_binned: segment kernel (variant 0) vs row-run kernels (variant 1), aligned / unaligned rows
+    python profiles/r02_probe.py zerocopy   gather reading a pinned HOST slide in place (PCIe) vs ring depth
+    python profiles/r02_probe.py gather     gather kernel, bf16 / fp32 output modes at 8 192 patches per launch
+    python profiles/r02_probe.py cnn        where the ResNet18 forward (torch/cuDNN) spends its time, and library-level variants"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from deephisto_b200 import _lib, ops  # noqa: E402
+
+peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+lib = _lib.require_device()
+PS, N = 224, 5
+rows = []
+
+
+def timeit(fn, reps=10, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def say(**kw):
+    rows.append(kw)
+    print("  ".join(f"{k}={v:.4g}" if isinstance(v, float) else f"{k}={v}" for k, v in kw.items()), file=sys.stderr)
+
+
+def cover_list(H, W, B=1024):
+    st = ops.CoverState(H, W, PS, 16, 2, B, seed=0)
+    cells = (H // 16) * (W // 16)
+    parts = []
+    while True:
+        c, counts = st.next_group(16)
+        parts.append(c.reshape(-1, 2))
+        if int(counts[-1].item()) >= cells:
+            keep = int((counts < cells).sum().item()) + 1
+            parts[-1] = parts[-1][: keep * B]
+            break
+    return torch.cat(parts).contiguous()
+
+
+def cover():
+    for variant in (0, 1):
+        lib.dh_cover_set_variant(variant)
+        for (h, w, B) in ((40000, 40000, 64), (40000, 40000, 1024), (100000, 100000, 64), (8192, 8192, 64)):
+            for group in (1, 16, 64):
+                st = ops.CoverState(h, w, PS, 16, 2, B, seed=0)
+                st.next_group(4)                                      # state built, kernels loaded
+                ms = timeit(lambda: st.next_group(group), reps=8, warm=1) / group
+                say(kernel="cover", variant=variant, slide=h, B=B, group=group, us_per_batch=1e3 * ms, patches_per_s=B / ms * 1e3)
+    lib.dh_cover_set_variant(0)
+    # the whole sampler through the public API: 40k x 40k to full coverage at batch 64, gather included
+    import time
+
+    from deephisto_b200.patch_samplers import full_samplers as fs
+    from deephisto_b200.slide import SyntheticSlide
+
+    src = SyntheticSlide(40000, 40000, seed=0)
+    for rep in range(2):
+        s = fs.FullImageRndSampler(src, 1, PS, 64, fs.SamplerExecutionMode.INMEMORY_SINGLEPROC, seed=rep, quiet=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n = 0
+        for f, c, r in s.generator_torch():
+            n += f.shape[0]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        say(kernel="FullImageRndSampler.generator_torch 40k^2 to coverage", rep=rep, patches=n, ms=1e3 * dt, patches_per_s=n / dt)
+
+
+def binned():
+    which = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [40000, 39999]
+    codes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0]
+    for hw in which:
+        H = W = hw
+        coords = cover_list(H, W)
+        P = coords.shape[0]
+        logits = torch.randn((P, N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
+        for d in (16, 4, 2, 1):
+            dh, dw = H // d, W // d
+            cells = dh * dw
+            reps = 10 if d >= 4 else 4
+            for label, kw, out_bytes in (("sum", dict(want_sum=True), cells * N * 4), ("argmax", dict(want_sum=False, want_argmax=True), cells)):
+                res = {}
+                for variant in (0, 1):
+                    for code in (codes if label == "sum" else [0]):
+                        lib.dh_stitch_binned_set_variant(variant)
+                        lib.dh_stitch_binned_set_tile_rows(code)
+                        keep = {}
+
+                        def run():
+                            keep["o"] = None
+                            keep["o"] = ops.stitch_binned(logits, coords, PS, d, dh, dw, **kw)
+
+                        ms = timeit(run, reps)
+                        res[variant] = keep["o"]
+                        alg = out_bytes + P * N * 4
+                        say(kernel="stitch_binned", hw=hw, P=P, d=d, out=label, variant=variant, code=code, ms=ms, GBs=alg / ms / 1e6, frac=alg / ms / 1e6 / peak)
+                        keep.clear()
+                lib.dh_stitch_binned_set_tile_rows(0)
+                a, b = res[0], res[1]
+                same = all((x is None and y is None) or torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
+                                                                    y.view(torch.int32) if y.dtype == torch.float32 else y) for x, y in zip(a, b))
+                say(kernel="stitch_binned bit-identical (variant 0 vs 1)", hw=hw, d=d, out=label, same=bool(same))
+                del res, a, b
+                torch.cuda.empty_cache()
+    lib.dh_stitch_binned_set_variant(0)
+
+
+def zerocopy():
+    from deephisto_b200.slide import PinnedSlide
+
+    H = W = 32768
+    dev = ops.DeviceSlide.synthetic(H, W, 0)
+    host = PinnedSlide.from_device(dev)
+    mapped = ops.MappedHostSlide(host.host, H, W, host.pitch)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for n in (5120, 1024):
+        coords = torch.stack([torch.randint(0, H - PS, (n,), generator=g, device="cuda"), torch.randint(0, W - PS, (n,), generator=g, device="cuda")], 1).to(torch.int32).contiguous()
+        out = torch.empty((n, PS, PS, 3), dtype=torch.float32, device="cuda")
+        for stages in (2, 3, 4, 6, 8):
+            os.environ["DH_GATHER_STAGES"] = str(stages)
+            for occ in (0, 1, 2, 4):
+                os.environ["DH_GATHER_OCC"] = str(occ)
+                ms = timeit(lambda: ops.gather_normalize(mapped, coords, PS, out=out), reps=5, warm=1)
+                say(kernel="gather zero-copy (pinned host slide)", patches=n, stages=stages, occ=occ, ms=ms, pcie_GBs=n * PS * PS * 3 / ms / 1e6, patches_per_s=n / ms * 1e3)
+        os.environ.pop("DH_GATHER_STAGES")
+        os.environ.pop("DH_GATHER_OCC")
+        ref = ops.gather_normalize(dev, coords, PS)
+        say(kernel="zero-copy == resident", patches=n, same=bool(torch.equal(ref, ops.gather_normalize(mapped, coords, PS))))
+    up = torch.empty(H * host.pitch, dtype=torch.uint8, device="cuda")
+    ms = timeit(lambda: up.copy_(host.host, non_blocking=True), reps=3, warm=1)
+    say(kernel="contiguous upload of the slide (copy engine)", ms=ms, pcie_GBs=H * host.pitch / ms / 1e6)
+
+
+def gather():
+    H = W = 32768
+    dev = ops.DeviceSlide.synthetic(H, W, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 8192
+    coords = torch.stack([torch.randint(0, H - PS, (n,), generator=g, device="cuda"), torch.randint(0, W - PS, (n,), generator=g, device="cuda")], 1).to(torch.int32).contiguous()
+    for dtype, esz in ((torch.bfloat16, 2), (torch.float32, 4)):
+        for layout in ("NHWC", "NCHW"):
+            out = torch.empty((2, n, PS, PS, 3) if layout == "NHWC" else (2, n, 3, PS, PS), dtype=dtype, device="cuda")
+            for stages in (2, 3, 4):
+                os.environ["DH_GATHER_STAGES"] = str(stages)
+                for occ in (0, 2, 3, 4, 5):
+                    os.environ["DH_GATHER_OCC"] = str(occ)
+                    i = [0]
+
+                    def run():
+                        i[0] ^= 1
+                        ops.gather_normalize(dev, coords, PS, dtype=dtype, layout=layout, out=out[i[0]])
+
+                    ms = timeit(run, reps=7, warm=2)
+                    alg = n * PS * PS * 3 * (1 + esz)
+                    say(kernel="gather", dtype=str(dtype).split(".")[-1], layout=layout, stages=stages, occ=occ, ms=ms, GBs=alg / ms / 1e6, frac=alg / ms / 1e6 / peak)
+            os.environ.pop("DH_GATHER_STAGES")
+            os.environ.pop("DH_GATHER_OCC")
+            del out
+            torch.cuda.empty_cache()
+
+
+def cnn():
+    from deephisto_b200.examples import predict_full_patched as pfp
+
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    model = pfp.get_model(5)
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    pred = pfp.DeviceBatchPredictor(model, "cuda", torch.bfloat16, fold_bn=True)
+    m = pred.model
+    x = torch.rand((B, PS, PS, 3), device="cuda").to(torch.bfloat16).permute(0, 3, 1, 2)        # NHWC storage viewed as NCHW
+    with torch.no_grad():
+        ms = timeit(lambda: m(x), reps=5, warm=3)
+        say(kernel="ResNet18 forward (bf16 channels_last, BN folded, cudnn.benchmark)", batch=B, ms=ms, patches_per_s=B / ms * 1e3,
+            tflops=B * 3.64e9 / ms / 1e9)
+        # per stage
+        stages = [("conv1", lambda t: m.conv1(t)), ("bn1+relu", lambda t: m.relu(m.bn1(t))), ("maxpool", lambda t: m.maxpool(t)),
+                  ("layer1", lambda t: m.layer1(t)), ("layer2", lambda t: m.layer2(t)), ("layer3", lambda t: m.layer3(t)), ("layer4", lambda t: m.layer4(t)),
+                  ("avgpool+fc", lambda t: m.fc(torch.flatten(m.avgpool(t), 1)))]
+        t = x
+        for name, fn in stages:
+            ms = timeit(lambda: fn(t), reps=5, warm=2)
+            out = fn(t)
+            say(kernel=f"  stage {name}", ms=ms, in_shape=str(tuple(t.shape)), out_MB=out.numel() * out.element_size() / 1e6)
+            t = out
+        # conv1 with the input padded to 4 / 8 channels (zero weights: same function)
+        for cpad in (4, 8):
+            xp = torch.zeros((B, PS, PS, cpad), device="cuda", dtype=torch.bfloat16)
+            xp[..., :3] = x.permute(0, 2, 3, 1)
+            xp = xp.permute(0, 3, 1, 2)
+            wpad = torch.zeros((64, cpad, 7, 7), device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            wpad[:, :3] = m.conv1.weight
+            bias = m.conv1.bias
+            ms = timeit(lambda: torch.nn.functional.conv2d(xp, wpad, bias, stride=2, padding=3), reps=5, warm=2)
+            err = (torch.nn.functional.conv2d(xp, wpad, bias, stride=2, padding=3).float() - m.conv1(x).float()).abs().max().item()
+            say(kernel=f"  conv1 with input padded to {cpad} channels", ms=ms, max_abs_diff=err)
+        # fused conv + bias + relu through cuDNN (torch.cudnn_convolution_relu) on a layer1-sized convolution
+        t1 = torch.rand((B, 64, 56, 56), device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        conv = m.layer1[0].conv1
+        ms_a = timeit(lambda: torch.relu_(torch.nn.functional.conv2d(t1, conv.weight, conv.bias, padding=1)), reps=5, warm=2)
+        say(kernel="  layer1 conv3x3 + bias, then relu (2 kernels)", ms=ms_a)
+        try:
+            ms_b = timeit(lambda: torch.cudnn_convolution_relu(t1, conv.weight, conv.bias, (1, 1), (1, 1), (1, 1), 1), reps=5, warm=2)
+            a = torch.relu(torch.nn.functional.conv2d(t1, conv.weight, conv.bias, padding=1))
+            b = torch.cudnn_convolution_relu(t1, conv.weight, conv.bias, (1, 1), (1, 1), (1, 1), 1)
+            say(kernel="  torch.cudnn_convolution_relu (1 kernel)", ms=ms_b, max_abs_diff=(a.float() - b.float()).abs().max().item(),
+                channels_last_out=bool(b.is_contiguous(memory_format=torch.channels_last)))
+            z = torch.rand_like(t1)
+            ms_c = timeit(lambda: torch.relu_(torch.nn.functional.conv2d(t1, conv.weight, conv.bias, padding=1).add_(z)), reps=5, warm=2)
+            ms_d = timeit(lambda: torch.cudnn_convolution_add_relu(t1, conv.weight, z, 1.0, conv.bias, (1, 1), (1, 1), (1, 1), 1), reps=5, warm=2)
+            say(kernel="  conv + add + relu: 3 kernels vs torch.cudnn_convolution_add_relu", ms_3=ms_c, ms_fused=ms_d)
+        except Exception as e:  # noqa: BLE001
+            say(kernel="  torch.cudnn_convolution_relu failed", error=repr(e)[:200])
+        # whole forward under a CUDA graph
+        try:
+            gph = torch.cuda.CUDAGraph()
+            static_x = x.clone()
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    m(static_x)
+            torch.cuda.current_stream().wait_stream(s)
+            with torch.cuda.graph(gph):
+                static_y = m(static_x)
+            ms = timeit(lambda: gph.replay(), reps=5, warm=2)
+            say(kernel="ResNet18 forward under a CUDA graph", batch=B, ms=ms, patches_per_s=B / ms * 1e3)
+        except Exception as e:  # noqa: BLE001
+            say(kernel="CUDA graph capture failed", error=repr(e)[:200])
+
+
+if __name__ == "__main__":
+    {"cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))

@@ -304,6 +304,46 @@ def test_cover_sampler_bit_exact_vs_oracle(ops, cfg):
     assert np.array_equal(st.accum.cpu().numpy().astype(np.int64), ref.accum)
 
 
+@pytest.mark.parametrize("cfg", [(1500, 1300, 224, 32, 5), (3000, 2600, 224, 1024, 1), (640, 800, 64, 200, 9)])
+def test_cover_sampler_group_launch_equals_single_launches(ops, cfg):
+    """dh_cover_sample_group (ONE persistent launch for a group of batches, count tree in shared memory) yields exactly the batches
+    of one launch per batch, with either kernel variant (dh_cover_set_variant 1 = the per-batch kernel with a full scan), up to and
+    beyond full coverage (batches after it are no-ops); accumulators equal."""
+    from deephisto_b200 import _lib
+
+    H, W, ps, B, seed = cfg
+    lib = _lib.require_device()
+    cells = (H // 16) * (W // 16)
+    a = ops.CoverState(H, W, ps, 16, 2, B, seed)
+    c = ops.CoverState(H, W, ps, 16, 2, B, seed)
+    done, groups = False, 0
+    while not done:
+        n = 7 if groups % 2 else 16
+        ga, na = a.next_group(n)
+        try:
+            lib.dh_cover_set_variant(1)
+            gc, nc = c.next_group(n)
+        finally:
+            lib.dh_cover_set_variant(0)
+        na = na.cpu().tolist()
+        for i in range(n):
+            live = i == 0 or na[i - 1] < cells                # batches enqueued after full coverage leave their (zeroed) slots untouched
+            assert na[i] == int(nc[i].item())
+            if live:
+                assert torch.equal(ga[i], gc[i]), (groups, i)
+        done = na[-1] >= cells
+        groups += 1
+        assert groups < 400
+    assert torch.equal(a.accum, c.accum) and int(a.accum.min()) >= 1
+    # one launch per batch through dh_cover_sample against a grouped run
+    d = ops.CoverState(H, W, ps, 16, 2, B, seed)
+    e = ops.CoverState(H, W, ps, 16, 2, B, seed)
+    g1, n1 = d.next_group(5)
+    for i in range(5):
+        ci, ni = e.next_coords(stop_when_full=True)
+        assert torch.equal(ci, g1[i]) and int(ni.item()) == int(n1[i].item())
+
+
 # ---- C/D regions ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", list(region_polygons().keys()))
 def test_region_accept_dense_bit_exact(ops, golden, name):
