@@ -1,0 +1,67 @@
+// Predictor-side helper kernel: 3x3 stride-2 max pooling over an NHWC bf16 tensor.
+//
+// Reference path: examples/predict_full_patched.py:66-78 batch_predictor -> model(features) with the patch_cls_simple ResNet18
+// (models/patch_cls_simple/model.py:5-11): its stem is conv1 -> bn1 -> relu -> maxpool(kernel 3, stride 2, padding 1). The
+// convolutions stay with cuDNN (torch); the pooling between them is pure HBM traffic -- [B,112,112,64] bf16 read once,
+// [B,56,56,64] written once -- and torch's channels_last kernel needs 3.0 ms for it at batch 1024 (15 % of the whole forward,
+// profiles/r02_predict.md) where the bytes take 0.3 ms. One thread per output pixel and 8 channels: nine 16-byte loads (the 2.25x
+// window overlap is served by L1 / L2: neighbouring outputs share rows that were just read), packed bf16 maxima, one 16-byte store.
+// Padding is -inf and NaN propagates, like torch.nn.functional.max_pool2d.
+#include "dh_common.cuh"
+
+namespace dh {
+
+__device__ __forceinline__ uint32_t max2_bf16(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t total, int H, int W,
+                                                                     int C8, int OH, int OW) {
+    const uint32_t ninf = 0xFF80FF80u;  // two bf16 -inf
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(idx % C8);
+        const int64_t pix = idx / C8;
+        const int ox = (int)(pix % OW);
+        const int64_t t = pix / OW;
+        const int oy = (int)(t % OH);
+        const int64_t b = t / OH;
+        uint4 m = make_uint4(ninf, ninf, ninf, ninf);
+        const uint4* plane = in + b * H * (int64_t)W * C8 + c8;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int iy = 2 * oy - 1 + dy;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int ix = 2 * ox - 1 + dx;
+                if (ix < 0 || ix >= W) continue;
+                const uint4 v = __ldg(plane + ((int64_t)iy * W + ix) * C8);
+                m.x = max2_bf16(m.x, v.x); m.y = max2_bf16(m.y, v.y); m.z = max2_bf16(m.z, v.z); m.w = max2_bf16(m.w, v.w);
+            }
+        }
+        out[idx] = m;
+    }
+}
+
+}  // namespace dh
+
+using namespace dh;
+
+extern "C" DH_API int dh_maxpool3x3s2_nhwc(const void* in, int64_t B, int H, int W, int C, void* out, int dtype, void* stream) {
+    if (B == 0) return DH_OK;
+    DH_REQUIRE(in && out, "dh_maxpool3x3s2_nhwc: null pointer");
+    DH_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "dh_maxpool3x3s2_nhwc: bad shape");
+    DH_REQUIRE(dtype == DH_BF16, "dh_maxpool3x3s2_nhwc: only bf16 is implemented");
+    DH_REQUIRE(C % 8 == 0, "dh_maxpool3x3s2_nhwc: the channel count must be a multiple of 8 (16-byte vectors)");
+    DH_REQUIRE(reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "dh_maxpool3x3s2_nhwc: buffers must be 16-byte aligned");
+    const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+    const int C8 = C / 8;
+    const int64_t total = B * OH * (int64_t)OW * C8;
+    const int64_t blocks = (total + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)kNumSMs * 32 ? blocks : (int64_t)kNumSMs * 32);
+    maxpool3x3s2_nhwc_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), total, H, W, C8, OH,
+                                                                       OW);
+    DH_CHECK_LAUNCH("maxpool3x3s2_nhwc_bf16_kernel");
+    return DH_OK;
+}

@@ -290,7 +290,9 @@ __device__ __forceinline__ uint32_t tree_find(const CoverTree& t, const uint32_t
     const int ib = is * 32 + tree_step(t.cnt[is * 32 + lane], r, lane);
     const uint32_t w0 = (uint32_t)ib * (kCellsPerBlock / 32);
     // each lane owns 2 of the block's 64 mask words (L2 reads: the words are updated by atomics of this very launch)
-    const uint2 mw = __ldcg(reinterpret_cast<const uint2*>(mask + w0) + lane);
+    uint2 mw;                                                 // (the mask is only 4-byte aligned inside the scratch buffer)
+    mw.x = __ldcg(mask + w0 + 2 * lane);
+    mw.y = __ldcg(mask + w0 + 2 * lane + 1);
     const uint32_t p0 = __popc(mw.x);
     const int src = tree_step(p0 + __popc(mw.y), r, lane);
     uint32_t found = 0;

@@ -58,13 +58,22 @@ class DeviceBatchPredictor:
 
     dtype float32 keeps torch's defaults (what the reference runs on a GPU); bfloat16 runs the CNN in bf16 channels_last."""
 
-    def __init__(self, model: torch.nn.Module, device="cuda", dtype=torch.float32, channels_last: bool = True, fold_bn: bool = False):
+    def __init__(self, model: torch.nn.Module, device="cuda", dtype=torch.float32, channels_last: bool = True, fold_bn: bool = False,
+                 fused: bool = False):
         """fold_bn=True folds every eval-mode BatchNorm into the preceding convolution (torch.nn.utils.fusion): the same
-        function with ~20 fewer memory-bound elementwise kernels per forward; logits change at rounding level only."""
+        function with ~20 fewer memory-bound elementwise kernels per forward; logits change at rounding level only.
+        fused=True (bfloat16 / float16, torchvision BasicBlock ResNets): the forward runs through FusedResNetForward -- space-to-depth
+        stem, dh_maxpool3x3s2_nhwc, cuDNN's fused conv+bias(+residual)+ReLU calls -- over the same weights; `gather` then writes the
+        stem's space-to-depth input directly."""
         self.device = torch.device(device)
         self.dtype = dtype
         self.channels_last = channels_last and dtype != torch.float32
         model = model.to(self.device).eval()
+        self.fused = None
+        if fused:
+            if dtype == torch.float32:
+                raise ValueError("fused=True needs dtype bfloat16 or float16 (the float32 predictor is the parity path)")
+            self.fused = FusedResNetForward(model, dtype)
         if fold_bn:
             model = fold_batchnorm(model)
         if dtype != torch.float32:
@@ -80,12 +89,18 @@ class DeviceBatchPredictor:
     def gather(self, slide, coords: torch.Tensor, ps: int) -> torch.Tensor:
         """[B,3,ps,ps] model input for patches at `coords`, written by dh_gather_normalize in the memory format the model runs in:
         channels_last models get an NHWC buffer viewed as NCHW (no layout pass between the gather and the first convolution)."""
+        if self.fused is not None:
+            return self.fused.space_to_depth(ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True))
         if self.channels_last:
             return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True).permute(0, 3, 1, 2)
         return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NCHW", scale255=True)
 
     @torch.no_grad()
     def logits(self, features: torch.Tensor) -> torch.Tensor:
+        if self.fused is not None:
+            if features.shape[1] != 16:                      # a plain [B,3,H,W] batch (list[Patch] callers): fold it here
+                features = self.fused.space_to_depth(features.permute(0, 2, 3, 1))
+            return self.fused(features)
         if self.channels_last:
             features = features.contiguous(memory_format=torch.channels_last)
         return self.model(features).float()
@@ -103,6 +118,99 @@ class DeviceBatchPredictor:
         if isinstance(batch, torch.Tensor):
             return self.logits(batch)
         return self.logits(self.features_from_patches(batch)).cpu().numpy()
+
+
+class FusedResNetForward:
+    """The eval-mode forward of a torchvision BasicBlock ResNet (ResNet18 / 34: models/patch_cls_simple/model.py:5-11) restated over
+    the same weights with cuDNN's fused epilogues and a tensor-core friendly stem. Every convolution is still cuDNN through torch;
+    what changes is how it is called (measured on a B200, batch 1024, bf16 channels_last, profiles/r02_predict.md):
+
+      stem   conv1 is a 7x7 stride-2 convolution over THREE input channels: cuDNN has no tensor-core kernel for C = 3 (8.2 ms of the
+             19.8 ms forward). The same function as a 4x4 stride-1 convolution over the 2x2 space-to-depth image (12 channels, padded
+             to 16; the 7x7 kernel zero-extended to 8x8 and folded the same way): K = 256, tensor cores, bias + ReLU in the epilogue.
+      pool   3x3 stride-2 max pooling of the [B,112,112,64] stem output by dh_maxpool_nhwc (HBM-bound; torch's kernel takes 3.0 ms).
+      blocks conv + bias + ReLU and conv + bias + residual + ReLU are ONE cuDNN call each (torch.cudnn_convolution_relu /
+             cudnn_convolution_add_relu) instead of three kernels; BatchNorm is folded into the convolutions first (eval mode).
+
+    Logits equal the plain bf16 model's up to bf16 rounding / accumulation order (tests/test_predict_gpu.py); the float32 predictor
+    (bit-level parity path against the reference's arithmetic) does not use this class."""
+
+    def __init__(self, model: torch.nn.Module, dtype=torch.bfloat16):
+        from torchvision.models.resnet import BasicBlock, ResNet
+
+        if not isinstance(model, ResNet) or not all(isinstance(b, BasicBlock) for layer in (model.layer1, model.layer2, model.layer3, model.layer4) for b in layer):
+            raise TypeError("FusedResNetForward needs a torchvision ResNet made of BasicBlocks (ResNet18 / ResNet34)")
+        m = fold_batchnorm(model).to(dtype)
+        dev = next(m.parameters()).device
+        cl = torch.channels_last
+
+        def wb(conv):
+            w = conv.weight.detach().to(dtype).contiguous(memory_format=cl)
+            b = conv.bias.detach().to(dtype) if conv.bias is not None else torch.zeros(w.shape[0], dtype=dtype, device=w.device)
+            return w, b
+
+        if tuple(m.conv1.kernel_size) != (7, 7) or tuple(m.conv1.stride) != (2, 2) or tuple(m.conv1.padding) != (3, 3) or m.conv1.in_channels != 3:
+            raise TypeError("FusedResNetForward: unexpected stem convolution")
+        w7, self.stem_b = wb(m.conv1)
+        # out[oy] = sum_ky w[ky] in[2 oy + ky - 3]; with in[2 (oy + a) + p] =: S[oy + a][p] and ky = 2 a + p + 3: taps a in {-2..1}
+        # (a = -2, p = 0 would be ky = -1: zero). Channel order inside a space-to-depth pixel: (p, q, c) -> p * 8 + q * 3 + c, two pad
+        # channels behind each input row's 6 values, so that a 16-byte half pixel holds bytes of ONE input row (dh_gather_normalize S2D mode).
+        w4 = torch.zeros((w7.shape[0], 16, 4, 4), dtype=torch.float32, device=dev)
+        w7f = m.conv1.weight.detach().float()
+        for a in range(-2, 2):
+            for p_ in range(2):
+                ky = 2 * a + p_ + 3
+                if not 0 <= ky < 7:
+                    continue
+                for b_ in range(-2, 2):
+                    for q in range(2):
+                        kx = 2 * b_ + q + 3
+                        if 0 <= kx < 7:
+                            w4[:, p_ * 8 + q * 3 : p_ * 8 + q * 3 + 3, a + 2, b_ + 2] = w7f[:, :, ky, kx]
+        self.stem_w = w4.to(dtype).contiguous(memory_format=cl)
+        self.blocks = []
+        for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
+            for blk in layer:
+                w1, b1 = wb(blk.conv1)
+                w2, b2 = wb(blk.conv2)
+                down = None
+                if blk.downsample is not None:
+                    dconv = blk.downsample[0]
+                    down = (*wb(dconv), tuple(dconv.stride))
+                self.blocks.append((w1, b1, tuple(blk.conv1.stride), w2, b2, down))
+        self.fc_w, self.fc_b = m.fc.weight.detach().to(dtype), m.fc.bias.detach().to(dtype)
+        self.dtype = dtype
+
+    @staticmethod
+    def s2d_shape(batch: int, ps: int) -> tuple:
+        """Logical NCHW shape of the stem input for a batch of ps x ps patches: [B, 16, ps/2 + 3, ps/2 + 3] stored channels_last, i.e.
+        [B][ps/2 + 3][ps/2 + 3][16] in memory with a zero border of 2 (top / left) and 1 (bottom / right) space-to-depth pixels."""
+        return (batch, 16, ps // 2 + 3, ps // 2 + 3)
+
+    @staticmethod
+    def space_to_depth(x_nhwc: torch.Tensor) -> torch.Tensor:
+        """[B, H, W, 3] (values already normalised) -> the zero-bordered 16-channel space-to-depth stem input (torch ops; the predictor
+        lets dh_gather_normalize write this layout directly)."""
+        B, H, W, _ = x_nhwc.shape
+        out = torch.zeros((B, H // 2 + 3, W // 2 + 3, 16), dtype=x_nhwc.dtype, device=x_nhwc.device)
+        v = x_nhwc.reshape(B, H // 2, 2, W // 2, 2, 3).permute(0, 1, 3, 2, 4, 5)            # [B, y', x', p, q, c]
+        inner = out[:, 2 : 2 + H // 2, 2 : 2 + W // 2]
+        inner[..., 0:6] = v[:, :, :, 0].reshape(B, H // 2, W // 2, 6)
+        inner[..., 8:14] = v[:, :, :, 1].reshape(B, H // 2, W // 2, 6)
+        return out.permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def __call__(self, s2d: torch.Tensor) -> torch.Tensor:
+        """s2d: stem input as produced by space_to_depth / the gather's S2D mode -> float32 logits [B, n]."""
+        one = (1, 1)
+        x = torch.cudnn_convolution_relu(s2d, self.stem_w, self.stem_b, one, (0, 0), one, 1)            # [B, 64, ps/2, ps/2]
+        x = ops.maxpool3x3s2_nhwc(x)
+        for w1, b1, stride, w2, b2, down in self.blocks:
+            identity = x if down is None else torch.nn.functional.conv2d(x, down[0], down[1], stride=down[2])
+            h = torch.cudnn_convolution_relu(x, w1, b1, stride, one, one, 1)
+            x = torch.cudnn_convolution_add_relu(h, w2, identity, 1.0, b2, one, one, one, 1)
+        x = x.float().mean(dim=(2, 3))
+        return torch.nn.functional.linear(x, self.fc_w.float(), self.fc_b.float())
 
 
 def fold_batchnorm(model: torch.nn.Module) -> torch.nn.Module:

@@ -291,6 +291,18 @@ def stitch_finalize(sum_map: torch.Tensor, count_map: Optional[torch.Tensor] = N
     return norm, amax
 
 
+def maxpool3x3s2_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """max_pool2d(kernel 3, stride 2, padding 1) of a channels_last bf16 tensor [B,C,H,W] (NHWC in memory) -> channels_last [B,C,OH,OW]."""
+    lib = _lib.require_device()
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("maxpool3x3s2_nhwc needs a CUDA bfloat16 [B,C,H,W] tensor in channels_last memory format")
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, (H - 1) // 2 + 1, (W - 1) // 2 + 1), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        check(lib.dh_maxpool3x3s2_nhwc(x.data_ptr(), B, H, W, Cc, out.data_ptr(), DH_BF16, _stream()), "dh_maxpool3x3s2_nhwc")
+    return out
+
+
 def colorize_overlay(argmax: torch.Tensor, lut_rgb: torch.Tensor, slide: Optional[DeviceSlide] = None, d: int = 1, alpha: float = 0.6,
                      want_mask: bool = True, want_thumb: bool = False, want_overlay: bool = False):
     """Class map u8 [dh,dw] -> (mask, thumbnail, overlay), each uint8 [dh,dw,3] or None (predict_full_patched.py:81-113)."""

@@ -16,6 +16,7 @@ AnnoRegionDenseSampler :799-871, extract_and_save_subset :874-909). Differences,
 from __future__ import annotations
 
 import json
+import warnings
 from collections import defaultdict
 from pathlib import Path
 from typing import Iterator
@@ -26,6 +27,20 @@ from torch.utils.data import IterableDataset
 
 from .. import geometry, ops
 from ..slide import Patch, PinnedSlide, layer_to_device, open_slide, sharded_upload, tile_spans, upload_rects
+
+
+_STREAMS: dict = {}
+
+
+def _shared_stream(device, role: str) -> "torch.cuda.Stream":
+    """One side stream per (device, role) for ALL samplers of the process. torch's caching allocator keeps a separate pool of freed
+    blocks per stream: a sampler that created its own producer stream would pay a cudaMalloc of its multi-GB prefetch buffers (~2 ms
+    per GB, measured in the bench's e2e leg) even when an earlier sampler has just released buffers of the same size."""
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(), role)
+    if key not in _STREAMS:
+        _STREAMS[key] = torch.cuda.Stream(dev)
+    return _STREAMS[key]
 
 
 class RegionAnnotation:
@@ -128,8 +143,10 @@ def _parse_annotations(img_anno_paths, layer: int, classes: list[str] = None, *,
                                            layer=layer, layer_size=size, image_index=j, seed=seed, device=device)
                     regions_per_image[j][cls].append(reg)
                     regions_all[cls].append(reg)
-                except Exception:
+                except Exception as e:
                     regions_failed += 1
+                    # the reference only counts failures (:235-236); a dropped region changes class areas and sampling weights, so name it
+                    warnings.warn(f"annotation dropped: image {j}, region {i} (class {cls!r}): {e}", RuntimeWarning, stacklevel=2)
     if verbose:
         if regions_failed > 0:
             print(f"Failed to parse {regions_failed} regions.")
@@ -218,6 +235,11 @@ class AnnoRegionRndSampler:
         self._upload_done = [None] * len(img_anno_paths)   # event of a background upload still in flight (resident slides wait on it)
         self._copy_stream = None
         self.ingest_events: list[dict] = []    # one record per upload: host ms of the allocation, CUDA events of copy / all-gather
+        # Redraws of (class, region) after a failed region (too small / miss limit): the reference's worker loop retries without bound
+        # (region_samplers.py:571-572,589-590) -- and hangs when no region can ever succeed. Here a slot gives up after max_redraw
+        # redraws (early exit on success, so the bound costs nothing): 4096 makes a spurious abort in a dataset with many
+        # below-threshold regions astronomically unlikely (p_fail^4096) while a dataset that cannot be sampled at all still raises.
+        self.max_redraw = 4096
         self._slot_cursor = 0
         self._yield_cursor = None      # slot cursor behind the last batch a running torch_generator has handed out
         self._producer = None          # CUDA stream the gathers of torch_generator's prefetch groups run on
@@ -366,7 +388,7 @@ class AnnoRegionRndSampler:
         """Make every pinned slide that is not resident yet resident on the copy stream, behind `after_event` (the last gather that
         reads host memory in place, so the two do not share the PCIe link); later gathers wait on the upload's event (_slide)."""
         if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(self._device)
+            self._copy_stream = _shared_stream(self._device, "copy")
         with torch.cuda.stream(self._copy_stream):
             if after_event is not None:
                 self._copy_stream.wait_event(after_event)
@@ -392,7 +414,7 @@ class AnnoRegionRndSampler:
         ps = self.patch_size
         return ops.region_sample(
             self._tables.struct, n_slots, self.patches_from_one_region, ps, ps * ps * self.region_intersection, miss_limit=500,
-            max_redraw=64, fixed_class=-1 if cls_idx is None else cls_idx, slots_per_table_draw=max(slots_per_image_draw, 1),
+            max_redraw=self.max_redraw, fixed_class=-1 if cls_idx is None else cls_idx, slots_per_table_draw=max(slots_per_image_draw, 1),
             seed=self._seed, slot_offset=slot_offset, device=self._device)
 
     def sample_coords(self, n_slots: int, slots_per_image_draw: int, cls_idx: int = None, slot_offset: int = None):
@@ -473,8 +495,8 @@ class AnnoRegionRndSampler:
             job = n_batches * batch_size * ps * ps * 3
             mapped = job <= self._zero_copy_fraction * sum(self._sources[j].nbytes for j in pending_up)
         if on_gpu and self._producer is None:
-            self._producer = torch.cuda.Stream(self._device)
-            self._drawer = torch.cuda.Stream(self._device)
+            self._producer = _shared_stream(self._device, "producer")
+            self._drawer = _shared_stream(self._device, "drawer")
             self._producer.wait_stream(cur)                 # tables (and anything else set up on the caller's stream) are complete
             self._drawer.wait_stream(cur)
 

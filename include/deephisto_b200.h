@@ -172,6 +172,14 @@ DH_API int dh_stitch_binned_set_tile_rows(int rows);
 DH_API int dh_stitch_binned_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------
+ * A3  batch_predictor's model forward (examples/predict_full_patched.py:66-78; ResNet18 stem, models/patch_cls_simple/model.py:5-11):
+ * the 3x3 / stride 2 / padding 1 max pooling behind conv1 + ReLU, over an NHWC tensor [B][H][W][C] -> [B][(H-1)/2+1][(W-1)/2+1][C].
+ * -inf padding, NaN propagates (torch.nn.functional.max_pool2d semantics). dtype: DH_BF16; C % 8 == 0; 16-byte aligned buffers.
+ * The convolutions stay with cuDNN (torch); this is the HBM-bound step between them.
+ * ------------------------------------------------------------------------------------------ */
+DH_API int dh_maxpool3x3s2_nhwc(const void* in, int64_t B, int H, int W, int C, void* out, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Prediction post-processing: perform_and_save_visualizations (examples/predict_full_patched.py:81-113).
  *   mask    [dh][dw][3] = lut_rgb[class]                                   (:89-95)
  *   thumb   [dh][dw][3] = integer area average of the d x d slide block under the cell, rounded half up

@@ -247,6 +247,55 @@ def cnn():
             say(kernel="CUDA graph capture failed", error=repr(e)[:200])
 
 
+def cnn2():
+    """FusedResNetForward vs the plain bf16 model: total and per stage."""
+    from deephisto_b200.examples import predict_full_patched as pfp
+
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
+    model = pfp.get_model(5)
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    plain = pfp.DeviceBatchPredictor(model, "cuda", torch.bfloat16, fold_bn=True)
+    fused = pfp.DeviceBatchPredictor(model, "cuda", torch.bfloat16, fused=True)
+    f = fused.fused
+    x = torch.rand((B, PS, PS, 3), device="cuda").to(torch.bfloat16)
+    with torch.no_grad():
+        ms = timeit(lambda: plain.logits(x.permute(0, 3, 1, 2)), reps=5, warm=3)
+        say(kernel="plain forward (bf16 channels_last, BN folded)", batch=B, ms=ms, patches_per_s=B / ms * 1e3)
+        ms = timeit(lambda: f.space_to_depth(x), reps=5, warm=2)
+        say(kernel="space_to_depth (torch ops)", ms=ms)
+        s2d = f.space_to_depth(x)
+        ms = timeit(lambda: f(s2d), reps=5, warm=3)
+        say(kernel="FusedResNetForward", batch=B, ms=ms, patches_per_s=B / ms * 1e3, tflops=B * 3.64e9 / ms / 1e9)
+        a, b = plain.logits(x.permute(0, 3, 1, 2)), f(s2d)
+        say(kernel="fused vs plain logits", max_abs_diff=(a - b).abs().max().item(), max_abs=a.abs().max().item(),
+            argmax_agree=(a.argmax(1) == b.argmax(1)).float().mean().item())
+        one = (1, 1)
+        ms = timeit(lambda: torch.cudnn_convolution_relu(s2d, f.stem_w, f.stem_b, one, (0, 0), one, 1), reps=5, warm=2)
+        say(kernel="  stem: 4x4 conv over 16 s2d channels + bias + relu (cuDNN fused)", ms=ms)
+        y = torch.cudnn_convolution_relu(s2d, f.stem_w, f.stem_b, one, (0, 0), one, 1)
+        ms = timeit(lambda: ops.maxpool3x3s2_nhwc(y), reps=5, warm=2)
+        say(kernel="  dh_maxpool3x3s2_nhwc", ms=ms, GBs=(y.numel() * 2 * 1.25) / ms / 1e6, frac=(y.numel() * 2 * 1.25) / ms / 1e6 / peak)
+        ms_t = timeit(lambda: torch.nn.functional.max_pool2d(y, 3, 2, 1), reps=5, warm=2)
+        say(kernel="  torch max_pool2d", ms=ms_t, same=bool(torch.equal(torch.nn.functional.max_pool2d(y, 3, 2, 1), ops.maxpool3x3s2_nhwc(y))))
+        t = ops.maxpool3x3s2_nhwc(y)
+        i = 0
+        for w1, b1, stride, w2, b2, down in f.blocks:
+            def blk(t=t):
+                identity = t if down is None else torch.nn.functional.conv2d(t, down[0], down[1], stride=down[2])
+                h = torch.cudnn_convolution_relu(t, w1, b1, stride, one, one, 1)
+                return torch.cudnn_convolution_add_relu(h, w2, identity, 1.0, b2, one, one, one, 1)
+            ms = timeit(blk, reps=5, warm=2)
+            say(kernel=f"  block {i}", ms=ms, in_shape=str(tuple(t.shape)))
+            t = blk()
+            i += 1
+        for bs in (256, 512, 2048):
+            xs = torch.rand((bs, PS, PS, 3), device="cuda").to(torch.bfloat16)
+            s2 = f.space_to_depth(xs)
+            ms = timeit(lambda: f(s2), reps=5, warm=3)
+            say(kernel="FusedResNetForward", batch=bs, ms=ms, patches_per_s=bs / ms * 1e3)
+
+
 if __name__ == "__main__":
-    {"cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
