@@ -14,7 +14,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("DEEPHISTO_B200_LIB", _HERE / "libdeephisto_b200.so"))
 
 DH_F32, DH_BF16, DH_U8 = 0, 1, 2
-DH_NHWC, DH_NCHW = 0, 1
+DH_NHWC, DH_NCHW, DH_S2D16 = 0, 1, 2
 DH_FLIP_H, DH_FLIP_V = 1, 2
 DH_SLOT_OK, DH_SLOT_MISS_LIMIT, DH_SLOT_EMPTY_RANGE = 0, 1, 2
 

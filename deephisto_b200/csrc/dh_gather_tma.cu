@@ -184,14 +184,22 @@ __device__ __forceinline__ void store_unit(__nv_bfloat16* dst, const float (&f)[
 
 template <typename OutT> struct UnitOf { static constexpr int kElems = 16 / (int)sizeof(OutT); };
 
+// LAY: DH_NHWC, DH_NCHW, or DH_S2D16 (bf16 only): the 2x2 space-to-depth image of the patch with 16 channels per pixel and a zero
+// border of 2 (top / left) and 1 (bottom / right) pixels, [ps/2 + 3][ps/2 + 3][16] -- the input of the predictor's 4x4 stem convolution
+// (examples/predict_full_patched.py FusedResNetForward). Channel p * 8 + q * 3 + c of s2d pixel (y', x') is channel c of patch pixel
+// (2 y' + p, 2 x' + q); channels 6, 7, 14, 15 are zero. One unit = the 8 channels of one p = 6 consecutive bytes of ONE staged row.
+// The border is NOT written: the caller passes a buffer whose border is zero (it never changes between launches).
 // DBG: profiling instantiation (p.debug switches; only fp32 NHWC /255 FULL is built with it). Production kernels carry none of it.
-template <typename OutT, bool NCHW, bool SCALE, bool AFFINE, bool FULL, bool DBG = false>
+template <typename OutT, int LAY, bool SCALE, bool AFFINE, bool FULL, bool DBG = false>
 __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGatherParams p) {
+    constexpr bool NCHW = LAY == DH_NCHW;
+    constexpr bool S2D = LAY == DH_S2D16;
+    static_assert(!S2D || sizeof(OutT) == 2, "the space-to-depth layout is built for 2-byte outputs");
     constexpr int E = UnitOf<OutT>::kElems;          // elements (NHWC) or pixels (NCHW) per unit: 4 or 8
-    constexpr int IN_BYTES = NCHW ? 3 * E : E;       // input bytes per unit
+    constexpr int IN_BYTES = S2D ? 8 : (NCHW ? 3 * E : E);   // input bytes fetched per unit (S2D: 6 used)
     constexpr int NW = IN_BYTES / 4;                 // aligned words per unit after the funnel shift
     // FULL: every consumer thread owns exactly KU units of every tile (the ps = 224 shapes) -> no per-unit guards
-    constexpr int KU = FULL ? (NCHW ? (E == 4 ? 4 : 2) : 6) : kTmaMaxUnits;
+    constexpr int KU = FULL ? (S2D ? 4 : (NCHW ? (E == 4 ? 4 : 2) : 6)) : kTmaMaxUnits;
     extern __shared__ __align__(128) uint8_t stages[];
     __shared__ __align__(16) TileMeta meta[kTmaMaxStages];
     __shared__ __align__(8) uint64_t full[kTmaMaxStages];
@@ -248,7 +256,12 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             if (lane == 0) {
                 const int64_t slot = p.out_index ? (int64_t)__ldg(p.out_index + patch) : patch;
                 TileMeta m;
-                m.out_off = slot * 3 * plane + (int64_t)tr * R * (NCHW ? ps : row_bytes);
+                if (S2D) {
+                    const int64_t PH = ps / 2 + 3;
+                    m.out_off = slot * PH * PH * 16 + ((2 + (int64_t)tr * (R / 2)) * PH + 2) * 16;
+                } else {
+                    m.out_off = slot * 3 * plane + (int64_t)tr * R * (NCHW ? ps : row_bytes);
+                }
                 m.y = y; m.x = x; m.flags = (int)fl | (inside ? kInside : 0); m.tr = tr; m.pad[0] = img; m.pad[1] = 0;
                 meta[s] = m;
                 if (stage_it) mbar_expect_tx(&full[s], bytes * (uint32_t)R);
@@ -271,25 +284,31 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
 
     // ---------------- consumer warps ----------------
     const int tid = threadIdx.x - 32;
-    const int upr = p.units_per_row;
-    const int units_per_tile = R * upr;
+    const int upr = p.units_per_row;             // S2D: units per space-to-depth row = 2 halves x ps/2 pixels
+    const int units_per_tile = (S2D ? R / 2 : R) * upr;
     // per-thread unit geometry is the same for every tile: unit u_k = tid + k * kConsumers
     uint32_t s_off[kTmaMaxUnits];
     uint32_t s_mirror[kTmaMaxUnits];   // s_off of the mirrored unit of the same row = s_mirror - s_off (NCHW horizontal flip)
-    int cph[kTmaMaxUnits];
+    int cph[kTmaMaxUnits];             // S2D: element offset of the unit inside the tile's output
     int nu = 0;
 #pragma unroll
     for (int k = 0; k < kTmaMaxUnits; ++k) {
         const int u = tid + k * kConsumers;
         const int r = u / upr, c = u - r * upr;
-        s_off[k] = (uint32_t)(r * RP + IN_BYTES * c);
-        s_mirror[k] = (uint32_t)(2 * r * RP + IN_BYTES * (upr - 1));
-        cph[k] = (E * c) % 3;                    // channel of the unit's first element (NHWC, AFFINE only)
+        if (S2D) {
+            s_off[k] = (uint32_t)((2 * r + (c & 1)) * RP + 6 * (c >> 1));      // staged row 2r + p, byte 6 x' (not word aligned for odd x')
+            s_mirror[k] = 0;
+            cph[k] = (r * (ps / 2 + 3) + (c >> 1)) * 16 + 8 * (c & 1);
+        } else {
+            s_off[k] = (uint32_t)(r * RP + IN_BYTES * c);
+            s_mirror[k] = (uint32_t)(2 * r * RP + IN_BYTES * (upr - 1));
+            cph[k] = (E * c) % 3;                    // channel of the unit's first element (NHWC, AFFINE only)
+        }
         if (u < units_per_tile) nu = k + 1;
     }
     const uint32_t stage0 = smem_u32(stages);
     const uint32_t magic = opaque_u32(0x4B000000u);
-    OutT* const out_base = reinterpret_cast<OutT*>(p.out) + (int64_t)E * tid;
+    OutT* const out_base = reinterpret_cast<OutT*>(p.out) + (S2D ? 0 : (int64_t)E * tid);
 
     int s = 0;
     uint32_t ph = 0;
@@ -299,6 +318,24 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
         const uint32_t sbase = stage0 + (uint32_t)(s * stage_bytes);
         OutT* const o = out_base + m.out_off;
         if ((m.flags & kInside) && (NCHW || !(m.flags & DH_FLIP_H))) {
+          if constexpr (S2D) {
+            const int a = (3 * m.x) & 15;
+#pragma unroll
+            for (int k = 0; k < KU; ++k) {
+                if (FULL || k < nu) {
+                    const uint32_t t = (uint32_t)(a & 3) + (s_off[k] & 3u);    // byte phase of this unit relative to two word-aligned bases
+                    const uint32_t addr = sbase + (uint32_t)(a & ~3) + (s_off[k] & ~3u) + (t & ~3u);
+                    const uint32_t sh = (t & 3u) * 8u;
+                    const uint32_t q0 = lds32(addr), q1 = lds32(addr + 4), q2 = lds32(addr + 8);
+                    const uint32_t w0 = __funnelshift_r(q0, q1, sh), w1 = __funnelshift_r(q1, q2, sh);
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) f[j] = conv_byte<OutT, SCALE, AFFINE>(j < 4 ? w0 : w1, j & 3, magic, j % 3, p);
+                    f[6] = 0.f; f[7] = 0.f;
+                    store_unit(o + cph[k], f);
+                }
+            }
+          } else {
             // fast path: aligned LDS words + funnel shift. A horizontal flip in NCHW mode reads the mirrored unit of the row and
             // reverses the pixel order inside the unit (compile-time byte permutation); in NHWC mode it takes the byte path.
             const int a = (3 * m.x) & 15;
@@ -351,13 +388,15 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                 }
             }
 #undef DH_STORE
+          }
         } else {
             // slow path: horizontally flipped patches (bytes from the stage) and patches that overhang the slide (guarded global loads)
             const bool inside = m.flags & kInside, fv = m.flags & DH_FLIP_V, fh = m.flags & DH_FLIP_H;
             const int a = (3 * m.x) & 15;
             const SlideRef sl = slide_of(p, m.pad[0]);
             for (int u = tid; u < units_per_tile; u += kConsumers) {
-                const int ur = u / upr, uc = u - ur * upr;
+                const int ur0 = u / upr, uc = u - ur0 * upr;
+                const int ur = S2D ? 2 * ur0 + (uc & 1) : ur0;              // staged row of this unit
                 const int orow = m.tr * R + ur;
                 const int srow = fv ? ps - 1 - orow : orow;
                 auto pix = [&](int scol, int ch) -> float {
@@ -371,7 +410,15 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                     return norm_f<SCALE, AFFINE>((float)v, ch, p);
                 };
                 OutT* const ou = reinterpret_cast<OutT*>(p.out) + m.out_off + (int64_t)E * u;
-                if (!NCHW) {
+                if constexpr (S2D) {
+                    float f[E];
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        const int col = 2 * (uc >> 1) + j / 3;
+                        f[j] = j < 6 ? pix(fh ? ps - 1 - col : col, j % 3) : 0.f;
+                    }
+                    store_unit(reinterpret_cast<OutT*>(p.out) + m.out_off + ((int64_t)ur0 * (ps / 2 + 3) + (uc >> 1)) * 16 + 8 * (uc & 1), f);
+                } else if (!NCHW) {
                     float f[E];
 #pragma unroll
                     for (int j = 0; j < E; ++j) {
@@ -421,17 +468,22 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
                       int64_t B, int ps, void* out, int out_dtype, int out_layout, int scale255, const float* mean3, const float* std3,
                       const uint8_t* flip, int debug, cudaStream_t st) {
     const bool nchw = out_layout == DH_NCHW;
+    const bool s2d = out_layout == DH_S2D16;
     if (out_dtype == DH_U8) return DH_ERR_UNSUPPORTED;
+    if (s2d && (out_dtype != DH_BF16 || ps % 2 != 0)) return DH_ERR_UNSUPPORTED;
     const int E = out_dtype == DH_F32 ? 4 : 8;
-    if (ps % E != 0 || pitch % 16 != 0 || reinterpret_cast<uintptr_t>(slide) % 16 != 0) return DH_ERR_UNSUPPORTED;
+    if ((!s2d && ps % E != 0) || pitch % 16 != 0 || reinterpret_cast<uintptr_t>(slide) % 16 != 0) return DH_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out) % 16 != 0) return DH_ERR_UNSUPPORTED;
     const int row_bytes = 3 * ps;
-    if (!nchw && row_bytes % E != 0) return DH_ERR_UNSUPPORTED;
+    if (!nchw && !s2d && row_bytes % E != 0) return DH_ERR_UNSUPPORTED;
     const int row_pitch = ((15 + row_bytes + 15) & ~15) + 16;  // largest copy + one spare 16-byte line for the funnel shift
-    const int units_per_row = nchw ? ps / E : row_bytes / E;
+    const int units_per_row = s2d ? ps : (nchw ? ps / E : row_bytes / E);   // s2d: per space-to-depth row (two half pixels per pixel)
     int R = 0;
-    for (int r = 32; r >= 1; --r)
-        if (ps % r == 0 && r * units_per_row <= kConsumers * kTmaMaxUnits && r * row_pitch <= 12 * 1024) { R = r; break; }
+    for (int r = 32; r >= 1; --r) {
+        if (s2d && (r & 1)) continue;                                       // a space-to-depth row needs both of its input rows in the tile
+        const int tile_units = (s2d ? r / 2 : r) * units_per_row;
+        if (ps % r == 0 && tile_units <= kConsumers * kTmaMaxUnits && r * row_pitch <= 12 * 1024) { R = r; break; }
+    }
     if (!R) return DH_ERR_UNSUPPORTED;
     if (B * (int64_t)(ps / R) >= (1ll << 40)) return DH_ERR_UNSUPPORTED;
 
@@ -450,8 +502,8 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     const size_t smem = (size_t)stages * R * row_pitch;
     const int64_t n_tiles = B * (int64_t)p.tiles_per_patch;
     int rc_launch = DH_OK;
-    // every consumer thread owns exactly KU units (see the kernel): true for ps = 224 in all four output modes
-    const bool full_units = R * units_per_row == kConsumers * (nchw ? (E == 4 ? 4 : 2) : 6);
+    // every consumer thread owns exactly KU units (see the kernel): true for ps = 224 in all output modes
+    const bool full_units = (s2d ? R / 2 : R) * units_per_row == kConsumers * (s2d ? 4 : (nchw ? (E == 4 ? 4 : 2) : 6));
     const char* env_occ = getenv("DH_GATHER_OCC");  // profiling override of the resident CTAs per SM (grid size), 0 = default
     const int occ_o = env_occ ? atoi(env_occ) : 0;
 #define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st, occ_o) \
@@ -463,9 +515,10 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     } while (0)
     if (debug) {  // profiling switches exist for one instantiation only
         if (!(out_dtype == DH_F32 && !nchw && scale255 && !affine && full_units)) return DH_ERR_UNSUPPORTED;
-        rc_launch = launch_one(gather_tma_kernel<float, false, true, false, true, true>, p, n_tiles, smem, st, occ_o);
-    } else if (out_dtype == DH_F32) { if (nchw) DH_TMA_SA(float, true); else DH_TMA_SA(float, false); }
-    else                     { if (nchw) DH_TMA_SA(__nv_bfloat16, true); else DH_TMA_SA(__nv_bfloat16, false); }
+        rc_launch = launch_one(gather_tma_kernel<float, DH_NHWC, true, false, true, true>, p, n_tiles, smem, st, occ_o);
+    } else if (s2d)          { DH_TMA_SA(__nv_bfloat16, DH_S2D16); }
+    else if (out_dtype == DH_F32) { if (nchw) DH_TMA_SA(float, DH_NCHW); else DH_TMA_SA(float, DH_NHWC); }
+    else                     { if (nchw) DH_TMA_SA(__nv_bfloat16, DH_NCHW); else DH_TMA_SA(__nv_bfloat16, DH_NHWC); }
 #undef DH_TMA_SA
 #undef DH_TMA
     if (rc_launch != DH_OK) return rc_launch;

@@ -70,6 +70,7 @@ class DeviceBatchPredictor:
         self.channels_last = channels_last and dtype != torch.float32
         model = model.to(self.device).eval()
         self.fused = None
+        self._s2d = None                                       # space-to-depth stem input of the last gather() (fused predictors)
         if fused:
             if dtype == torch.float32:
                 raise ValueError("fused=True needs dtype bfloat16 or float16 (the float32 predictor is the parity path)")
@@ -90,6 +91,15 @@ class DeviceBatchPredictor:
         """[B,3,ps,ps] model input for patches at `coords`, written by dh_gather_normalize in the memory format the model runs in:
         channels_last models get an NHWC buffer viewed as NCHW (no layout pass between the gather and the first convolution)."""
         if self.fused is not None:
+            if self.dtype == torch.bfloat16 and ps % 2 == 0:
+                # dh_gather_normalize writes the stem's space-to-depth input itself, into a buffer of this predictor whose zero border
+                # is written once (the kernel only touches the interior). The returned tensor is valid until the next gather() call.
+                B = coords.shape[0]
+                side = ps // 2 + 3
+                if self._s2d is None or self._s2d.shape[0] < B or self._s2d.shape[1] != side:
+                    self._s2d = torch.zeros((max(B, 1), side, side, 16), dtype=self.dtype, device=coords.device)
+                out = ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="S2D16", scale255=True, out=self._s2d[:B])
+                return out.permute(0, 3, 1, 2)
             return self.fused.space_to_depth(ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True))
         if self.channels_last:
             return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True).permute(0, 3, 1, 2)

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DH_BF16, DH_F32, DH_NCHW, DH_NHWC, DH_U8, check
+from ._lib import DH_BF16, DH_F32, DH_NCHW, DH_NHWC, DH_S2D16, DH_U8, check
 
 _DTYPES = {torch.float32: DH_F32, torch.bfloat16: DH_BF16, torch.uint8: DH_U8}
 
@@ -142,16 +142,18 @@ def gather_normalize(slide: "DeviceSlide | MappedHostSlide", coords: torch.Tenso
                      scale255: bool = True, mean: Optional[Sequence[float]] = None, std: Optional[Sequence[float]] = None,
                      flip: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
                      out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Patches at int32 `coords` [B,2] (y,x) -> [B,ps,ps,3] (NHWC) or [B,3,ps,ps] (NCHW)."""
+    """Patches at int32 `coords` [B,2] (y,x) -> [B,ps,ps,3] (NHWC) or [B,3,ps,ps] (NCHW), or -- layout "S2D16", bfloat16 -- the
+    2x2 space-to-depth image [B, ps/2+3, ps/2+3, 16] with a zero border (DH_S2D16 in include/deephisto_b200.h). The kernel writes
+    only the interior: an `out` buffer passed by the caller must have a zero border (it stays zero across calls)."""
     lib = _lib.require_device()
     _need_cuda(coords, "coords", torch.int32)
     if coords.ndim != 2 or coords.shape[1] != 2:
         raise ValueError("coords must be [B, 2]")
     B = coords.shape[0]
-    lay = {"NHWC": DH_NHWC, "NCHW": DH_NCHW}[layout]
-    shape = (B, ps, ps, 3) if lay == DH_NHWC else (B, 3, ps, ps)
+    lay = {"NHWC": DH_NHWC, "NCHW": DH_NCHW, "S2D16": DH_S2D16}[layout]
+    shape = (B, ps, ps, 3) if lay == DH_NHWC else ((B, 3, ps, ps) if lay == DH_NCHW else (B, ps // 2 + 3, ps // 2 + 3, 16))
     if out is None:
-        out = torch.empty(shape, dtype=dtype, device=coords.device)
+        out = (torch.zeros if lay == DH_S2D16 else torch.empty)(shape, dtype=dtype, device=coords.device)
     else:
         _need_cuda(out, "out", dtype)
         if out_index is None and tuple(out.shape) != shape:

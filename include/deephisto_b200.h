@@ -42,7 +42,16 @@ typedef enum dh_status {
 } dh_status;
 
 typedef enum dh_dtype { DH_F32 = 0, DH_BF16 = 1, DH_U8 = 2 } dh_dtype;
-typedef enum dh_layout { DH_NHWC = 0, DH_NCHW = 1 } dh_layout;
+typedef enum dh_layout {
+    DH_NHWC = 0,
+    DH_NCHW = 1,
+    /* dh_gather_normalize, bf16 only: the patch as a 2x2 SPACE-TO-DEPTH image with 16 channels and room for a zero border,
+     * out[b][ps/2 + 3][ps/2 + 3][16]: channel p*8 + q*3 + c of pixel (y' + 2, x' + 2) = channel c of patch pixel (2y' + p, 2x' + q);
+     * channels 6, 7, 14, 15 are written as zero. The border pixels (2 top / left, 1 bottom / right) are NOT written: pass a buffer
+     * whose border is zero. It is the input of a 4x4 stride-1 convolution that equals the ResNet stem's 7x7 stride-2 convolution
+     * (examples/predict_full_patched.py:66-78 batch_predictor -> model.conv1), with 16 instead of 3 input channels. */
+    DH_S2D16 = 2
+} dh_layout;
 
 /* flip bits for dh_gather_normalize (train.py:71-81 RandomHorizontalFlip / RandomVerticalFlip) */
 #define DH_FLIP_H 1u

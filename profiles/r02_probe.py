@@ -296,6 +296,26 @@ def cnn2():
             say(kernel="FusedResNetForward", batch=bs, ms=ms, patches_per_s=bs / ms * 1e3)
 
 
+def ncu_binned():
+    """One dh_stitch_binned call per variant (for `ncu -k regex:bin_`): 40k x 40k coverage list, sum map at downscale argv[2]."""
+    d = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    hw = int(sys.argv[3]) if len(sys.argv) > 3 else 40000
+    coords = cover_list(hw, hw)
+    logits = torch.randn((coords.shape[0], N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
+    for variant in (0, 1, 0, 1):
+        lib.dh_stitch_binned_set_variant(variant)
+        ops.stitch_binned(logits, coords, PS, d, hw // d, hw // d, want_sum=True)
+        torch.cuda.synchronize()
+    lib.dh_stitch_binned_set_variant(0)
+
+
+def ncu_cover():
+    st = ops.CoverState(40000, 40000, PS, 16, 2, 64, seed=0)
+    for _ in range(3):
+        st.next_group(16)
+        torch.cuda.synchronize()
+
+
 if __name__ == "__main__":
-    {"cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
