@@ -169,7 +169,7 @@ def make_config(world: int) -> dict:
                      "of two alternating buffers (126 MB L2)",
         "parallelism": f"replicated slide, batches sharded by rank (x{world}), no data-path collective",
         "predict_workload": f"examples.predict_full_patched (BASELINE configs[3]) in the same line as e2e.predict_*: patch_cls_simple ResNet18 "
-                            f"(random init, seed 0) on a synthetic {PREDICT_HW[0]}x{PREDICT_HW[1]} slide, 224x224 patches at stride 112, dense "
+                            f"(random init, seed 0; bf16 channels_last, FusedResNetForward) on a synthetic {PREDICT_HW[0]}x{PREDICT_HW[1]} slide, 224x224 patches at stride 112, dense "
                             f"sampler batch 64, stitch downscale 16, argmax map; row bands x{world} with patch-size halo + NCCL all-gather of "
                             f"the u8 class-map bands; 1 warm-up + {PREDICT_STEPS} timed slides (strong scaling: the slide is the same for every N)",
         "stitch_workload": f"roofline.stitch_*: dh_stitch_dense / dh_stitch_binned sum maps of the {STITCH_HW[0]}x{STITCH_HW[1]} stride-112 case "
@@ -511,7 +511,7 @@ def ours(args):
     stitch = stitch_rooflines(torch) if (world == 1 and args.workload == "annotated_rnd" and not args.no_stitch) else {}
     predict = {}
     if args.workload == "annotated_rnd" and not args.no_predict:
-        pargs = argparse.Namespace(slide=list(PREDICT_HW), bf16=True, fold_bn=True, cudnn_benchmark=True, cnn_batch=1024,
+        pargs = argparse.Namespace(slide=list(PREDICT_HW), bf16=True, fold_bn=True, cudnn_benchmark=True, cnn_batch=1024, fused=True,
                                    steps=PREDICT_STEPS, warmup=1)
         predict = predict_measure(pargs, dev, world, rank, e2e_steps=1)["flat"]
     clk = clocks.finish()
@@ -702,7 +702,7 @@ def predict_config(world, args):
     return hw, {
         "workload": f"examples.predict_full_patched (BASELINE configs[{2 if hw[0] <= 40000 else 3}]): patch_cls_simple ResNet18 (random init, seed 0, "
                     f"{'bf16 channels_last' if args.bf16 else 'fp32, torch defaults (TF32 convolutions)'}{', BatchNorm folded' if args.fold_bn else ''}"
-                    f"{', cudnn.benchmark' if args.cudnn_benchmark else ''}) on a synthetic {hw[0]}x{hw[1]} slide, "
+                    f"{', cudnn.benchmark' if args.cudnn_benchmark else ''}{', fused forward' if getattr(args, 'fused', False) else ''}) on a synthetic {hw[0]}x{hw[1]} slide, "
                     f"224x224 patches at stride 112, dense sampler batch 64 (CNN batch {args.cnn_batch}), stitch downscale 16, argmax map",
         "slide": list(hw), "patch": PS, "stride": 112, "downscale": 16, "cnn_batch": args.cnn_batch,
         "l2_policy": "inputs larger than L2: each step re-reads the whole slide band (GBs) from HBM",
@@ -759,7 +759,8 @@ def predict_measure(args, dev, world, rank, e2e_steps=None) -> dict:
     torch.manual_seed(0)
     model = pfp.get_model(5)
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
-    pred = pfp.DeviceBatchPredictor(model, dev, torch.bfloat16 if args.bf16 else torch.float32, fold_bn=bool(args.fold_bn))
+    pred = pfp.DeviceBatchPredictor(model, dev, torch.bfloat16 if args.bf16 else torch.float32, fold_bn=bool(args.fold_bn),
+                                    fused=bool(getattr(args, "fused", False)))
     anno = AnnoDescription.with_auto_colors(["AT", "BG", "LP", "MM", "TUM"])
     src = SyntheticSlide(H, W, seed=0)
     mode = fs.SamplerExecutionMode.INMEMORY_SINGLEPROC
@@ -839,7 +840,10 @@ def predict_measure(args, dev, world, rank, e2e_steps=None) -> dict:
         "predict_slide_px": H * W, "predict_steps": K, "predict_e2e_steps": Ke, "predict_h2d_bytes_per_slide_per_rank": h2d,
         "predict_d2h_bytes_per_slide": d2h,
         "predict_cnn": ("bf16 channels_last" if args.bf16 else "fp32 (TF32 convolutions)") + (", BatchNorm folded" if args.fold_bn else "")
-                       + (", cudnn.benchmark" if args.cudnn_benchmark else "") + f", CNN batch {args.cnn_batch} (torch/cuDNN: not part of the rebuilt path)",
+                       + (", cudnn.benchmark" if args.cudnn_benchmark else "")
+                       + (", FusedResNetForward (space-to-depth stem written by the gather, dh_maxpool3x3s2_nhwc, cuDNN fused conv+bias(+add)+relu calls)"
+                          if getattr(args, "fused", False) else "")
+                       + f", CNN batch {args.cnn_batch} (convolutions = torch/cuDNN: not part of the rebuilt path)",
     }
     return {"flat": flat, "cfg": cfg, "ms_total": ms_total, "e2e_s": e2e_s, "Ke": Ke, "stage_ms": stage_ms, "grid": g, "plan": plan, "hw": (H, W),
             "h2d": h2d, "d2h": d2h}
@@ -907,6 +911,7 @@ def main():
     ap.add_argument("--cnn-batch", type=int, default=1024)
     ap.add_argument("--fold-bn", action="store_true", help="predict workload: fold eval-mode BatchNorm into the convolutions")
     ap.add_argument("--cudnn-benchmark", action="store_true", help="predict workload: torch.backends.cudnn.benchmark = True")
+    ap.add_argument("--fused", action="store_true", help="predict workload: FusedResNetForward (bf16; space-to-depth stem, fused cuDNN epilogues)")
     ap.add_argument("--with-training", action="store_true", help="train_input workload: also time a ResNet18 bf16 training step fed by the sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true", help="default workload: skip the e2e.predict_* part (100k x 100k whole-slide prediction)")

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(1024) cover_batch_kernel(uint32_t* __restrict_
                                                            uint32_t* __restrict__ nonzero_out, int stop_when_full, int hsize, int off_in_smem) {
     __shared__ uint32_t carry;
     __shared__ uint32_t wtot[32];
-    extern __shared__ uint32_t cover_smem[];
+    extern __shared__ __align__(16) uint32_t cover_smem[];
     uint32_t* hkey = cover_smem;               // [hsize] open-addressing hash of the Fisher-Yates swaps, hsize = pow2 >= 2 B
     uint32_t* hval = hkey + hsize;             // [hsize]
     uint32_t* s_rank = hval + hsize;           // [B] first the draws j_i, then (in place) the ranks
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(1024) cover_group_kernel(uint32_t* __restrict_
                                                            int64_t H, int64_t W, int ps, int speedup, uint32_t dense_level, int B, uint32_t key0,
                                                            uint32_t key1, uint64_t first_batch, int n_batches, int32_t* __restrict__ coords,
                                                            uint32_t* __restrict__ nonzero_out, int stop_when_full, int hsize) {
-    extern __shared__ uint32_t cover_smem[];
+    extern __shared__ __align__(16) uint32_t cover_smem[];
     __shared__ uint32_t s_M, s_nz, s_extra;
     const int nsup = (nb + 31) / 32, ntop = (nsup + 31) / 32;
     CoverTree tr;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(1024) cover_group_kernel(uint32_t* __restrict_
     uint32_t* hkey = tr.top + 32;               // [hsize] Fisher-Yates swap hash (only when two draws of a batch collide)
     uint32_t* hval = hkey + hsize;              // [hsize]
     uint32_t* s_rank = hval + hsize;            // [B]
-    int32_t* s_yx = reinterpret_cast<int32_t*>(s_rank + B);   // [B][2]
+    int4* s_fp = reinterpret_cast<int4*>(s_rank + ((B + 3) & ~3));   // [B] footprint of every pick: first coarse cell, rows, columns
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
     // ---- build the tree from the block counts of the state
@@ -348,6 +348,13 @@ __global__ void __launch_bounds__(1024) cover_group_kernel(uint32_t* __restrict_
     const int fmax = ps / speedup + 1;                      // largest footprint side in coarse cells
     const int fcells = fmax * fmax;
     const int64_t pd2 = ps / speedup / 2;
+    // accumulator update: thread -> (group of picks, footprint offset), fixed for the launch
+    const int fpad = (fcells + 31) & ~31;
+    const int fgroups = fpad <= 1024 ? 1024 / fpad : 0;
+    const int fgrp = fgroups ? tid / fpad : 0, foff = fgroups ? tid - fgrp * fpad : 0;
+    const bool fvalid = fgroups && fgrp < fgroups && foff < fcells;
+    const int frow = foff / fmax, fcol = foff - frow * fmax;
+    const int64_t frowoff = (int64_t)frow * dw;
     for (int g = 0; g < n_batches; ++g) {
         const uint64_t batch = first_batch + (uint64_t)g;
         const uint32_t batch_lo = (uint32_t)batch, batch_hi = (uint32_t)(batch >> 32);
@@ -426,47 +433,62 @@ __global__ void __launch_bounds__(1024) cover_group_kernel(uint32_t* __restrict_
             const uint32_t cell = rank >= M ? s.extra[rank - M] : tree_find(tr, s.mask, rank, lane);
             if (lane == 0) {
                 const Philox4 pj = philox4x32_10((uint32_t)slot, batch_lo, batch_hi, kStreamCoverJit, key0, key1);
-                const int64_t cy = cell / dw, cx = cell - cy * dw;
+                const uint32_t ucy = cell / (uint32_t)dw;                          // cells < 2^31 (host check): 32-bit division
+                const int64_t cy = ucy, cx = cell - ucy * (uint32_t)dw;
                 int64_t y = (cy - pd2) * speedup + (int64_t)bounded_u32(pj.v[0], (uint32_t)speedup);
                 int64_t x = (cx - pd2) * speedup + (int64_t)bounded_u32(pj.v[1], (uint32_t)speedup);
                 y = y > H - ps ? H - ps : y; y = y < 0 ? 0 : y;
                 x = x > W - ps ? W - ps : x; x = x < 0 ? 0 : x;
-                s_yx[2 * slot] = (int32_t)y; s_yx[2 * slot + 1] = (int32_t)x;
+                const uint32_t uy = (uint32_t)y, ux = (uint32_t)x, us = (uint32_t)speedup;
+                const uint32_t r0 = uy / us, r1 = (uy + (uint32_t)ps) / us, c0 = ux / us, c1 = (ux + (uint32_t)ps) / us;
+                s_fp[slot] = make_int4((int)(r0 * (uint32_t)dw + c0), (int)(r1 - r0), (int)(c1 - c0), 0);
                 reinterpret_cast<int2*>(out)[slot] = make_int2((int32_t)y, (int32_t)x);
             }
         }
         __syncthreads();  // every pick has been located against the state of the PREVIOUS batch before the state changes
-        // ---- update (full_samplers.py:86-92): accum[y//s:(y+ps)//s, x//s:(x+ps)//s] += 1 over all B footprints, flat over the block
+        // ---- update (full_samplers.py:86-92): accum[y//s:(y+ps)//s, x//s:(x+ps)//s] += 1 over all B footprints. A thread owns ONE
+        // footprint offset (frow, fcol) for the whole launch (computed once, above) and walks the picks in steps of `fgroups`; the
+        // pick's footprint (first cell, height, width) was stored by the placement. No division in this loop.
         uint32_t became_nonzero = 0;
-        const int total = B * fcells;
-        for (int w0 = tid; w0 < total; w0 += 1024 * 8) {
-            int64_t cell[8];
-            uint32_t old[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int w = w0 + 1024 * u;
-                cell[u] = -1;
-                if (w < total) {
-                    const int slot = w / fcells, f = w - slot * fcells;
-                    const int rr = f / fmax, cc = f - rr * fmax;
-                    const int y = s_yx[2 * slot], x = s_yx[2 * slot + 1];
-                    const int r0 = y / speedup, r1 = (y + ps) / speedup, c0 = x / speedup, c1 = (x + ps) / speedup;
-                    if (r0 + rr < r1 && c0 + cc < c1) cell[u] = (int64_t)(r0 + rr) * dw + c0 + cc;
-                }
+        auto touch = [&](int64_t cell, uint32_t old) {
+            became_nonzero += old == 0u;
+            if (old + 1u == dense_level) {          // the cell leaves the eligible set
+                atomicAnd(s.mask + (cell >> 5), ~(1u << (cell & 31)));
+                const int b = (int)(cell / kCellsPerBlock);
+                atomicSub(tr.cnt + b, 1u);
+                atomicSub(tr.sup + (b >> 5), 1u);
+                atomicSub(tr.top + (b >> 10), 1u);
+                atomicSub(&s_M, 1u);
             }
+        };
+        if (fgroups > 0) {
+            for (int s0 = fgrp; s0 < B; s0 += fgroups * 8) {
+                int64_t cell[8];
+                uint32_t old[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) old[u] = cell[u] >= 0 ? atomicAdd(accum + cell[u], 1u) : 1u;
+                for (int u = 0; u < 8; ++u) {
+                    const int slot = s0 + u * fgroups;
+                    cell[u] = -1;
+                    if (fvalid && slot < B) {
+                        const int4 fp = s_fp[slot];                                  // first cell, rows, columns of the footprint
+                        if (frow < fp.y && fcol < fp.z) cell[u] = (int64_t)fp.x + frowoff + fcol;
+                    }
+                }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (cell[u] < 0) continue;
-                became_nonzero += old[u] == 0u;
-                if (old[u] + 1u == dense_level) {      // the cell leaves the eligible set
-                    atomicAnd(s.mask + (cell[u] >> 5), ~(1u << (cell[u] & 31)));
-                    const int b = (int)(cell[u] / kCellsPerBlock);
-                    atomicSub(tr.cnt + b, 1u);
-                    atomicSub(tr.sup + (b >> 5), 1u);
-                    atomicSub(tr.top + (b >> 10), 1u);
-                    atomicSub(&s_M, 1u);
+                for (int u = 0; u < 8; ++u) old[u] = cell[u] >= 0 ? atomicAdd(accum + cell[u], 1u) : 1u;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (cell[u] >= 0) touch(cell[u], old[u]);
+            }
+        } else {                                       // footprints of more than 1024 coarse cells: flat index with divisions
+            const int total = B * fcells;
+            for (int w = tid; w < total; w += 1024) {
+                const int slot = w / fcells, f = w - slot * fcells;
+                const int rr = f / fmax, cc = f - rr * fmax;
+                const int4 fp = s_fp[slot];
+                if (rr < fp.y && cc < fp.z) {
+                    const int64_t cell = (int64_t)fp.x + (int64_t)rr * dw + cc;
+                    touch(cell, atomicAdd(accum + cell, 1u));
                 }
             }
         }
@@ -551,7 +573,7 @@ static int cover_launch(uint32_t* accum, int64_t dh_, int64_t dw_, int64_t H, in
     int hsize = 64;
     while (hsize < 2 * B) hsize *= 2;
     const int nsup = (nb + 31) / 32, ntop = (nsup + 31) / 32;
-    const size_t tree_smem = (size_t)(ntop * 1024 + ntop * 32 + 32 + 2 * hsize + 3 * B) * sizeof(uint32_t);
+    const size_t tree_smem = (size_t)(ntop * 1024 + ntop * 32 + 32 + 2 * hsize + ((B + 3) & ~3) + 4 * B) * sizeof(uint32_t);
     if (ntop <= 32 && tree_smem <= 200 * 1024 && g_cover_variant != 1) {
         // persistent kernel: the whole group in one launch (up to 32 768 blocks = 67 M coarse cells = a 131k x 131k slide at speedup 16)
         static size_t configured = 0;

@@ -34,7 +34,7 @@ constexpr int kBinCap = 128;    // patches per tile staged in shared memory; lon
 constexpr int kBinMaxN = 8;     // classes the cell kernel keeps in registers
 
 static int g_bin_tile_rows = 0;  // 0 = heuristic; profiling override (dh_stitch_binned_set_tile_rows)
-static int g_bin_variant = 0;    // 0 = segment kernel whenever n <= 8; 1 = round-1 row-run kernels (A/B, dh_stitch_binned_set_variant)
+static int g_bin_variant = 1;    // 1 = row-run kernels (default); 0 = segment kernel whenever n <= 8 (dh_stitch_binned_set_variant)
 
 struct BinGeom {
     int64_t rows, row_offset, dw;

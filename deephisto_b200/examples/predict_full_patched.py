@@ -74,14 +74,20 @@ class DeviceBatchPredictor:
         if fused:
             if dtype == torch.float32:
                 raise ValueError("fused=True needs dtype bfloat16 or float16 (the float32 predictor is the parity path)")
-            self.fused = FusedResNetForward(model, dtype)
-        if fold_bn:
-            model = fold_batchnorm(model)
-        if dtype != torch.float32:
-            model = model.to(dtype)
-        if self.channels_last:
-            model = model.to(memory_format=torch.channels_last)
-        self.model = model
+            self.fused = FusedResNetForward(model, dtype)      # works on its own folded copy of the weights
+            self.model = None
+        else:
+            if fold_bn:
+                model = fold_batchnorm(model)                   # a copy
+            elif dtype != torch.float32:
+                import copy
+
+                model = copy.deepcopy(model)                    # the caller's module keeps its precision
+            if dtype != torch.float32:
+                model = model.to(dtype)
+            if self.channels_last:
+                model = model.to(memory_format=torch.channels_last)
+            self.model = model
         self._source_model = None                              # weak reference to the caller's module (batch_predictor's cache check)
 
     def source_model(self):

@@ -177,7 +177,9 @@ DH_API int dh_stitch_binned(const float* logits, const int32_t* coords, int64_t 
                      float* sum_map, uint32_t* count_map, uint8_t* argmax_u8, int64_t rows, int64_t dw,
                      int64_t row_offset, void* scratch, int64_t scratch_bytes, void* stream);
 DH_API int dh_stitch_binned_set_tile_rows(int rows);
-/* Profiling / tests: 0 = auto (segment kernel for n <= 8 classes), 1 = the row-run tile kernels of round 1. Same bits either way. */
+/* Tile-kernel formulation: 1 (default) = row-run kernels (every lane re-sums its own floats at each footprint boundary),
+ * 0 = segment kernel for n <= 8 classes (one lane per column segment sums, all lanes fetch; measured slower so far:
+ * profiles/r02_stitch.md). Same bits either way (tests/test_gpu_parity.py). */
 DH_API int dh_stitch_binned_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------

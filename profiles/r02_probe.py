@@ -296,6 +296,24 @@ def cnn2():
             say(kernel="FusedResNetForward", batch=bs, ms=ms, patches_per_s=bs / ms * 1e3)
 
 
+def cnn3():
+    """Stem alternatives (timing only, random tensors): 2x2 space-to-depth (16 ch, 4x4 conv, 64 out) vs 4x4 space-to-depth (48 ch, 3x3 conv,
+    256 out = 2x2 output pixels x 64)."""
+    torch.backends.cudnn.benchmark = True
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+    cl = torch.channels_last
+    one = (1, 1)
+    for name, cin, hw, cout, k, pad in (("s2d-2: [B,16,115,115] -> 64, 4x4", 16, 115, 64, 4, 0), ("s2d-4: [B,48,56,56] -> 256, 3x3 pad 1", 48, 56, 256, 3, 1),
+                                        ("s2d-4 with 64 padded input channels", 64, 56, 256, 3, 1), ("s2d-2 with 32 channels", 32, 115, 64, 4, 0)):
+        x = torch.rand((B, cin, hw, hw), device="cuda").to(torch.bfloat16).contiguous(memory_format=cl)
+        w = torch.rand((cout, cin, k, k), device="cuda").to(torch.bfloat16).contiguous(memory_format=cl)
+        b = torch.zeros(cout, device="cuda", dtype=torch.bfloat16)
+        ms = timeit(lambda: torch.cudnn_convolution_relu(x, w, b, one, (pad, pad), one, 1), reps=5, warm=3)
+        ms2 = timeit(lambda: torch.relu_(torch.nn.functional.conv2d(x, w, b, padding=pad)), reps=5, warm=3)
+        oh = hw + 2 * pad - k + 1
+        say(kernel=name, batch=B, ms_fused=ms, ms_conv_relu=ms2, tflops=2.0 * B * oh * oh * cout * cin * k * k / ms / 1e9)
+
+
 def ncu_binned():
     """One dh_stitch_binned call per variant (for `ncu -k regex:bin_`): 40k x 40k coverage list, sum map at downscale argv[2]."""
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 4
@@ -317,5 +335,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"cnn3": cnn3, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))

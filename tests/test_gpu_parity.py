@@ -657,9 +657,21 @@ def test_cover_sampler_resume_from_saved_state(ops):
     assert torch.equal(a.accum, b.accum)
 
 
-def test_stitch_binned_random_shapes_vs_oracle(ops):
+@pytest.mark.parametrize("variant", [1, 0])
+def test_stitch_binned_random_shapes_vs_oracle(ops, variant):
     """Randomised shapes (slide size, patch size, downscale, class count, list length, overhanging and duplicated origins, row
-    bands): every output of dh_stitch_binned is bit-identical to the reference loop."""
+    bands): every output of dh_stitch_binned is bit-identical to the reference loop -- with the row-run tile kernels (variant 1,
+    the default) and with the segment kernel (variant 0)."""
+    from deephisto_b200 import _lib
+
+    _lib.require_device().dh_stitch_binned_set_variant(variant)
+    try:
+        _stitch_binned_random_shapes(ops)
+    finally:
+        _lib.require_device().dh_stitch_binned_set_variant(1)
+
+
+def _stitch_binned_random_shapes(ops):
     rng = np.random.default_rng(2024)
     for trial in range(24):
         ps = int(rng.choice([32, 50, 64, 100, 224]))
