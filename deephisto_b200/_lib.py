@@ -14,7 +14,7 @@ _HERE = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("DEEPHISTO_B200_LIB", _HERE / "libdeephisto_b200.so"))
 
 DH_F32, DH_BF16, DH_U8 = 0, 1, 2
-DH_NHWC, DH_NCHW, DH_S2D16 = 0, 1, 2
+DH_NHWC, DH_NCHW, DH_S2D16, DH_S2D48 = 0, 1, 2, 3
 DH_FLIP_H, DH_FLIP_V = 1, 2
 DH_SLOT_OK, DH_SLOT_MISS_LIMIT, DH_SLOT_EMPTY_RANGE = 0, 1, 2
 
@@ -77,6 +77,7 @@ SIGNATURES = {
     "dh_stitch_binned_set_tile_rows": (C.c_int, [_i32]),
     "dh_stitch_binned_set_variant": (C.c_int, [_i32]),
     "dh_maxpool3x3s2_nhwc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "dh_maxpool3x3s2_d2s": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "dh_colorize_overlay": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _f64, _vp, _vp, _vp, _vp]),
     "dh_cover_scratch_words": (_i64, [_i64, _i64]),
     "dh_cover_init": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp]),

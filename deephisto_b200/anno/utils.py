@@ -21,18 +21,18 @@ class AnnoClass:
     description: str = None
     color: tuple = None
 
-    def __str__(self) -> str:
-        label = self.label
-        if self.alternate_labels:
-            label += " (" + ", ".join(self.alternate_labels) + ")"
-        description = ", " + self.description if self.description else ""
-        return f"AnnoClass [{self.id}, {label}, {self.color}{description}]"
-
     @property
     def label_full(self) -> str:
-        if not self.alternate_labels:
-            return self.label
-        return self.label + " (" + ", ".join(self.alternate_labels) + ")"
+        """Main label followed by its alternatives in parentheses (same text as the reference's property, anno/utils.py:37-42)."""
+        alts = ", ".join(self.alternate_labels or ())
+        return f"{self.label} ({alts})" if alts else self.label
+
+    def __str__(self) -> str:
+        """Same text as the reference's AnnoClass.__str__ (anno/utils.py:30-35)."""
+        fields = [str(self.id), self.label_full, str(self.color)]
+        if self.description:
+            fields.append(self.description)
+        return "AnnoClass [" + ", ".join(fields) + "]"
 
 
 def _spread_colors(n: int) -> list[tuple[int, int, int]]:

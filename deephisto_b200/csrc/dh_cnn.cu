@@ -44,9 +44,56 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_nhwc_bf16_kernel(const uint4
     }
 }
 
+// The same pooling over a DEPTH-TO-SPACE stem output: in[b][Y][X][(P*2 + Q)*C + o] holds pixel (2Y + P, 2X + Q), channel o, of the
+// [2H][2W][C] convolution output (the 4x4 space-to-depth stem produces 2x2 output pixels per block, examples/predict_full_patched.py
+// FusedResNetForward); out[b][Y][X][o] = max over rows 2Y-1..2Y+1, columns 2X-1..2X+1 = blocks (Y-1, P=1), (Y, P=0), (Y, P=1) x likewise.
+__global__ void __launch_bounds__(256) maxpool3x3s2_d2s_bf16_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t total, int H, int W,
+                                                                    int C8) {
+    const uint32_t ninf = 0xFF80FF80u;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(idx % C8);
+        const int64_t pix = idx / C8;
+        const int ox = (int)(pix % W);
+        const int64_t t = pix / W;
+        const int oy = (int)(t % H);
+        const int64_t b = t / H;
+        uint4 m = make_uint4(ninf, ninf, ninf, ninf);
+        const uint4* img = in + b * H * (int64_t)W * 4 * C8 + c8;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int Y = dy < 0 ? oy - 1 : oy, P = dy == 0 ? 0 : 1;
+            if (Y < 0) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int X = dx < 0 ? ox - 1 : ox, Q = dx == 0 ? 0 : 1;
+                if (X < 0) continue;
+                const uint4 v = __ldg(img + (((int64_t)Y * W + X) * 4 + (P * 2 + Q)) * C8);
+                m.x = max2_bf16(m.x, v.x); m.y = max2_bf16(m.y, v.y); m.z = max2_bf16(m.z, v.z); m.w = max2_bf16(m.w, v.w);
+            }
+        }
+        out[idx] = m;
+    }
+}
+
 }  // namespace dh
 
 using namespace dh;
+
+extern "C" DH_API int dh_maxpool3x3s2_d2s(const void* in, int64_t B, int H, int W, int C, void* out, int dtype, void* stream) {
+    if (B == 0) return DH_OK;
+    DH_REQUIRE(in && out, "dh_maxpool3x3s2_d2s: null pointer");
+    DH_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "dh_maxpool3x3s2_d2s: bad shape");
+    DH_REQUIRE(dtype == DH_BF16, "dh_maxpool3x3s2_d2s: only bf16 is implemented");
+    DH_REQUIRE(C % 8 == 0, "dh_maxpool3x3s2_d2s: the channel count must be a multiple of 8 (16-byte vectors)");
+    DH_REQUIRE(reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0, "dh_maxpool3x3s2_d2s: buffers must be 16-byte aligned");
+    const int C8 = C / 8;
+    const int64_t total = B * H * (int64_t)W * C8;
+    const int64_t blocks = (total + 255) / 256;
+    const int grid = (int)(blocks < (int64_t)kNumSMs * 32 ? blocks : (int64_t)kNumSMs * 32);
+    maxpool3x3s2_d2s_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), total, H, W, C8);
+    DH_CHECK_LAUNCH("maxpool3x3s2_d2s_bf16_kernel");
+    return DH_OK;
+}
 
 extern "C" DH_API int dh_maxpool3x3s2_nhwc(const void* in, int64_t B, int H, int W, int C, void* out, int dtype, void* stream) {
     if (B == 0) return DH_OK;

@@ -333,10 +333,11 @@ extern "C" DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64
     DH_REQUIRE(ps > 0 && ps <= 8192, "dh_gather_normalize: patch size %d out of range", ps);
     DH_REQUIRE(B >= 0, "dh_gather_normalize: negative batch");
     DH_REQUIRE(out_dtype == DH_F32 || out_dtype == DH_BF16 || out_dtype == DH_U8, "dh_gather_normalize: bad dtype %d", out_dtype);
-    DH_REQUIRE(out_layout == DH_NHWC || out_layout == DH_NCHW || out_layout == DH_S2D16, "dh_gather_normalize: bad layout %d", out_layout);
-    DH_REQUIRE(out_layout != DH_S2D16 || (out_dtype == DH_BF16 && ps % 2 == 0 && pitch % 16 == 0 && reinterpret_cast<uintptr_t>(slide) % 16 == 0 &&
-                                          reinterpret_cast<uintptr_t>(out) % 16 == 0 && out_index == nullptr),
-               "dh_gather_normalize: the space-to-depth layout needs bf16 output, an even patch size, a 16-byte aligned slide (pitch %% 16 == 0) and output, no out_index");
+    const bool s2d_any = out_layout == DH_S2D16 || out_layout == DH_S2D48;
+    DH_REQUIRE(out_layout == DH_NHWC || out_layout == DH_NCHW || s2d_any, "dh_gather_normalize: bad layout %d", out_layout);
+    DH_REQUIRE(!s2d_any || (out_dtype == DH_BF16 && ps % (out_layout == DH_S2D48 ? 4 : 2) == 0 && pitch % 16 == 0 && reinterpret_cast<uintptr_t>(slide) % 16 == 0 &&
+                            reinterpret_cast<uintptr_t>(out) % 16 == 0 && (out_layout == DH_S2D48 || out_index == nullptr)),
+               "dh_gather_normalize: the space-to-depth layouts need bf16 output, a patch size divisible by 2 (S2D16) / 4 (S2D48), a 16-byte aligned slide (pitch %% 16 == 0) and output");
     DH_REQUIRE((mean3_host == nullptr) == (std3_host == nullptr), "dh_gather_normalize: mean and std must both be given or both be NULL");
     if (B == 0) return DH_OK;
     cudaStream_t st = as_stream(stream);
@@ -352,11 +353,11 @@ extern "C" DH_API int dh_gather_normalize(const uint8_t* slide, int64_t H, int64
         if (mean3_host) DH_REQUIRE(p.stdv[c] != 0.f, "dh_gather_normalize: std[%d] == 0", c);
     }
     const bool nchw = out_layout == DH_NCHW;
-    if (g_variant != 1 || out_layout == DH_S2D16) {  // TMA-staged kernel whenever the shape allows it (the only one with the space-to-depth mode)
+    if (g_variant != 1 || s2d_any) {  // TMA-staged kernel whenever the shape allows it (the only one with the space-to-depth mode)
         int rc = gather_tma_launch(slide, H, W, pitch, nullptr, 1, nullptr, coords, out_index, B, ps, out, out_dtype, out_layout, p.scale255,
                                    mean3_host ? p.mean : nullptr, mean3_host ? p.stdv : nullptr, flip, g_variant >= 3 ? (g_variant == 6 ? 4 : (g_variant == 7 ? 8 : (g_variant == 8 ? 16 : (g_variant == 9 ? 24 : g_variant - 2)))) : 0, st);
         if (rc != DH_ERR_UNSUPPORTED) return rc;
-        if (out_layout == DH_S2D16) { set_error("dh_gather_normalize: patch size %d not supported by the space-to-depth mode of the TMA-staged kernel", ps); return rc; }
+        if (s2d_any) { set_error("dh_gather_normalize: patch size %d not supported by the space-to-depth mode of the TMA-staged kernel", ps); return rc; }
         if (g_variant >= 2) { set_error("dh_gather_normalize: shape not supported by the TMA-staged kernel (needs ps %% 4 == 0 for f32, ps %% 8 == 0 for bf16, pitch %% 16 == 0)"); return rc; }
     }
     const size_t esz = out_dtype == DH_F32 ? 4 : (out_dtype == DH_BF16 ? 2 : 1);

@@ -194,7 +194,11 @@ template <typename OutT, int LAY, bool SCALE, bool AFFINE, bool FULL, bool DBG =
 __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGatherParams p) {
     constexpr bool NCHW = LAY == DH_NCHW;
     constexpr bool S2D = LAY == DH_S2D16;
-    static_assert(!S2D || sizeof(OutT) == 2, "the space-to-depth layout is built for 2-byte outputs");
+    // DH_S2D48 (bf16 only): the 4x4 space-to-depth image [ps/4][ps/4][48], channel p*12 + q*3 + c of block (Y, X) = channel c of patch
+    // pixel (4Y + p, 4X + q). Same bytes as NHWC in another order; a unit (8 channels) is 8 bytes of one input row, or 4 + 4 bytes of
+    // two consecutive rows (units 1 and 4 of a block's six).
+    constexpr bool S4 = LAY == DH_S2D48;
+    static_assert(!(S2D || S4) || sizeof(OutT) == 2, "the space-to-depth layouts are built for 2-byte outputs");
     constexpr int E = UnitOf<OutT>::kElems;          // elements (NHWC) or pixels (NCHW) per unit: 4 or 8
     constexpr int IN_BYTES = S2D ? 8 : (NCHW ? 3 * E : E);   // input bytes fetched per unit (S2D: 6 used)
     constexpr int NW = IN_BYTES / 4;                 // aligned words per unit after the funnel shift
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
     // ---------------- consumer warps ----------------
     const int tid = threadIdx.x - 32;
     const int upr = p.units_per_row;             // S2D: units per space-to-depth row = 2 halves x ps/2 pixels
-    const int units_per_tile = (S2D ? R / 2 : R) * upr;
+    const int units_per_tile = (S4 ? R / 4 : (S2D ? R / 2 : R)) * upr;   // S4: upr = units per block row = 6 * ps/4
     // per-thread unit geometry is the same for every tile: unit u_k = tid + k * kConsumers
     uint32_t s_off[kTmaMaxUnits];
     uint32_t s_mirror[kTmaMaxUnits];   // s_off of the mirrored unit of the same row = s_mirror - s_off (NCHW horizontal flip)
@@ -299,6 +303,12 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             s_off[k] = (uint32_t)((2 * r + (c & 1)) * RP + 6 * (c >> 1));      // staged row 2r + p, byte 6 x' (not word aligned for odd x')
             s_mirror[k] = 0;
             cph[k] = (r * (ps / 2 + 3) + (c >> 1)) * 16 + 8 * (c & 1);
+        } else if (S4) {
+            const int X = c / 6, j = c - 6 * X;                               // block column, unit of the block's six
+            const int row_a = 4 * r + (2 * j) / 3, byte_a = (8 * j) % 12;     // first staged row of the unit and its byte inside the block's 12
+            s_off[k] = (uint32_t)(row_a * RP + 12 * X + byte_a);              // word aligned: 12 X + {0, 4, 8}
+            s_mirror[k] = (uint32_t)((row_a + 1) * RP + 12 * X);              // where the second half of a two-row unit starts
+            cph[k] = ((8 * j) % 3) | (byte_a == 8 ? 4 : 0);                   // channel of the unit's first byte | two-row flag
         } else {
             s_off[k] = (uint32_t)(r * RP + IN_BYTES * c);
             s_mirror[k] = (uint32_t)(2 * r * RP + IN_BYTES * (upr - 1));
@@ -318,7 +328,28 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
         const uint32_t sbase = stage0 + (uint32_t)(s * stage_bytes);
         OutT* const o = out_base + m.out_off;
         if ((m.flags & kInside) && (NCHW || !(m.flags & DH_FLIP_H))) {
-          if constexpr (S2D) {
+          if constexpr (S4) {
+            const int a = (3 * m.x) & 15;
+            const uint32_t sh = (uint32_t)(a & 3) * 8u;
+            const uint32_t abase = sbase + (uint32_t)(a & ~3);
+#pragma unroll
+            for (int k = 0; k < KU; ++k) {
+                if (FULL || k < nu) {
+                    const uint32_t q0 = lds32(abase + s_off[k]), q1 = lds32(abase + s_off[k] + 4), q2 = lds32(abase + s_off[k] + 8);
+                    const uint32_t r0 = lds32(abase + s_mirror[k]), r1 = lds32(abase + s_mirror[k] + 4);
+                    const uint32_t w0 = __funnelshift_r(q0, q1, sh);
+                    const uint32_t w1 = (cph[k] & 4) ? __funnelshift_r(r0, r1, sh) : __funnelshift_r(q1, q2, sh);
+                    float f[8];
+                    int c = cph[k] & 3;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        f[j] = conv_byte<OutT, SCALE, AFFINE>(j < 4 ? w0 : w1, j & 3, magic, c, p);
+                        if (AFFINE) c = c == 2 ? 0 : c + 1;
+                    }
+                    store_unit(o + k * (kConsumers * E), f);
+                }
+            }
+          } else if constexpr (S2D) {
             const int a = (3 * m.x) & 15;
 #pragma unroll
             for (int k = 0; k < KU; ++k) {
@@ -396,7 +427,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             const SlideRef sl = slide_of(p, m.pad[0]);
             for (int u = tid; u < units_per_tile; u += kConsumers) {
                 const int ur0 = u / upr, uc = u - ur0 * upr;
-                const int ur = S2D ? 2 * ur0 + (uc & 1) : ur0;              // staged row of this unit
+                const int ur = S2D ? 2 * ur0 + (uc & 1) : ur0;              // staged row of this unit (S4: per element, below)
                 const int orow = m.tr * R + ur;
                 const int srow = fv ? ps - 1 - orow : orow;
                 auto pix = [&](int scol, int ch) -> float {
@@ -410,7 +441,27 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
                     return norm_f<SCALE, AFFINE>((float)v, ch, p);
                 };
                 OutT* const ou = reinterpret_cast<OutT*>(p.out) + m.out_off + (int64_t)E * u;
-                if constexpr (S2D) {
+                if constexpr (S4) {
+                    const int X = uc / 6, j6 = uc - 6 * X;
+                    float f[E];
+#pragma unroll
+                    for (int j = 0; j < E; ++j) {
+                        const int ch48 = 8 * j6 + j, pr = ch48 / 12, rem = ch48 - 12 * pr, q = rem / 3, ch = rem - 3 * q;
+                        const int srow_u = 4 * ur0 + pr;                                   // staged (= output) row inside the tile
+                        const int orow_u = m.tr * R + srow_u;
+                        const int src_row = fv ? ps - 1 - orow_u : orow_u;
+                        const int col = 4 * X + q, scol = fh ? ps - 1 - col : col;
+                        uint32_t v = 0;
+                        if (inside) {
+                            v = stages[(size_t)s * stage_bytes + srow_u * RP + a + 3 * scol + ch];
+                        } else {
+                            const int64_t yy = (int64_t)m.y + src_row, xx = (int64_t)m.x + scol;
+                            if (yy >= 0 && yy < sl.H && xx >= 0 && xx < sl.W) v = __ldg(sl.data + yy * sl.pitch + 3 * xx + ch);
+                        }
+                        f[j] = norm_f<SCALE, AFFINE>((float)v, ch, p);
+                    }
+                    store_unit(ou, f);
+                } else if constexpr (S2D) {
                     float f[E];
 #pragma unroll
                     for (int j = 0; j < E; ++j) {
@@ -468,20 +519,23 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
                       int64_t B, int ps, void* out, int out_dtype, int out_layout, int scale255, const float* mean3, const float* std3,
                       const uint8_t* flip, int debug, cudaStream_t st) {
     const bool nchw = out_layout == DH_NCHW;
-    const bool s2d = out_layout == DH_S2D16;
+    const bool s2d = out_layout == DH_S2D16, s4 = out_layout == DH_S2D48;
     if (out_dtype == DH_U8) return DH_ERR_UNSUPPORTED;
     if (s2d && (out_dtype != DH_BF16 || ps % 2 != 0)) return DH_ERR_UNSUPPORTED;
+    if (s4 && (out_dtype != DH_BF16 || ps % 4 != 0)) return DH_ERR_UNSUPPORTED;
     const int E = out_dtype == DH_F32 ? 4 : 8;
-    if ((!s2d && ps % E != 0) || pitch % 16 != 0 || reinterpret_cast<uintptr_t>(slide) % 16 != 0) return DH_ERR_UNSUPPORTED;
+    if ((!s2d && !s4 && ps % E != 0) || pitch % 16 != 0 || reinterpret_cast<uintptr_t>(slide) % 16 != 0) return DH_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out) % 16 != 0) return DH_ERR_UNSUPPORTED;
     const int row_bytes = 3 * ps;
-    if (!nchw && !s2d && row_bytes % E != 0) return DH_ERR_UNSUPPORTED;
+    if (!nchw && !s2d && !s4 && row_bytes % E != 0) return DH_ERR_UNSUPPORTED;
     const int row_pitch = ((15 + row_bytes + 15) & ~15) + 16;  // largest copy + one spare 16-byte line for the funnel shift
-    const int units_per_row = s2d ? ps : (nchw ? ps / E : row_bytes / E);   // s2d: per space-to-depth row (two half pixels per pixel)
+    // units per (output) row: s2d per space-to-depth row (two half pixels per pixel), s4 per block row (six units per 4x4 block)
+    const int units_per_row = s4 ? (ps / 4) * 6 : (s2d ? ps : (nchw ? ps / E : row_bytes / E));
+    const int rows_per_out = s4 ? 4 : (s2d ? 2 : 1);
     int R = 0;
     for (int r = 32; r >= 1; --r) {
-        if (s2d && (r & 1)) continue;                                       // a space-to-depth row needs both of its input rows in the tile
-        const int tile_units = (s2d ? r / 2 : r) * units_per_row;
+        if (r % rows_per_out) continue;                                     // a space-to-depth row needs all of its input rows in the tile
+        const int tile_units = (r / rows_per_out) * units_per_row;
         if (ps % r == 0 && tile_units <= kConsumers * kTmaMaxUnits && r * row_pitch <= 12 * 1024) { R = r; break; }
     }
     if (!R) return DH_ERR_UNSUPPORTED;
@@ -503,7 +557,7 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     const int64_t n_tiles = B * (int64_t)p.tiles_per_patch;
     int rc_launch = DH_OK;
     // every consumer thread owns exactly KU units (see the kernel): true for ps = 224 in all output modes
-    const bool full_units = (s2d ? R / 2 : R) * units_per_row == kConsumers * (s2d ? 4 : (nchw ? (E == 4 ? 4 : 2) : 6));
+    const bool full_units = (R / rows_per_out) * units_per_row == kConsumers * (s2d ? 4 : (nchw ? (E == 4 ? 4 : 2) : 6));
     const char* env_occ = getenv("DH_GATHER_OCC");  // profiling override of the resident CTAs per SM (grid size), 0 = default
     const int occ_o = env_occ ? atoi(env_occ) : 0;
 #define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st, occ_o) \
@@ -517,6 +571,7 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
         if (!(out_dtype == DH_F32 && !nchw && scale255 && !affine && full_units)) return DH_ERR_UNSUPPORTED;
         rc_launch = launch_one(gather_tma_kernel<float, DH_NHWC, true, false, true, true>, p, n_tiles, smem, st, occ_o);
     } else if (s2d)          { DH_TMA_SA(__nv_bfloat16, DH_S2D16); }
+    else if (s4)             { DH_TMA_SA(__nv_bfloat16, DH_S2D48); }
     else if (out_dtype == DH_F32) { if (nchw) DH_TMA_SA(float, DH_NCHW); else DH_TMA_SA(float, DH_NHWC); }
     else                     { if (nchw) DH_TMA_SA(__nv_bfloat16, DH_NCHW); else DH_TMA_SA(__nv_bfloat16, DH_NHWC); }
 #undef DH_TMA_SA

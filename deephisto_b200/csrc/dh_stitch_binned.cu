@@ -475,7 +475,8 @@ constexpr int kSegVals = 288;       // floats per value buffer: segments * n <= 
 constexpr int kSegWords = 16;       // boundary bitmap words (<= 512 tile cells)
 
 __host__ __device__ inline int seg_warp_smem_bytes() {
-    return kBinCap * 8 /* r0 r1 c0 c1 (u16) */ + kBinCap * 32 /* logits, stride 8 */ + 2 * kSegWords * 4 + kSegCap * 2 + 2 * kSegVals * 4;
+    return kBinCap * 8 /* r0 r1 c0 c1 (u16) */ + kBinCap * 32 /* logits, stride 8 */ + (2 * kSegWords + 4) * 4 /* bitmaps */ + kSegCap * 2 /* segments */ +
+           80 /* runs */ + 2 * kSegVals * 4 /* values */;
 }
 
 template <int KIND, int G>
@@ -509,8 +510,10 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     float* s_lg = reinterpret_cast<float*>(base + kBinCap * 8);                      // [L][8]
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(base + kBinCap * 40);            // [kSegWords] segment-start bitmap over the tile's cells
     uint32_t* s_wpre = s_bits + kSegWords;                                          // [kSegWords] set bits before each word
-    uint16_t* s_segc = reinterpret_cast<uint16_t*>(s_wpre + kSegWords);             // [S] first cell of each segment (tile relative)
-    float* s_val = reinterpret_cast<float*>(base + kBinCap * 40 + 2 * kSegWords * 4 + kSegCap * 2);   // [2][kSegVals] double-buffered
+    uint32_t* s_rbits = s_wpre + kSegWords;                                         // [2] run-start bitmap over the tile's rows (TH <= 64)
+    uint16_t* s_segc = reinterpret_cast<uint16_t*>(s_rbits + 4);                    // [S] first cell of each segment (tile relative)
+    uint8_t* s_run = reinterpret_cast<uint8_t*>(s_segc + kSegCap);                  // [NR + 1] first row of each run, then TH
+    float* s_val = reinterpret_cast<float*>(base + kBinCap * 40 + (2 * kSegWords + 4) * 4 + kSegCap * 2 + 80);   // [2][kSegVals] double-buffered
     uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_val);                            // staging only: unsorted / sorted ids alias the values
     uint32_t* s_ids = s_raw + kBinCap;
 
@@ -526,6 +529,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     // ---- stage: ids in ascending order, footprints clipped to the tile (rows / cells relative to the tile), logits
     for (int j = lane; j < L; j += 32) s_raw[j] = list[beg + j];
     if (lane < kSegWords) s_bits[lane] = lane == 0 ? 1u : 0u;                       // cell 0 starts segment 0
+    if (lane < 2) s_rbits[lane] = lane == 0 ? 1u : 0u;                              // row 0 starts run 0
     __syncwarp();
     for (int j = lane; j < L; j += 32) {  // rank sort: patch indices are distinct within a tile
         const uint32_t v = s_raw[j];
@@ -541,6 +545,8 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
         const int a = f.r0 - R0, b = f.r1 - R0;
         s_r0[j] = (uint16_t)(a < 0 ? 0 : a);
         s_r1[j] = (uint16_t)(b > TH ? TH : (b < 0 ? 0 : b));
+        if (a > 0 && a < TH) atomicOr(s_rbits + (a >> 5), 1u << (a & 31));             // the covering set changes at every footprint edge
+        if (b > 0 && b < TH) atomicOr(s_rbits + (b >> 5), 1u << (b & 31));
         int c0 = f.u0 / scale - C0, c1 = f.u1 / scale - C0;                          // footprints are whole cells: u0, u1 are multiples of scale
         c0 = c0 < 0 ? 0 : (c0 > ncells ? ncells : c0);
         c1 = c1 < 0 ? 0 : (c1 > ncells ? ncells : c1);
@@ -578,6 +584,20 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
             }
         }
     }
+    int NR;         // row runs: maximal row ranges with the same covering patches
+    {
+        const uint32_t w0 = s_rbits[0], w1 = s_rbits[1];
+        NR = __popc(w0) + __popc(w1);
+        if (lane < 2) {
+            uint32_t rest = lane == 0 ? w0 : w1;
+            int k = lane == 0 ? 0 : __popc(w0);
+            while (rest) {
+                s_run[k++] = (uint8_t)(lane * 32 + __ffs(rest) - 1);
+                rest &= rest - 1;
+            }
+            if (lane == 1) s_run[NR] = (uint8_t)TH;
+        }
+    }
     __syncwarp();   // also: every lane is done with s_ids before the value buffers (which alias it) are written
     // ---- the lane's output units and their slots in the value buffer
     const int ub = U0 + lane * VEC;
@@ -596,57 +616,8 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     const bool want_vals = CELL ? argmax_map != nullptr : true;
     const int pstep = RF & 3;
 
-    int r = 0, buf = 0;
-    while (r < TH) {
-        float* const val = s_val + buf * kSegVals;
-        int next = TH;
-        // ---- one lane per segment: the covering patches' logits in ascending list index = the reference's order
-        for (int s0 = 0; s0 < S; s0 += 32) {
-            const int sg = s0 + lane;
-            const int sc = sg < S ? (int)s_segc[sg] : 0xffff;
-            float acc[kBinMaxN];
-#pragma unroll
-            for (int q = 0; q < kBinMaxN; ++q) acc[q] = 0.f;
-            uint32_t hits = 0;
-            for (int j0 = 0; j0 < L; j0 += 32) {
-                const int j = j0 + lane;
-                const int a = j < L ? (int)s_r0[j] : 0x7fff, b = j < L ? (int)s_r1[j] : 0x7fff;
-                if (s0 == 0) {
-                    const int cand = a > r ? a : (b > r ? b : 0x7fff);
-                    const int nbound = __reduce_min_sync(0xffffffffu, cand);
-                    next = nbound < next ? nbound : next;
-                }
-                unsigned m = __ballot_sync(0xffffffffu, a <= r && r < b);
-                while (m) {  // warp-uniform trip count
-                    const int jj = j0 + __ffs(m) - 1;
-                    m &= m - 1;
-                    const bool cov = (int)s_c0[jj] <= sc && sc < (int)s_c1[jj];
-                    hits += cov;
-                    if (want_vals) {
-                        const float4 lo = *reinterpret_cast<const float4*>(s_lg + jj * 8);
-                        // adding under the predicate only: a sum that starts at +0.0f and adds v is the reference's 0.0 + v
-                        // (classes q >= n add the +0.0f padding to sums nobody reads)
-                        if (cov) { acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w; }
-                        if (n > 4) {
-                            const float4 hi = *reinterpret_cast<const float4*>(s_lg + jj * 8 + 4);
-                            if (cov) { acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w; }
-                        }
-                    }
-                }
-            }
-            if (sg < S) {
-                if constexpr (CELL) {
-                    const uint32_t am = want_vals ? (uint32_t)first_argmax(acc, n) : 0u;
-                    reinterpret_cast<uint32_t*>(val)[sg] = am | (hits << 8);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < kBinMaxN; ++q)
-                        if (q < n) val[sg * n + q] = acc[q];
-                }
-            }
-        }
-        __syncwarp();
-        // ---- fetch this lane's units, stream them to every row of the run
+    // fetch this lane's units of one run from `val` and stream them to every row of the run [r, next)
+    auto emit = [&](int r, int next, const float* val) {
         if constexpr (CELL) {
             uint32_t pk[K];
 #pragma unroll
@@ -710,8 +681,66 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
                 }
             }
         }
-        r = next;
-        buf ^= 1;   // the next run writes the other buffer: one warp barrier per run is enough
+    };
+
+    // ---- passes: a lane owns one REGION = (run, segment) of the pass -- RPP = 32 / S runs at a time (one run, segments in chunks of 32,
+    // when a tile has more than 32 segments). The patch loop walks the patches that cover ANY run of the pass (consecutive runs differ
+    // by one patch each), in ascending list index = the reference's order; a lane adds those that cover its own row and columns.
+    const bool multi = S <= 32;
+    const int RPP = multi ? 32 / S : 1;
+    const int k_l = multi ? lane / S : 0;
+    const int seg_l = multi ? lane - k_l * S : 0;
+    const int vstride = CELL ? S : S * n;                         // value-buffer stride between the runs of a pass
+    int buf = 0;
+    for (int run0 = 0; run0 < NR; run0 += RPP) {
+        float* const val = s_val + buf * kSegVals;
+        const int nrun = NR - run0 < RPP ? NR - run0 : RPP;
+        const int row_first = (int)s_run[run0], row_last = (int)s_run[run0 + nrun - 1];
+        for (int s0 = 0; s0 < S; s0 += 32) {                      // one iteration when multi
+            const int sg = multi ? seg_l : s0 + lane;
+            const bool live = multi ? k_l < nrun : sg < S;
+            const int myrow = live ? (int)s_run[run0 + k_l] : 0x7fff;
+            const int sc = live ? (int)s_segc[sg] : 0xffff;
+            float acc[kBinMaxN];
+#pragma unroll
+            for (int q = 0; q < kBinMaxN; ++q) acc[q] = 0.f;
+            uint32_t hits = 0;
+            for (int j0 = 0; j0 < L; j0 += 32) {
+                const int j = j0 + lane;
+                const int a = j < L ? (int)s_r0[j] : 0x7fff, b = j < L ? (int)s_r1[j] : 0;
+                unsigned m = __ballot_sync(0xffffffffu, a <= row_last && b > row_first);
+                while (m) {  // warp-uniform trip count
+                    const int jj = j0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const bool cov = (int)s_r0[jj] <= myrow && myrow < (int)s_r1[jj] && (int)s_c0[jj] <= sc && sc < (int)s_c1[jj];
+                    hits += cov;
+                    if (want_vals) {
+                        const float4 lo = *reinterpret_cast<const float4*>(s_lg + jj * 8);
+                        // adding under the predicate only: a sum that starts at +0.0f and adds v is the reference's 0.0 + v
+                        // (classes q >= n add the +0.0f padding to sums nobody reads)
+                        if (cov) { acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w; }
+                        if (n > 4) {
+                            const float4 hi = *reinterpret_cast<const float4*>(s_lg + jj * 8 + 4);
+                            if (cov) { acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w; }
+                        }
+                    }
+                }
+            }
+            if (live) {
+                const int region = multi ? lane : sg;             // (run k_l, segment seg_l) -> k_l * S + seg_l == lane
+                if constexpr (CELL) {
+                    const uint32_t am = want_vals ? (uint32_t)first_argmax(acc, n) : 0u;
+                    reinterpret_cast<uint32_t*>(val)[region] = am | (hits << 8);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < kBinMaxN; ++q)
+                        if (q < n) val[region * n + q] = acc[q];
+                }
+            }
+        }
+        __syncwarp();
+        for (int k = 0; k < nrun; ++k) emit((int)s_run[run0 + k], (int)s_run[run0 + k + 1], val + k * vstride);
+        buf ^= 1;   // the next pass writes the other buffer: one warp barrier per pass is enough
     }
 }
 
@@ -874,7 +903,7 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         // (not for small footprints: 7 instead of 4 sums per lane cost more than the vector stores save -- measured at d = 16)
         const bool phased = !v4 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 && dw * (int64_t)n >= 8 && ps / d >= 24;
         const BinGeom g = make_geom(false, v4 || phased ? 4 : 1, ps, d, n, rows, dw, row_offset, phased);
-        const bool seg = staged && g_bin_variant == 0 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
+        const bool seg = staged && g_bin_variant == 0 && g.TH <= 64 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
         if (seg && phased) rc = run_binned<4, 1, false, true, true, 1>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4 && g.G == 2) rc = run_binned<4, 2, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4) rc = run_binned<4, 1, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
@@ -897,7 +926,7 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         const bool c4 = ps / d >= 96 && dw % 4 == 0 && reinterpret_cast<uintptr_t>(cell_argmax) % 4 == 0 &&
                         reinterpret_cast<uintptr_t>(count_map) % 16 == 0;
         const BinGeom g = make_geom(true, c4 ? 4 : 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
-        if (g_bin_variant == 0)
+        if (g_bin_variant == 0 && g.TH <= 64)
             rc = c4 ? run_binned<4, 1, true, true, false, 4>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
                     : run_binned<1, 1, true, true, false, 3>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
         else

@@ -59,7 +59,7 @@ class DeviceBatchPredictor:
     dtype float32 keeps torch's defaults (what the reference runs on a GPU); bfloat16 runs the CNN in bf16 channels_last."""
 
     def __init__(self, model: torch.nn.Module, device="cuda", dtype=torch.float32, channels_last: bool = True, fold_bn: bool = False,
-                 fused: bool = False):
+                 fused: bool = False, stem: str = "s2d4"):
         """fold_bn=True folds every eval-mode BatchNorm into the preceding convolution (torch.nn.utils.fusion): the same
         function with ~20 fewer memory-bound elementwise kernels per forward; logits change at rounding level only.
         fused=True (bfloat16 / float16, torchvision BasicBlock ResNets): the forward runs through FusedResNetForward -- space-to-depth
@@ -74,7 +74,7 @@ class DeviceBatchPredictor:
         if fused:
             if dtype == torch.float32:
                 raise ValueError("fused=True needs dtype bfloat16 or float16 (the float32 predictor is the parity path)")
-            self.fused = FusedResNetForward(model, dtype)      # works on its own folded copy of the weights
+            self.fused = FusedResNetForward(model, dtype, stem=stem)      # works on its own folded copy of the weights
             self.model = None
         else:
             if fold_bn:
@@ -97,16 +97,19 @@ class DeviceBatchPredictor:
         """[B,3,ps,ps] model input for patches at `coords`, written by dh_gather_normalize in the memory format the model runs in:
         channels_last models get an NHWC buffer viewed as NCHW (no layout pass between the gather and the first convolution)."""
         if self.fused is not None:
+            f = self.fused
+            if f.stem == "s2d4" and ps % 4:
+                raise ValueError(f"the s2d4 stem needs a patch size divisible by 4, got {ps}: build the predictor with stem='s2d2'")
             if self.dtype == torch.bfloat16 and ps % 2 == 0:
-                # dh_gather_normalize writes the stem's space-to-depth input itself, into a buffer of this predictor whose zero border
-                # is written once (the kernel only touches the interior). The returned tensor is valid until the next gather() call.
+                # dh_gather_normalize writes the stem's space-to-depth input itself, into a buffer of this predictor (s2d2: its zero
+                # border is written once, the kernel only touches the interior). The returned tensor is valid until the next gather().
                 B = coords.shape[0]
-                side = ps // 2 + 3
-                if self._s2d is None or self._s2d.shape[0] < B or self._s2d.shape[1] != side:
-                    self._s2d = torch.zeros((max(B, 1), side, side, 16), dtype=self.dtype, device=coords.device)
-                out = ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="S2D16", scale255=True, out=self._s2d[:B])
+                shape = f.s2d_shape(max(B, 1), ps)
+                if self._s2d is None or self._s2d.shape[0] < B or tuple(self._s2d.shape[1:]) != (shape[2], shape[3], shape[1]):
+                    self._s2d = torch.zeros((shape[0], shape[2], shape[3], shape[1]), dtype=self.dtype, device=coords.device)
+                out = ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout=f.gather_layout, scale255=True, out=self._s2d[:B])
                 return out.permute(0, 3, 1, 2)
-            return self.fused.space_to_depth(ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True))
+            return f.space_to_depth(ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True))
         if self.channels_last:
             return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True).permute(0, 3, 1, 2)
         return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NCHW", scale255=True)
@@ -114,8 +117,15 @@ class DeviceBatchPredictor:
     @torch.no_grad()
     def logits(self, features: torch.Tensor) -> torch.Tensor:
         if self.fused is not None:
-            if features.shape[1] != 16:                      # a plain [B,3,H,W] batch (list[Patch] callers): fold it here
+            if features.shape[1] == 3:                       # a plain [B,3,H,W] batch (list[Patch] callers): fold it here
                 features = self.fused.space_to_depth(features.permute(0, 2, 3, 1))
+            B = features.shape[0]
+            buf = self._s2d
+            if buf is not None and features.data_ptr() == buf.data_ptr() and B < buf.shape[0] <= 8 * B:
+                # a short batch inside this predictor's gather buffer (the tail of a patch range): run the buffer's full batch -- the rows
+                # behind B hold the previous batch, their logits are dropped -- so that cuDNN sees ONE input shape per predictor
+                # (cudnn.benchmark re-tunes every new shape; a streamed slide has a different tail per row chunk)
+                return self.fused(buf.permute(0, 3, 1, 2))[:B]
             return self.fused(features)
         if self.channels_last:
             features = features.contiguous(memory_format=torch.channels_last)
@@ -142,17 +152,23 @@ class FusedResNetForward:
     what changes is how it is called (measured on a B200, batch 1024, bf16 channels_last, profiles/r02_predict.md):
 
       stem   conv1 is a 7x7 stride-2 convolution over THREE input channels: cuDNN has no tensor-core kernel for C = 3 (8.2 ms of the
-             19.8 ms forward). The same function as a 4x4 stride-1 convolution over the 2x2 space-to-depth image (12 channels, padded
-             to 16; the 7x7 kernel zero-extended to 8x8 and folded the same way): K = 256, tensor cores, bias + ReLU in the epilogue.
-      pool   3x3 stride-2 max pooling of the [B,112,112,64] stem output by dh_maxpool_nhwc (HBM-bound; torch's kernel takes 3.0 ms).
+             19.8 ms forward). The same function on a SPACE-TO-DEPTH image, the 7x7 kernel zero-extended and folded the same way:
+             stem "s2d4" (patch size % 4 == 0): 4x4 blocks -> 48 input channels, a 3x3 stride-1 padding-1 convolution with 4 x 64
+             output channels (the 2x2 output pixels of a block), 0.70 ms; stem "s2d2": 2x2 blocks -> 12 channels padded to 16, a 4x4
+             convolution over an explicitly zero-bordered image, 2.05 ms. Bias + ReLU in the cuDNN epilogue either way.
+      pool   3x3 stride-2 max pooling of the stem output by dh_maxpool3x3s2_d2s / _nhwc (HBM-bound; torch's kernel takes 3.0 ms).
       blocks conv + bias + ReLU and conv + bias + residual + ReLU are ONE cuDNN call each (torch.cudnn_convolution_relu /
              cudnn_convolution_add_relu) instead of three kernels; BatchNorm is folded into the convolutions first (eval mode).
 
     Logits equal the plain bf16 model's up to bf16 rounding / accumulation order (tests/test_predict_gpu.py); the float32 predictor
     (bit-level parity path against the reference's arithmetic) does not use this class."""
 
-    def __init__(self, model: torch.nn.Module, dtype=torch.bfloat16):
+    def __init__(self, model: torch.nn.Module, dtype=torch.bfloat16, stem: str = "s2d4"):
         from torchvision.models.resnet import BasicBlock, ResNet
+
+        if stem not in ("s2d4", "s2d2"):
+            raise ValueError("stem must be 's2d4' or 's2d2'")
+        self.stem = stem
 
         if not isinstance(model, ResNet) or not all(isinstance(b, BasicBlock) for layer in (model.layer1, model.layer2, model.layer3, model.layer4) for b in layer):
             raise TypeError("FusedResNetForward needs a torchvision ResNet made of BasicBlocks (ResNet18 / ResNet34)")
@@ -184,6 +200,27 @@ class FusedResNetForward:
                         if 0 <= kx < 7:
                             w4[:, p_ * 8 + q * 3 : p_ * 8 + q * 3 + 3, a + 2, b_ + 2] = w7f[:, :, ky, kx]
         self.stem_w = w4.to(dtype).contiguous(memory_format=cl)
+        if stem == "s2d4":
+            # output row oy = 2Y + P reads input rows 2 oy + ky - 3 = 4 (Y + A) + p  =>  ky = 4A + p - 2P + 3, block taps A in {-1, 0, 1}:
+            # a 3x3 convolution over the block image with padding 1 (a zero block = the original zero padding of 3 pixels and beyond).
+            # Input channel p*12 + q*3 + c (DH_S2D48), output channel (P*2 + Q)*64 + o (depth-to-space, dh_maxpool3x3s2_d2s).
+            co = w7f.shape[0]
+            w48 = torch.zeros((4 * co, 48, 3, 3), dtype=torch.float32, device=dev)
+            for P_ in range(2):
+                for A in range(-1, 2):
+                    for p_ in range(4):
+                        ky = 4 * A + p_ - 2 * P_ + 3
+                        if not 0 <= ky < 7:
+                            continue
+                        for Q_ in range(2):
+                            for B_ in range(-1, 2):
+                                for q in range(4):
+                                    kx = 4 * B_ + q - 2 * Q_ + 3
+                                    if 0 <= kx < 7:
+                                        oc = (P_ * 2 + Q_) * co
+                                        w48[oc : oc + co, p_ * 12 + q * 3 : p_ * 12 + q * 3 + 3, A + 1, B_ + 1] = w7f[:, :, ky, kx]
+            self.stem_w = w48.to(dtype).contiguous(memory_format=cl)
+            self.stem_b = self.stem_b.repeat(4)
         self.blocks = []
         for layer in (m.layer1, m.layer2, m.layer3, m.layer4):
             for blk in layer:
@@ -197,17 +234,23 @@ class FusedResNetForward:
         self.fc_w, self.fc_b = m.fc.weight.detach().to(dtype), m.fc.bias.detach().to(dtype)
         self.dtype = dtype
 
-    @staticmethod
-    def s2d_shape(batch: int, ps: int) -> tuple:
-        """Logical NCHW shape of the stem input for a batch of ps x ps patches: [B, 16, ps/2 + 3, ps/2 + 3] stored channels_last, i.e.
-        [B][ps/2 + 3][ps/2 + 3][16] in memory with a zero border of 2 (top / left) and 1 (bottom / right) space-to-depth pixels."""
-        return (batch, 16, ps // 2 + 3, ps // 2 + 3)
+    def s2d_shape(self, batch: int, ps: int) -> tuple:
+        """Logical NCHW shape of the stem input for a batch of ps x ps patches, stored channels_last. s2d4: [B, 48, ps/4, ps/4];
+        s2d2: [B, 16, ps/2 + 3, ps/2 + 3] with a zero border of 2 (top / left) and 1 (bottom / right) space-to-depth pixels."""
+        return (batch, 48, ps // 4, ps // 4) if self.stem == "s2d4" else (batch, 16, ps // 2 + 3, ps // 2 + 3)
 
-    @staticmethod
-    def space_to_depth(x_nhwc: torch.Tensor) -> torch.Tensor:
-        """[B, H, W, 3] (values already normalised) -> the zero-bordered 16-channel space-to-depth stem input (torch ops; the predictor
-        lets dh_gather_normalize write this layout directly)."""
+    @property
+    def gather_layout(self) -> str:
+        """The dh_gather_normalize layout that writes this stem's input."""
+        return "S2D48" if self.stem == "s2d4" else "S2D16"
+
+    def space_to_depth(self, x_nhwc: torch.Tensor) -> torch.Tensor:
+        """[B, H, W, 3] (values already normalised) -> the stem input (torch ops; the predictor lets dh_gather_normalize write this
+        layout directly)."""
         B, H, W, _ = x_nhwc.shape
+        if self.stem == "s2d4":
+            v = x_nhwc.reshape(B, H // 4, 4, W // 4, 4, 3).permute(0, 1, 3, 2, 4, 5)        # [B, Y, X, p, q, c]
+            return v.reshape(B, H // 4, W // 4, 48).contiguous().permute(0, 3, 1, 2)
         out = torch.zeros((B, H // 2 + 3, W // 2 + 3, 16), dtype=x_nhwc.dtype, device=x_nhwc.device)
         v = x_nhwc.reshape(B, H // 2, 2, W // 2, 2, 3).permute(0, 1, 3, 2, 4, 5)            # [B, y', x', p, q, c]
         inner = out[:, 2 : 2 + H // 2, 2 : 2 + W // 2]
@@ -219,8 +262,12 @@ class FusedResNetForward:
     def __call__(self, s2d: torch.Tensor) -> torch.Tensor:
         """s2d: stem input as produced by space_to_depth / the gather's S2D mode -> float32 logits [B, n]."""
         one = (1, 1)
-        x = torch.cudnn_convolution_relu(s2d, self.stem_w, self.stem_b, one, (0, 0), one, 1)            # [B, 64, ps/2, ps/2]
-        x = ops.maxpool3x3s2_nhwc(x)
+        if self.stem == "s2d4":
+            x = torch.cudnn_convolution_relu(s2d, self.stem_w, self.stem_b, one, one, one, 1)           # [B, 4 * 64, ps/4, ps/4], depth-to-space
+            x = ops.maxpool3x3s2_d2s(x)
+        else:
+            x = torch.cudnn_convolution_relu(s2d, self.stem_w, self.stem_b, one, (0, 0), one, 1)        # [B, 64, ps/2, ps/2]
+            x = ops.maxpool3x3s2_nhwc(x)
         for w1, b1, stride, w2, b2, down in self.blocks:
             identity = x if down is None else torch.nn.functional.conv2d(x, down[0], down[1], stride=down[2])
             h = torch.cudnn_convolution_relu(x, w1, b1, stride, one, one, 1)

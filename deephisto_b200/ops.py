@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import DH_BF16, DH_F32, DH_NCHW, DH_NHWC, DH_S2D16, DH_U8, check
+from ._lib import DH_BF16, DH_F32, DH_NCHW, DH_NHWC, DH_S2D16, DH_S2D48, DH_U8, check
 
 _DTYPES = {torch.float32: DH_F32, torch.bfloat16: DH_BF16, torch.uint8: DH_U8}
 
@@ -144,14 +144,15 @@ def gather_normalize(slide: "DeviceSlide | MappedHostSlide", coords: torch.Tenso
                      out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Patches at int32 `coords` [B,2] (y,x) -> [B,ps,ps,3] (NHWC) or [B,3,ps,ps] (NCHW), or -- layout "S2D16", bfloat16 -- the
     2x2 space-to-depth image [B, ps/2+3, ps/2+3, 16] with a zero border (DH_S2D16 in include/deephisto_b200.h). The kernel writes
-    only the interior: an `out` buffer passed by the caller must have a zero border (it stays zero across calls)."""
+    only the interior: an `out` buffer passed by the caller must have a zero border (it stays zero across calls). Layout "S2D48",
+    bfloat16: the 4x4 space-to-depth image [B, ps/4, ps/4, 48] (DH_S2D48; no border, no padding)."""
     lib = _lib.require_device()
     _need_cuda(coords, "coords", torch.int32)
     if coords.ndim != 2 or coords.shape[1] != 2:
         raise ValueError("coords must be [B, 2]")
     B = coords.shape[0]
-    lay = {"NHWC": DH_NHWC, "NCHW": DH_NCHW, "S2D16": DH_S2D16}[layout]
-    shape = (B, ps, ps, 3) if lay == DH_NHWC else ((B, 3, ps, ps) if lay == DH_NCHW else (B, ps // 2 + 3, ps // 2 + 3, 16))
+    lay = {"NHWC": DH_NHWC, "NCHW": DH_NCHW, "S2D16": DH_S2D16, "S2D48": DH_S2D48}[layout]
+    shape = {DH_NHWC: (B, ps, ps, 3), DH_NCHW: (B, 3, ps, ps), DH_S2D16: (B, ps // 2 + 3, ps // 2 + 3, 16), DH_S2D48: (B, ps // 4, ps // 4, 48)}[lay]
     if out is None:
         out = (torch.zeros if lay == DH_S2D16 else torch.empty)(shape, dtype=dtype, device=coords.device)
     else:
@@ -302,6 +303,19 @@ def maxpool3x3s2_nhwc(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((B, Cc, (H - 1) // 2 + 1, (W - 1) // 2 + 1), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
     with torch.cuda.device(x.device):
         check(lib.dh_maxpool3x3s2_nhwc(x.data_ptr(), B, H, W, Cc, out.data_ptr(), DH_BF16, _stream()), "dh_maxpool3x3s2_nhwc")
+    return out
+
+
+def maxpool3x3s2_d2s(x: torch.Tensor) -> torch.Tensor:
+    """max_pool2d(kernel 3, stride 2, padding 1) of a convolution output stored depth-to-space: x channels_last bf16 [B, 4*C, H, W] with
+    channel (P*2 + Q)*C + o of block (Y, X) = pixel (2Y + P, 2X + Q), channel o -> channels_last [B, C, H, W]."""
+    lib = _lib.require_device()
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last) or x.shape[1] % 4:
+        raise ValueError("maxpool3x3s2_d2s needs a CUDA bfloat16 [B,4C,H,W] tensor in channels_last memory format")
+    B, C4, H, W = x.shape
+    out = torch.empty((B, C4 // 4, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        check(lib.dh_maxpool3x3s2_d2s(x.data_ptr(), B, H, W, C4 // 4, out.data_ptr(), DH_BF16, _stream()), "dh_maxpool3x3s2_d2s")
     return out
 
 

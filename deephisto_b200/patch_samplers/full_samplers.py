@@ -183,25 +183,29 @@ class FullImageRndSampler:
         return None if self._state is None else self._state.accum.cpu().numpy().astype(np.float32)
 
     def plot_empty_area_history(self, filename: str):
+        """Coverage per iteration as a JPEG (reference :292-298: same title, axis labels, 300 dpi)."""
         try:
-            import matplotlib.pyplot as plt
+            from matplotlib.figure import Figure
         except ImportError as e:
             raise RuntimeError("plot_empty_area_history needs matplotlib") from e
-        plt.plot(self._filled_ratio)
-        plt.title("Empty area")
-        plt.xlabel("iteration")
-        plt.ylabel("empty area percentage")
-        plt.savefig(filename, format="jpg", dpi=300)
+        fig = Figure()
+        ax = fig.add_subplot()
+        ax.plot(range(len(self._filled_ratio)), self._filled_ratio)
+        ax.set(title="Empty area", xlabel="iteration", ylabel="empty area percentage")
+        fig.savefig(filename, format="jpg", dpi=300)
 
     def visualize_heatmap(self, name: str):
+        """Two images like the reference's (:292-299): the coverage counts scaled to 0..255 under `name`, the covered / uncovered
+        mask under "_" + name."""
         from PIL import Image
 
-        acc = self._accum
-        if acc is not None:
-            a = (acc / np.max(acc) * 255).astype(np.uint8)
-            Image.fromarray(a).save(name)
-            a = np.where(a > 0, 255, 0).astype(np.uint8)
-            Image.fromarray(a).save("_" + name, quality=98)
+        counts = self._accum
+        if counts is None:
+            return
+        peak = float(counts.max())
+        scaled = (counts / peak * 255).astype(np.uint8)                  # an untouched accumulator divides by zero, as in the reference
+        Image.fromarray(scaled).save(name)
+        Image.fromarray(((scaled > 0) * np.uint8(255)).astype(np.uint8)).save("_" + name, quality=98)
 
 
 class FullImageDenseSampler:

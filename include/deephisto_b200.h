@@ -50,7 +50,12 @@ typedef enum dh_layout {
      * channels 6, 7, 14, 15 are written as zero. The border pixels (2 top / left, 1 bottom / right) are NOT written: pass a buffer
      * whose border is zero. It is the input of a 4x4 stride-1 convolution that equals the ResNet stem's 7x7 stride-2 convolution
      * (examples/predict_full_patched.py:66-78 batch_predictor -> model.conv1), with 16 instead of 3 input channels. */
-    DH_S2D16 = 2
+    DH_S2D16 = 2,
+    /* dh_gather_normalize, bf16 only: the 4x4 space-to-depth image out[b][ps/4][ps/4][48] (ps % 4 == 0): channel p*12 + q*3 + c of
+     * block (Y, X) = channel c of patch pixel (4Y + p, 4X + q). The same bytes as DH_NHWC in another order, no padding. Input of a
+     * 3x3 stride-1 padding-1 convolution with 4 x 64 output channels (2x2 output pixels per block) that equals the 7x7 stride-2 stem:
+     * 48 input and 256 output channels keep cuDNN's tensor-core kernels busy (3x faster than the 16-channel variant). */
+    DH_S2D48 = 3
 } dh_layout;
 
 /* flip bits for dh_gather_normalize (train.py:71-81 RandomHorizontalFlip / RandomVerticalFlip) */
@@ -189,6 +194,10 @@ DH_API int dh_stitch_binned_set_variant(int variant);
  * The convolutions stay with cuDNN (torch); this is the HBM-bound step between them.
  * ------------------------------------------------------------------------------------------ */
 DH_API int dh_maxpool3x3s2_nhwc(const void* in, int64_t B, int H, int W, int C, void* out, int dtype, void* stream);
+/* The same pooling when the convolution output is stored DEPTH-TO-SPACE, as the 4x4 space-to-depth stem produces it:
+ * in [B][H][W][4*C], channel (P*2 + Q)*C + o of block (Y, X) = pixel (2Y + P, 2X + Q), channel o of the [2H][2W][C] image;
+ * out [B][H][W][C] = max_pool2d(kernel 3, stride 2, padding 1) of that image. */
+DH_API int dh_maxpool3x3s2_d2s(const void* in, int64_t B, int H, int W, int C, void* out, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Prediction post-processing: perform_and_save_visualizations (examples/predict_full_patched.py:81-113).

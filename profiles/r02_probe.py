@@ -271,14 +271,14 @@ def cnn2():
         say(kernel="fused vs plain logits", max_abs_diff=(a - b).abs().max().item(), max_abs=a.abs().max().item(),
             argmax_agree=(a.argmax(1) == b.argmax(1)).float().mean().item())
         one = (1, 1)
-        ms = timeit(lambda: torch.cudnn_convolution_relu(s2d, f.stem_w, f.stem_b, one, (0, 0), one, 1), reps=5, warm=2)
-        say(kernel="  stem: 4x4 conv over 16 s2d channels + bias + relu (cuDNN fused)", ms=ms)
-        y = torch.cudnn_convolution_relu(s2d, f.stem_w, f.stem_b, one, (0, 0), one, 1)
-        ms = timeit(lambda: ops.maxpool3x3s2_nhwc(y), reps=5, warm=2)
-        say(kernel="  dh_maxpool3x3s2_nhwc", ms=ms, GBs=(y.numel() * 2 * 1.25) / ms / 1e6, frac=(y.numel() * 2 * 1.25) / ms / 1e6 / peak)
-        ms_t = timeit(lambda: torch.nn.functional.max_pool2d(y, 3, 2, 1), reps=5, warm=2)
-        say(kernel="  torch max_pool2d", ms=ms_t, same=bool(torch.equal(torch.nn.functional.max_pool2d(y, 3, 2, 1), ops.maxpool3x3s2_nhwc(y))))
-        t = ops.maxpool3x3s2_nhwc(y)
+        pad = one if f.stem == "s2d4" else (0, 0)
+        pool = ops.maxpool3x3s2_d2s if f.stem == "s2d4" else ops.maxpool3x3s2_nhwc
+        ms = timeit(lambda: torch.cudnn_convolution_relu(s2d, f.stem_w, f.stem_b, one, pad, one, 1), reps=5, warm=2)
+        say(kernel=f"  stem {f.stem}: conv + bias + relu (cuDNN fused)", ms=ms)
+        y = torch.cudnn_convolution_relu(s2d, f.stem_w, f.stem_b, one, pad, one, 1)
+        ms = timeit(lambda: pool(y), reps=5, warm=2)
+        say(kernel=f"  {pool.__name__}", ms=ms, GBs=(y.numel() * 2 * 1.25) / ms / 1e6, frac=(y.numel() * 2 * 1.25) / ms / 1e6 / peak)
+        t = pool(y)
         i = 0
         for w1, b1, stride, w2, b2, down in f.blocks:
             def blk(t=t):

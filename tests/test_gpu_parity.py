@@ -304,7 +304,7 @@ def test_cover_sampler_bit_exact_vs_oracle(ops, cfg):
     assert np.array_equal(st.accum.cpu().numpy().astype(np.int64), ref.accum)
 
 
-@pytest.mark.parametrize("ps", [224, 64, 30])
+@pytest.mark.parametrize("ps", [224, 64, 30, 100])
 def test_gather_space_to_depth_layout(ops, ps):
     """DH_S2D16 (the predictor's stem input): the kernel's output equals the 2x2 space-to-depth fold of its own NHWC bf16 output,
     channel p*8 + q*3 + c, channels 6/7/14/15 zero, a zero border of 2 / 1 pixels left untouched -- for interior patches (bulk-copy
@@ -332,6 +332,10 @@ def test_gather_space_to_depth_layout(ops, ps):
         inner[..., 0:6] = v[:, :, :, 0].reshape(B, ps // 2, ps // 2, 6)
         inner[..., 8:14] = v[:, :, :, 1].reshape(B, ps // 2, ps // 2, 6)
         assert torch.equal(got.view(torch.int16), want.view(torch.int16)), kw.keys()
+        if ps % 4 == 0:                                            # DH_S2D48: 4x4 blocks, channel p*12 + q*3 + c, same bytes as NHWC reordered
+            got48 = ops.gather_normalize(slide, coords, ps, dtype=torch.bfloat16, layout="S2D48", **kw)
+            want48 = nhwc.reshape(B, ps // 4, 4, ps // 4, 4, 3).permute(0, 1, 3, 2, 4, 5).reshape(B, ps // 4, ps // 4, 48)
+            assert got48.shape == want48.shape and torch.equal(got48.view(torch.int16), want48.contiguous().view(torch.int16)), kw.keys()
     fresh = ops.gather_normalize(slide, coords, ps, dtype=torch.bfloat16, layout="S2D16")              # allocated here: zero border
     assert float(fresh[:, :2].abs().max()) == 0 and float(fresh[:, -1].abs().max()) == 0 and float(fresh[:, :, :2].abs().max()) == 0
     with pytest.raises(Exception):
