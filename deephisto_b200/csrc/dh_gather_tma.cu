@@ -307,7 +307,9 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
             const int X = c / 6, j = c - 6 * X;                               // block column, unit of the block's six
             const int row_a = 4 * r + (2 * j) / 3, byte_a = (8 * j) % 12;     // first staged row of the unit and its byte inside the block's 12
             s_off[k] = (uint32_t)(row_a * RP + 12 * X + byte_a);              // word aligned: 12 X + {0, 4, 8}
-            s_mirror[k] = (uint32_t)((row_a + 1) * RP + 12 * X);              // where the second half of a two-row unit starts
+            // where the second half of a two-row unit starts (one-row units re-read their own words: the load is unconditional, and
+            // row_a + 1 of a block's last row would lie behind the stage)
+            s_mirror[k] = byte_a == 8 ? (uint32_t)((row_a + 1) * RP + 12 * X) : s_off[k];
             cph[k] = ((8 * j) % 3) | (byte_a == 8 ? 4 : 0);                   // channel of the unit's first byte | two-row flag
         } else {
             s_off[k] = (uint32_t)(r * RP + IN_BYTES * c);

@@ -470,12 +470,13 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_phased_kernel(const f
 // ---- segment formulation ---------------------------------------------------------------------------------------------------
 // KIND: 0 = sum map, 16-byte stores, G groups of 128 floats per tile; 1 = sum map, rows not 16-byte aligned (per-row shift, 7 units
 // gathered, 4 stored); 2 = sum map, scalar stores (32 floats per tile); 3 / 4 = class map and / or count, 1 / 4 cells per lane.
+constexpr int kSegPatches = 64;     // patches per tile staged by the segment kernel (longer lists: the global-memory path); 5.6 KB per warp -> 4 CTAs per SM
 constexpr int kSegCap = 264;        // segments per tile: <= cells of the tile + 1
 constexpr int kSegVals = 288;       // floats per value buffer: segments * n <= tile units + 3 n
 constexpr int kSegWords = 16;       // boundary bitmap words (<= 512 tile cells)
 
 __host__ __device__ inline int seg_warp_smem_bytes() {
-    return kBinCap * 8 /* r0 r1 c0 c1 (u16) */ + kBinCap * 32 /* logits, stride 8 */ + (2 * kSegWords + 4) * 4 /* bitmaps */ + kSegCap * 2 /* segments */ +
+    return kSegPatches * 8 /* r0 r1 c0 c1 (u16) */ + kSegPatches * 32 /* logits, stride 8 */ + (2 * kSegWords + 4) * 4 /* bitmaps */ + kSegCap * 2 /* segments */ +
            80 /* runs */ + 2 * kSegVals * 4 /* values */;
 }
 
@@ -498,24 +499,24 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     const uint32_t beg = off[t];
     const int L = (int)len[t];
     const int n = g.n;
-    if (L > kBinCap) {
+    if (L > kSegPatches) {
         bin_tile_slow<VEC, CELL>(logits, coords, g, beg, L, list, sorted, sum_map, count_map, argmax_map, ty, tx);
         return;
     }
     unsigned char* base = bin_smem + (size_t)w * seg_warp_smem_bytes();
     uint16_t* s_r0 = reinterpret_cast<uint16_t*>(base);
-    uint16_t* s_r1 = s_r0 + kBinCap;
-    uint16_t* s_c0 = s_r1 + kBinCap;
-    uint16_t* s_c1 = s_c0 + kBinCap;
-    float* s_lg = reinterpret_cast<float*>(base + kBinCap * 8);                      // [L][8]
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(base + kBinCap * 40);            // [kSegWords] segment-start bitmap over the tile's cells
+    uint16_t* s_r1 = s_r0 + kSegPatches;
+    uint16_t* s_c0 = s_r1 + kSegPatches;
+    uint16_t* s_c1 = s_c0 + kSegPatches;
+    float* s_lg = reinterpret_cast<float*>(base + kSegPatches * 8);                      // [L][8]
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(base + kSegPatches * 40);            // [kSegWords] segment-start bitmap over the tile's cells
     uint32_t* s_wpre = s_bits + kSegWords;                                          // [kSegWords] set bits before each word
     uint32_t* s_rbits = s_wpre + kSegWords;                                         // [2] run-start bitmap over the tile's rows (TH <= 64)
     uint16_t* s_segc = reinterpret_cast<uint16_t*>(s_rbits + 4);                    // [S] first cell of each segment (tile relative)
     uint8_t* s_run = reinterpret_cast<uint8_t*>(s_segc + kSegCap);                  // [NR + 1] first row of each run, then TH
-    float* s_val = reinterpret_cast<float*>(base + kBinCap * 40 + (2 * kSegWords + 4) * 4 + kSegCap * 2 + 80);   // [2][kSegVals] double-buffered
+    float* s_val = reinterpret_cast<float*>(base + kSegPatches * 40 + (2 * kSegWords + 4) * 4 + kSegCap * 2 + 80);   // [2][kSegVals] double-buffered
     uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_val);                            // staging only: unsorted / sorted ids alias the values
-    uint32_t* s_ids = s_raw + kBinCap;
+    uint32_t* s_ids = s_raw + kSegPatches;
 
     const int R0 = (int)(ty * g.TH);
     const int TH = (int)((int64_t)R0 + g.TH < g.rows ? g.TH : g.rows - R0);         // rows of this tile
