@@ -34,7 +34,8 @@ constexpr int kBinCap = 128;    // patches per tile staged in shared memory; lon
 constexpr int kBinMaxN = 8;     // classes the cell kernel keeps in registers
 
 static int g_bin_tile_rows = 0;  // 0 = heuristic; profiling override (dh_stitch_binned_set_tile_rows)
-static int g_bin_variant = 1;    // 1 = row-run kernels (default); 0 = segment kernel whenever n <= 8 (dh_stitch_binned_set_variant)
+static int g_bin_variant = 0;    // 0 = auto (segment kernel for sum maps whose rows are not 16-byte aligned, row-run kernels otherwise),
+                                 // 1 = row-run kernels only, 2 = segment kernel whenever n <= 8 (dh_stitch_binned_set_variant)
 
 struct BinGeom {
     int64_t rows, row_offset, dw;
@@ -861,7 +862,7 @@ extern "C" DH_API int dh_stitch_binned_set_tile_rows(int rows) {
 }
 
 extern "C" DH_API int dh_stitch_binned_set_variant(int variant) {
-    if (variant < 0 || variant > 1) { set_error("dh_stitch_binned_set_variant: variant must be 0 (segment kernel) or 1 (row-run kernels)"); return DH_ERR_INVALID; }
+    if (variant < 0 || variant > 2) { set_error("dh_stitch_binned_set_variant: variant must be 0 (auto), 1 (row-run kernels) or 2 (segment kernel)"); return DH_ERR_INVALID; }
     g_bin_variant = variant;
     return DH_OK;
 }
@@ -904,7 +905,9 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         // (not for small footprints: 7 instead of 4 sums per lane cost more than the vector stores save -- measured at d = 16)
         const bool phased = !v4 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 && dw * (int64_t)n >= 8 && ps / d >= 24;
         const BinGeom g = make_geom(false, v4 || phased ? 4 : 1, ps, d, n, rows, dw, row_offset, phased);
-        const bool seg = staged && g_bin_variant == 0 && g.TH <= 64 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
+        // measured (profiles/r02_stitch.md): the segment kernel wins where the row-run kernel has to sum 7 floats per lane (rows not
+        // 16-byte aligned: 0.61 vs 0.51 of the HBM peak at d = 4), the row-run kernel wins on aligned rows (0.71 vs 0.68)
+        const bool seg = staged && (g_bin_variant == 2 || (g_bin_variant == 0 && phased)) && g.TH <= 64 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
         if (seg && phased) rc = run_binned<4, 1, false, true, true, 1>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4 && g.G == 2) rc = run_binned<4, 2, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4) rc = run_binned<4, 1, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
@@ -927,7 +930,7 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         const bool c4 = ps / d >= 96 && dw % 4 == 0 && reinterpret_cast<uintptr_t>(cell_argmax) % 4 == 0 &&
                         reinterpret_cast<uintptr_t>(count_map) % 16 == 0;
         const BinGeom g = make_geom(true, c4 ? 4 : 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
-        if (g_bin_variant == 0 && g.TH <= 64)
+        if (g_bin_variant == 2 && g.TH <= 64)
             rc = c4 ? run_binned<4, 1, true, true, false, 4>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
                     : run_binned<1, 1, true, true, false, 3>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
         else

@@ -182,9 +182,10 @@ DH_API int dh_stitch_binned(const float* logits, const int32_t* coords, int64_t 
                      float* sum_map, uint32_t* count_map, uint8_t* argmax_u8, int64_t rows, int64_t dw,
                      int64_t row_offset, void* scratch, int64_t scratch_bytes, void* stream);
 DH_API int dh_stitch_binned_set_tile_rows(int rows);
-/* Tile-kernel formulation: 1 (default) = row-run kernels (every lane re-sums its own floats at each footprint boundary),
- * 0 = segment kernel for n <= 8 classes (one lane per column segment sums, all lanes fetch; measured slower so far:
- * profiles/r02_stitch.md). Same bits either way (tests/test_gpu_parity.py). */
+/* Tile-kernel formulation (same bits either way, tests/test_gpu_parity.py): 0 = auto -- the segment kernel (one lane per (row run,
+ * column segment) region sums the covering patches, all lanes fetch their floats from shared memory) for sum maps whose rows are
+ * not 16-byte aligned, the row-run kernels (every lane re-sums its own floats at each footprint boundary) otherwise; 1 = row-run
+ * kernels only; 2 = segment kernel wherever it applies (n <= 8 classes). Measurements: profiles/r02_stitch.md. */
 DH_API int dh_stitch_binned_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------

@@ -661,18 +661,18 @@ def test_cover_sampler_resume_from_saved_state(ops):
     assert torch.equal(a.accum, b.accum)
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_stitch_binned_random_shapes_vs_oracle(ops, variant):
     """Randomised shapes (slide size, patch size, downscale, class count, list length, overhanging and duplicated origins, row
-    bands): every output of dh_stitch_binned is bit-identical to the reference loop -- with the row-run tile kernels (variant 1,
-    the default) and with the segment kernel (variant 0)."""
+    bands): every output of dh_stitch_binned is bit-identical to the reference loop -- with the default choice of tile kernel
+    (variant 0), the row-run kernels only (1) and the segment kernel wherever it applies (2)."""
     from deephisto_b200 import _lib
 
     _lib.require_device().dh_stitch_binned_set_variant(variant)
     try:
         _stitch_binned_random_shapes(ops)
     finally:
-        _lib.require_device().dh_stitch_binned_set_variant(1)
+        _lib.require_device().dh_stitch_binned_set_variant(0)
 
 
 def _stitch_binned_random_shapes(ops):
