@@ -121,7 +121,7 @@ class DeviceBatchPredictor:
                 features = self.fused.space_to_depth(features.permute(0, 2, 3, 1))
             B = features.shape[0]
             buf = self._s2d
-            if buf is not None and features.data_ptr() == buf.data_ptr() and B < buf.shape[0] <= 8 * B:
+            if buf is not None and features.data_ptr() == buf.data_ptr() and B < buf.shape[0]:
                 # a short batch inside this predictor's gather buffer (the tail of a patch range): run the buffer's full batch -- the rows
                 # behind B hold the previous batch, their logits are dropped -- so that cuDNN sees ONE input shape per predictor
                 # (cudnn.benchmark re-tunes every new shape; a streamed slide has a different tail per row chunk)

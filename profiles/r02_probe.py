@@ -178,6 +178,38 @@ def gather():
             torch.cuda.empty_cache()
 
 
+def gather2():
+    """bf16 output modes, occupancy x ring depth, three interleaved repetitions (box noise is ~1-2 %)."""
+    H = W = 32768
+    dev = ops.DeviceSlide.synthetic(H, W, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 8192
+    coords = torch.stack([torch.randint(0, H - PS, (n,), generator=g, device="cuda"), torch.randint(0, W - PS, (n,), generator=g, device="cuda")], 1).to(torch.int32).contiguous()
+    for layout in ("NHWC", "NCHW", "S2D48"):
+        shape = {"NHWC": (2, n, PS, PS, 3), "NCHW": (2, n, 3, PS, PS), "S2D48": (2, n, PS // 4, PS // 4, 48)}[layout]
+        out = torch.empty(shape, dtype=torch.bfloat16, device="cuda")
+        res = {}
+        for rep in range(3):
+            for stages in (2, 3):
+                for occ in (2, 3, 4):
+                    os.environ["DH_GATHER_STAGES"], os.environ["DH_GATHER_OCC"] = str(stages), str(occ)
+                    i = [0]
+
+                    def run():
+                        i[0] ^= 1
+                        ops.gather_normalize(dev, coords, PS, dtype=torch.bfloat16, layout=layout, out=out[i[0]])
+
+                    res.setdefault((stages, occ), []).append(timeit(run, reps=11, warm=2))
+        os.environ.pop("DH_GATHER_STAGES")
+        os.environ.pop("DH_GATHER_OCC")
+        alg = n * PS * PS * 3 * 3
+        for (stages, occ), ms in sorted(res.items()):
+            say(kernel="gather bf16", layout=layout, stages=stages, occ=occ, ms_reps=" ".join(f"{m:.4f}" for m in ms), frac_best=alg / min(ms) / 1e6 / peak,
+                frac_median=alg / sorted(ms)[1] / 1e6 / peak)
+        del out
+        torch.cuda.empty_cache()
+
+
 def cnn():
     from deephisto_b200.examples import predict_full_patched as pfp
 
@@ -335,5 +367,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"cnn3": cnn3, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"gather2": gather2, "cnn3": cnn3, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
