@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kTmaThreads, 4) gather_tma_kernel(const TmaGat
 
 // persistent grid = SMs x resident CTAs of this instantiation, so every CTA is co-resident
 template <typename K>
-static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_t smem, cudaStream_t st, int occ_override) {
+static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_t smem, cudaStream_t st, int occ_override, int occ_cap = 3) {
     static int occ_cache[64] = {0};  // per instantiation, indexed by shared-memory size in KB
     int& occ = occ_cache[(smem >> 10) & 63];
     if (occ == 0) {
@@ -507,7 +507,9 @@ static int launch_one(K kernel, const TmaGatherParams& p, int64_t n_tiles, size_
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kTmaThreads, smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
         if (occ < 1) occ = 1;
-        if (occ > 3) occ = 3;  // measured (profiles/r01_gather.md): 3 resident CTAs per SM beat 4 (and 5, 6) -- less concurrency, less HBM read/write interference
+        // measured (profiles/r01_gather.md): 3 resident CTAs per SM beat 4 (and 5, 6) -- less concurrency, less HBM read/write interference;
+        // bf16 NHWC is best with 2 (0.846 vs 0.808 of the measured peak; the other bf16 layouts lose 10-15 % at 2: profiles/r02_gather.md)
+        if (occ > occ_cap) occ = occ_cap;
     }
     const int64_t want = (int64_t)kNumSMs * (occ_override > 0 ? occ_override : occ);   // profiling: DH_GATHER_OCC resident CTAs per SM
     const int grid = (int)(n_tiles < want ? n_tiles : want);
@@ -562,8 +564,8 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     const bool full_units = (R / rows_per_out) * units_per_row == kConsumers * (s2d ? 4 : (nchw ? (E == 4 ? 4 : 2) : 6));
     const char* env_occ = getenv("DH_GATHER_OCC");  // profiling override of the resident CTAs per SM (grid size), 0 = default
     const int occ_o = env_occ ? atoi(env_occ) : 0;
-#define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st, occ_o) \
-                                            : launch_one(gather_tma_kernel<T, N, S, A, false>, p, n_tiles, smem, st, occ_o)
+#define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st, occ_o, (sizeof(T) == 2 && (N) == DH_NHWC) ? 2 : 3) \
+                                            : launch_one(gather_tma_kernel<T, N, S, A, false>, p, n_tiles, smem, st, occ_o, (sizeof(T) == 2 && (N) == DH_NHWC) ? 2 : 3)
 #define DH_TMA_SA(T, N)                                                                  \
     do {                                                                                 \
         if (scale255) { if (affine) DH_TMA(T, N, true, true); else DH_TMA(T, N, true, false); } \
