@@ -529,14 +529,16 @@ def ours(args):
     traffic, traffic_src = None, None
     tf = ROOT / "profiles" / "gather_traffic.json"
     if tf.exists() and args.workload == "annotated_rnd":
-        cap = json.loads(tf.read_text())
-        cap_patches = int(cap.get("algorithmic_bytes_per_launch", 0)) // per_patch
-        if launch_patches == [cap_patches]:                             # the ncu capture has exactly the launch shape timed here
-            traffic, traffic_src = cap.get("dram_bytes_per_launch"), "profiles/gather_traffic.json (ncu --set full of this launch shape)"
+        doc = json.loads(tf.read_text())
+        caps = doc.get("captures", [doc])                                # one ncu --set full capture per launch shape
+        by_patches = {int(c.get("algorithmic_bytes_per_launch", 0)) // per_patch: c for c in caps}
+        if len(launch_patches) == 1 and launch_patches[0] in by_patches:  # a capture of exactly the launch shape timed here
+            cap = by_patches[launch_patches[0]]
+            traffic = cap.get("dram_bytes_per_launch")
+            traffic_src = f"profiles/gather_traffic.json: {cap.get('source', 'ncu --set full')} ({launch_patches[0]} patches per launch, as timed here)"
         else:
-            traffic_src = (f"not reported: the committed ncu capture (profiles/gather_traffic.json) is of a {cap_patches}-patch launch "
-                           f"({cap.get('dram_bytes_per_launch')} DRAM bytes vs {cap.get('algorithmic_bytes_per_launch')} algorithmic), the launches timed here hold "
-                           f"{launch_patches} patches")
+            traffic_src = (f"not reported: profiles/gather_traffic.json holds ncu captures of {sorted(by_patches)}-patch launches, the launches timed "
+                           f"here hold {launch_patches} patches")
     line = {
         "metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": mode["dtype"],

@@ -90,6 +90,10 @@ class DeviceSlide:
         """Address the kernels read the slide from."""
         return self.storage.data_ptr()
 
+    def view_rows(self, y0: int, y1: int) -> "DeviceSlide":
+        """Rows [y0, y1) as a slide of their own (a view: row 0 of the result is row y0)."""
+        return DeviceSlide(self.storage[y0 * self.pitch : y1 * self.pitch], y1 - y0, self.W, self.pitch)
+
 
 class MappedHostSlide:
     """A slide layer that stays in PAGE-LOCKED HOST memory and is read by the gather kernels in place, through its device-visible
@@ -113,6 +117,15 @@ class MappedHostSlide:
     @property
     def device(self):
         return self._device
+
+    def view_rows(self, y0: int, y1: int) -> "MappedHostSlide":
+        return MappedHostSlide(self.host[y0 * self.pitch : y1 * self.pitch], y1 - y0, self.W, self.pitch, self._device)
+
+    def rows2d(self) -> torch.Tensor:
+        return self.host[: self.H * self.pitch].view(self.H, self.pitch)
+
+    def to_numpy(self) -> np.ndarray:
+        return self.rows2d()[:, : 3 * self.W].numpy().reshape(self.H, self.W, 3)
 
 
 def dense_count(H: int, W: int, ps: int, stride: int, batch_size: int) -> tuple[int, int]:

@@ -42,21 +42,24 @@ class FullImageRndSampler:
 
     Extra keyword-only arguments (not in the reference): `seed` (Philox key; the reference uses the unseeded
     global numpy RNG), `device`, `lazy_slide` (row-band sharded prediction: the layer is not uploaded by the constructor, every
-    rank makes only its band resident through `band_sampler`)."""
+    rank makes only its band resident through `band_sampler`), `resident=False` (PinnedSlide sources: the layer is never uploaded,
+    patches are gathered in place from pinned host memory over PCIe -- slides that do not fit HBM)."""
 
     def __init__(self, psimage_path: Path, layer: int, patch_size: int, batch_size: int, mode: SamplerExecutionMode,
-                 dense_level: int = 2, speedup: int = 16, *, seed: int = 0, device="cuda", lazy_slide: bool = False, quiet: bool = False):
+                 dense_level: int = 2, speedup: int = 16, *, seed: int = 0, device="cuda", lazy_slide: bool = False, quiet: bool = False,
+                 resident: bool = True):
         self.mode = mode
         self._psim_path = psimage_path
         self._src = open_slide(psimage_path)
         self._slide_dev = None
         self._device = device
+        self._resident = resident
         with self._src as psim:
             self.layer = layer
             psim._assert_layer(layer)
             self.h, self.w = psim.layer_size(self.layer)
             if not lazy_slide:
-                self._slide_dev = layer_to_device(psim, layer, device)
+                self._slide_dev = layer_to_device(psim, layer, device, resident=resident)
         self.dh = self.h // speedup
         self.dw = self.w // speedup
         if not quiet:
@@ -76,7 +79,7 @@ class FullImageRndSampler:
     def _slide(self):
         if self._slide_dev is None:
             with self._src as psim:
-                self._slide_dev = layer_to_device(psim, self.layer, self._device)
+                self._slide_dev = layer_to_device(psim, self.layer, self._device, resident=self._resident)
         return self._slide_dev
 
     def band_sampler(self, y0: int, y1: int, stream_index: int) -> "FullImageRndSampler":
@@ -86,8 +89,9 @@ class FullImageRndSampler:
         if not (0 <= y0 < y1 <= self.h) or y1 - y0 < self.patch_size:
             raise ValueError(f"band [{y0}, {y1}) must lie inside the {self.h}-row layer and hold at least one patch")
         if self._slide_dev is not None:
-            s = self._slide_dev
-            band = ops.DeviceSlide(s.storage[y0 * s.pitch : y1 * s.pitch], y1 - y0, s.W, s.pitch)
+            band = self._slide_dev.view_rows(y0, y1)
+        elif not self._resident:
+            band = self._slide.view_rows(y0, y1)
         else:
             with self._src as psim:
                 band = band_to_device(psim, self.layer, y0, y1, self._device)

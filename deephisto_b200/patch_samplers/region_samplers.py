@@ -196,7 +196,8 @@ class AnnoRegionRndSampler:
                  patches_from_one_region: int = 4, region_area_influence: float = 0.5, classes: list[str] = None,
                  one_image_for_batch: bool = False, *, seed: int = 0, device="cuda", out_dtype=torch.float32, out_layout: str = "NHWC",
                  flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = None, shard_upload=None,
-                 prefetch_bytes: int = 5 << 30, prefetch_batches: int = 32, zero_copy: bool = None, zero_copy_fraction: float = 0.5):
+                 prefetch_bytes: int = 5 << 30, prefetch_batches: int = 32, zero_copy: bool = None, zero_copy_fraction: float = 0.5,
+                 resident: bool = True):
         self.img_anno_paths = img_anno_paths
         self.layer = layer
         self.patch_size = patch_size
@@ -228,6 +229,10 @@ class AnnoRegionRndSampler:
         # of the slide bytes gathers them straight from host memory (the gather's bulk row copies read the mapped pinned buffer over
         # PCIe) instead of waiting for the whole layer to be uploaded; the layer is then made resident in the background, behind the
         # job's last gather. None = that cost rule, True = always while a slide is not resident, False = never.
+        # resident=False: the slides are NEVER uploaded (datasets larger than HBM): every job is gathered in place, at PCIe speed.
+        self._resident = bool(resident)
+        if not self._resident:
+            zero_copy = True
         self._zero_copy, self._zero_copy_fraction = zero_copy, float(zero_copy_fraction)
         self.zero_copy_bytes = 0               # patch bytes (ps * ps * 3 each) read in place from pinned host memory so far
         self._mapped = [None] * len(img_anno_paths)        # ops.MappedHostSlide views of pinned sources
@@ -332,6 +337,10 @@ class AnnoRegionRndSampler:
         return n
 
     def _slide(self, j: int):
+        if not self._resident:
+            if not self._whole_pinned(j):
+                raise ValueError("resident=False needs every slide as a PinnedSlide in page-locked host memory")
+            return self._mapped_slide(j)
         if self._slides[j] is not None and self._upload_done[j] is not None:
             if self._upload_done[j].query():
                 self._upload_done[j] = None
@@ -487,7 +496,7 @@ class AnnoRegionRndSampler:
         cur = torch.cuda.current_stream(self._device) if on_gpu else None
         # zero-copy ingestion: slides that are still only in pinned host memory are read in place when this job touches less of them
         # than an upload would move (cost rule above); the upload then runs in the background behind the job's last gather
-        pending_up = [j for j in range(len(self._slides)) if self._slides[j] is None]
+        pending_up = [j for j in range(len(self._slides)) if self._slides[j] is None or not self._resident]
         mapped = bool(on_gpu and pending_up and self._zero_copy is not False and all(self._whole_pinned(j) for j in pending_up)
                       and (len(pending_up) == len(self._slides) or len(self._slides) == 1)
                       and (self._sparse_upload is not True or self._zero_copy is True))
@@ -527,7 +536,7 @@ class AnnoRegionRndSampler:
             if gi >= len(groups):
                 return None
             out = launch(groups[gi])
-            if mapped and gi == len(groups) - 1:
+            if mapped and self._resident and gi == len(groups) - 1:
                 self._background_upload(after_event=out[1])
             return out
 

@@ -206,7 +206,7 @@ def open_slide(source):
     """Return a PSImage-duck-typed object for `source` (see module docstring)."""
     if isinstance(source, (ArraySlide, SyntheticSlide, DeviceSlideSource, PinnedSlide)):
         return source
-    if isinstance(source, DeviceSlide):
+    if isinstance(source, DeviceSlide) or type(source).__name__ == "MappedHostSlide":
         return DeviceSlideSource(source)
     if isinstance(source, np.ndarray):
         return ArraySlide(source)
@@ -352,8 +352,16 @@ class DeviceSlideSource:
         return s.rows2d()[y0:y1, 3 * x0 : 3 * x1].cpu().numpy().reshape(y1 - y0, x1 - x0, 3)
 
 
-def layer_to_device(src, layer: int, device="cuda") -> DeviceSlide:
-    """Upload layer `layer` of an opened slide to HBM once (the analogue of full_samplers.py:53-55)."""
+def layer_to_device(src, layer: int, device="cuda", resident: bool = True):
+    """Upload layer `layer` of an opened slide to HBM once (the analogue of full_samplers.py:53-55). resident=False (PinnedSlide
+    sources only): no upload -- a MappedHostSlide that the gather kernels read in place over PCIe (slides larger than HBM)."""
+    if not resident:
+        from .ops import MappedHostSlide
+
+        if not (isinstance(src, PinnedSlide) and src.pinned and src.y_origin == 0 and src.rows == src.height):
+            raise ValueError("resident=False needs a PinnedSlide that holds the whole layer in page-locked memory")
+        src._assert_layer(layer)
+        return MappedHostSlide(src.host, src.rows, src.width, src.pitch, device)
     if isinstance(src, DeviceSlideSource):
         src._assert_layer(layer)
         return src.dev

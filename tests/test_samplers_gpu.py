@@ -217,6 +217,44 @@ def test_anno_region_rnd_sampler_sparse_upload_from_pinned_slides(api, tmp_path)
     assert big.zero_copy_bytes == 0 and big.uploaded_bytes == total
 
 
+def test_samplers_over_slides_that_stay_in_host_memory(api, tmp_path):
+    """resident=False (slides larger than HBM): nothing is ever uploaded, every gather reads the pinned host buffer in place; batches
+    are bit-identical to the resident samplers' -- AnnoRegionRndSampler (torch and structs generators), FullImageRndSampler (incl. a
+    row-band sub-sampler)."""
+    _, fs, rs = api
+    from deephisto_b200.slide import PinnedSlide
+
+    hw, items, _ = _dataset(tmp_path)
+    pinned = [(PinnedSlide.from_numpy(np.asarray(img)), anno) for img, anno in items]
+    ps, B = 224, 16
+    a = rs.AnnoRegionRndSampler(items, layer=1, patch_size=ps, seed=4, verbose=False)
+    b = rs.AnnoRegionRndSampler(pinned, layer=1, patch_size=ps, seed=4, verbose=False, resident=False)
+    for _ in range(2):                                              # two jobs: still nothing resident after the first
+        for (fa, la, ca), (fb, lb, cb) in zip(a.torch_generator(B, 5), b.torch_generator(B, 5)):
+            assert torch.equal(fa, fb) and torch.equal(la, lb) and torch.equal(ca, cb)
+    torch.cuda.synchronize()
+    assert b.uploaded_bytes == 0 and all(s is None for s in b._slides) and b.zero_copy_bytes == 2 * 5 * B * ps * ps * 3
+    sa = next(iter(a.structs_generator(batch_size=4, n_batches=1)))
+    sb = next(iter(b.structs_generator(batch_size=4, n_batches=1)))
+    assert all(np.array_equal(x[0].data, y[0].data) and x[1] == y[1] for x, y in zip(sa, sb)) and b.uploaded_bytes == 0
+    with pytest.raises(ValueError, match="resident=False"):
+        list(rs.AnnoRegionRndSampler(items, layer=1, patch_size=ps, seed=4, verbose=False, resident=False).torch_generator(B, 1))
+    host = synth.synth_slide(1200, 1000, 5)
+    full = fs.FullImageRndSampler(host, 1, ps, 8, _mode(fs), seed=1, quiet=True)
+    inplace = fs.FullImageRndSampler(PinnedSlide.from_numpy(host), 1, ps, 8, _mode(fs), seed=1, quiet=True, resident=False)
+    assert type(inplace._slide).__name__ == "MappedHostSlide"
+    n = 0
+    for (fa, ca, ra), (fb, cb, rb) in zip(full.generator_torch(), inplace.generator_torch()):
+        assert torch.equal(fa, fb) and torch.equal(ca, cb) and ra == rb
+        n += 1
+    assert n > 10
+    sub = inplace.band_sampler(304, 1200, 1)
+    co = next(sub.coords_generator())[0]
+    got = next(sub.generator_torch())[0]
+    want = torch.from_numpy(np.stack([host[304 + y : 304 + y + ps, x : x + ps] for y, x in co.cpu().numpy().tolist()]).astype(np.float32)).cuda()
+    assert type(sub._slide).__name__ == "MappedHostSlide" and torch.equal(got, want)
+
+
 def test_anno_region_rnd_sampler_extras_and_structs(api, tmp_path):
     _, _, rs = api
     hw, items, polys_all = _dataset(tmp_path, 1)
