@@ -537,10 +537,13 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     const int units_per_row = s4 ? (ps / 4) * 6 : (s2d ? ps : (nchw ? ps / E : row_bytes / E));
     const int rows_per_out = s4 ? 4 : (s2d ? 2 : 1);
     int R = 0;
+    const char* env_rows = getenv("DH_GATHER_ROWS");  // profiling override: rows per tile (stage of up to 24 KB instead of 12 KB)
+    const int want_rows = env_rows ? atoi(env_rows) : 0;
     for (int r = 32; r >= 1; --r) {
         if (r % rows_per_out) continue;                                     // a space-to-depth row needs all of its input rows in the tile
+        if (want_rows > 0 && r != want_rows) continue;
         const int tile_units = (r / rows_per_out) * units_per_row;
-        if (ps % r == 0 && tile_units <= kConsumers * kTmaMaxUnits && r * row_pitch <= 12 * 1024) { R = r; break; }
+        if (ps % r == 0 && tile_units <= kConsumers * kTmaMaxUnits && r * row_pitch <= (want_rows > 0 ? 24 : 12) * 1024) { R = r; break; }
     }
     if (!R) return DH_ERR_UNSUPPORTED;
     if (B * (int64_t)(ps / R) >= (1ll << 40)) return DH_ERR_UNSUPPORTED;

@@ -210,6 +210,36 @@ def gather2():
         torch.cuda.empty_cache()
 
 
+def gather3():
+    """bf16 NCHW / NHWC / S2D48: rows per tile (DH_GATHER_ROWS) x CTAs per SM, 2-deep ring."""
+    H = W = 32768
+    dev = ops.DeviceSlide.synthetic(H, W, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 8192
+    coords = torch.stack([torch.randint(0, H - PS, (n,), generator=g, device="cuda"), torch.randint(0, W - PS, (n,), generator=g, device="cuda")], 1).to(torch.int32).contiguous()
+    for layout in ("NCHW", "NHWC", "S2D48"):
+        shape = {"NHWC": (2, n, PS, PS, 3), "NCHW": (2, n, 3, PS, PS), "S2D48": (2, n, PS // 4, PS // 4, 48)}[layout]
+        out = torch.empty(shape, dtype=torch.bfloat16, device="cuda")
+        for rows in (8, 16, 28, 32):
+            for occ in (2, 3):
+                os.environ["DH_GATHER_ROWS"], os.environ["DH_GATHER_OCC"] = str(rows), str(occ)
+                i = [0]
+
+                def run():
+                    i[0] ^= 1
+                    ops.gather_normalize(dev, coords, PS, dtype=torch.bfloat16, layout=layout, out=out[i[0]])
+
+                try:
+                    ms = timeit(run, reps=11, warm=2)
+                    say(kernel="gather bf16", layout=layout, rows=rows, occ=occ, ms=ms, frac=n * PS * PS * 9 / ms / 1e6 / peak)
+                except Exception as e:  # noqa: BLE001
+                    say(kernel="gather bf16", layout=layout, rows=rows, occ=occ, error=repr(e)[:80])
+        os.environ.pop("DH_GATHER_ROWS")
+        os.environ.pop("DH_GATHER_OCC")
+        del out
+        torch.cuda.empty_cache()
+
+
 def cnn():
     from deephisto_b200.examples import predict_full_patched as pfp
 
@@ -367,5 +397,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"gather2": gather2, "cnn3": cnn3, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
