@@ -696,6 +696,7 @@ def main(argv=None):
     ap.add_argument("--downscale", type=int, default=16)
     ap.add_argument("--random-sampler", action="store_true", help="the reference's default (coverage-driven random sampling)")
     ap.add_argument("--bf16", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="bf16 fast path: FusedResNetForward (space-to-depth stem, fused cuDNN epilogues); implies --bf16")
     ap.add_argument("--out", default="./output/")
     args = ap.parse_args(argv)
 
@@ -720,11 +721,13 @@ def main(argv=None):
         ap.error("give --image or --synthetic H W")
     mode = SamplerExecutionMode.INMEMORY_SINGLEPROC
     if args.random_sampler:
-        sampler = FullImageRndSampler(src, layer=args.layer, patch_size=224, batch_size=64, mode=mode, device=device)
+        sampler = FullImageRndSampler(src, layer=args.layer, patch_size=224, batch_size=64, mode=mode, device=device, lazy_slide=world > 1)
     else:
         sampler = FullImageDenseSampler(src, layer=args.layer, patch_size=224, batch_size=64, mode=mode, stride=args.stride, device=device,
                                         lazy_slide=world > 1)
-    predictor = ImagePredictorPatched(src, patch_sampler=sampler, batch_predictor=DeviceBatchPredictor(model, device, torch.bfloat16 if args.bf16 else torch.float32),
+    bf16 = args.bf16 or args.fused
+    predictor = ImagePredictorPatched(src, patch_sampler=sampler,
+                                      batch_predictor=DeviceBatchPredictor(model, device, torch.bfloat16 if bf16 else torch.float32, fused=args.fused),
                                       anno=anno_dsc, layer=args.layer, downscale=args.downscale, device=device)
     t0 = time.perf_counter()
     pred = predictor.process(rank=rank, world=world) if world > 1 else predictor.process()

@@ -389,6 +389,21 @@ def ncu_binned():
     lib.dh_stitch_binned_set_variant(0)
 
 
+def ncu_dense():
+    """A few dh_stitch_dense calls (for `ncu -k regex:stitch_dense`): 40k x 40k, sum map at downscale argv[2]."""
+    d = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    H = W = 40000
+    npad = ops.dense_count(H, W, PS, 112, 64)[1]
+    lg = torch.randn((npad, N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
+    for _ in range(3):
+        ops.stitch_dense(lg, H, W, PS, 112, d, 64, want_sum=True)
+        torch.cuda.synchronize()
+    ms = timeit(lambda: ops.stitch_dense(lg, H, W, PS, 112, d, 64, want_sum=True), reps=10)
+    say(kernel="stitch_dense sum", d=d, ms=ms, frac=((H // d) * (W // d) * N * 4 + npad * N * 4) / ms / 1e6 / peak)
+    ms = timeit(lambda: ops.stitch_dense(lg, H, W, PS, 112, d, 64, want_sum=False, want_argmax=True), reps=10)
+    say(kernel="stitch_dense argmax only", d=d, ms=ms)
+
+
 def ncu_cover():
     st = ops.CoverState(40000, 40000, PS, 16, 2, 64, seed=0)
     for _ in range(3):

@@ -370,6 +370,8 @@ def test_install_dropin_registers_reference_module_names(api):
     ("sample_annotated_rnd", ["--synthetic", "6000", "6000", "-n", "4", "--quiet"]),
     ("sample_annotated_dense", ["--synthetic", "6000", "6000", "--polygons", "3", "--stride", "200"]),
     ("predict_full_patched", ["--synthetic", "1500", "1300", "--downscale", "16"]),
+    ("predict_full_patched", ["--synthetic", "1500", "1300", "--downscale", "16", "--fused"]),
+    ("predict_full_patched", ["--synthetic", "1500", "1300", "--downscale", "16", "--random-sampler"]),
     ("extract_patches_for_test_set", ["--synthetic", "6000", "6000", "--polygons", "5", "--patches-per-class", "8", "--out", "{tmp}"]),
 ])
 def test_example_entry_points_run(script, extra, tmp_path):
