@@ -102,6 +102,14 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(co
 
     RowClass rc;
     rc.init(i0, g.ps, g.stride, g.d);
+    // the column cover of a thread's cells (<= 2: tj <= 2 * kStitchThreads) does not depend on the row class: computed once
+    // (cover_1d is two 64-bit divisions; at d = 16 a class is only 7 rows of stores long)
+    Cover cxs[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int t = tid + k * kStitchThreads;
+        cxs[k] = cover_1d(j0 + (t < tj ? t : 0), g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+    }
     float4 vreg[PHASED ? 4 : 1][kStitchV];
     uint32_t creg[2] = {0, 0};
     uint32_t areg[2] = {0, 0};
@@ -120,9 +128,11 @@ __global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(co
         if (i + run > i1) run = i1 - i;
         {
             __syncthreads();  // previous class has been read into registers by everybody
-            for (int t = tid; t < tj; t += kStitchThreads) {
-                const int64_t j = j0 + t;
-                Cover cx = cover_1d(j, g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {
+                const int t = tid + kc * kStitchThreads;
+                if (t >= tj) break;
+                const Cover cx = cxs[kc];
                 const int64_t main_n = g.ny * g.nx;
                 float best = 0.f;
                 int best_c = 0;
