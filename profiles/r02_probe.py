@@ -412,5 +412,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
