@@ -40,6 +40,9 @@ __host__ __device__ __forceinline__ Cover cover_1d(int64_t i, int64_t cnt, int p
 }
 
 constexpr int kStitchThreads = 256;
+#ifndef DH_STITCH_MINB
+#define DH_STITCH_MINB 3   // resident CTAs per SM the dense kernel is compiled for (80 registers, no spills; 4 = 64 registers, 120 B of spills)
+#endif
 
 // ---- register-resident row classes ----------------------------------------------------------------------
 // When dw*n is a multiple of 4 floats and the column tile is a multiple of 4 cells, every row segment of a tile starts on
@@ -79,8 +82,11 @@ struct RowClass {
 // A thread then keeps one register set per phase -- the same class values cut into vectors at the four possible offsets -- and the
 // row loop picks the set of the row's phase; the <= 3 floats before the first and after the last aligned vector of a row are
 // stored as scalars from shared memory.
+// Register budget: 4 resident CTAs per SM (64 registers) unless PHASED keeps four register sets. ncu at d = 16 (profiles/
+// r02_dense_d16_ncu.txt): 101 registers -> 2 CTAs per SM, 24 % warps active, the short row classes (7 rows of stores per L2 round trip
+// for the logits) left the kernel latency-bound at 0.29 of the HBM peak.
 template <bool WITH_SUM, bool WITH_ARGMAX, bool WITH_COUNT, bool PHASED>
-__global__ void __launch_bounds__(kStitchThreads) stitch_dense_aligned_kernel(const float* __restrict__ logits, StitchGrid g,
+__global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) stitch_dense_aligned_kernel(const float* __restrict__ logits, StitchGrid g,
                                                                               float* __restrict__ sum_map,
                                                                               uint32_t* __restrict__ count_map,
                                                                               uint8_t* __restrict__ argmax_map,
