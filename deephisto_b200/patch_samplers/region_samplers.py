@@ -502,7 +502,15 @@ class AnnoRegionRndSampler:
                       and (self._sparse_upload is not True or self._zero_copy is True))
         if mapped and self._zero_copy is None:
             job = n_batches * batch_size * ps * ps * 3
-            mapped = job <= self._zero_copy_fraction * sum(self._sources[j].nbytes for j in pending_up)
+            upload = sum(self._sources[j].nbytes for j in pending_up)
+            if self._shard_upload is not None:
+                # collective ingestion moves only 1/world of the layer over this rank's PCIe link (the rest arrives over NVLink), while
+                # in-place gathers of all ranks share the host's links: measured at N = 4, 20 batches: 604 k patches/s in place vs the
+                # sharded upload's 1/4 of 3.2 GB per rank (profiles/r02_e2e.md)
+                import torch.distributed as dist
+
+                upload //= max(1, dist.get_world_size(None if self._shard_upload is True else self._shard_upload))
+            mapped = job <= self._zero_copy_fraction * upload
         if on_gpu and self._producer is None:
             self._producer = _shared_stream(self._device, "producer")
             self._drawer = _shared_stream(self._device, "drawer")
