@@ -397,18 +397,37 @@ class ImagePredictorPatched:
     # ---- dense, device resident, bit-exact sums -----------------------------------------------------------------------
     def _logits_for(self, sampler: FullImageDenseSampler, slide, logits: torch.Tensor, first: int, count: int, y_off: int = 0):
         """Fill logits[first:first+count] for entries [first, first+count) of the padded dense enumeration."""
+        self._logits_for_ranges(sampler, slide, logits, [(first, count)], y_off)
+
+    def _logits_for_ranges(self, sampler: FullImageDenseSampler, slide, logits: torch.Tensor, ranges, y_off: int = 0):
+        """Fill the rows of `logits` listed by `ranges` = [(first, count)] (entries of the padded dense enumeration). The ranges are
+        concatenated into ONE coordinate list and cut into CNN batches, so a band pays for one short tail batch, not one per range
+        (a band plan has three ranges: main-grid rows, their last-column patches, the last row / corner / padding copies)."""
         pred: DeviceBatchPredictor = self.batch_predictor
         step = self._cnn_batch or max(sampler.batch_size, 512)
         ps = sampler.patch_size
-        for a in range(first, first + count, step):
-            c = min(step, first + count - a)
+        ranges = [(int(f), int(c)) for f, c in ranges if c > 0]
+        total = sum(c for _, c in ranges)
+        if total == 0:
+            return
+        with self._mark("coords+gather"):
+            parts = [ops.dense_coords(sampler.h, sampler.w, ps, sampler.stride, sampler.batch_size, first=f, count=c, device=self._device) for f, c in ranges]
+            coords = parts[0] if len(parts) == 1 else torch.cat(parts)
+            if y_off:
+                coords[:, 0] -= y_off
+        single = len(ranges) == 1
+        out = logits[ranges[0][0] : ranges[0][0] + total] if single else torch.empty((total, logits.shape[1]), dtype=logits.dtype, device=self._device)
+        for a in range(0, total, step):
+            c = min(step, total - a)
             with self._mark("coords+gather"):
-                coords = ops.dense_coords(sampler.h, sampler.w, ps, sampler.stride, sampler.batch_size, first=a, count=c, device=self._device)
-                if y_off:
-                    coords[:, 0] -= y_off
-                feats = pred.gather(slide, coords, ps)
+                feats = pred.gather(slide, coords[a : a + c], ps)
             with self._mark("cnn"):
-                logits[a : a + c] = pred.logits(feats)
+                out[a : a + c] = pred.logits(feats)
+        if not single:
+            a = 0
+            for f, c in ranges:
+                logits[f : f + c] = out[a : a + c]
+                a += c
 
     def _logits_streamed(self, sampler: FullImageDenseSampler, logits: torch.Tensor, patch_ranges, max_band_bytes: Optional[int] = None):
         """Logits of `patch_ranges` (as produced by bands.plan_band) for a slide that is NOT resident in HBM: the slide rows are
@@ -440,8 +459,7 @@ class ImagePredictorPatched:
             nxt = upload(jobs[i + 1]) if i + 1 < len(jobs) else None
             cur.wait_event(ready)
             band.storage.record_stream(cur)
-            for first, count in job[2]:
-                self._logits_for(sampler, band, logits, first, count, y_off=job[0])
+            self._logits_for_ranges(sampler, band, logits, job[2], y_off=job[0])
             del band
 
     def _dense_device(self, want_sum: bool, want_count: bool) -> dict:
@@ -470,8 +488,7 @@ class ImagePredictorPatched:
             self._logits_streamed(s, logits, plan.patch_ranges)               # band rows streamed through HBM, upload hidden behind the CNN
         elif plan.patch_ranges:
             slide, y_off = s.band_slide(plan.slide_y0, plan.slide_y1)
-            for first, count in plan.patch_ranges:
-                self._logits_for(s, slide, logits, first, count, y_off)
+            self._logits_for_ranges(s, slide, logits, plan.patch_ranges, y_off)
         dw = s.w // d
         amax_band = torch.zeros((plan.rows_max, dw), dtype=torch.uint8, device=self._device)
         sum_band = torch.zeros((plan.rows_max, dw, n), dtype=torch.float32, device=self._device) if want_sum else None
