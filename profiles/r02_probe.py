@@ -210,6 +210,35 @@ def gather2():
         torch.cuda.empty_cache()
 
 
+def gather4():
+    """fp32 NHWC (the bench's roofline kernel) at 5 120 and 8 192 patches per launch: occupancy x ring depth, three interleaved repetitions."""
+    H = W = 32768
+    dev = ops.DeviceSlide.synthetic(H, W, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for n in (5120, 8192):
+        coords = torch.stack([torch.randint(0, H - PS, (n,), generator=g, device="cuda"), torch.randint(0, W - PS, (n,), generator=g, device="cuda")], 1).to(torch.int32).contiguous()
+        out = torch.empty((2, n, PS, PS, 3), dtype=torch.float32, device="cuda")
+        res = {}
+        for rep in range(3):
+            for stages in (2, 3):
+                for occ in (2, 3, 4):
+                    os.environ["DH_GATHER_STAGES"], os.environ["DH_GATHER_OCC"] = str(stages), str(occ)
+                    i = [0]
+
+                    def run():
+                        i[0] ^= 1
+                        ops.gather_normalize(dev, coords, PS, out=out[i[0]])
+
+                    res.setdefault((stages, occ), []).append(timeit(run, reps=11, warm=2))
+        os.environ.pop("DH_GATHER_STAGES")
+        os.environ.pop("DH_GATHER_OCC")
+        alg = n * PS * PS * 3 * 5
+        for (stages, occ), ms in sorted(res.items()):
+            say(kernel="gather fp32 NHWC", patches=n, stages=stages, occ=occ, ms_reps=" ".join(f"{m:.4f}" for m in ms), frac_median=alg / sorted(ms)[1] / 1e6 / peak)
+        del out
+        torch.cuda.empty_cache()
+
+
 def gather3():
     """bf16 NCHW / NHWC / S2D48: rows per tile (DH_GATHER_ROWS) x CTAs per SM, 2-deep ring."""
     H = W = 32768
@@ -412,5 +441,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
