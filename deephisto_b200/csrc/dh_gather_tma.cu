@@ -557,7 +557,11 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     const bool affine = mean3 != nullptr;
     const char* env = getenv("DH_GATHER_STAGES");  // profiling override
     const int env_stages = env ? atoi(env) : 0;
-    int stages = env_stages >= 2 && env_stages <= kTmaMaxStages ? env_stages : 2;  // measured: a shallow ring interferes least with the store stream (profiles/r01_gather.md)
+    // measured (profiles/r01_gather.md, r02_gather.md): a shallow ring and few resident CTAs interfere least with the store stream; the optimum
+    // is sharp and layout dependent -- fp32 NHWC: 3 stages x 2 CTAs per SM (0.862 / 0.873 of the measured peak at 5 120 / 8 192 patches per launch
+    // vs 0.852 / 0.861 with 2 x 3), bf16 NHWC: 2 x 2, every other mode: 2 x 3
+    const bool f32_nhwc = out_dtype == DH_F32 && !nchw && !s2d && !s4;
+    int stages = env_stages >= 2 && env_stages <= kTmaMaxStages ? env_stages : (f32_nhwc ? 3 : 2);
     while (stages > 2 && (size_t)stages * R * row_pitch > 56 * 1024) --stages;
     p.stages = stages;
     const size_t smem = (size_t)stages * R * row_pitch;
@@ -567,8 +571,8 @@ int gather_tma_launch(const uint8_t* slide, int64_t H, int64_t W, int64_t pitch,
     const bool full_units = (R / rows_per_out) * units_per_row == kConsumers * (s2d ? 4 : (nchw ? (E == 4 ? 4 : 2) : 6));
     const char* env_occ = getenv("DH_GATHER_OCC");  // profiling override of the resident CTAs per SM (grid size), 0 = default
     const int occ_o = env_occ ? atoi(env_occ) : 0;
-#define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st, occ_o, (sizeof(T) == 2 && (N) == DH_NHWC) ? 2 : 3) \
-                                            : launch_one(gather_tma_kernel<T, N, S, A, false>, p, n_tiles, smem, st, occ_o, (sizeof(T) == 2 && (N) == DH_NHWC) ? 2 : 3)
+#define DH_TMA(T, N, S, A) rc_launch = full_units ? launch_one(gather_tma_kernel<T, N, S, A, true>, p, n_tiles, smem, st, occ_o, (N) == DH_NHWC ? 2 : 3) \
+                                            : launch_one(gather_tma_kernel<T, N, S, A, false>, p, n_tiles, smem, st, occ_o, (N) == DH_NHWC ? 2 : 3)
 #define DH_TMA_SA(T, N)                                                                  \
     do {                                                                                 \
         if (scale255) { if (affine) DH_TMA(T, N, true, true); else DH_TMA(T, N, true, false); } \
