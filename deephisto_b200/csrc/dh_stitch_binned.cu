@@ -478,7 +478,7 @@ constexpr int kSegWords = 16;       // boundary bitmap words (<= 512 tile cells)
 
 __host__ __device__ inline int seg_warp_smem_bytes() {
     return kSegPatches * 8 /* r0 r1 c0 c1 (u16) */ + kSegPatches * 32 /* logits, stride 8 */ + (2 * kSegWords + 4) * 4 /* bitmaps */ + kSegCap * 2 /* segments */ +
-           80 /* runs */ + 2 * kSegVals * 4 /* values */;
+           144 /* runs */ + 2 * kSegVals * 4 /* values */;
 }
 
 template <int KIND, int G>
@@ -512,10 +512,10 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     float* s_lg = reinterpret_cast<float*>(base + kSegPatches * 8);                      // [L][8]
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(base + kSegPatches * 40);            // [kSegWords] segment-start bitmap over the tile's cells
     uint32_t* s_wpre = s_bits + kSegWords;                                          // [kSegWords] set bits before each word
-    uint32_t* s_rbits = s_wpre + kSegWords;                                         // [2] run-start bitmap over the tile's rows (TH <= 64)
+    uint32_t* s_rbits = s_wpre + kSegWords;                                         // [4] run-start bitmap over the tile's rows (TH <= 128)
     uint16_t* s_segc = reinterpret_cast<uint16_t*>(s_rbits + 4);                    // [S] first cell of each segment (tile relative)
     uint8_t* s_run = reinterpret_cast<uint8_t*>(s_segc + kSegCap);                  // [NR + 1] first row of each run, then TH
-    float* s_val = reinterpret_cast<float*>(base + kSegPatches * 40 + (2 * kSegWords + 4) * 4 + kSegCap * 2 + 80);   // [2][kSegVals] double-buffered
+    float* s_val = reinterpret_cast<float*>(base + kSegPatches * 40 + (2 * kSegWords + 4) * 4 + kSegCap * 2 + 144);  // [2][kSegVals] double-buffered
     uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_val);                            // staging only: unsorted / sorted ids alias the values
     uint32_t* s_ids = s_raw + kSegPatches;
 
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     // ---- stage: ids in ascending order, footprints clipped to the tile (rows / cells relative to the tile), logits
     for (int j = lane; j < L; j += 32) s_raw[j] = list[beg + j];
     if (lane < kSegWords) s_bits[lane] = lane == 0 ? 1u : 0u;                       // cell 0 starts segment 0
-    if (lane < 2) s_rbits[lane] = lane == 0 ? 1u : 0u;                              // row 0 starts run 0
+    if (lane < 4) s_rbits[lane] = lane == 0 ? 1u : 0u;                              // row 0 starts run 0
     __syncwarp();
     for (int j = lane; j < L; j += 32) {  // rank sort: patch indices are distinct within a tile
         const uint32_t v = s_raw[j];
@@ -588,16 +588,24 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     }
     int NR;         // row runs: maximal row ranges with the same covering patches
     {
-        const uint32_t w0 = s_rbits[0], w1 = s_rbits[1];
-        NR = __popc(w0) + __popc(w1);
-        if (lane < 2) {
-            uint32_t rest = lane == 0 ? w0 : w1;
-            int k = lane == 0 ? 0 : __popc(w0);
+        const uint32_t rw = lane < 4 ? s_rbits[lane] : 0u;
+        const int pc = __popc(rw);
+        int before = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int v = __shfl_sync(0xffffffffu, pc, k);
+            if (lane > k) before += v;
+        }
+        NR = before + pc;                                     // lane 3 holds the total
+        NR = __shfl_sync(0xffffffffu, NR, 3);
+        if (lane < 4) {
+            uint32_t rest = rw;
+            int k = before;
             while (rest) {
                 s_run[k++] = (uint8_t)(lane * 32 + __ffs(rest) - 1);
                 rest &= rest - 1;
             }
-            if (lane == 1) s_run[NR] = (uint8_t)TH;
+            if (lane == 3) s_run[NR] = (uint8_t)TH;
         }
     }
     __syncwarp();   // also: every lane is done with s_ids before the value buffers (which alias it) are written
@@ -907,7 +915,7 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         const BinGeom g = make_geom(false, v4 || phased ? 4 : 1, ps, d, n, rows, dw, row_offset, phased);
         // measured (profiles/r02_stitch.md): the segment kernel wins where the row-run kernel has to sum 7 floats per lane (rows not
         // 16-byte aligned: 0.61 vs 0.51 of the HBM peak at d = 4), the row-run kernel wins on aligned rows (0.71 vs 0.68)
-        const bool seg = staged && (g_bin_variant == 2 || (g_bin_variant == 0 && phased)) && g.TH <= 64 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
+        const bool seg = staged && (g_bin_variant == 2 || (g_bin_variant == 0 && phased)) && g.TH <= 128 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
         if (seg && phased) rc = run_binned<4, 1, false, true, true, 1>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4 && g.G == 2) rc = run_binned<4, 2, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4) rc = run_binned<4, 1, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
@@ -930,7 +938,7 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         const bool c4 = ps / d >= 96 && dw % 4 == 0 && reinterpret_cast<uintptr_t>(cell_argmax) % 4 == 0 &&
                         reinterpret_cast<uintptr_t>(count_map) % 16 == 0;
         const BinGeom g = make_geom(true, c4 ? 4 : 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
-        if (g_bin_variant == 2 && g.TH <= 64)
+        if (g_bin_variant == 2 && g.TH <= 128)
             rc = c4 ? run_binned<4, 1, true, true, false, 4>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
                     : run_binned<1, 1, true, true, false, 3>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
         else
