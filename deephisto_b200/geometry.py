@@ -6,7 +6,10 @@ Mirrors the set-up work of the reference (patch_samplers/region_samplers.py):
   _calc_area_weights/_calc_weights :339-482 sampling weights
 and packs the result into flat device tables (struct dh_region_tables, include/deephisto_b200.h)
 consumed by the sm_100a kernels. shapely's `buffer(0)` repair of invalid polygons is not available
-(GEOS is not a dependency): self-intersecting polygons are rejected and counted as failed regions."""
+(GEOS is not a dependency). A self-intersecting ring is, by default, KEPT with winding-number semantics -- the kernels' clip area is
+|sum of signed edge integrals| = |sum over the ring's faces of winding x area|, which equals `buffer(0)`'s area up to the faces a
+crossing creates (buffer(0) keeps the positively wound faces once; a small hand-drawn loop changes the result by the loop's own area) --
+and named in a warning; `invalid="skip"` drops it instead (round-1 behaviour)."""
 
 from __future__ import annotations
 
@@ -157,8 +160,9 @@ class RegionTables:
         )
 
 
-def make_region(image: int, region_idx: int, class_: str, vertices: np.ndarray, layer: int) -> Region:
-    """RegionAnnotation.__init__ (region_samplers.py:64-73) without shapely."""
+def make_region(image: int, region_idx: int, class_: str, vertices: np.ndarray, layer: int, invalid: str = "approximate") -> Region:
+    """RegionAnnotation.__init__ (region_samplers.py:64-73) without shapely. `invalid`: what to do with a self-intersecting ring, which
+    the reference repairs with buffer(0) (:69-71): "approximate" keeps it with winding-number area semantics and warns, "skip" raises."""
     v = np.asarray(vertices)
     if v.ndim != 2 or v.shape[1] != 2:
         raise RuntimeError("Invalid region shape. It should be (N, 2).")
@@ -168,5 +172,11 @@ def make_region(image: int, region_idx: int, class_: str, vertices: np.ndarray, 
         raise RuntimeError("A polygon needs at least 3 vertices.")
     v = v if layer == 1 else v.copy() / layer
     if _segments_intersect_properly(v):
-        raise RuntimeError("invalid (self-intersecting) polygon: buffer(0) repair needs GEOS and is not supported")
+        if invalid == "skip":
+            raise RuntimeError("invalid (self-intersecting) polygon: buffer(0) repair needs GEOS and is not supported")
+        import warnings
+
+        warnings.warn(f"image {image}, region {region_idx} (class {class_!r}): self-intersecting polygon kept with winding-number area semantics "
+                      f"(signed area {polygon_area(v):.1f} px^2); shapely's buffer(0) repair may differ by the area of the crossing loops",
+                      RuntimeWarning, stacklevel=3)
     return Region(image, region_idx, class_, v, polygon_area(v), polygon_bounds(v), build_edges(v))

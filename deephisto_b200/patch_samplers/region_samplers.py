@@ -10,8 +10,8 @@ AnnoRegionDenseSampler :799-871, extract_and_save_subset :874-909). Differences,
   * `torch_generator` yields CUDA tensors;
   * random origins are clamped so that patches never overhang the slide; `cls_idx=0` means class 0,
     not "any class" (Q5); `torch_iterable_dataset` yields (y, x), not (y, y) (Q6);
-  * invalid (self-intersecting) polygons are skipped and counted as failed regions: shapely's buffer(0) repair
-    (:69-71) needs GEOS."""
+  * invalid (self-intersecting) polygons: shapely's buffer(0) repair (:69-71) needs GEOS; by default such a ring is kept with
+    winding-number area semantics and named in a warning (`invalid_polygons="skip"` drops it, also with a warning)."""
 
 from __future__ import annotations
 
@@ -47,14 +47,14 @@ class RegionAnnotation:
     """One annotated polygon (reference :18-191). `polygon` is replaced by `vertices_scaled` + an edge table."""
 
     def __init__(self, img_path: Path, region_idx: int, class_: str, vertices: np.ndarray, layer: int,
-                 layer_size: tuple[int, int], *, image_index: int = 0, seed: int = 0, device="cuda"):
+                 layer_size: tuple[int, int], *, image_index: int = 0, seed: int = 0, device="cuda", invalid: str = "approximate"):
         self.file_path = img_path
         self.region_idx = region_idx
         self.class_ = class_
         self.vertices = vertices
         self._layer = layer
         self._layer_size = layer_size
-        self._region = geometry.make_region(image_index, region_idx, class_, vertices, layer)  # raises like :64-67
+        self._region = geometry.make_region(image_index, region_idx, class_, vertices, layer, invalid=invalid)  # raises like :64-67
         self.area = self._region.area
         self.bounds = self._region.bounds
         self._seed, self._device, self._calls = seed, device, 0
@@ -122,7 +122,8 @@ def _load_annotation(anno) -> list[dict]:
     return list(anno)
 
 
-def _parse_annotations(img_anno_paths, layer: int, classes: list[str] = None, *, seed: int = 0, device="cuda", verbose: bool = True):
+def _parse_annotations(img_anno_paths, layer: int, classes: list[str] = None, *, seed: int = 0, device="cuda", verbose: bool = True,
+                       invalid: str = "approximate"):
     """Reference :194-249. Returns (regions_all, regions_per_image, layer sizes, opened slide sources)."""
     regions_all = defaultdict(list)
     regions_per_image = [defaultdict(list) for _ in img_anno_paths]
@@ -140,7 +141,7 @@ def _parse_annotations(img_anno_paths, layer: int, classes: list[str] = None, *,
                     continue
                 try:
                     reg = RegionAnnotation(img_path=psim_path, region_idx=i, class_=cls, vertices=np.array(a["vertices"], dtype=np.float64),
-                                           layer=layer, layer_size=size, image_index=j, seed=seed, device=device)
+                                           layer=layer, layer_size=size, image_index=j, seed=seed, device=device, invalid=invalid)
                     regions_per_image[j][cls].append(reg)
                     regions_all[cls].append(reg)
                 except Exception as e:
@@ -157,7 +158,7 @@ def _parse_annotations(img_anno_paths, layer: int, classes: list[str] = None, *,
     return regions_all, regions_per_image, sizes, sources
 
 
-def build_tables(images, layer: int, area_influence: float, classes, one_image_for_batch: bool, device="cuda"):
+def build_tables(images, layer: int, area_influence: float, classes, one_image_for_batch: bool, device="cuda", invalid: str = "approximate"):
     """(RegionTables, flat region list, sorted class names) from [(layer_hw, [ {"class","vertices"} ...]) ...].
     Table layout: struct dh_region_tables; weights: reference _calc_weights :395-482."""
     regions: list[geometry.Region] = []
@@ -169,7 +170,9 @@ def build_tables(images, layer: int, area_influence: float, classes, one_image_f
             if classes is not None and cls not in classes:
                 continue
             try:
-                reg = geometry.make_region(j, i, cls, np.array(a["vertices"], dtype=np.float64), layer)
+                with warnings.catch_warnings():                       # callers that parsed the annotations first have warned already
+                    warnings.simplefilter("ignore", RuntimeWarning)
+                    reg = geometry.make_region(j, i, cls, np.array(a["vertices"], dtype=np.float64), layer, invalid=invalid)
             except Exception:
                 continue
             per_image[j].setdefault(cls, []).append(len(regions))
@@ -197,7 +200,7 @@ class AnnoRegionRndSampler:
                  one_image_for_batch: bool = False, *, seed: int = 0, device="cuda", out_dtype=torch.float32, out_layout: str = "NHWC",
                  flips: bool = False, mean=None, std=None, verbose: bool = True, sparse_upload: bool = None, shard_upload=None,
                  prefetch_bytes: int = 5 << 30, prefetch_batches: int = 32, zero_copy: bool = None, zero_copy_fraction: float = 0.5,
-                 resident: bool = True):
+                 resident: bool = True, invalid_polygons: str = "approximate"):
         self.img_anno_paths = img_anno_paths
         self.layer = layer
         self.patch_size = patch_size
@@ -207,8 +210,10 @@ class AnnoRegionRndSampler:
         self.one_image_for_batch = one_image_for_batch
         self._seed, self._device = seed, device
         self._out_dtype, self._out_layout, self._flips, self._mean, self._std = out_dtype, out_layout, flips, mean, std
+        if invalid_polygons not in ("approximate", "skip"):
+            raise ValueError("invalid_polygons must be 'approximate' or 'skip'")
         self.regions, self.regions_per_image, self._sizes, self._sources = _parse_annotations(
-            img_anno_paths, layer=layer, classes=classes, seed=seed, device=device, verbose=verbose)
+            img_anno_paths, layer=layer, classes=classes, seed=seed, device=device, verbose=verbose, invalid=invalid_polygons)
         self.classes = sorted(list(self.regions.keys()))
         annos = [[{"class": r.class_, "vertices": r.vertices} for rs in rpi.values() for r in rs] for rpi in self.regions_per_image]
         # keep the per-image dict order of the reference (class first-appearance order, then file order)
@@ -217,7 +222,8 @@ class AnnoRegionRndSampler:
             ordered = sorted((r for rs in rpi.values() for r in rs), key=lambda r: r.region_idx)
             images.append((self._sizes[j], [{"class": r.class_, "vertices": r.vertices} for r in ordered]))
         del annos
-        self._tables, self._flat_regions, names = build_tables(images, layer, region_area_influence, None, one_image_for_batch, device)
+        self._tables, self._flat_regions, names = build_tables(images, layer, region_area_influence, None, one_image_for_batch, device,
+                                                               invalid=invalid_polygons)
         assert names == self.classes
         self._slides = [None] * len(img_anno_paths)
         self._prefetch_bytes, self._prefetch_batches = int(prefetch_bytes), int(prefetch_batches)   # torch_generator: features per prefetch group
@@ -601,7 +607,7 @@ class AnnoRegionDenseSampler:
     """Dense grid inside every annotated region (reference :799-871)."""
 
     def __init__(self, img_anno_paths, layer: int, patch_size: int, stride: int, region_intersection: float = 0.75,
-                 classes: list[str] = None, *, device="cuda", verbose: bool = True):
+                 classes: list[str] = None, *, device="cuda", verbose: bool = True, invalid_polygons: str = "approximate"):
         self.img_anno_paths = img_anno_paths
         self.layer = layer
         self.patch_size = patch_size
@@ -609,7 +615,7 @@ class AnnoRegionDenseSampler:
         self.region_intersection = region_intersection
         self._device = device
         self.regions, _, self._sizes, self._sources = _parse_annotations(img_anno_paths, layer=layer, classes=classes, device=device,
-                                                                       verbose=verbose)
+                                                                       verbose=verbose, invalid=invalid_polygons)
         self.classes = sorted(list(self.regions.keys()))
         self._slides = [None] * len(img_anno_paths)
 
