@@ -104,6 +104,8 @@ class FullImageRndSampler:
     def state_dict(self) -> dict:
         """State as of the LAST BATCH HANDED TO THE CONSUMER. The device runs up to two groups ahead of the consumer; those batches are
         not part of the state -- a restored sampler draws them again (bit-identically) instead of counting their footprints as covered."""
+        if self._resume is not None:                                # restored but not iterated yet: still the restored state
+            return dict(self._resume)
         k = int(self._consumed)
         return {"seed": int(self._seed), "batch_index": k, "accum": None, "filled_ratio": list(self._filled_ratio[:k])}
 

@@ -351,7 +351,9 @@ class AnnoRegionRndSampler:
             if self._upload_done[j].query():
                 self._upload_done[j] = None
             else:
-                torch.cuda.current_stream(self._device).wait_event(self._upload_done[j])   # background upload still in flight
+                cur = torch.cuda.current_stream(self._device)
+                cur.wait_event(self._upload_done[j])                            # background upload still in flight
+                self._slides[j].storage.record_stream(cur)                      # allocated on the copy stream, read on this one
         if self._slides[j] is None:
             with self._sources[j] as psim:
                 whole_pinned = isinstance(psim, PinnedSlide) and psim.y_origin == 0 and psim.rows == psim.height
