@@ -65,9 +65,13 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """SM clock / throttle reasons through NVML while the GPU is under load."""
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
+        """enabled=False (ranks other than 0: only rank 0 reports clocks): no NVML polling thread next to the rank's launch thread."""
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag, self.ok = index, [], False, False
+        self.max_sm = None
+        if not enabled:
+            return
         try:
             import pynvml
 
@@ -92,7 +96,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((sm, reasons, util))
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.02)
 
     def finish(self):
         self.stop_flag = True
@@ -423,7 +427,7 @@ def ours(args):
             done += nb
         return done
 
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, enabled=rank == 0)
     clocks.start()
     run_steps(0, Wm)
     torch.maximum(fail, status.max().reshape(1), out=fail)
@@ -863,7 +867,7 @@ def ours_predict(args):
     if world > 1:
         init_nccl(dev)
     _lib.require_device()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local, enabled=rank == 0)
     clocks.start()
     m = predict_measure(args, dev, world, rank)
     clk = clocks.finish()

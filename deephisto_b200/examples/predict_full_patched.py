@@ -59,18 +59,22 @@ class DeviceBatchPredictor:
     dtype float32 keeps torch's defaults (what the reference runs on a GPU); bfloat16 runs the CNN in bf16 channels_last."""
 
     def __init__(self, model: torch.nn.Module, device="cuda", dtype=torch.float32, channels_last: bool = True, fold_bn: bool = False,
-                 fused: bool = False, stem: str = "s2d4"):
+                 fused: bool = False, stem: str = "s2d4", cuda_graph: bool = True):
         """fold_bn=True folds every eval-mode BatchNorm into the preceding convolution (torch.nn.utils.fusion): the same
         function with ~20 fewer memory-bound elementwise kernels per forward; logits change at rounding level only.
         fused=True (bfloat16 / float16, torchvision BasicBlock ResNets): the forward runs through FusedResNetForward -- space-to-depth
         stem, dh_maxpool3x3s2_nhwc, cuDNN's fused conv+bias(+residual)+ReLU calls -- over the same weights; `gather` then writes the
-        stem's space-to-depth input directly."""
+        stem's space-to-depth input directly. cuda_graph (fused predictors): the forward over the predictor's gather buffer always has
+        the same shape and addresses, so after two eager runs (cuDNN picks its algorithms there) it is captured once and replayed --
+        one launch per CNN batch instead of ~45, which keeps a rank's launch thread off the critical path when many ranks share the
+        host's cores."""
         self.device = torch.device(device)
         self.dtype = dtype
         self.channels_last = channels_last and dtype != torch.float32
         model = model.to(self.device).eval()
         self.fused = None
         self._s2d = None                                       # space-to-depth stem input of the last gather() (fused predictors)
+        self._graph_on, self._graph, self._graph_out, self._graph_buf, self._eager_runs = bool(cuda_graph), None, None, None, 0
         if fused:
             if dtype == torch.float32:
                 raise ValueError("fused=True needs dtype bfloat16 or float16 (the float32 predictor is the parity path)")
@@ -125,11 +129,43 @@ class DeviceBatchPredictor:
                 # a short batch inside this predictor's gather buffer (the tail of a patch range): run the buffer's full batch -- the rows
                 # behind B hold the previous batch, their logits are dropped -- so that cuDNN sees ONE input shape per predictor
                 # (cudnn.benchmark re-tunes every new shape; a streamed slide has a different tail per row chunk)
-                return self.fused(buf.permute(0, 3, 1, 2))[:B]
+                return self._forward_buffer()[:B]
+            if buf is not None and features.data_ptr() == buf.data_ptr() and B == buf.shape[0]:
+                return self._forward_buffer()
             return self.fused(features)
         if self.channels_last:
             features = features.contiguous(memory_format=torch.channels_last)
         return self.model(features).float()
+
+    def _forward_buffer(self) -> torch.Tensor:
+        """Logits of the whole gather buffer (fused predictors). Eager for the first two runs of a buffer, then a captured CUDA graph
+        is replayed; the result is copied out of the graph's static output (callers may keep it across calls)."""
+        buf = self._s2d
+        x = buf.permute(0, 3, 1, 2)
+        if not self._graph_on:
+            return self.fused(x)
+        if self._graph is not None and self._graph_buf is buf:
+            self._graph.replay()
+            return self._graph_out.clone()
+        if self._graph_buf is not buf:                        # a new (larger) buffer: start over
+            self._graph, self._graph_out, self._graph_buf, self._eager_runs = None, None, buf, 0
+        self._eager_runs += 1
+        if self._eager_runs <= 2:
+            return self.fused(x)
+        try:
+            torch.cuda.current_stream(self.device).synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.fused(x)
+            self._graph, self._graph_out = g, out
+            g.replay()
+            return out.clone()
+        except Exception as e:                                # capture is an optimisation: fall back to eager launches
+            import warnings
+
+            warnings.warn(f"CUDA graph capture of the fused forward failed ({e!r}); running eagerly", RuntimeWarning)
+            self._graph_on, self._graph, self._graph_out = False, None, None
+            return self.fused(x)
 
     def features_from_patches(self, patches: list[Patch]) -> torch.Tensor:
         """uint8 patch pixels -> [B,3,ps,ps] in [0,1] through the gather kernel: the stacked batch is a (B*ps) x ps 'slide'."""
