@@ -153,14 +153,21 @@ def patch_origin(g: DenseGrid, i: int) -> tuple[int, int]:
     return g.H - g.ps, g.W - g.ps
 
 
-def stream_jobs(g: DenseGrid, patch_ranges, row_bytes: int, budget_bytes: int) -> list[tuple[int, int, list[tuple[int, int]]]]:
+def stream_jobs(g: DenseGrid, patch_ranges, row_bytes: int, budget_bytes: int,
+                first_budget_bytes: int = None) -> list[tuple[int, int, list[tuple[int, int]]]]:
     """Row chunks for predicting a slide that is NOT resident in HBM: [(slide_y0, slide_y1, [(first, count)])] -- each job uploads
     slide rows [slide_y0, slide_y1) (at most ~budget_bytes of `row_bytes`-wide rows, never less than one patch row) and computes
     the listed entries of the padded dense enumeration. `patch_ranges` is what plan_band produces: whole main-grid rows, their
     last-column entries (these ride with their grid rows) and optionally the tail (last row, corner, padding copies). Consecutive
-    chunks re-upload the ps - stride rows they share."""
+    chunks re-upload the ps - stride rows they share. `first_budget_bytes` (optional) bounds the FIRST chunk alone: nothing can hide
+    its upload, so a small first chunk lets the CNN start early."""
     ps, stride = g.ps, g.stride
-    per = max(1, (max(budget_bytes // max(row_bytes, 1), ps) - ps) // stride + 1)   # main-grid rows per chunk
+
+    def rows_for(budget):
+        return max(1, (max(budget // max(row_bytes, 1), ps) - ps) // stride + 1)   # main-grid rows per chunk
+
+    per = rows_for(budget_bytes)
+    first_per = per if first_budget_bytes is None else min(per, rows_for(first_budget_bytes))
     jobs = []
     for first, count in patch_ranges:
         if count <= 0:
@@ -169,16 +176,20 @@ def stream_jobs(g: DenseGrid, patch_ranges, row_bytes: int, budget_bytes: int) -
             if first % g.nx or count % g.nx:
                 raise ValueError("main-grid patch ranges must cover whole grid rows")
             lo, hi = first // g.nx, (first + count) // g.nx
-            for a in range(lo, hi, per):
-                b = min(a + per, hi)
+            a = lo
+            while a < hi:
+                b = min(a + (first_per if not jobs else per), hi)
                 jobs.append((a * stride, (b - 1) * stride + ps, [(a * g.nx, (b - a) * g.nx), (g.main_n + a, b - a)]))
+                a = b
         elif first >= g.main_n + g.ny:                                     # last row, corner, padding copies
             jobs.append((g.H - ps, g.H, [(first, count)]))
         elif g.nx == 0:                                                    # W == ps: the last column IS the grid, nothing to ride with
             lo, hi = first - g.main_n, first - g.main_n + count
-            for a in range(lo, hi, per):
-                b = min(a + per, hi)
+            a = lo
+            while a < hi:
+                b = min(a + (first_per if not jobs else per), hi)
                 jobs.append((a * stride, (b - 1) * stride + ps, [(g.main_n + a, b - a)]))
+                a = b
         # otherwise entries [main_n + lo, main_n + hi) (last column) ride with their grid rows above
     covered = sum(c for _, _, rs in jobs for _, c in rs)
     wanted = sum(c for _, c in patch_ranges if c > 0)

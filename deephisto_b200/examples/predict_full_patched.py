@@ -62,7 +62,7 @@ class DeviceBatchPredictor:
                  fused: bool = False, stem: str = "s2d4", cuda_graph: bool = True):
         """fold_bn=True folds every eval-mode BatchNorm into the preceding convolution (torch.nn.utils.fusion): the same
         function with ~20 fewer memory-bound elementwise kernels per forward; logits change at rounding level only.
-        fused=True (bfloat16 / float16, torchvision BasicBlock ResNets): the forward runs through FusedResNetForward -- space-to-depth
+        fused=True (bfloat16, torchvision BasicBlock ResNets): the forward runs through FusedResNetForward -- space-to-depth
         stem, dh_maxpool3x3s2_nhwc, cuDNN's fused conv+bias(+residual)+ReLU calls -- over the same weights; `gather` then writes the
         stem's space-to-depth input directly. cuda_graph (fused predictors): the forward over the predictor's gather buffer always has
         the same shape and addresses, so after two eager runs (cuDNN picks its algorithms there) it is captured once and replayed --
@@ -76,8 +76,8 @@ class DeviceBatchPredictor:
         self._s2d = None                                       # space-to-depth stem input of the last gather() (fused predictors)
         self._graph_on, self._graph, self._graph_out, self._graph_buf, self._eager_runs = bool(cuda_graph), None, None, None, 0
         if fused:
-            if dtype == torch.float32:
-                raise ValueError("fused=True needs dtype bfloat16 or float16 (the float32 predictor is the parity path)")
+            if dtype != torch.bfloat16:
+                raise ValueError("fused=True needs dtype=torch.bfloat16 (the float32 predictor is the parity path; the gather writes bf16 stem inputs)")
             self.fused = FusedResNetForward(model, dtype, stem=stem)      # works on its own folded copy of the weights
             self.model = None
         else:
@@ -474,7 +474,8 @@ class ImagePredictorPatched:
         from ..slide import band_to_device
 
         g = bands.dense_grid(sampler.h, sampler.w, sampler.patch_size, sampler.stride, sampler.batch_size)
-        jobs = bands.stream_jobs(g, patch_ranges, ops.DeviceSlide.pitch_for(sampler.w), int(max_band_bytes or self._stream_band_bytes))
+        budget = int(max_band_bytes or self._stream_band_bytes)
+        jobs = bands.stream_jobs(g, patch_ranges, ops.DeviceSlide.pitch_for(sampler.w), budget, first_budget_bytes=max(budget // 8, 1))
         cur = torch.cuda.current_stream(self._device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self._device)

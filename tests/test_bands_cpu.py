@@ -213,6 +213,11 @@ def test_stream_jobs_cover_every_patch_once_with_its_rows(case, world):
                         assert y0 <= y and y + ps <= y1, (i, y, y0, y1)
                         seen.append(i)
             assert sorted(seen) == sorted(bands.patch_indices(plan))
+            # a bounded first chunk (its upload cannot hide behind the CNN): same coverage, the first job is not larger than the others
+            ramp = bands.stream_jobs(g, plan.patch_ranges, row_bytes, budget_rows * row_bytes, first_budget_bytes=ps * row_bytes)
+            assert sorted(i for _, _, rs in ramp for f, c in rs for i in range(f, f + c)) == sorted(bands.patch_indices(plan))
+            if ramp:
+                assert ramp[0][1] - ramp[0][0] <= max(j[1] - j[0] for j in ramp)
     if g.ny > 0 and g.nx > 1:
         with pytest.raises(ValueError):
             bands.stream_jobs(g, [(1, g.nx)], row_bytes, 1 << 30)          # main-grid ranges must be whole grid rows
