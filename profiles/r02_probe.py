@@ -239,6 +239,30 @@ def gather4():
         torch.cuda.empty_cache()
 
 
+def gather5():
+    """bf16 with per-batch random H/V flips (BASELINE configs[4]): NCHW (mirrored units on the fast path) vs NHWC (H flips on the byte path)."""
+    H = W = 32768
+    dev = ops.DeviceSlide.synthetic(H, W, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 8192
+    coords = torch.stack([torch.randint(0, H - PS, (n,), generator=g, device="cuda"), torch.randint(0, W - PS, (n,), generator=g, device="cuda")], 1).to(torch.int32).contiguous()
+    flips = {"none": None, "all four combinations": torch.randint(0, 4, (n,), generator=g, device="cuda").to(torch.uint8),
+             "V only": (torch.randint(0, 2, (n,), generator=g, device="cuda") * 2).to(torch.uint8), "H only": torch.randint(0, 2, (n,), generator=g, device="cuda").to(torch.uint8)}
+    for layout in ("NCHW", "NHWC"):
+        out = torch.empty((2, n, PS, PS, 3) if layout == "NHWC" else (2, n, 3, PS, PS), dtype=torch.bfloat16, device="cuda")
+        for name, fl in flips.items():
+            i = [0]
+
+            def run():
+                i[0] ^= 1
+                ops.gather_normalize(dev, coords, PS, dtype=torch.bfloat16, layout=layout, flip=fl, out=out[i[0]])
+
+            ms = timeit(run, reps=11, warm=2)
+            say(kernel="gather bf16 + flips", layout=layout, flips=name, ms=ms, frac=n * PS * PS * 9 / ms / 1e6 / peak)
+        del out
+        torch.cuda.empty_cache()
+
+
 def gather3():
     """bf16 NCHW / NHWC / S2D48: rows per tile (DH_GATHER_ROWS) x CTAs per SM, 2-deep ring."""
     H = W = 32768
@@ -441,5 +465,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
