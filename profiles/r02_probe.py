@@ -457,6 +457,20 @@ def ncu_dense():
     say(kernel="stitch_dense argmax only", d=d, ms=ms)
 
 
+def ncu_predict_parts():
+    """One S2D48 gather launch and one stem pooling launch at the predictor's batch size (for ncu)."""
+    H = W = 32768
+    dev = ops.DeviceSlide.synthetic(H, W, 0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 1024
+    coords = torch.stack([torch.randint(0, H - PS, (n,), generator=g, device="cuda"), torch.randint(0, W - PS, (n,), generator=g, device="cuda")], 1).to(torch.int32).contiguous()
+    y = torch.randn((n, 256, 56, 56), generator=g, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    for _ in range(3):
+        ops.gather_normalize(dev, coords, PS, dtype=torch.bfloat16, layout="S2D48")
+        ops.maxpool3x3s2_d2s(y)
+        torch.cuda.synchronize()
+
+
 def ncu_cover():
     st = ops.CoverState(40000, 40000, PS, 16, 2, 64, seed=0)
     for _ in range(3):
@@ -465,5 +479,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"ncu_predict_parts": ncu_predict_parts, "gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
