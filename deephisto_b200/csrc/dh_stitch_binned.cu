@@ -34,8 +34,10 @@ constexpr int kBinCap = 128;    // patches per tile staged in shared memory; lon
 constexpr int kBinMaxN = 8;     // classes the cell kernel keeps in registers
 
 static int g_bin_tile_rows = 0;  // 0 = heuristic; profiling override (dh_stitch_binned_set_tile_rows)
-static int g_bin_variant = 0;    // 0 = auto (segment kernel for sum maps whose rows are not 16-byte aligned, row-run kernels otherwise),
-                                 // 1 = row-run kernels only, 2 = segment kernel whenever n <= 8 (dh_stitch_binned_set_variant)
+static int g_bin_variant = 0;    // 0 = auto (sum maps of n <= 8 classes: cell-lane kernel for footprints under 1024 floats on aligned rows and
+                                 // under 24 cells on unaligned rows, segment kernel for wider footprints on unaligned rows; row-run kernels otherwise),
+                                 // 1 = row-run kernels only, 2 = segment kernel whenever n <= 8, 3 = cell-lane kernel whenever n <= 8
+                                 // (dh_stitch_binned_set_variant)
 
 struct BinGeom {
     int64_t rows, row_offset, dw;
@@ -99,12 +101,29 @@ __global__ void __launch_bounds__(256) bin_patches_kernel(const int32_t* __restr
         if (!bin_footprint(g, __ldg(coords + 2 * p), __ldg(coords + 2 * p + 1), f)) continue;
         const int ty0 = f.r0 / g.TH, ty1 = (f.r1 - 1) / g.TH, tx1 = (f.u1 - 1) / g.TW;
         const int tx0 = g.phased ? (f.u0 >= 3 ? (f.u0 - 3) / g.TW : 0) : f.u0 / g.TW;   // phased tiles reach 3 units to the right
-        for (int ty = ty0; ty <= ty1; ++ty)
-            for (int tx = tx0; tx <= tx1; ++tx) {
-                const int64_t t = (int64_t)ty * g.ntx + tx;
-                if (FILL) list[off[t] + atomicSub(cnt + t, 1u) - 1u] = (uint32_t)p;  // the counters run back to zero
-                else atomicAdd(cnt + t, 1u);
+        if constexpr (FILL) {
+            // four tiles per trip: the atomics (whose results place the entries) are issued back to back instead of one round trip each
+            const int nx = tx1 - tx0 + 1, nt = (ty1 - ty0 + 1) * nx;
+            int ty = ty0, tx = tx0;
+            for (int k0 = 0; k0 < nt; k0 += 4) {
+                uint32_t slot[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    slot[u] = 0xffffffffu;
+                    if (k0 + u < nt) {
+                        const int64_t t = (int64_t)ty * g.ntx + tx;
+                        slot[u] = off[t] + atomicSub(cnt + t, 1u) - 1u;                  // the counters run back to zero
+                        if (++tx > tx1) { tx = tx0; ++ty; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k0 + u < nt) list[slot[u]] = (uint32_t)p;
             }
+        } else {
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(cnt + (int64_t)ty * g.ntx + tx, 1u);
+        }
     }
 }
 
@@ -137,11 +156,12 @@ __device__ __noinline__ void bin_tile_slow(const float* __restrict__ logits, con
     }
     __syncwarp();
   constexpr int W1 = CELL ? 1 : VEC;                       // units a lane handles per pass (the fast kernel's lane-to-unit map does not matter here)
-  const int npass = g.TW / (32 * W1);
   // phased tiles also own the 3 units right of the tile (a neighbour's vectors start 0..3 units late); writing them from both sides
   // stores identical values
-  const int64_t ulimit = g.phased ? ((tx + 1) * g.TW + 3 < g.units_per_row ? (tx + 1) * g.TW + 3 : g.units_per_row) : g.units_per_row;
-  for (int gi = 0; gi < npass + (g.phased ? 1 : 0); ++gi) {
+  const int64_t tile_end = (tx + 1) * g.TW + (g.phased ? 3 : 0);
+  const int64_t ulimit = tile_end < g.units_per_row ? tile_end : g.units_per_row;
+  const int npass = (g.TW + (g.phased ? 3 : 0) + 32 * W1 - 1) / (32 * W1);   // TW need not be a multiple of 32 * W1 (cell-lane tiles)
+  for (int gi = 0; gi < npass; ++gi) {
     const int64_t ubase = tx * g.TW + (int64_t)gi * 32 * W1 + (int64_t)lane * W1;
     const bool active = ubase < ulimit;
     int cls[W1];
@@ -754,6 +774,233 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     }
 }
 
+// ---- cell-lane formulation (sum map, n <= 8 classes known at compile time) ----------------------------------------------------
+// A lane owns one CELL of the tile (32 cells x TH rows) and keeps its N class sums in registers: per covering patch one coverage
+// test (a precomputed 32-bit lane mask) and N adds, instead of a test and an add per output FLOAT as in the row-run kernels (whose
+// 4 floats per lane straddle two cells). The run's row image (32 * N floats) goes through shared memory once per run, every lane
+// picks up its 16-byte vectors and streams them to the rows of the run. Runs come from a row bitmap built while staging.
+// PHASED (rows not 16-byte aligned): a tile is TW = 4 * floor((31 N - 2) / 4) units wide, so that the units [U0, U0 + TW + 3) any of
+// its shifted vectors can touch lie inside 32 cells; the vectors of a row are read from the row image at the row's shift.
+constexpr int kCellRunBytes = 160;   // [4] row bitmap words + [TH + 1 <= 129] run starts (u8)
+constexpr int kCellCap = 128;        // patches per tile staged in shared memory (longer lists: the global-memory path); 6.7 KB per warp -> 4 CTAs per SM
+
+__host__ __device__ inline int cell_warp_smem_bytes() {
+    return 1024 /* ids while staging, then the run's row image */ + kCellCap * 8 /* rows */ + kCellCap * 4 /* lane masks */ + kCellCap * 32 /* logits, stride 8 */ +
+           kCellRunBytes;
+}
+
+__host__ __device__ inline int cell_tile_units(int n, bool phased) { return phased ? (31 * n - 2) / 4 * 4 : 32 * n; }
+
+template <int N>
+__device__ __forceinline__ void cell_add(float (&acc)[N], bool cov, const float4& lo, const float4& hi) {
+    if (cov) {
+        acc[0] += lo.x;
+        if (N > 1) acc[N > 1 ? 1 : 0] += lo.y;
+        if (N > 2) acc[N > 2 ? 2 : 0] += lo.z;
+        if (N > 3) acc[N > 3 ? 3 : 0] += lo.w;
+        if (N > 4) acc[N > 4 ? 4 : 0] += hi.x;
+        if (N > 5) acc[N > 5 ? 5 : 0] += hi.y;
+        if (N > 6) acc[N > 6 ? 6 : 0] += hi.z;
+        if (N > 7) acc[N > 7 ? 7 : 0] += hi.w;
+    }
+}
+
+template <int N, bool PHASED, bool NOSTORE = false>
+__global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords, BinGeom g,
+                                                                      const uint32_t* __restrict__ off, const uint32_t* __restrict__ len,
+                                                                      const uint32_t* __restrict__ list, uint32_t* __restrict__ sorted,
+                                                                      float* __restrict__ sum_map) {
+    constexpr int LS = 8;                                   // logits row stride in shared memory
+    constexpr int TWU = PHASED ? (31 * N - 2) / 4 * 4 : 32 * N;
+    constexpr int NV = TWU / 4;                             // 16-byte vectors per tile row
+    constexpr int V = (NV + 31) / 32;                       // vectors per lane and row
+    extern __shared__ __align__(16) unsigned char bin_smem[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t ctas_x = (g.ntx + kBinWarps - 1) / kBinWarps;
+    const int64_t ty = blockIdx.x / ctas_x;
+    const int64_t tx = (blockIdx.x % ctas_x) * kBinWarps + w;
+    if (tx >= g.ntx) return;
+    const int64_t t = ty * g.ntx + tx;
+    const uint32_t beg = off[t];
+    const int L = (int)len[t];
+    if (L > kCellCap) {
+        bin_tile_slow<1, false>(logits, coords, g, beg, L, list, sorted, sum_map, nullptr, nullptr, ty, tx);
+        return;
+    }
+    unsigned char* base = bin_smem + (size_t)w * cell_warp_smem_bytes();
+    uint32_t* s_raw = reinterpret_cast<uint32_t*>(base);               // [kCellCap] the tile's patch indices, unordered (staging only)
+    float* s_out = reinterpret_cast<float*>(base);                     // [32 * N <= 256] the run's row image (aliases the indices)
+    int2* s_rows = reinterpret_cast<int2*>(base + 1024);               // [L] tile-relative rows [r0, r1), clipped
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(base + 1024 + kCellCap * 8);   // [L] lanes (cells) the patch covers
+    float* s_lg = reinterpret_cast<float*>(base + 1024 + kCellCap * 12);           // [L][8]
+    uint32_t* s_rbits = reinterpret_cast<uint32_t*>(base + 1024 + kCellCap * 44);  // [4] run-start bitmap over the tile's rows (TH <= 128)
+    uint8_t* s_run = reinterpret_cast<uint8_t*>(s_rbits + 4);                     // [NR + 1] first row of each run, then TH
+
+    const int R0 = (int)(ty * g.TH);
+    const int TH = (int)((int64_t)R0 + g.TH < g.rows ? g.TH : g.rows - R0);
+    const int RF = (int)g.units_per_row;
+    const int U0 = (int)(tx * TWU);
+    const int C0 = U0 / N;                                   // the tile's first cell; lane l owns cell C0 + l
+
+    // ---- stage. In chunks of 64 list entries a lane owns the patches lane and lane + 32: it loads their origins and logits straight
+    // after the index (dependent chain: off/len -> list -> coords, logits -- one level shorter than sorting first), ranks them by
+    // patch index while those loads are in flight, and files footprint, lane mask and logits at the rank.
+    for (int j = lane; j < L; j += 32) s_raw[j] = list[beg + j];
+    if (lane < 4) s_rbits[lane] = lane == 0 ? 1u : 0u;       // row 0 starts run 0
+    __syncwarp();
+    for (int ch = 0; ch < L; ch += 64) {
+        uint32_t myid[2];
+        int py[2], px[2];
+        float lgv[2][LS];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            const int j = ch + lane + 32 * sl;
+            myid[sl] = j < L ? s_raw[j] : 0xffffffffu;
+            if (j < L) {
+                py[sl] = __ldg(coords + 2 * (int64_t)myid[sl]);
+                px[sl] = __ldg(coords + 2 * (int64_t)myid[sl] + 1);
+#pragma unroll
+                for (int q = 0; q < LS; ++q) lgv[sl][q] = q < N ? __ldg(logits + (int64_t)myid[sl] * N + q) : 0.f;
+            }
+        }
+        int rank[2] = {0, 0};
+        for (int i = 0; i < L; ++i) {                         // patch indices are distinct within a tile
+            const uint32_t o = s_raw[i];
+            rank[0] += o < myid[0];
+            rank[1] += o < myid[1];
+        }
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            if (ch + lane + 32 * sl < L) {
+                const int k = rank[sl];
+                BinRec f;
+                f.r0 = f.r1 = f.u0 = f.u1 = 0;
+                bin_footprint(g, py[sl], px[sl], f);
+                int a = f.r0 - R0, b = f.r1 - R0;
+                a = a < 0 ? 0 : a;
+                b = b > TH ? TH : (b < 0 ? 0 : b);
+                s_rows[k] = make_int2(a, b);
+                if (a > 0 && a < TH) atomicOr(s_rbits + (a >> 5), 1u << (a & 31));  // the covering set changes at every footprint edge
+                if (b > 0 && b < TH) atomicOr(s_rbits + (b >> 5), 1u << (b & 31));
+                int c0 = f.u0 / N - C0, c1 = f.u1 / N - C0;                         // footprints are whole cells: u0, u1 are multiples of N
+                c0 = c0 < 0 ? 0 : (c0 > 32 ? 32 : c0);
+                c1 = c1 < 0 ? 0 : (c1 > 32 ? 32 : c1);
+                const int wd = c1 - c0;
+                s_mask[k] = wd <= 0 ? 0u : ((wd >= 32 ? 0xffffffffu : ((1u << wd) - 1u)) << c0);
+                *reinterpret_cast<float4*>(s_lg + k * LS) = make_float4(lgv[sl][0], lgv[sl][1], lgv[sl][2], lgv[sl][3]);
+                if constexpr (N > 4) *reinterpret_cast<float4*>(s_lg + k * LS + 4) = make_float4(lgv[sl][4], lgv[sl][5], lgv[sl][6], lgv[sl][7]);
+            }
+        }
+    }
+    __syncwarp();
+    int NR;         // row runs: maximal row ranges with the same covering patches
+    {
+        const uint32_t rw = lane < 4 ? s_rbits[lane] : 0u;
+        const int pc = __popc(rw);
+        int before = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int v = __shfl_sync(0xffffffffu, pc, k);
+            if (lane > k) before += v;
+        }
+        NR = __shfl_sync(0xffffffffu, before + pc, 3);
+        if (lane < 4) {
+            uint32_t rest = rw;
+            int k = before;
+            while (rest) {
+                s_run[k++] = (uint8_t)(lane * 32 + __ffs(rest) - 1);
+                rest &= rest - 1;
+            }
+            if (lane == 3) s_run[NR] = (uint8_t)TH;
+        }
+    }
+    __syncwarp();   // also: every lane is done with s_raw before the row image (which aliases it) is written
+
+    const uint32_t lanebit = 1u << lane;
+    const int img0 = U0 - C0 * N;                            // the tile's first unit inside the row image (0 when aligned)
+    bool vfull[V];                                           // aligned rows: the lane's vectors that exist (RF % 4 == 0: whole or not at all)
+#pragma unroll
+    for (int i = 0; i < V; ++i) vfull[i] = lane + 32 * i < NV && U0 + 4 * (lane + 32 * i) < RF;
+    const int pstep = RF & 3;
+
+    for (int k = 0; k < NR; ++k) {
+        const int r = (int)s_run[k];
+        int next = (int)s_run[k + 1];
+        float acc[N];
+#pragma unroll
+        for (int q = 0; q < N; ++q) acc[q] = 0.f;
+        for (int j0 = 0; j0 < L; j0 += 32) {
+            const int j = j0 + lane;
+            const int2 rw = j < L ? s_rows[j] : make_int2(0x7fff, 0);
+            unsigned m = __ballot_sync(0xffffffffu, rw.x <= r && r < rw.y);
+            while (m) {  // covering patches in ascending list index = the reference's order, two per trip (independent shared-memory
+                         // loads); warp-uniform trip count
+                const int ja = j0 + __ffs(m) - 1;
+                m &= m - 1;
+                const bool two = m != 0u;
+                const int jb = two ? j0 + __ffs(m) - 1 : ja;
+                m &= m - 1;
+                const bool cova = (s_mask[ja] & lanebit) != 0u;
+                const bool covb = two && (s_mask[jb] & lanebit) != 0u;
+                // adding under the predicate only: a sum that starts at +0.0f and adds v is the reference's 0.0 + v
+                const float4 loa = *reinterpret_cast<const float4*>(s_lg + ja * LS);
+                const float4 lob = *reinterpret_cast<const float4*>(s_lg + jb * LS);
+                float4 hia = make_float4(0.f, 0.f, 0.f, 0.f), hib = hia;
+                if constexpr (N > 4) {
+                    hia = *reinterpret_cast<const float4*>(s_lg + ja * LS + 4);
+                    hib = *reinterpret_cast<const float4*>(s_lg + jb * LS + 4);
+                }
+                cell_add<N>(acc, cova, loa, hia);
+                cell_add<N>(acc, covb, lob, hib);
+            }
+        }
+        __syncwarp();                                        // the previous run's image has been read by every lane
+#pragma unroll
+        for (int q = 0; q < N; ++q) s_out[lane * N + q] = acc[q];
+        __syncwarp();
+        if constexpr (!PHASED) {
+            float4 v[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i)
+                if (lane + 32 * i < NV) v[i] = reinterpret_cast<const float4*>(s_out)[lane + 32 * i];
+            float* o = sum_map + (int64_t)(R0 + r) * RF + U0 + 4 * lane;
+            if (NOSTORE && RF > 0) next = r + (v[0].x == 12345.f && v[V - 1].w == 54321.f);   // profiling variant 4: everything but the stores
+            for (int rr = r; rr < next; ++rr, o += RF) {
+#pragma unroll
+                for (int i = 0; i < V; ++i)
+                    if (vfull[i]) *reinterpret_cast<float4*>(o + 128 * i) = v[i];
+            }
+        } else {
+            // in row rr the tile's vectors start sft = (4 - rr * RF) mod 4 units later (then 16-byte aligned); the first sft units of a
+            // row are scalar stores of tile 0, the last vector of a row is clipped
+            float* rowp = sum_map + (int64_t)(R0 + r) * RF;
+            int p = (int)(((int64_t)(R0 + r) * RF) & 3);     // sum_map is 16-byte aligned (host check)
+            for (int rr = r; rr < next; ++rr) {
+                const int sft = (4 - p) & 3;
+#pragma unroll
+                for (int i = 0; i < V; ++i) {
+                    const int f = lane + 32 * i;
+                    const int u = U0 + sft + 4 * f;
+                    if (f < NV && u < RF) {
+                        const float* s = s_out + img0 + sft + 4 * f;
+                        const float w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3];   // inside the 32-cell image (tile width rule above)
+                        if (u + 4 <= RF) {
+                            *reinterpret_cast<float4*>(rowp + u) = make_float4(w0, w1, w2, w3);
+                        } else {
+                            rowp[u] = w0;
+                            if (u + 1 < RF) rowp[u + 1] = w1;
+                            if (u + 2 < RF) rowp[u + 2] = w2;
+                        }
+                    }
+                }
+                if (tx == 0 && lane < sft) rowp[lane] = s_out[lane];
+                rowp += RF;
+                p = (p + pstep) & 3;
+            }
+        }
+    }
+}
+
 // profiling override: rows + 1000 * groups + 100000 * extra shared-memory KB per CTA (each field 0 = heuristic / none)
 static int tile_rows_for(int ps, int d) {
     if (g_bin_tile_rows % 1000 > 0) return g_bin_tile_rows % 1000;
@@ -768,7 +1015,8 @@ static int groups_for(bool cell, int vec, int ps, int d, int n) {
     return (int64_t)(ps / d) * n >= 512 ? 2 : 1;  // wide footprints: 256-float tiles halve the per-tile staging work (measured: profiles/r01_stitch.md)
 }
 
-static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows, int64_t dw, int64_t row_offset, bool phased = false) {
+static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows, int64_t dw, int64_t row_offset, bool phased = false,
+                         bool cell_lane = false) {
     BinGeom g;
     g.phased = phased ? 1 : 0;
     g.rows = rows; g.row_offset = row_offset; g.dw = dw;
@@ -778,6 +1026,7 @@ static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows,
     g.TH = tile_rows_for(ps, d);
     g.G = phased ? 1 : groups_for(cell, vec, ps, d, n);
     g.TW = 32 * vec * g.G;
+    if (cell_lane) { g.G = 1; g.TW = cell_tile_units(n, phased); }   // bin_cell_sum_kernel: 32 cells per tile
     g.nty = (rows + g.TH - 1) / g.TH;
     g.ntx = (g.units_per_row + g.TW - 1) / g.TW;
     return g;
@@ -811,7 +1060,7 @@ static void carve_bin(const BinGeom& g, int64_t P, void* base, BinScratch& s) {
 static bool sum_vec4(const float* sum_map, int64_t dw, int n) { return (dw * n) % 4 == 0 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0; }
 
 // SEGK >= 0: bin_seg_kernel<SEGK, G> (n <= kBinMaxN); -1: the row-run kernels
-template <int VEC, int G, bool CELL, bool STAGED, bool PHASED = false, int SEGK = -1>
+template <int VEC, int G, bool CELL, bool STAGED, bool PHASED = false, int SEGK = -1, int CELLN = 0>
 static int run_binned(const float* logits, const int32_t* coords, int64_t P, const BinGeom& g, float* sum_map, uint32_t* count_map,
                       uint8_t* argmax_u8, void* scratch, int64_t scratch_bytes, cudaStream_t st) {
     BinScratch s;
@@ -835,7 +1084,35 @@ static int run_binned(const float* logits, const int32_t* coords, int64_t P, con
     // at least 50 KB per CTA = at most 4 resident CTAs per SM: a fifth one only adds HBM write interleaving (measured 1.5-3 % slower)
     int smem = kBinWarps * bin_warp_smem_bytes(g.n, STAGED) + (g_bin_tile_rows / 100000) * 1024;
     if (!CELL && smem < 50 * 1024) smem = 50 * 1024;
-    if constexpr (SEGK >= 0) {
+    if constexpr (CELLN == 5 && !PHASED) {
+        if (g_bin_variant == 4) {   // profiling only: the cell-lane kernel without its stores (the map is left untouched)
+            auto kern = bin_cell_sum_kernel<5, false, true>;
+            smem = kBinWarps * cell_warp_smem_bytes() + (g_bin_tile_rows / 100000) * 1024;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_cell_sum_kernel)");
+            kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map);
+            DH_CHECK_LAUNCH("bin_cell_sum_kernel<nostore>");
+            return DH_OK;
+        }
+    }
+    if constexpr (CELLN > 0) {
+        auto kern = bin_cell_sum_kernel<CELLN, PHASED>;
+        smem = kBinWarps * cell_warp_smem_bytes();
+        // Resident CTAs per SM through the shared-memory request. Tiled writes reach a higher share of the HBM write rate with FEWER
+        // concurrent writers (an all-zero map written by this kernel: 0.80-0.88 of the copy peak at 4 CTAs per SM, 0.87-0.90 at 3,
+        // 0.90-0.94 at 2), the staging and summing want more warps to overlap with. Measured optimum (profiles/r02_stitch.md):
+        // 3 CTAs for footprints under 512 floats on aligned rows, 2 for wider ones, 4 on unaligned rows.
+        if (!PHASED && g_bin_tile_rows / 100000 == 0) {
+            const int per_sm = (int64_t)(g.ps / g.d) * g.n < 512 ? 3 : 2;
+            const int want = (227 * 1024 / per_sm - 1024) / 1024 * 1024;            // the largest request that still fits per_sm CTAs
+            const int cap = 227 * 1024 / (per_sm + 1) - 1024;                        // anything above this excludes per_sm + 1 CTAs
+            if (smem <= cap) smem = cap + 1024 <= want ? cap + 1024 : want;
+        }
+        smem += (g_bin_tile_rows / 100000) * 1024;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_cell_sum_kernel)");
+        kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map);
+    } else if constexpr (SEGK >= 0) {
         auto kern = bin_seg_kernel<SEGK, G>;
         smem = kBinWarps * seg_warp_smem_bytes() + (g_bin_tile_rows / 100000) * 1024;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -870,7 +1147,7 @@ extern "C" DH_API int dh_stitch_binned_set_tile_rows(int rows) {
 }
 
 extern "C" DH_API int dh_stitch_binned_set_variant(int variant) {
-    if (variant < 0 || variant > 2) { set_error("dh_stitch_binned_set_variant: variant must be 0 (auto), 1 (row-run kernels) or 2 (segment kernel)"); return DH_ERR_INVALID; }
+    if (variant < 0 || variant > 4) { set_error("dh_stitch_binned_set_variant: variant must be 0 (auto), 1 (row-run kernels), 2 (segment kernel), 3 (cell-lane kernel) or 4 (profiling: cell-lane kernel without stores)"); return DH_ERR_INVALID; }
     g_bin_variant = variant;
     return DH_OK;
 }
@@ -878,8 +1155,9 @@ extern "C" DH_API int dh_stitch_binned_set_variant(int variant) {
 extern "C" DH_API int64_t dh_stitch_binned_scratch_bytes(int64_t P, int ps, int d, int n, int64_t rows, int64_t dw) {
     if (P <= 0 || ps <= 0 || d <= 0 || n <= 0 || rows <= 0 || dw <= 0) return 256;
     int64_t need = 0;
-    for (int mode = 0; mode < 5; ++mode) {  // sum (16-byte stores), sum (scalar stores), cell, cell x 4, sum (phased 16-byte stores)
-        BinGeom g = make_geom(mode == 2 || mode == 3, mode == 1 || mode == 2 ? 1 : 4, ps, d, n, rows, dw, 0, mode == 4);
+    for (int mode = 0; mode < 7; ++mode) {  // sum (16-byte stores), sum (scalar stores), cell, cell x 4, sum (phased 16-byte stores), cell-lane sum (aligned, phased)
+        BinGeom g = mode >= 5 ? make_geom(false, 4, ps, d, n, rows, dw, 0, mode == 6, true)
+                              : make_geom(mode == 2 || mode == 3, mode == 1 || mode == 2 ? 1 : 4, ps, d, n, rows, dw, 0, mode == 4);
         BinScratch s;
         carve_bin(g, P, nullptr, s);
         need = s.total_bytes > need ? s.total_bytes : need;
@@ -911,12 +1189,35 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         const bool v4 = sum_vec4(sum_map, dw, n);
         // rows not 16-byte aligned (dw * n % 4 != 0) but an aligned base: 16-byte stores at a per-row shift (bin_tile_phased_kernel)
         // (not for small footprints: 7 instead of 4 sums per lane cost more than the vector stores save -- measured at d = 16)
-        const bool phased = !v4 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 && dw * (int64_t)n >= 8 && ps / d >= 24;
+        const bool shiftable = !v4 && reinterpret_cast<uintptr_t>(sum_map) % 16 == 0 && dw * (int64_t)n >= 8;
+        const bool phased = shiftable && ps / d >= 24;
         const BinGeom g = make_geom(false, v4 || phased ? 4 : 1, ps, d, n, rows, dw, row_offset, phased);
         // measured (profiles/r02_stitch.md): the segment kernel wins where the row-run kernel has to sum 7 floats per lane (rows not
         // 16-byte aligned: 0.61 vs 0.51 of the HBM peak at d = 4), the row-run kernel wins on aligned rows (0.71 vs 0.68)
-        const bool seg = staged && (g_bin_variant == 2 || (g_bin_variant == 0 && phased)) && g.TH <= 128 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
-        if (seg && phased) rc = run_binned<4, 1, false, true, true, 1>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        // the cell-lane kernel (one cell per lane, issue-active 42 % where the row-run kernel has 72 %), measured on the 40 000^2 coverage
+        // list: aligned rows d = 16 / 4 / 2: 0.145 / 0.75 / 0.89 of the HBM copy peak vs 0.106 / 0.72 / 0.87 with the row-run kernel;
+        // d = 1 (footprints of 1120 floats) stays with the row-run kernel (0.96 vs 0.95). Unaligned rows: small footprints only
+        // (d = 16: 0.126 vs 0.089); the segment kernel keeps the wide ones (d = 4: 0.61 vs 0.56).
+        const bool cell_phased = shiftable;
+        const bool cell_lane = staged && tile_rows_for(ps, d) <= 128 &&
+                               ((g_bin_variant >= 3 && (v4 || cell_phased)) || (g_bin_variant == 0 && ((v4 && (int64_t)(ps / d) * n < 1024) || (shiftable && ps / d < 24))));
+        if (cell_lane) {
+            const BinGeom gc = make_geom(false, 4, ps, d, n, rows, dw, row_offset, !v4, true);
+#define DH_CELL_CASE(NN)                                                                                                                            \
+    case NN:                                                                                                                                        \
+        rc = !v4 ? run_binned<4, 1, false, true, true, -1, NN>(logits, coords, P, gc, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)        \
+                    : run_binned<4, 1, false, true, false, -1, NN>(logits, coords, P, gc, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);   \
+        break;
+            switch (n) {
+                DH_CELL_CASE(1) DH_CELL_CASE(2) DH_CELL_CASE(3) DH_CELL_CASE(4) DH_CELL_CASE(5) DH_CELL_CASE(6) DH_CELL_CASE(7) DH_CELL_CASE(8)
+                default: rc = DH_ERR_INVALID; break;
+            }
+#undef DH_CELL_CASE
+            if (rc != DH_OK) return rc;
+        }
+        const bool seg = !cell_lane && staged && (g_bin_variant == 2 || (g_bin_variant == 0 && phased)) && g.TH <= 128 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
+        if (cell_lane) {}
+        else if (seg && phased) rc = run_binned<4, 1, false, true, true, 1>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4 && g.G == 2) rc = run_binned<4, 2, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4) rc = run_binned<4, 1, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg) rc = run_binned<1, 1, false, true, false, 2>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);

@@ -182,10 +182,12 @@ DH_API int dh_stitch_binned(const float* logits, const int32_t* coords, int64_t 
                      float* sum_map, uint32_t* count_map, uint8_t* argmax_u8, int64_t rows, int64_t dw,
                      int64_t row_offset, void* scratch, int64_t scratch_bytes, void* stream);
 DH_API int dh_stitch_binned_set_tile_rows(int rows);
-/* Tile-kernel formulation (same bits either way, tests/test_gpu_parity.py): 0 = auto -- the segment kernel (one lane per (row run,
- * column segment) region sums the covering patches, all lanes fetch their floats from shared memory) for sum maps whose rows are
- * not 16-byte aligned, the row-run kernels (every lane re-sums its own floats at each footprint boundary) otherwise; 1 = row-run
- * kernels only; 2 = segment kernel wherever it applies (n <= 8 classes). Measurements: profiles/r02_stitch.md. */
+/* Tile-kernel formulation (same bits every way, tests/test_gpu_parity.py). 0 = auto: for sum maps of n <= 8 classes the cell-lane
+ * kernel (a lane owns one cell and its n class sums; the run's row image goes through shared memory) on 16-byte aligned rows with
+ * footprints under 1024 floats and on unaligned rows with footprints under 24 cells, the segment kernel (one lane per (row run,
+ * column segment) region) on unaligned rows with wider footprints, the row-run kernels (every lane re-sums its own floats at each
+ * footprint boundary) otherwise; 1 = row-run kernels only; 2 = segment kernel wherever it applies; 3 = cell-lane kernel wherever it
+ * applies; 4 = profiling only: the cell-lane kernel without its stores. Measurements: profiles/r02_stitch.md. */
 DH_API int dh_stitch_binned_set_variant(int variant);
 
 /* ------------------------------------------------------------------------------------------

@@ -99,7 +99,7 @@ def binned():
             reps = 10 if d >= 4 else 4
             for label, kw, out_bytes in (("sum", dict(want_sum=True), cells * N * 4), ("argmax", dict(want_sum=False, want_argmax=True), cells)):
                 res = {}
-                for variant in (2, 1):
+                for variant in ((3, 2, 1) if label == "sum" else (2, 1)):
                     for code in (codes if label == "sum" else [0]):
                         lib.dh_stitch_binned_set_variant(variant)
                         lib.dh_stitch_binned_set_tile_rows(code)
@@ -115,10 +115,11 @@ def binned():
                         say(kernel="stitch_binned", hw=hw, P=P, d=d, out=label, variant=variant, code=code, ms=ms, GBs=alg / ms / 1e6, frac=alg / ms / 1e6 / peak)
                         keep.clear()
                 lib.dh_stitch_binned_set_tile_rows(0)
-                a, b = res[2], res[1]
-                same = all((x is None and y is None) or torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
-                                                                    y.view(torch.int32) if y.dtype == torch.float32 else y) for x, y in zip(a, b))
-                say(kernel="stitch_binned bit-identical (variant 2 vs 1)", hw=hw, d=d, out=label, same=bool(same))
+                for va in sorted(v for v in res if v != 1):
+                    a, b = res[va], res[1]
+                    same = all((x is None and y is None) or torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
+                                                                        y.view(torch.int32) if y.dtype == torch.float32 else y) for x, y in zip(a, b))
+                    say(kernel="stitch_binned bit-identical (variant %d vs 1)" % va, hw=hw, d=d, out=label, same=bool(same))
                 del res, a, b
                 torch.cuda.empty_cache()
     lib.dh_stitch_binned_set_variant(0)
@@ -435,11 +436,68 @@ def ncu_binned():
     hw = int(sys.argv[3]) if len(sys.argv) > 3 else 40000
     coords = cover_list(hw, hw)
     logits = torch.randn((coords.shape[0], N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
-    for variant in (2, 1, 2, 1):
+    for variant in ([int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else (2, 1, 2, 1)):
         lib.dh_stitch_binned_set_variant(variant)
         ops.stitch_binned(logits, coords, PS, d, hw // d, hw // d, want_sum=True)
         torch.cuda.synchronize()
     lib.dh_stitch_binned_set_variant(0)
+
+
+def binned2():
+    """What bounds the tile kernels at d = 4? (a) the same map with ONE patch (tiles only write zeros: the write pattern alone),
+    (b) tile heights / groups, (c) dh_stitch_dense and a plain memset of the same map for reference."""
+    hw, d = 40000, int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    dh = dw = hw // d
+    coords = cover_list(hw, hw)
+    logits = torch.randn((coords.shape[0], N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
+    one_c, one_l = coords[:1].contiguous(), logits[:1].contiguous()
+    alg = dh * dw * N * 4
+    buf = torch.empty((dh, dw, N), device="cuda")
+    ms = timeit(lambda: buf.zero_(), 10)
+    say(kernel="memset of the map", d=d, ms=ms, GBs=alg / ms / 1e6, frac=alg / ms / 1e6 / peak)
+    del buf
+    for name, c, l in (("coverage list", coords, logits), ("one patch", one_c, one_l)):
+        for variant in (4, 3, 1):
+            for code in (0, 1000000, 3000000) if variant == 1 else (0, 1000000, 3000000):
+                lib.dh_stitch_binned_set_variant(variant)
+                lib.dh_stitch_binned_set_tile_rows(code)
+                keep = {}
+
+                def run():
+                    keep["o"] = None
+                    keep["o"] = ops.stitch_binned(l, c, PS, d, dh, dw, want_sum=True)
+
+                ms = timeit(run, 10)
+                keep.clear()
+                say(kernel="stitch_binned", list=name, d=d, variant=variant, code=code, ms=ms, GBs=alg / ms / 1e6, frac=alg / ms / 1e6 / peak)
+    lib.dh_stitch_binned_set_variant(0)
+    lib.dh_stitch_binned_set_tile_rows(0)
+
+
+def binned3():
+    """Resident CTAs per SM (extra dynamic shared memory: code = 100000 * KB) x tile kernel, every downscale, aligned and unaligned rows."""
+    which = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [40000, 39999]
+    for hw in which:
+        coords = cover_list(hw, hw)
+        logits = torch.randn((coords.shape[0], N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
+        for d in (16, 4, 2, 1):
+            dh = dw = hw // d
+            alg = dh * dw * N * 4 + coords.shape[0] * N * 4
+            for variant in (3, 2, 1):
+                for code in (0, 1000000, 3000000):
+                    lib.dh_stitch_binned_set_variant(variant)
+                    lib.dh_stitch_binned_set_tile_rows(code)
+                    keep = {}
+
+                    def run():
+                        keep["o"] = None
+                        keep["o"] = ops.stitch_binned(logits, coords, PS, d, dh, dw, want_sum=True)
+
+                    ms = timeit(run, 10 if d >= 4 else 4)
+                    keep.clear()
+                    say(kernel="stitch_binned", hw=hw, d=d, variant=variant, code=code, ms=ms, frac=alg / ms / 1e6 / peak)
+    lib.dh_stitch_binned_set_variant(0)
+    lib.dh_stitch_binned_set_tile_rows(0)
 
 
 def ncu_dense():
@@ -479,5 +537,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"ncu_predict_parts": ncu_predict_parts, "gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"binned3": binned3, "binned2": binned2, "ncu_predict_parts": ncu_predict_parts, "gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))

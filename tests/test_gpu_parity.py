@@ -271,6 +271,39 @@ def test_stitch_binned_long_lists_and_tile_heights(ops):
         lib.dh_stitch_binned_set_tile_rows(0)
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_stitch_binned_cell_lane_kernel_every_class_count(ops, n):
+    """bin_cell_sum_kernel (one cell per lane, N class sums in registers; one instantiation per class count 1..8, rows 16-byte aligned
+    or not): bit-identical to the reference loop on a crowded list (every tile sees many patches, some tiles more than the staging
+    holds), on every tile height, and on a row band."""
+    from deephisto_b200 import _lib
+    lib = _lib.require_device()
+    rng = np.random.default_rng(100 + n)
+    ps = 224
+    try:
+        for (H, W, d, P, hot) in ((1500, 1300, 4, 500, 0), (1499, 1203, 4, 400, 0), (1100, 1037, 2, 200, 0), (1024, 1024, 16, 900, 700), (900, 1001, 8, 300, 200)):
+            coords = np.stack([rng.integers(0, H - ps + 1, P), rng.integers(0, W - ps + 1, P)], 1).astype(np.int32)
+            if hot:
+                coords[:hot] = np.stack([rng.integers(300, 340, hot), rng.integers(300, 340, hot)], 1)   # more patches over one tile than fit the staging
+            coords[5:9] = coords[4]
+            logits = (rng.standard_normal((P, n)) * 3).astype(np.float32)
+            want, _, _ = ostitch.stitch(logits, coords, H, W, ps, d)
+            dh, dw = H // d, W // d
+            lg, cd = torch.from_numpy(logits).cuda(), torch.from_numpy(coords).cuda()
+            for th in (0, 16, 64, 128):
+                lib.dh_stitch_binned_set_variant(3)
+                lib.dh_stitch_binned_set_tile_rows(th)
+                s, _, _ = ops.stitch_binned(lg, cd, ps, d, dh, dw)
+                assert np.array_equal(bits(s), want.view(np.int32)), (H, W, d, n, th)
+            lib.dh_stitch_binned_set_tile_rows(0)
+            r0, r1 = dh // 3, dh // 3 + dh // 2
+            sb, _, _ = ops.stitch_binned(lg, cd, ps, d, r1 - r0, dw, row_offset=r0)
+            assert torch.equal(sb, s[r0:r1]), (H, W, d, n)
+    finally:
+        lib.dh_stitch_binned_set_variant(0)
+        lib.dh_stitch_binned_set_tile_rows(0)
+
+
 def test_stitch_binned_equals_dense_stitch_on_the_dense_enumeration(ops):
     """Fed with the dense sampler's own (padded) coordinate list, the binned stitch reproduces dh_stitch_dense bit for bit --
     two independent implementations of the reference order (predict_full_patched.py:47-54 over full_samplers.py:374-404)."""
@@ -661,11 +694,11 @@ def test_cover_sampler_resume_from_saved_state(ops):
     assert torch.equal(a.accum, b.accum)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_stitch_binned_random_shapes_vs_oracle(ops, variant):
     """Randomised shapes (slide size, patch size, downscale, class count, list length, overhanging and duplicated origins, row
     bands): every output of dh_stitch_binned is bit-identical to the reference loop -- with the default choice of tile kernel
-    (variant 0), the row-run kernels only (1) and the segment kernel wherever it applies (2)."""
+    (variant 0), the row-run kernels only (1), the segment kernel wherever it applies (2) and the cell-lane sum kernel (3)."""
     from deephisto_b200 import _lib
 
     _lib.require_device().dh_stitch_binned_set_variant(variant)
