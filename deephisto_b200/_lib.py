@@ -76,6 +76,7 @@ SIGNATURES = {
     "dh_stitch_binned": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _i64, _vp]),
     "dh_stitch_binned_set_tile_rows": (C.c_int, [_i32]),
     "dh_stitch_binned_set_variant": (C.c_int, [_i32]),
+    "dh_stitch_dense_set_variant": (C.c_int, [_i32]),
     "dh_maxpool3x3s2_nhwc": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "dh_maxpool3x3s2_d2s": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _i32, _vp]),
     "dh_colorize_overlay": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _vp, _f64, _vp, _vp, _vp, _vp]),

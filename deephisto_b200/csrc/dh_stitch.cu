@@ -40,6 +40,7 @@ __host__ __device__ __forceinline__ Cover cover_1d(int64_t i, int64_t cnt, int p
 }
 
 constexpr int kStitchThreads = 256;
+static int g_stitch_stage = 1;   // 0: profiling A/B, logits read from HBM per row class (dh_stitch_dense_set_variant)
 #ifndef DH_STITCH_MINB
 #define DH_STITCH_MINB 3   // resident CTAs per SM the dense kernel is compiled for (80 registers, no spills; 4 = 64 registers, 120 B of spills)
 #endif
@@ -53,28 +54,28 @@ constexpr int kStitchThreads = 256;
 constexpr int kStitchV = 2;  // float4 per thread per row
 constexpr int kStitchNC = 8; // classes summed in registers by the pipelined per-cell loop (more classes: one class at a time)
 
-struct RowClass {
-    int64_t lo_raw, hi_raw;  // unclamped main-grid row range covering the current map row
-    int64_t rem_lo, rem_hi;
+struct RowClass {            // 32-bit: (i + 1) * d <= H + d < 2^31 (host check)
+    int lo_raw, hi_raw;      // unclamped main-grid row range covering the current map row
+    int rem_lo, rem_hi;
     __device__ __forceinline__ void init(int64_t i, int ps, int stride, int d) {
-        const int64_t e = (i + 1) * (int64_t)d;
+        const int e = (int)(i + 1) * d;
         hi_raw = (e - 1) / stride;
         rem_hi = (e - 1) - hi_raw * stride;
-        const int64_t u = e - ps + stride - 1;  // lo = max(0, floor(u / stride))
+        const int u = e - ps + stride - 1;  // lo = max(0, floor(u / stride))
         if (u >= 0) { lo_raw = u / stride; rem_lo = u - lo_raw * stride; }
         else        { lo_raw = 0; rem_lo = u; }
     }
     // number of consecutive map rows, starting at the current one, with the same (lo_raw, hi_raw)
-    __device__ __forceinline__ int64_t run_length(int stride, int d) const {
-        const int64_t a = (stride - rem_hi + d - 1) / d;  // rows until hi_raw changes (rem_hi < stride)
-        const int64_t b = (stride - rem_lo + d - 1) / d;  // rows until lo_raw changes (rem_lo may be negative)
+    __device__ __forceinline__ int run_length(int stride, int d) const {
+        const int a = (stride - rem_hi + d - 1) / d;  // rows until hi_raw changes (rem_hi < stride)
+        const int b = (stride - rem_lo + d - 1) / d;  // rows until lo_raw changes (rem_lo may be negative)
         return a < b ? a : b;
     }
-    __device__ __forceinline__ void advance(int64_t rows, int stride, int d) {
+    __device__ __forceinline__ void advance(int rows, int stride, int d) {
         rem_hi += rows * d;
-        if (rem_hi >= stride) { int64_t q = rem_hi / stride; hi_raw += q; rem_hi -= q * stride; }
+        if (rem_hi >= stride) { const int q = rem_hi / stride; hi_raw += q; rem_hi -= q * stride; }
         rem_lo += rows * d;
-        if (rem_lo >= stride) { int64_t q = rem_lo / stride; lo_raw += q; rem_lo -= q * stride; }
+        if (rem_lo >= stride) { const int q = rem_lo / stride; lo_raw += q; rem_lo -= q * stride; }
     }
 };
 
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
                                                                               uint32_t* __restrict__ count_map,
                                                                               uint8_t* __restrict__ argmax_map,
                                                                               int64_t row_begin, int64_t row_end, int tj_max,
-                                                                              int rows_per_block, int amax_vec) {
+                                                                              int rows_per_block, int amax_vec, int stage_off) {
     extern __shared__ __align__(16) float smem[];
     const int n = g.n;
     float* vals = smem;                                                       // [tj_max * n]
@@ -110,11 +111,47 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
     rc.init(i0, g.ps, g.stride, g.d);
     // the column cover of a thread's cells (<= 2: tj <= 2 * kStitchThreads) does not depend on the row class: computed once
     // (cover_1d is two 64-bit divisions; at d = 16 a class is only 7 rows of stores long)
-    Cover cxs[2];
+    int cx_lo[2], cx_hi[2];
+    bool cx_last[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int t = tid + k * kStitchThreads;
-        cxs[k] = cover_1d(j0 + (t < tj ? t : 0), g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+        const Cover c = cover_1d(j0 + (t < tj ? t : 0), g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+        cx_lo[k] = (int)c.lo; cx_hi[k] = (int)c.hi; cx_last[k] = c.last;
+    }
+    // ---- stage the logits this block can touch (stage_off > 0: they fit the shared-memory budget, host check). The rows [i0, i1) are
+    // covered by the main-grid patch rows [gy0, gy1], the tile's cells by the patch columns [gx0, gx1] (cover_1d is monotone), plus the
+    // last-column / last-row / corner patches: a handful of CONTIGUOUS pieces of the logits array, fetched with one round of
+    // asynchronous 4-byte copies. Every row class of the block then sums from shared memory -- without this a class of 7 rows
+    // (d = 16) cost its own chain of L2 round trips (profiles/r02_stitch.md).
+    const bool staged = stage_off > 0 && (WITH_SUM || WITH_ARGMAX);
+    int gy0 = 0, gx0 = 0, nc = 0;                       // patch grid indices fit 32 bits (host check)
+    int o_lc = 0, o_lr = 0, o_cn = 0;                   // float offsets of the last-column / last-row / corner pieces behind the main piece
+    const float* const s_main = smem + stage_off;
+    if (staged) {
+        float* base = smem + stage_off;
+        const Cover ra = cover_1d(i0, g.ny, g.ps, g.stride, g.d, g.lastrow_cell), rb = cover_1d(i1 - 1, g.ny, g.ps, g.stride, g.d, g.lastrow_cell);
+        const Cover ca = cover_1d(j0, g.nx, g.ps, g.stride, g.d, g.lastcol_cell), cb = cover_1d(j0 + tj - 1, g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+        gy0 = (int)ra.lo; gx0 = (int)ca.lo;
+        const int nr = rb.hi >= ra.lo ? (int)(rb.hi - ra.lo + 1) : 0;
+        nc = cb.hi >= ca.lo ? (int)(cb.hi - ca.lo + 1) : 0;
+        const int64_t main_n = g.ny * g.nx;
+        float* d_main = base;
+        float* d_lc = d_main + (int64_t)nr * nc * n;
+        float* d_lr = d_lc + (cb.last ? nr * n : 0);
+        float* d_cn = d_lr + (rb.last ? nc * n : 0);
+        o_lc = (int)(d_lc - d_main); o_lr = (int)(d_lr - d_main); o_cn = (int)(d_cn - d_main);
+        auto fetch = [&](float* dst, const float* src, int len) {
+            for (int k = tid; k < len; k += kStitchThreads) {
+                const uint32_t a = (uint32_t)__cvta_generic_to_shared(dst + k);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(src + k) : "memory");
+            }
+        };
+        for (int r = 0; r < nr; ++r) fetch(d_main + (int64_t)r * nc * n, logits + ((int64_t)(gy0 + r) * g.nx + gx0) * n, nc * n);
+        if (cb.last) fetch(d_lc, logits + (main_n + gy0) * n, nr * n);
+        if (rb.last) fetch(d_lr, logits + (main_n + g.ny + gx0) * n, nc * n);
+        if (cb.last && rb.last) fetch(d_cn, logits + (g.N - 1) * n, (int)(g.pads + 1) * n);
+        asm volatile("cp.async.wait_all;" ::: "memory");   // the barrier that opens the first row class publishes the copies
     }
     float4 vreg[PHASED ? 4 : 1][kStitchV];
     uint32_t creg[2] = {0, 0};
@@ -138,8 +175,13 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
             for (int kc = 0; kc < 2; ++kc) {
                 const int t = tid + kc * kStitchThreads;
                 if (t >= tj) break;
-                const Cover cx = cxs[kc];
+                Cover cx;
+                cx.lo = cx_lo[kc]; cx.hi = cx_hi[kc]; cx.last = cx_last[kc];
                 const int64_t main_n = g.ny * g.nx;
+                auto p_main = [&](int64_t gy, int64_t gx) { return staged ? s_main + (((int)gy - gy0) * nc + ((int)gx - gx0)) * n : logits + (gy * g.nx + gx) * n; };
+                auto p_lastcol = [&](int64_t gy) { return staged ? s_main + o_lc + ((int)gy - gy0) * n : logits + (main_n + gy) * n; };
+                auto p_lastrow = [&](int64_t gx) { return staged ? s_main + o_lr + ((int)gx - gx0) * n : logits + (main_n + g.ny + gx) * n; };
+                auto p_corner = [&](int64_t k) { return staged ? s_main + o_cn + (int)k * n : logits + (g.N - 1 + k) * n; };
                 float best = 0.f;
                 int best_c = 0;
                 if (n <= kStitchNC) {
@@ -150,11 +192,10 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
 #pragma unroll
                     for (int c = 0; c < kStitchNC; ++c) { acc[c] = 0.f; cur[c] = 0.f; }
                     bool have = false;
-                    auto visit = [&](int64_t idx) {
-                        const float* lg = logits + idx * n;
+                    auto visit = [&](const float* lg) {      // lg: the patch's logits, in shared memory (staged) or in HBM
                         float nxt[kStitchNC];
 #pragma unroll
-                        for (int c = 0; c < kStitchNC; ++c) nxt[c] = c < n ? __ldg(lg + c) : 0.f;
+                        for (int c = 0; c < kStitchNC; ++c) nxt[c] = c < n ? lg[c] : 0.f;
                         if (have) {
 #pragma unroll
                             for (int c = 0; c < kStitchNC; ++c) acc[c] = __fadd_rn(acc[c], cur[c]);
@@ -164,13 +205,13 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
                         have = true;
                     };
                     for (int64_t gy = cy.lo; gy <= cy.hi; ++gy)
-                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) visit(gy * g.nx + gx);
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) visit(p_main(gy, gx));
                     if (cx.last)
-                        for (int64_t gy = cy.lo; gy <= cy.hi; ++gy) visit(main_n + gy);
+                        for (int64_t gy = cy.lo; gy <= cy.hi; ++gy) visit(p_lastcol(gy));
                     if (cy.last)
-                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) visit(main_n + g.ny + gx);
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) visit(p_lastrow(gx));
                     if (cx.last && cy.last)
-                        for (int64_t k = 0; k <= g.pads; ++k) visit(g.N - 1 + k);
+                        for (int64_t k = 0; k <= g.pads; ++k) visit(p_corner(k));
                     if (have) {
 #pragma unroll
                         for (int c = 0; c < kStitchNC; ++c) acc[c] = __fadd_rn(acc[c], cur[c]);
@@ -188,13 +229,13 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
                 for (int c = 0; c < n; ++c) {
                     float acc = 0.f;
                     for (int64_t gy = cy.lo; gy <= cy.hi; ++gy)
-                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, __ldg(logits + (gy * g.nx + gx) * n + c));
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, p_main(gy, gx)[c]);
                     if (cx.last)
-                        for (int64_t gy = cy.lo; gy <= cy.hi; ++gy) acc = __fadd_rn(acc, __ldg(logits + (main_n + gy) * n + c));
+                        for (int64_t gy = cy.lo; gy <= cy.hi; ++gy) acc = __fadd_rn(acc, p_lastcol(gy)[c]);
                     if (cy.last)
-                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, __ldg(logits + (main_n + g.ny + gx) * n + c));
+                        for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, p_lastrow(gx)[c]);
                     if (cx.last && cy.last)
-                        for (int64_t k = 0; k <= g.pads; ++k) acc = __fadd_rn(acc, __ldg(logits + (g.N - 1 + k) * n + c));
+                        for (int64_t k = 0; k <= g.pads; ++k) acc = __fadd_rn(acc, p_corner(k)[c]);
                     if (WITH_SUM) vals[t * n + c] = acc;
                     if (WITH_ARGMAX) {
                         if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; best_c = c; }  // np.argmax: first maximum; NaN wins
@@ -313,7 +354,7 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
         }
         cell_row += run * g.dw;
         i += run;
-        rc.advance(run, g.stride, g.d);
+        rc.advance((int)run, g.stride, g.d);
     }
 }
 
@@ -565,6 +606,7 @@ static int make_stitch_grid(int64_t H, int64_t W, int ps, int stride, int d, int
     DH_REQUIRE(ps > 0 && stride > 0 && d > 0, "stitch: ps, stride and downscale must be positive");
     DH_REQUIRE(n > 0 && n <= 64, "stitch: n classes %d outside 1..64", n);
     DH_REQUIRE(H >= ps && W >= ps, "stitch: slide smaller than a patch");
+    DH_REQUIRE(H + d < (1ll << 31) && W + d < (1ll << 31) && ps < (1 << 30) && stride < (1 << 30), "stitch: sizes exceed 32-bit pixel coordinates");
     g->H = H; g->W = W; g->ps = ps; g->stride = stride; g->d = d; g->n = n;
     g->ny = (H - ps) <= 0 ? 0 : (H - ps + stride - 1) / stride;
     g->nx = (W - ps) <= 0 ? 0 : (W - ps + stride - 1) / stride;
@@ -611,7 +653,15 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
         const int amax_vec = (a && g.dw % 4 == 0 && reinterpret_cast<uintptr_t>(argmax_u8) % 4 == 0) ? 1 : 0;
         dim3 grid((unsigned)col_tiles, (unsigned)row_groups);
         size_t smem = (size_t)tj * n * sizeof(float) + (size_t)tj * sizeof(uint32_t) + (size_t)tj;
-#define DH_STA(S, A, C, P) stitch_dense_aligned_kernel<S, A, C, P><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, (int)rpb, amax_vec)
+        // logits a block can touch: patch rows x patch columns of the main grid + last column + last row + corner copies
+        const int64_t nr_max = ((rpb - 1) * d + ps - 1) / stride + 2, nc_max = ((int64_t)(tj - 1) * d + ps - 1) / stride + 2;
+        const int64_t stage_floats = (nr_max * nc_max + nr_max + nc_max + g.pads + 1) * n;
+        int stage_off = 0;
+        if ((s || a) && g_stitch_stage && smem + 16 + (size_t)stage_floats * 4 <= 48 * 1024) {
+            stage_off = (int)((smem + 15) / 16 * 4);     // in floats, 16-byte aligned
+            smem = (size_t)stage_off * 4 + (size_t)stage_floats * 4;
+        }
+#define DH_STA(S, A, C, P) stitch_dense_aligned_kernel<S, A, C, P><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, (int)rpb, amax_vec, stage_off)
         if (s && phased) { if (a) { if (c) DH_STA(true, true, true, true); else DH_STA(true, true, false, true); } else { if (c) DH_STA(true, false, true, true); else DH_STA(true, false, false, true); } }
         else if (s) { if (a) { if (c) DH_STA(true, true, true, false); else DH_STA(true, true, false, false); } else { if (c) DH_STA(true, false, true, false); else DH_STA(true, false, false, false); } }
         else   { if (a) { if (c) DH_STA(false, true, true, false); else DH_STA(false, true, false, false); } else { DH_STA(false, false, true, false); } }
@@ -619,6 +669,12 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
         DH_CHECK_LAUNCH("stitch_dense_aligned_kernel");
         return DH_OK;
     }
+}
+
+extern "C" DH_API int dh_stitch_dense_set_variant(int variant) {
+    if (variant < 0 || variant > 1) { set_error("dh_stitch_dense_set_variant: variant must be 0 (logits staged in shared memory per block) or 1 (read per row class)"); return DH_ERR_INVALID; }
+    g_stitch_stage = variant == 0 ? 1 : 0;
+    return DH_OK;
 }
 
 extern "C" DH_API int dh_stitch_dense(const float* logits, int64_t H, int64_t W, int ps, int stride, int d, int n, int batch_size,

@@ -182,6 +182,9 @@ DH_API int dh_stitch_binned(const float* logits, const int32_t* coords, int64_t 
                      float* sum_map, uint32_t* count_map, uint8_t* argmax_u8, int64_t rows, int64_t dw,
                      int64_t row_offset, void* scratch, int64_t scratch_bytes, void* stream);
 DH_API int dh_stitch_binned_set_tile_rows(int rows);
+/* dh_stitch_dense A/B switch (same bits): 0 = a block stages the logits its rows and cells can touch in shared memory once (default
+ * whenever they fit 48 KB), 1 = every row class reads its covering patches from HBM / L2 (round-1 behaviour). */
+DH_API int dh_stitch_dense_set_variant(int variant);
 /* Tile-kernel formulation (same bits every way, tests/test_gpu_parity.py). 0 = auto: for sum maps of n <= 8 classes the cell-lane
  * kernel (a lane owns one cell and its n class sums; the run's row image goes through shared memory) on 16-byte aligned rows with
  * footprints under 1024 floats and on unaligned rows with footprints under 24 cells, the segment kernel (one lane per (row run,

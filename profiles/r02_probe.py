@@ -515,6 +515,39 @@ def ncu_dense():
     say(kernel="stitch_dense argmax only", d=d, ms=ms)
 
 
+def dense2():
+    """dh_stitch_dense: logits staged per block (variant 0) vs read per row class (variant 1), every downscale and output set,
+    aligned (40000) and unaligned (39999) rows; bit-identical check."""
+    for hw in (40000, 39999):
+        H = W = hw
+        npad = ops.dense_count(H, W, PS, 112, 64)[1]
+        lg = torch.randn((npad, N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
+        for d in (16, 4, 2, 1):
+            alg = (H // d) * (W // d) * N * 4 + npad * N * 4
+            for label, kw in (("sum", dict(want_sum=True)), ("sum+argmax+count", dict(want_sum=True, want_argmax=True, want_count=True)), ("argmax", dict(want_sum=False, want_argmax=True))):
+                if d < 4 and label != "sum":
+                    continue
+                res = {}
+                for variant in (0, 1):
+                    lib.dh_stitch_dense_set_variant(variant)
+                    keep = {}
+
+                    def run():
+                        keep["o"] = None
+                        keep["o"] = ops.stitch_dense(lg, H, W, PS, 112, d, 64, **kw)
+
+                    ms = timeit(run, 10 if d >= 4 else 4)
+                    res[variant] = keep["o"]
+                    keep.clear()
+                    say(kernel="stitch_dense", hw=hw, d=d, out=label, variant=variant, ms=ms, frac=alg / ms / 1e6 / peak)
+                same = all((x is None and y is None) or torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
+                                                                    y.view(torch.int32) if y.dtype == torch.float32 else y) for x, y in zip(res[0], res[1]))
+                say(kernel="stitch_dense bit-identical (variant 0 vs 1)", hw=hw, d=d, out=label, same=bool(same))
+                del res
+                torch.cuda.empty_cache()
+    lib.dh_stitch_dense_set_variant(0)
+
+
 def ncu_predict_parts():
     """One S2D48 gather launch and one stem pooling launch at the predictor's batch size (for ncu)."""
     H = W = 32768
@@ -537,5 +570,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"binned3": binned3, "binned2": binned2, "ncu_predict_parts": ncu_predict_parts, "gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"dense2": dense2, "binned3": binned3, "binned2": binned2, "ncu_predict_parts": ncu_predict_parts, "gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
