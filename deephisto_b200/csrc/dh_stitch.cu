@@ -92,12 +92,19 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
                                                                               uint32_t* __restrict__ count_map,
                                                                               uint8_t* __restrict__ argmax_map,
                                                                               int64_t row_begin, int64_t row_end, int tj_max,
-                                                                              int rows_per_block, int amax_vec, int stage_off) {
+                                                                              int rows_per_block, int amax_vec, int cls_off, int stage_off) {
     extern __shared__ __align__(16) float smem[];
     const int n = g.n;
     float* vals = smem;                                                       // [tj_max * n]
     uint32_t* cnts = reinterpret_cast<uint32_t*>(smem + tj_max * n);          // [tj_max]
     uint8_t* amax = reinterpret_cast<uint8_t*>(cnts + tj_max);                // [tj_max] (tj_max % 16 == 0)
+    // column classes (below): per-class sums / count / arg max, the class covers, the scan's per-warp totals
+    const int cw = n > 2 ? n : 2;
+    float* cvals = smem + cls_off;                                            // [tj_max * max(n, 2)] (the cell covers alias it during set-up)
+    int2* ccov = reinterpret_cast<int2*>(cvals + tj_max * cw);                // [tj_max]
+    uint32_t* ccnt = reinterpret_cast<uint32_t*>(ccov + tj_max);              // [tj_max]
+    uint32_t* wsum = ccnt + tj_max;                                           // [16]
+    uint8_t* camax = reinterpret_cast<uint8_t*>(wsum + 16);                   // [tj_max]
 
     const int64_t j0 = (int64_t)blockIdx.x * tj_max;
     const int tj = (int)((g.dw - j0) < tj_max ? (g.dw - j0) : tj_max);
@@ -111,13 +118,52 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
     rc.init(i0, g.ps, g.stride, g.d);
     // the column cover of a thread's cells (<= 2: tj <= 2 * kStitchThreads) does not depend on the row class: computed once
     // (cover_1d is two 64-bit divisions; at d = 16 a class is only 7 rows of stores long)
-    int cx_lo[2], cx_hi[2];
-    bool cx_last[2];
+    // COLUMN CLASSES: neighbouring cells are covered by the same patch columns (stride / d cells in a row, 7 at d = 16), so their
+    // values are equal in every row. The tile's cells are cut into classes once per block (cover per cell -> class starts -> block scan);
+    // per row class one thread per COLUMN class sums the covering patches, every thread then copies the values of its own cells
+    // (ncu at d = 16 before this: 60 % issue-active, 21 % of the instructions in the per-cell logit loads, profiles/r02_stitch.md).
+    int my_cls[2] = {0, 0};
+    int ncls = 0;
+    {
+        int2* cov = reinterpret_cast<int2*>(cvals);
+        int2 mine[2];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int t = tid + k * kStitchThreads;
-        const Cover c = cover_1d(j0 + (t < tj ? t : 0), g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
-        cx_lo[k] = (int)c.lo; cx_hi[k] = (int)c.hi; cx_last[k] = c.last;
+        for (int k = 0; k < 2; ++k) {
+            const int t = tid + k * kStitchThreads;
+            const Cover c = cover_1d(j0 + (t < tj ? t : 0), g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+            mine[k] = make_int2((int)c.lo, (int)c.hi * 2 + (c.last ? 1 : 0));      // patch grid indices fit 31 bits (host check)
+            if (t < tj) cov[t] = mine[k];
+        }
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        int rank[2];
+        bool start[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int t = tid + k * kStitchThreads;
+            bool st = false;
+            if (t < tj) {
+                st = t == 0;
+                if (t > 0) { const int2 prev = cov[t - 1]; st = prev.x != mine[k].x || prev.y != mine[k].y; }
+            }
+            start[k] = st;
+            const unsigned b = __ballot_sync(0xffffffffu, st);
+            rank[k] = __popc(b & (0xffffffffu >> (31 - lane)));                   // class starts up to and including this cell, within the warp
+            if (lane == 0) wsum[k * 8 + warp] = __popc(b);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            int before = 0;
+            for (int q = 0; q < 16; ++q) {
+                const int v = (int)wsum[q];
+                if (q < k * 8 + warp) before += v;
+                if (k == 0) ncls += v;
+            }
+            my_cls[k] = before + rank[k] - 1;
+            if (start[k]) ccov[my_cls[k]] = mine[k];
+        }
+        // the barrier that opens the first row class publishes ccov and retires the reads of cov (which aliases cvals)
     }
     // ---- stage the logits this block can touch (stage_off > 0: they fit the shared-memory budget, host check). The rows [i0, i1) are
     // covered by the main-grid patch rows [gy0, gy1], the tile's cells by the patch columns [gx0, gx1] (cover_1d is monotone), plus the
@@ -173,10 +219,10 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
             __syncthreads();  // previous class has been read into registers by everybody
 #pragma unroll
             for (int kc = 0; kc < 2; ++kc) {
-                const int t = tid + kc * kStitchThreads;
-                if (t >= tj) break;
+                const int t = tid + kc * kStitchThreads;       // column class
+                if (t >= ncls) break;
                 Cover cx;
-                cx.lo = cx_lo[kc]; cx.hi = cx_hi[kc]; cx.last = cx_last[kc];
+                { const int2 cc = ccov[t]; cx.lo = cc.x; cx.hi = cc.y >> 1; cx.last = (cc.y & 1) != 0; }
                 const int64_t main_n = g.ny * g.nx;
                 auto p_main = [&](int64_t gy, int64_t gx) { return staged ? s_main + (((int)gy - gy0) * nc + ((int)gx - gx0)) * n : logits + (gy * g.nx + gx) * n; };
                 auto p_lastcol = [&](int64_t gy) { return staged ? s_main + o_lc + ((int)gy - gy0) * n : logits + (main_n + gy) * n; };
@@ -219,7 +265,7 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
 #pragma unroll
                     for (int c = 0; c < kStitchNC; ++c) {
                         if (c < n) {
-                            if (WITH_SUM) vals[t * n + c] = acc[c];
+                            if (WITH_SUM) cvals[t * n + c] = acc[c];
                             if (WITH_ARGMAX) {
                                 if (c == 0 || acc[c] > best || (acc[c] != acc[c] && best == best)) { best = acc[c]; best_c = c; }  // np.argmax: first maximum; NaN wins
                             }
@@ -236,7 +282,7 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
                         for (int64_t gx = cx.lo; gx <= cx.hi; ++gx) acc = __fadd_rn(acc, p_lastrow(gx)[c]);
                     if (cx.last && cy.last)
                         for (int64_t k = 0; k <= g.pads; ++k) acc = __fadd_rn(acc, p_corner(k)[c]);
-                    if (WITH_SUM) vals[t * n + c] = acc;
+                    if (WITH_SUM) cvals[t * n + c] = acc;
                     if (WITH_ARGMAX) {
                         if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; best_c = c; }  // np.argmax: first maximum; NaN wins
                     }
@@ -245,9 +291,21 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
                 if (WITH_COUNT) {
                     int64_t ry = cy.hi >= cy.lo ? cy.hi - cy.lo + 1 : 0;
                     int64_t rx = cx.hi >= cx.lo ? cx.hi - cx.lo + 1 : 0;
-                    cnts[t] = (uint32_t)(ry * rx + (cx.last ? ry : 0) + (cy.last ? rx : 0) + ((cx.last && cy.last) ? 1 + g.pads : 0));
+                    ccnt[t] = (uint32_t)(ry * rx + (cx.last ? ry : 0) + (cy.last ? rx : 0) + ((cx.last && cy.last) ? 1 + g.pads : 0));
                 }
-                if (WITH_ARGMAX) amax[t] = (uint8_t)best_c;
+                if (WITH_ARGMAX) camax[t] = (uint8_t)best_c;
+            }
+            __syncthreads();
+            // every thread copies the class values of its own cells
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {
+                const int t = tid + kc * kStitchThreads;
+                if (t >= tj) break;
+                const int k = my_cls[kc];
+                if (WITH_SUM)
+                    for (int c = 0; c < n; ++c) vals[t * n + c] = cvals[k * n + c];
+                if (WITH_COUNT) cnts[t] = ccnt[k];
+                if (WITH_ARGMAX) amax[t] = camax[k];
             }
             __syncthreads();
             if (WITH_SUM) {
@@ -653,6 +711,8 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
         const int amax_vec = (a && g.dw % 4 == 0 && reinterpret_cast<uintptr_t>(argmax_u8) % 4 == 0) ? 1 : 0;
         dim3 grid((unsigned)col_tiles, (unsigned)row_groups);
         size_t smem = (size_t)tj * n * sizeof(float) + (size_t)tj * sizeof(uint32_t) + (size_t)tj;
+        const int cls_off = (int)((smem + 15) / 16 * 4);   // in floats, 16-byte aligned: per-class sums, covers, counts, scan totals, arg max
+        smem = (size_t)cls_off * 4 + (size_t)tj * (n > 2 ? n : 2) * 4 + (size_t)tj * 8 + (size_t)tj * 4 + 64 + (size_t)tj;
         // logits a block can touch: patch rows x patch columns of the main grid + last column + last row + corner copies
         const int64_t nr_max = ((rpb - 1) * d + ps - 1) / stride + 2, nc_max = ((int64_t)(tj - 1) * d + ps - 1) / stride + 2;
         const int64_t stage_floats = (nr_max * nc_max + nr_max + nc_max + g.pads + 1) * n;
@@ -661,7 +721,7 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
             stage_off = (int)((smem + 15) / 16 * 4);     // in floats, 16-byte aligned
             smem = (size_t)stage_off * 4 + (size_t)stage_floats * 4;
         }
-#define DH_STA(S, A, C, P) stitch_dense_aligned_kernel<S, A, C, P><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, (int)rpb, amax_vec, stage_off)
+#define DH_STA(S, A, C, P) stitch_dense_aligned_kernel<S, A, C, P><<<grid, kStitchThreads, smem, st>>>(logits, g, sum_map, count_map, argmax_u8, row_begin, row_end, tj, (int)rpb, amax_vec, cls_off, stage_off)
         if (s && phased) { if (a) { if (c) DH_STA(true, true, true, true); else DH_STA(true, true, false, true); } else { if (c) DH_STA(true, false, true, true); else DH_STA(true, false, false, true); } }
         else if (s) { if (a) { if (c) DH_STA(true, true, true, false); else DH_STA(true, true, false, false); } else { if (c) DH_STA(true, false, true, false); else DH_STA(true, false, false, false); } }
         else   { if (a) { if (c) DH_STA(false, true, true, false); else DH_STA(false, true, false, false); } else { DH_STA(false, false, true, false); } }
