@@ -178,7 +178,9 @@ def make_config(world: int) -> dict:
                             f"the u8 class-map bands; 1 warm-up + {PREDICT_STEPS} timed slides (strong scaling: the slide is the same for every N)",
         "stitch_workload": f"roofline.stitch_*: dh_stitch_dense / dh_stitch_binned sum maps of the {STITCH_HW[0]}x{STITCH_HW[1]} stride-112 case "
                            "(BASELINE configs[2]), n = 5 classes; binned = the coverage sampler's own coordinate list; unaligned = 39999x39999 "
-                           "(map rows not 16-byte aligned); N = 1 only",
+                           "(map rows not 16-byte aligned); N = 1 only; CUDA-event median of 5 timed regions of 8 / 4 / 2 / 1 back-to-back calls at "
+                           "d = 16 / 4 / 2 / 1 (per-call time = region / calls: the ~25 us python launch path is not timed as kernel time); d = 16 "
+                           "(125 MB map ~ L2) writes a ring of 3 maps, larger maps exceed the L2 by themselves",
     }
 
 
@@ -599,18 +601,29 @@ def stitch_rooflines(torch, reps=5) -> dict:
     out = {}
     n = 5
 
-    def timed(fn):
+    def timed(fn, group=1):
+        # `group` back-to-back calls per timed region: the python + ctypes launch path (~25 us per call) would otherwise sit between the
+        # first event and the kernel and be timed as kernel time -- 40 % of a d = 16 launch, 6 % at d = 4
         fn()
         torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            fn()
+            for _ in range(group):
+                fn()
             b.record()
             torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
+            ts.append(a.elapsed_time(b) / group)
         return median(ts)
+
+    def ring_for(d):
+        # d = 16: the 125 MB map is as large as the L2 (126 MB) -- the calls of a group write a ring of 3 maps, so every launch's lines
+        # have been evicted before they are written again; larger maps (>= 2 GB) need no ring
+        return 3 if d >= 8 else 1
+
+    def group_for(d):
+        return {16: 8, 4: 4, 2: 2}.get(d, 1)
 
     def cover_list(H, W):
         st = ops.CoverState(H, W, PS, 16, 2, 1024, seed=0)
@@ -631,10 +644,15 @@ def stitch_rooflines(torch, reps=5) -> dict:
     g = torch.Generator(device="cuda").manual_seed(0)
     dense_lg = torch.randn((npad, n), generator=g, device="cuda")
     for d in (1, 2, 4, 16):
+        ring = [None] * ring_for(d)
+        pos = [0]
+
         def run():
-            keep["o"] = None                                            # free the previous map first (d = 1: 32 GB)
-            keep["o"] = ops.stitch_dense(dense_lg, H, W, PS, 112, d, 64, want_sum=True)
-        ms = timed(run)
+            ring[pos[0]] = None                                         # free the oldest map first (d = 1: 32 GB)
+            ring[pos[0]] = ops.stitch_dense(dense_lg, H, W, PS, 112, d, 64, want_sum=True)
+            pos[0] = (pos[0] + 1) % len(ring)
+        ms = timed(run, group_for(d))
+        del ring
         alg = (H // d) * (W // d) * n * 4 + npad * n * 4
         out[f"stitch_dense_d{d}_frac"] = alg / ms / 1e6 / peak
         out[f"stitch_dense_d{d}_ms"] = ms
@@ -643,10 +661,15 @@ def stitch_rooflines(torch, reps=5) -> dict:
         coords = cover_list(h, w)
         lg = torch.randn((coords.shape[0], n), generator=g, device="cuda")
         for d in ds:
+            ring = [None] * ring_for(d)
+            pos = [0]
+
             def run():
-                keep["o"] = None
-                keep["o"] = ops.stitch_binned(lg, coords, PS, d, h // d, w // d, want_sum=True)
-            ms = timed(run)
+                ring[pos[0]] = None
+                ring[pos[0]] = ops.stitch_binned(lg, coords, PS, d, h // d, w // d, want_sum=True)
+                pos[0] = (pos[0] + 1) % len(ring)
+            ms = timed(run, group_for(d))
+            del ring
             alg = (h // d) * (w // d) * n * 4 + coords.shape[0] * n * 4
             out[f"stitch_binned_{tag}d{d}_frac"] = alg / ms / 1e6 / peak
             out[f"stitch_binned_{tag}d{d}_ms"] = ms

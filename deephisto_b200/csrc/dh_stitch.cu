@@ -28,12 +28,14 @@ struct Cover {
     bool last;       // covered by the last row / column patch
 };
 
-__host__ __device__ __forceinline__ Cover cover_1d(int64_t i, int64_t cnt, int ps, int stride, int d, int64_t last_cell) {
+// patches covering cell i of one axis; 32-bit arithmetic ((i + 1) * d <= H + d < 2^31, host check): a 64-bit division is ~100 instructions
+__device__ __forceinline__ Cover cover_1d32(int i, int cnt, int ps, int stride, int d, int last_cell) {
     Cover c;
-    int64_t e = (i + 1) * (int64_t)d;  // patch covers cell i  <=>  e - ps <= y <= e - 1
-    c.hi = (e - 1) / stride;
-    if (c.hi > cnt - 1) c.hi = cnt - 1;
-    int64_t t = e - ps;
+    const int e = (i + 1) * d;
+    int hi = (e - 1) / stride;
+    if (hi > cnt - 1) hi = cnt - 1;
+    const int t = e - ps;
+    c.hi = hi;
     c.lo = t <= 0 ? 0 : (t + stride - 1) / stride;
     c.last = i >= last_cell;
     return c;
@@ -117,7 +119,39 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
     RowClass rc;
     rc.init(i0, g.ps, g.stride, g.d);
     // the column cover of a thread's cells (<= 2: tj <= 2 * kStitchThreads) does not depend on the row class: computed once
-    // (cover_1d is two 64-bit divisions; at d = 16 a class is only 7 rows of stores long)
+    // ---- stage the logits this block can touch (stage_off > 0: they fit the shared-memory budget, host check). The rows [i0, i1) are
+    // covered by the main-grid patch rows [gy0, gy1], the tile's cells by the patch columns [gx0, gx1] (cover_1d32 is monotone), plus the
+    // last-column / last-row / corner patches: a handful of CONTIGUOUS pieces of the logits array, fetched with one round of
+    // asynchronous 4-byte copies. Every row class of the block then sums from shared memory -- without this a class of 7 rows
+    // (d = 16) cost its own chain of L2 round trips (profiles/r02_stitch.md).
+    const bool staged = stage_off > 0 && (WITH_SUM || WITH_ARGMAX);
+    int gy0 = 0, gx0 = 0, nc = 0;                       // patch grid indices fit 32 bits (host check)
+    int o_lc = 0, o_lr = 0, o_cn = 0;                   // float offsets of the last-column / last-row / corner pieces behind the main piece
+    const float* const s_main = smem + stage_off;
+    if (staged) {
+        float* base = smem + stage_off;
+        const Cover ra = cover_1d32((int)i0, (int)g.ny, g.ps, g.stride, g.d, (int)g.lastrow_cell), rb = cover_1d32((int)i1 - 1, (int)g.ny, g.ps, g.stride, g.d, (int)g.lastrow_cell);
+        const Cover ca = cover_1d32((int)j0, (int)g.nx, g.ps, g.stride, g.d, (int)g.lastcol_cell), cb = cover_1d32((int)j0 + tj - 1, (int)g.nx, g.ps, g.stride, g.d, (int)g.lastcol_cell);
+        gy0 = (int)ra.lo; gx0 = (int)ca.lo;
+        const int nr = rb.hi >= ra.lo ? (int)(rb.hi - ra.lo + 1) : 0;
+        nc = cb.hi >= ca.lo ? (int)(cb.hi - ca.lo + 1) : 0;
+        const int64_t main_n = g.ny * g.nx;
+        float* d_main = base;
+        float* d_lc = d_main + (int64_t)nr * nc * n;
+        float* d_lr = d_lc + (cb.last ? nr * n : 0);
+        float* d_cn = d_lr + (rb.last ? nc * n : 0);
+        o_lc = (int)(d_lc - d_main); o_lr = (int)(d_lr - d_main); o_cn = (int)(d_cn - d_main);
+        auto fetch = [&](float* dst, const float* src, int len) {
+            for (int k = tid; k < len; k += kStitchThreads) {
+                const uint32_t a = (uint32_t)__cvta_generic_to_shared(dst + k);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(src + k) : "memory");
+            }
+        };
+        for (int r = 0; r < nr; ++r) fetch(d_main + (int64_t)r * nc * n, logits + ((int64_t)(gy0 + r) * g.nx + gx0) * n, nc * n);
+        if (cb.last) fetch(d_lc, logits + (main_n + gy0) * n, nr * n);
+        if (rb.last) fetch(d_lr, logits + (main_n + g.ny + gx0) * n, nc * n);
+        if (cb.last && rb.last) fetch(d_cn, logits + (g.N - 1) * n, (int)(g.pads + 1) * n);
+    }
     // COLUMN CLASSES: neighbouring cells are covered by the same patch columns (stride / d cells in a row, 7 at d = 16), so their
     // values are equal in every row. The tile's cells are cut into classes once per block (cover per cell -> class starts -> block scan);
     // per row class one thread per COLUMN class sums the covering patches, every thread then copies the values of its own cells
@@ -130,7 +164,7 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int t = tid + k * kStitchThreads;
-            const Cover c = cover_1d(j0 + (t < tj ? t : 0), g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
+            const Cover c = cover_1d32((int)j0 + (t < tj ? t : 0), (int)g.nx, g.ps, g.stride, g.d, (int)g.lastcol_cell);
             mine[k] = make_int2((int)c.lo, (int)c.hi * 2 + (c.last ? 1 : 0));      // patch grid indices fit 31 bits (host check)
             if (t < tj) cov[t] = mine[k];
         }
@@ -165,40 +199,7 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
         }
         // the barrier that opens the first row class publishes ccov and retires the reads of cov (which aliases cvals)
     }
-    // ---- stage the logits this block can touch (stage_off > 0: they fit the shared-memory budget, host check). The rows [i0, i1) are
-    // covered by the main-grid patch rows [gy0, gy1], the tile's cells by the patch columns [gx0, gx1] (cover_1d is monotone), plus the
-    // last-column / last-row / corner patches: a handful of CONTIGUOUS pieces of the logits array, fetched with one round of
-    // asynchronous 4-byte copies. Every row class of the block then sums from shared memory -- without this a class of 7 rows
-    // (d = 16) cost its own chain of L2 round trips (profiles/r02_stitch.md).
-    const bool staged = stage_off > 0 && (WITH_SUM || WITH_ARGMAX);
-    int gy0 = 0, gx0 = 0, nc = 0;                       // patch grid indices fit 32 bits (host check)
-    int o_lc = 0, o_lr = 0, o_cn = 0;                   // float offsets of the last-column / last-row / corner pieces behind the main piece
-    const float* const s_main = smem + stage_off;
-    if (staged) {
-        float* base = smem + stage_off;
-        const Cover ra = cover_1d(i0, g.ny, g.ps, g.stride, g.d, g.lastrow_cell), rb = cover_1d(i1 - 1, g.ny, g.ps, g.stride, g.d, g.lastrow_cell);
-        const Cover ca = cover_1d(j0, g.nx, g.ps, g.stride, g.d, g.lastcol_cell), cb = cover_1d(j0 + tj - 1, g.nx, g.ps, g.stride, g.d, g.lastcol_cell);
-        gy0 = (int)ra.lo; gx0 = (int)ca.lo;
-        const int nr = rb.hi >= ra.lo ? (int)(rb.hi - ra.lo + 1) : 0;
-        nc = cb.hi >= ca.lo ? (int)(cb.hi - ca.lo + 1) : 0;
-        const int64_t main_n = g.ny * g.nx;
-        float* d_main = base;
-        float* d_lc = d_main + (int64_t)nr * nc * n;
-        float* d_lr = d_lc + (cb.last ? nr * n : 0);
-        float* d_cn = d_lr + (rb.last ? nc * n : 0);
-        o_lc = (int)(d_lc - d_main); o_lr = (int)(d_lr - d_main); o_cn = (int)(d_cn - d_main);
-        auto fetch = [&](float* dst, const float* src, int len) {
-            for (int k = tid; k < len; k += kStitchThreads) {
-                const uint32_t a = (uint32_t)__cvta_generic_to_shared(dst + k);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(a), "l"(src + k) : "memory");
-            }
-        };
-        for (int r = 0; r < nr; ++r) fetch(d_main + (int64_t)r * nc * n, logits + ((int64_t)(gy0 + r) * g.nx + gx0) * n, nc * n);
-        if (cb.last) fetch(d_lc, logits + (main_n + gy0) * n, nr * n);
-        if (rb.last) fetch(d_lr, logits + (main_n + g.ny + gx0) * n, nc * n);
-        if (cb.last && rb.last) fetch(d_cn, logits + (g.N - 1) * n, (int)(g.pads + 1) * n);
-        asm volatile("cp.async.wait_all;" ::: "memory");   // the barrier that opens the first row class publishes the copies
-    }
+    if (staged) asm volatile("cp.async.wait_all;" ::: "memory");   // issued before the class set-up; the same barrier publishes the copies
     float4 vreg[PHASED ? 4 : 1][kStitchV];
     uint32_t creg[2] = {0, 0};
     uint32_t areg[2] = {0, 0};
