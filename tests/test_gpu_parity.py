@@ -518,6 +518,52 @@ def test_gather_kernel_variants_agree_with_oracle(ops, variant, ps):
         ops.set_gather_variant("auto")
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_stitch_dense_random_shapes_vs_oracle(ops, variant):
+    """Randomised dense enumerations (slide, patch, stride, batch padding, class counts 1..64, downscales below and above the stride,
+    row bands): dh_stitch_dense is bit-identical to the reference loop over the reference's own coordinate list -- with the logits
+    staged per block and summed per column class (variant 0; strides too fine for the shared-memory budget fall back inside the same
+    kernel) and with the per-row-class reads (variant 1)."""
+    from deephisto_b200 import _lib
+
+    lib = _lib.require_device()
+    lib.dh_stitch_dense_set_variant(variant)
+    try:
+        rng = np.random.default_rng(77)
+        for trial in range(28):
+            ps = int(rng.choice([32, 48, 64, 100, 224]))
+            stride = int(rng.choice([3, 8, ps // 4, ps // 2, ps, ps + 16]))
+            d = int(rng.choice([1, 2, 3, 4, 7, 16, 32, 64]))
+            d = min(d, ps)
+            n = int(rng.choice([1, 2, 3, 5, 8, 9, 16, 64]))
+            B = int(rng.choice([1, 7, 64]))
+            H, W = int(rng.integers(ps, 700)), int(rng.integers(ps, 700))
+            if trial % 5 == 0:
+                H = ps + stride * int(rng.integers(0, 4))                  # (H - ps) % stride == 0: the last row coincides with nothing, edge of the enumeration
+            while ((H - ps) // stride + 2) * ((W - ps) // stride + 2) > 9000:
+                stride *= 2
+            coords, N = odense.dense_coords(H, W, ps, stride, B)
+            logits = (rng.standard_normal((coords.shape[0], n)) * 2).astype(np.float32)
+            want, wcnt, wam = ostitch.stitch(logits, coords, H, W, ps, d)
+            dh, dw = H // d, W // d
+            if dh == 0 or dw == 0:
+                continue
+            lg = torch.from_numpy(logits).cuda()
+            s, c, am = ops.stitch_dense(lg, H, W, ps, stride, d, B, want_count=True, want_argmax=True)
+            tag = (trial, H, W, ps, stride, d, n, B)
+            assert np.array_equal(bits(s), want.view(np.int32)), tag
+            assert np.array_equal(c.cpu().numpy().astype(np.int64), wcnt), tag
+            assert np.array_equal(am.cpu().numpy().astype(np.int64), wam), tag
+            _, _, am1 = ops.stitch_dense(lg, H, W, ps, stride, d, B, want_sum=False, want_argmax=True)
+            assert torch.equal(am1, am), tag
+            r0 = int(rng.integers(0, dh))
+            r1 = int(rng.integers(r0, dh)) + 1
+            sb, cb, ab = ops.stitch_dense(lg, H, W, ps, stride, d, B, row_begin=r0, row_end=r1, want_count=True, want_argmax=True)
+            assert torch.equal(sb, s[r0:r1]) and torch.equal(cb, c[r0:r1]) and torch.equal(ab, am[r0:r1]), tag
+    finally:
+        lib.dh_stitch_dense_set_variant(0)
+
+
 # ---- BASELINE full sizes through size-independent properties ---------------------------------------------------------------
 def test_stitch_full_size_properties(ops):
     """40k x 40k / stride 112 (BASELINE configs[2], 127 488 padded patches): with all logits = 1 the sum map IS the count map
