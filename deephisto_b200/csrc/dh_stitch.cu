@@ -12,6 +12,7 @@
 // column tile once per such row class into shared memory and streams it out for every row of the
 // class, so the kernel is a pure coalesced store stream (16-byte vectors) -> HBM write roofline.
 #include "dh_common.cuh"
+#include <cstdlib>
 
 namespace dh {
 
@@ -707,6 +708,22 @@ extern "C" DH_API int dh_stitch_dense_ex(const float* logits, int64_t H, int64_t
         const int64_t col_tiles = (g.dw + tj - 1) / tj;
         int64_t rpb = rows * col_tiles / ((int64_t)kNumSMs * 8);
         rpb = rpb < 4 ? 4 : (rpb > 128 ? 128 : rpb);
+        {
+            // Small maps (the d = 16 map of a 40k^2 slide is 125 MB): 1.x - 3.x waves of short blocks lose a large part of the last wave and
+            // pay the block set-up many times. Then: ONE wave of longer blocks, rows per block a multiple of the row-class length so that
+            // no class is cut in two (measured at d = 16: 14 rows = 2.8 waves 0.45 of the HBM peak, 42 rows = one wave 0.52;
+            // large maps keep the short blocks: one wave of 589-row blocks at d = 4 is 0.91 vs 0.99, profiles/r02_stitch.md)
+            const int64_t per_wave = (int64_t)kNumSMs * (phased ? 2 : DH_STITCH_MINB);
+            const int64_t blocks = (rows + rpb - 1) / rpb * col_tiles;
+            if (blocks > per_wave && blocks < 4 * per_wave && col_tiles <= per_wave) {
+                const int64_t groups = per_wave / col_tiles;
+                int64_t r1 = (rows + groups - 1) / groups;
+                const int64_t cls = stride % d == 0 ? stride / d : 1;
+                r1 = (r1 + cls - 1) / cls * cls;
+                rpb = r1;
+            }
+        }
+        if (const char* e = getenv("DH_STITCH_RPB")) { const int v = atoi(e); if (v > 0) rpb = v; }   // profiling override
         const int64_t row_groups = (rows + rpb - 1) / rpb;
         DH_REQUIRE(row_groups <= 65535, "dh_stitch_dense: too many row groups (%lld); stitch in bands", (long long)row_groups);
         const int amax_vec = (a && g.dw % 4 == 0 && reinterpret_cast<uintptr_t>(argmax_u8) % 4 == 0) ? 1 : 0;

@@ -548,6 +548,35 @@ def dense2():
     lib.dh_stitch_dense_set_variant(0)
 
 
+def dense3():
+    """dh_stitch_dense at d = argv[2]: rows per block (DH_STITCH_RPB) sweep, grouped launches into a ring of maps as in bench.py."""
+    import os
+    d = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    H = W = 40000
+    npad = ops.dense_count(H, W, PS, 112, 64)[1]
+    lg = torch.randn((npad, N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
+    alg = (H // d) * (W // d) * N * 4 + npad * N * 4
+    group = 8 if d >= 8 else 4
+    for label, kw in (("sum", dict(want_sum=True)), ("argmax", dict(want_sum=False, want_argmax=True))):
+        for rpb in [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else "0,8,10,14,17,20,25,30,40,60".split(","))]:
+            if rpb:
+                os.environ["DH_STITCH_RPB"] = str(rpb)
+            else:
+                os.environ.pop("DH_STITCH_RPB", None)
+            ring = [None, None, None]
+            pos = [0]
+
+            def run():
+                for _ in range(group):
+                    ring[pos[0]] = None
+                    ring[pos[0]] = ops.stitch_dense(lg, H, W, PS, 112, d, 64, **kw)
+                    pos[0] = (pos[0] + 1) % 3
+
+            ms = timeit(run, 7) / group
+            say(kernel="stitch_dense", d=d, out=label, rpb=rpb, ms=ms, frac=alg / ms / 1e6 / peak)
+    os.environ.pop("DH_STITCH_RPB", None)
+
+
 def ncu_predict_parts():
     """One S2D48 gather launch and one stem pooling launch at the predictor's batch size (for ncu)."""
     H = W = 32768
@@ -570,5 +599,5 @@ def ncu_cover():
 
 
 if __name__ == "__main__":
-    {"dense2": dense2, "binned3": binned3, "binned2": binned2, "ncu_predict_parts": ncu_predict_parts, "gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
+    {"dense3": dense3, "dense2": dense2, "binned3": binned3, "binned2": binned2, "ncu_predict_parts": ncu_predict_parts, "gather5": gather5, "gather4": gather4, "gather3": gather3, "gather2": gather2, "cnn3": cnn3, "ncu_dense": ncu_dense, "ncu_binned": ncu_binned, "ncu_cover": ncu_cover, "cnn2": cnn2, "cover": cover, "binned": binned, "zerocopy": zerocopy, "gather": gather, "cnn": cnn}[sys.argv[1]]()
     print(json.dumps({"peak_gbs": peak, "rows": rows}, indent=1))
