@@ -458,7 +458,7 @@ def binned2():
     del buf
     for name, c, l in (("coverage list", coords, logits), ("one patch", one_c, one_l)):
         for variant in (4, 3, 1):
-            for code in (0, 1000000, 3000000) if variant == 1 else (0, 1000000, 3000000):
+            for code in ([int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else (0, 1000000, 3000000)):
                 lib.dh_stitch_binned_set_variant(variant)
                 lib.dh_stitch_binned_set_tile_rows(code)
                 keep = {}
