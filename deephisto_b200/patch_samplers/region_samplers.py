@@ -26,7 +26,7 @@ import torch
 from torch.utils.data import IterableDataset
 
 from .. import geometry, ops
-from ..slide import Patch, PinnedSlide, layer_to_device, open_slide, sharded_upload, tile_spans, upload_rects
+from ..slide import Patch, PinnedSlide, alloc_bytes_on, layer_to_device, open_slide, sharded_upload, tile_spans, upload_rects
 
 
 _STREAMS: dict = {}
@@ -342,7 +342,7 @@ class AnnoRegionRndSampler:
                 n += self._sources[j].nbytes
         return n
 
-    def _slide(self, j: int):
+    def _slide(self, j: int, alloc_stream=None):
         if not self._resident:
             if not self._whole_pinned(j):
                 raise ValueError("resident=False needs every slide as a PinnedSlide in page-locked host memory")
@@ -362,7 +362,7 @@ class AnnoRegionRndSampler:
                     psim._assert_layer(self.layer)
                     group = None if self._shard_upload is True else self._shard_upload
                     rec = {}
-                    self._slides[j], n = sharded_upload(psim, self._device, group, stats=rec)
+                    self._slides[j], n = sharded_upload(psim, self._device, group, stats=rec, alloc_stream=alloc_stream)
                     rec["bytes"] = n
                     self.ingest_events.append(rec)
                     self.uploaded_bytes += n
@@ -387,7 +387,7 @@ class AnnoRegionRndSampler:
                     psim._assert_layer(self.layer)
                     rec = {}
                     t0 = time.perf_counter()
-                    storage = torch.empty(psim.rows * psim.pitch, dtype=torch.uint8, device=self._device)
+                    storage = alloc_bytes_on(alloc_stream, psim.rows * psim.pitch, self._device)
                     rec["alloc_ms"] = 1e3 * (time.perf_counter() - t0)
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     a.record()
@@ -406,12 +406,13 @@ class AnnoRegionRndSampler:
         reads host memory in place, so the two do not share the PCIe link); later gathers wait on the upload's event (_slide)."""
         if self._copy_stream is None:
             self._copy_stream = _shared_stream(self._device, "copy")
+        home = torch.cuda.current_stream(self._device)        # the slide buffer comes from the caller's allocator pool (alloc_bytes_on)
         with torch.cuda.stream(self._copy_stream):
             if after_event is not None:
                 self._copy_stream.wait_event(after_event)
             for j in range(len(self._slides)):
                 if self._slides[j] is None and self._whole_pinned(j):
-                    sl = self._slide(j)
+                    sl = self._slide(j, alloc_stream=home)
                     sl.storage.record_stream(self._copy_stream)
                     ev = torch.cuda.Event()
                     ev.record(self._copy_stream)

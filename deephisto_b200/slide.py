@@ -279,13 +279,32 @@ def upload_rects(host: "PinnedSlide", rects, device="cuda", tile: int = 512):
     return DeviceSlide(storage, host.height, host.width, host.pitch), nbytes
 
 
-def sharded_upload(host: "PinnedSlide", device="cuda", group=None, stats: dict = None):
+def alloc_bytes_on(alloc_stream, nbytes: int, device):
+    """A uint8 device buffer for work on the CURRENT stream, allocated from `alloc_stream`'s pool of torch's caching allocator (pools
+    are per stream: a background copy stream never finds the block the application freed on its own stream and pays a cudaMalloc
+    -- 2.5 ms for 3.2 GB, once measured at 126 ms next to another rank's allocation, profiles/r02_e2e.md). The current stream waits
+    for everything enqueued on `alloc_stream` so far (the block's previous owner), and the allocator is told about the new user."""
+    import torch
+
+    cur = torch.cuda.current_stream(device)
+    if alloc_stream is None or alloc_stream == cur:
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    with torch.cuda.stream(alloc_stream):
+        storage = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        ev = torch.cuda.Event()
+        ev.record(alloc_stream)
+    cur.wait_event(ev)
+    storage.record_stream(cur)
+    return storage
+
+
+def sharded_upload(host: "PinnedSlide", device="cuda", group=None, stats: dict = None, alloc_stream=None):
     """Collective slide ingestion for data-parallel sampling: every rank of `group` holds the same layer in host memory and needs
     it resident. Each rank copies only its 1/world share of the rows over ITS PCIe link and one all-gather over NVLink replicates
     the shares (in place: a rank's share sits at its offset of the full buffer) -- instead of `world` full uploads competing for
     the host's memory and PCIe bandwidth. Returns (DeviceSlide, bytes this rank copied from the host). Works with NCCL (CUDA) and
     gloo (CPU tensors; used by the world_size-2 CPU tests). `stats` (optional dict) receives "alloc_ms" (host time of the device
-    allocation) and, on CUDA, the event pairs "upload" and "allgather" for the two phases."""
+    allocation) and, on CUDA, the event pairs "upload" and "allgather" for the two phases. `alloc_stream`: see alloc_bytes_on."""
     import time
 
     import torch
@@ -297,7 +316,10 @@ def sharded_upload(host: "PinnedSlide", device="cuda", group=None, stats: dict =
     per = -(-host.rows // world)                                   # rows per rank; the last shares are padded
     pitch = host.pitch
     t0 = time.perf_counter()
-    storage = torch.empty(per * world * pitch, dtype=torch.uint8, device=device)
+    if torch.device(device).type == "cuda":
+        storage = alloc_bytes_on(alloc_stream, per * world * pitch, device)
+    else:
+        storage = torch.empty(per * world * pitch, dtype=torch.uint8, device=device)
     timed = stats is not None and storage.is_cuda
     if stats is not None:
         stats["alloc_ms"] = 1e3 * (time.perf_counter() - t0)
