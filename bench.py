@@ -175,7 +175,8 @@ def make_config(world: int) -> dict:
         "predict_workload": f"examples.predict_full_patched (BASELINE configs[3]) in the same line as e2e.predict_*: patch_cls_simple ResNet18 "
                             f"(random init, seed 0; bf16 channels_last, FusedResNetForward) on a synthetic {PREDICT_HW[0]}x{PREDICT_HW[1]} slide, 224x224 patches at stride 112, dense "
                             f"sampler batch 64, stitch downscale 16, argmax map; row bands x{world} with patch-size halo + NCCL all-gather of "
-                            f"the u8 class-map bands; 1 warm-up + {PREDICT_STEPS} timed slides (strong scaling: the slide is the same for every N)",
+                            f"the u8 class-map bands; 1 warm-up + {PREDICT_STEPS} timed slides (strong scaling: the slide is the same for every N); "
+                            f"predict_e2e_*: 1 warm-up + 1 timed slide streamed from pinned host memory",
         "stitch_workload": f"roofline.stitch_*: dh_stitch_dense / dh_stitch_binned sum maps of the {STITCH_HW[0]}x{STITCH_HW[1]} stride-112 case "
                            "(BASELINE configs[2]), n = 5 classes; binned = the coverage sampler's own coordinate list; unaligned = 39999x39999 "
                            "(map rows not 16-byte aligned); N = 1 only; CUDA-event median of 5 timed regions of 8 / 4 / 2 / 1 back-to-back calls at "
@@ -839,8 +840,9 @@ def predict_measure(args, dev, world, rank, e2e_steps=None) -> dict:
         return ipp2.process_device(rank=rank, world=world)["argmax"] if world > 1 else ipp2.dense_band_local(0, 1)["argmax_band"]
 
     Ke = K if e2e_steps is None else e2e_steps
-    if e2e_steps is None:
-        h_map.copy_(step2())                                           # warm-up of the streamed path (allocator)
+    h_map.copy_(step2())                                               # warm-up slide of the streamed path: a long-lived process re-uses its
+                                                                       # chunk buffers (the allocator pool was emptied above: the first streamed
+                                                                       # slide would pay cudaMalloc for every chunk, measured +0.1-0.2 s)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

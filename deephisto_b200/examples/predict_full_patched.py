@@ -118,6 +118,28 @@ class DeviceBatchPredictor:
             return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NHWC", scale255=True).permute(0, 3, 1, 2)
         return ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout="NCHW", scale255=True)
 
+    def batch_buffer(self, B: int, ps: int):
+        """The fused bf16 predictor's own stem-input buffer with room for B patches (None for every other predictor): callers that
+        fill a CNN batch from several sources (row chunks of a streamed slide) gather into slices of it with gather_into() and run
+        buffer_logits() when it is full."""
+        f = self.fused
+        if f is None or self.dtype != torch.bfloat16 or ps % 2 or (f.stem == "s2d4" and ps % 4):
+            return None
+        shape = f.s2d_shape(max(B, 1), ps)
+        if self._s2d is None or self._s2d.shape[0] < B or tuple(self._s2d.shape[1:]) != (shape[2], shape[3], shape[1]):
+            self._s2d = torch.zeros((shape[0], shape[2], shape[3], shape[1]), dtype=self.dtype, device=self.device)
+        return self._s2d
+
+    def gather_into(self, slide, coords: torch.Tensor, ps: int, offset: int) -> None:
+        """Patches at `coords` into rows [offset, offset + len(coords)) of batch_buffer()."""
+        ops.gather_normalize(slide, coords, ps, dtype=self.dtype, layout=self.fused.gather_layout, scale255=True,
+                             out=self._s2d[offset : offset + coords.shape[0]])
+
+    @torch.no_grad()
+    def buffer_logits(self) -> torch.Tensor:
+        """Logits of every row of batch_buffer() (rows that were not filled since the last call hold older patches)."""
+        return self._forward_buffer()
+
     @torch.no_grad()
     def logits(self, features: torch.Tensor) -> torch.Tensor:
         if self.fused is not None:
@@ -489,6 +511,24 @@ class ImagePredictorPatched:
                 ready.record(copy)
             return band, ready
 
+        # CNN batches are filled ACROSS chunks (fused bf16 predictor: its stem-input buffer is the batch): the patches a chunk leaves
+        # over wait in the buffer for the next chunk's first patches, so a slide pays for one short batch, not one per chunk
+        # (1 GiB chunks of a 100k-wide slide hold ~26.7 batches of 1024: 1.9 % of the CNN time went into padding, profiles/r02_predict.md)
+        pred: DeviceBatchPredictor = self.batch_predictor
+        step = self._cnn_batch or max(sampler.batch_size, 512)
+        ps = sampler.patch_size
+        buf = pred.batch_buffer(step, ps) if isinstance(pred, DeviceBatchPredictor) else None
+        fill = 0
+        dst = torch.empty(step, dtype=torch.int64, device=self._device) if buf is not None else None
+
+        def flush():
+            nonlocal fill
+            if fill:
+                with self._mark("cnn"):
+                    out = pred.buffer_logits()
+                    logits.index_copy_(0, dst[:fill], out[:fill].to(logits.dtype))
+                fill = 0
+
         copy.wait_stream(cur)
         nxt = upload(jobs[0]) if jobs else None
         for i, job in enumerate(jobs):
@@ -496,8 +536,32 @@ class ImagePredictorPatched:
             nxt = upload(jobs[i + 1]) if i + 1 < len(jobs) else None
             cur.wait_event(ready)
             band.storage.record_stream(cur)
-            self._logits_for_ranges(sampler, band, logits, job[2], y_off=job[0])
+            if buf is None:
+                self._logits_for_ranges(sampler, band, logits, job[2], y_off=job[0])
+            else:
+                with self._mark("coords+gather"):
+                    ranges = [(int(f), int(c)) for f, c in job[2] if c > 0]
+                    parts = [ops.dense_coords(sampler.h, sampler.w, ps, sampler.stride, sampler.batch_size, first=f, count=c, device=self._device)
+                             for f, c in ranges]
+                    if not parts:
+                        continue
+                    coords = parts[0] if len(parts) == 1 else torch.cat(parts)
+                    if job[0]:
+                        coords[:, 0] -= job[0]
+                    where = torch.cat([torch.arange(f, f + c, device=self._device) for f, c in ranges])
+                a, m = 0, int(coords.shape[0])
+                while a < m:
+                    c = min(step - fill, m - a)
+                    with self._mark("coords+gather"):
+                        pred.gather_into(band, coords[a : a + c], ps, fill)
+                        dst[fill : fill + c] = where[a : a + c]
+                    fill += c
+                    a += c
+                    if fill == step:
+                        flush()
             del band
+        if buf is not None:
+            flush()
 
     def _dense_device(self, want_sum: bool, want_count: bool) -> dict:
         s: FullImageDenseSampler = self.patch_sampler
