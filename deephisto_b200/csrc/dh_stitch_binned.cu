@@ -536,8 +536,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     uint16_t* s_segc = reinterpret_cast<uint16_t*>(s_rbits + 4);                    // [S] first cell of each segment (tile relative)
     uint8_t* s_run = reinterpret_cast<uint8_t*>(s_segc + kSegCap);                  // [NR + 1] first row of each run, then TH
     float* s_val = reinterpret_cast<float*>(base + kSegPatches * 40 + (2 * kSegWords + 4) * 4 + kSegCap * 2 + 144);  // [2][kSegVals] double-buffered
-    uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_val);                            // staging only: unsorted / sorted ids alias the values
-    uint32_t* s_ids = s_raw + kSegPatches;
+    uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_val);                            // staging only: the tile's patch indices (unordered) alias the values
 
     const int R0 = (int)(ty * g.TH);
     const int TH = (int)((int64_t)R0 + g.TH < g.rows ? g.TH : g.rows - R0);         // rows of this tile
@@ -548,39 +547,62 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
     const int C0 = U0 / scale;
     const int ncells = (U1 + scale - 1) / scale - C0;
 
-    // ---- stage: ids in ascending order, footprints clipped to the tile (rows / cells relative to the tile), logits
-    for (int j = lane; j < L; j += 32) s_raw[j] = list[beg + j];
+    // ---- stage: footprints clipped to the tile (rows / cells relative to the tile) and logits, filed in ascending patch index. A lane
+    // owns the list entries lane and lane + 32: it loads their origins and logits straight after the index (dependent chain off/len ->
+    // list -> coords, logits: one level shorter than sorting first) and ranks the indices while those loads are in flight.
+    const bool want_lg = !CELL || argmax_map != nullptr;
+    uint32_t myid[2];
+    int py[2] = {0, 0}, px[2] = {0, 0};
+    float lgv[2][8];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        const int j = lane + 32 * sl;
+        myid[sl] = j < L ? list[beg + j] : 0xffffffffu;
+        if (j < L) s_raw[j] = myid[sl];
+    }
     if (lane < kSegWords) s_bits[lane] = lane == 0 ? 1u : 0u;                       // cell 0 starts segment 0
     if (lane < 4) s_rbits[lane] = lane == 0 ? 1u : 0u;                              // row 0 starts run 0
-    __syncwarp();
-    for (int j = lane; j < L; j += 32) {  // rank sort: patch indices are distinct within a tile
-        const uint32_t v = s_raw[j];
-        int rank = 0;
-        for (int i = 0; i < L; ++i) rank += s_raw[i] < v;
-        s_ids[rank] = v;
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        if (lane + 32 * sl < L) {
+            py[sl] = __ldg(coords + 2 * (int64_t)myid[sl]);
+            px[sl] = __ldg(coords + 2 * (int64_t)myid[sl] + 1);
+            if (want_lg) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) lgv[sl][q] = q < n ? __ldg(logits + (int64_t)myid[sl] * n + q) : 0.f;   // zero padded: the adds below are unconditional in q
+            }
+        }
     }
     __syncwarp();
-    for (int j = lane; j < L; j += 32) {
-        const uint32_t id = s_ids[j];
-        BinRec f;
-        bin_footprint(g, __ldg(coords + 2 * (int64_t)id), __ldg(coords + 2 * (int64_t)id + 1), f);
-        const int a = f.r0 - R0, b = f.r1 - R0;
-        s_r0[j] = (uint16_t)(a < 0 ? 0 : a);
-        s_r1[j] = (uint16_t)(b > TH ? TH : (b < 0 ? 0 : b));
-        if (a > 0 && a < TH) atomicOr(s_rbits + (a >> 5), 1u << (a & 31));             // the covering set changes at every footprint edge
-        if (b > 0 && b < TH) atomicOr(s_rbits + (b >> 5), 1u << (b & 31));
-        int c0 = f.u0 / scale - C0, c1 = f.u1 / scale - C0;                          // footprints are whole cells: u0, u1 are multiples of scale
-        c0 = c0 < 0 ? 0 : (c0 > ncells ? ncells : c0);
-        c1 = c1 < 0 ? 0 : (c1 > ncells ? ncells : c1);
-        s_c0[j] = (uint16_t)c0;
-        s_c1[j] = (uint16_t)c1;
-        if (c0 > 0 && c0 < ncells) atomicOr(s_bits + (c0 >> 5), 1u << (c0 & 31));
-        if (c1 > 0 && c1 < ncells) atomicOr(s_bits + (c1 >> 5), 1u << (c1 & 31));
+    int rank[2] = {0, 0};
+    for (int i = 0; i < L; ++i) {                                                   // patch indices are distinct within a tile
+        const uint32_t o = s_raw[i];
+        rank[0] += o < myid[0];
+        rank[1] += o < myid[1];
     }
-    if (!CELL || argmax_map != nullptr) {
-        for (int e = lane; e < L * 8; e += 32) {                                   // rows of 8 floats, zero padded: the adds below are unconditional in q
-            const int j = e >> 3, q = e & 7;
-            s_lg[e] = q < n ? __ldg(logits + (int64_t)s_ids[j] * n + q) : 0.f;
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        if (lane + 32 * sl < L) {
+            const int j = rank[sl];
+            BinRec f;
+            f.r0 = f.r1 = f.u0 = f.u1 = 0;
+            bin_footprint(g, py[sl], px[sl], f);
+            const int a = f.r0 - R0, b = f.r1 - R0;
+            s_r0[j] = (uint16_t)(a < 0 ? 0 : a);
+            s_r1[j] = (uint16_t)(b > TH ? TH : (b < 0 ? 0 : b));
+            if (a > 0 && a < TH) atomicOr(s_rbits + (a >> 5), 1u << (a & 31));         // the covering set changes at every footprint edge
+            if (b > 0 && b < TH) atomicOr(s_rbits + (b >> 5), 1u << (b & 31));
+            int c0 = f.u0 / scale - C0, c1 = f.u1 / scale - C0;                      // footprints are whole cells: u0, u1 are multiples of scale
+            c0 = c0 < 0 ? 0 : (c0 > ncells ? ncells : c0);
+            c1 = c1 < 0 ? 0 : (c1 > ncells ? ncells : c1);
+            s_c0[j] = (uint16_t)c0;
+            s_c1[j] = (uint16_t)c1;
+            if (c0 > 0 && c0 < ncells) atomicOr(s_bits + (c0 >> 5), 1u << (c0 & 31));
+            if (c1 > 0 && c1 < ncells) atomicOr(s_bits + (c1 >> 5), 1u << (c1 & 31));
+            if (want_lg) {
+                *reinterpret_cast<float4*>(s_lg + j * 8) = make_float4(lgv[sl][0], lgv[sl][1], lgv[sl][2], lgv[sl][3]);
+                *reinterpret_cast<float4*>(s_lg + j * 8 + 4) = make_float4(lgv[sl][4], lgv[sl][5], lgv[sl][6], lgv[sl][7]);
+            }
         }
     }
     __syncwarp();
@@ -628,7 +650,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
             if (lane == 3) s_run[NR] = (uint8_t)TH;
         }
     }
-    __syncwarp();   // also: every lane is done with s_ids before the value buffers (which alias it) are written
+    __syncwarp();   // also: every lane is done with s_raw before the value buffers (which alias it) are written
     // ---- the lane's output units and their slots in the value buffer
     const int ub = U0 + lane * VEC;
     int slot[K];
@@ -1114,7 +1136,14 @@ static int run_binned(const float* logits, const int32_t* coords, int64_t P, con
         kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map);
     } else if constexpr (SEGK >= 0) {
         auto kern = bin_seg_kernel<SEGK, G>;
-        smem = kBinWarps * seg_warp_smem_bytes() + (g_bin_tile_rows / 100000) * 1024;
+        smem = kBinWarps * seg_warp_smem_bytes();
+        // wide footprints on unaligned rows: three resident CTAs per SM instead of four (fewer concurrent writers, see bin_cell_sum_kernel's
+        // launch): 39 999^2, d = 2 / 1: 0.80 / 0.86 -> 0.83 / 0.90 of the HBM peak (two CTAs: 0.65 / 0.71); d = 4 wants all four (0.65 vs 0.58)
+        if (SEGK == 1 && g_bin_tile_rows / 100000 == 0 && (int64_t)(g.ps / g.d) * g.n >= 512) {
+            const int cap = 227 * 1024 / 4 - 1024;              // anything above this excludes a fourth CTA
+            if (smem <= cap) smem = cap + 1024;
+        }
+        smem += (g_bin_tile_rows / 100000) * 1024;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_seg_kernel)");
         kern<<<(unsigned)ctas, kBinWarps * 32, smem, st>>>(logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map, count_map, argmax_u8);
