@@ -8,7 +8,8 @@
 // formulation for a coordinate LIST: the map is cut into warp-sized tiles, every patch is binned into the tiles its footprint
 // touches, and one warp per tile adds the covering patches in ascending patch index -- the reference's order -- with plain
 // fp32 adds starting from 0. The result is bit-identical to the numpy loop, has no atomics on the map, and writes every
-// output exactly once (HBM write roofline: dh*dw*n*4 bytes for the sum map, dh*dw for the class map).
+// output exactly once (HBM write roofline: dh*dw*n*4 bytes for the sum map, dh*dw for the class map) with streaming stores
+// (st.global.cs: a map line is never touched again; default-policy stores cost 8-12 % at d <= 4, profiles/r02_stitch.md).
 //
 //   count  : one thread per patch, atomicAdd on the per-tile counters                  (P * tiles-per-patch integer atomics)
 //   alloc  : one thread per tile: list segment = warp-aggregated atomicAdd on one cursor (segment placement is arbitrary)
@@ -34,7 +35,7 @@ constexpr int kBinCap = 128;    // patches per tile staged in shared memory; lon
 constexpr int kBinMaxN = 8;     // classes the cell kernel keeps in registers
 
 static int g_bin_tile_rows = 0;  // 0 = heuristic; profiling override (dh_stitch_binned_set_tile_rows)
-static int g_bin_variant = 0;    // 0 = auto (sum maps of n <= 8 classes: cell-lane kernel for footprints under 1024 floats on aligned rows and
+static int g_bin_variant = 0;    // 0 = auto (sum maps of n <= 8 classes: cell-lane kernel for footprints under 2048 floats on aligned rows and
                                  // under 24 cells on unaligned rows, segment kernel for wider footprints on unaligned rows; row-run kernels otherwise),
                                  // 1 = row-run kernels only, 2 = segment kernel whenever n <= 8, 3 = cell-lane kernel whenever n <= 8
                                  // (dh_stitch_binned_set_variant)
@@ -369,11 +370,11 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
                 int64_t o = (int64_t)r * g.units_per_row + ub;
                 for (int rr = r; rr < next; ++rr, o += g.units_per_row) {
                     if constexpr (VEC == 4) {
-                        if (argmax_map) *reinterpret_cast<uchar4*>(argmax_map + o) = make_uchar4(am[0], am[1], am[2], am[3]);
-                        if (count_map) *reinterpret_cast<uint4*>(count_map + o) = make_uint4(hits[0], hits[1], hits[2], hits[3]);
+                        if (argmax_map) __stcs(reinterpret_cast<uchar4*>(argmax_map + o), make_uchar4(am[0], am[1], am[2], am[3]));
+                        if (count_map) __stcs(reinterpret_cast<uint4*>(count_map + o), make_uint4(hits[0], hits[1], hits[2], hits[3]));
                     } else {
-                        if (argmax_map) argmax_map[o] = am[0];
-                        if (count_map) count_map[o] = hits[0];
+                        if (argmax_map) __stcs(argmax_map + o, am[0]);
+                        if (count_map) __stcs(count_map + o, hits[0]);
                     }
                 }
             }
@@ -383,10 +384,10 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_kernel(const float* _
 #pragma unroll
                 for (int gi = 0; gi < G; ++gi) {
                     if (ub + gi * GS >= g.units_per_row) continue;
-                    if constexpr (VEC == 4) *reinterpret_cast<float4*>(o + gi * GS) = make_float4(acc[gi][0], acc[gi][1], acc[gi][2], acc[gi][3]);
+                    if constexpr (VEC == 4) __stcs(reinterpret_cast<float4*>(o + gi * GS), make_float4(acc[gi][0], acc[gi][1], acc[gi][2], acc[gi][3]));
                     else {
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k) o[gi * GS + k] = acc[gi][k];
+                        for (int k = 0; k < VEC; ++k) __stcs(o + gi * GS + k, acc[gi][k]);
                     }
                 }
             }
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_tile_phased_kernel(const f
             }
             const int u = ub + s;
             if (u + 4 <= RF) {
-                *reinterpret_cast<float4*>(rowp + u) = make_float4(w0, w1, w2, w3);
+                __stcs(reinterpret_cast<float4*>(rowp + u), make_float4(w0, w1, w2, w3));
             } else if (u < RF) {                                 // the last vector of the row, clipped
                 rowp[u] = w0;
                 if (u + 1 < RF) rowp[u + 1] = w1;
@@ -678,11 +679,11 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
                 int64_t o = (int64_t)(R0 + r) * RF + ub;
                 for (int rr = r; rr < next; ++rr, o += RF) {
                     if constexpr (KIND == 4) {
-                        if (argmax_map) *reinterpret_cast<uchar4*>(argmax_map + o) = make_uchar4(pk[0] & 255u, pk[1] & 255u, pk[2] & 255u, pk[3] & 255u);
-                        if (count_map) *reinterpret_cast<uint4*>(count_map + o) = make_uint4(pk[0] >> 8, pk[1] >> 8, pk[2] >> 8, pk[3] >> 8);
+                        if (argmax_map) __stcs(reinterpret_cast<uchar4*>(argmax_map + o), make_uchar4(pk[0] & 255u, pk[1] & 255u, pk[2] & 255u, pk[3] & 255u));
+                        if (count_map) __stcs(reinterpret_cast<uint4*>(count_map + o), make_uint4(pk[0] >> 8, pk[1] >> 8, pk[2] >> 8, pk[3] >> 8));
                     } else {
-                        if (argmax_map) argmax_map[o] = (uint8_t)(pk[0] & 255u);
-                        if (count_map) count_map[o] = pk[0] >> 8;
+                        if (argmax_map) __stcs(argmax_map + o, (uint8_t)(pk[0] & 255u));
+                        if (count_map) __stcs(count_map + o, pk[0] >> 8);
                     }
                 }
             }
@@ -695,12 +696,12 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
                 for (int rr = r; rr < next; ++rr, o += RF) {
 #pragma unroll
                     for (int gi = 0; gi < G; ++gi)
-                        if (ub + gi * 128 < U1) *reinterpret_cast<float4*>(o + gi * 128) = make_float4(v[4 * gi], v[4 * gi + 1], v[4 * gi + 2], v[4 * gi + 3]);
+                        if (ub + gi * 128 < U1) __stcs(reinterpret_cast<float4*>(o + gi * 128), make_float4(v[4 * gi], v[4 * gi + 1], v[4 * gi + 2], v[4 * gi + 3]));
                 }
             } else if constexpr (KIND == 2) {
                 float* o = sum_map + (int64_t)(R0 + r) * RF + ub;
                 if (ub < U1)
-                    for (int rr = r; rr < next; ++rr, o += RF) *o = v[0];
+                    for (int rr = r; rr < next; ++rr, o += RF) __stcs(o, v[0]);
             } else {
                 // rows not 16-byte aligned: in row rr the lane's vector starts sft = (4 - rr * RF) mod 4 units later (then 16-byte aligned);
                 // the first sft units of a row are scalar stores of tile 0, the last vector of a row is clipped
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_seg_kernel(const float* __
                     }
                     const int u = ub + sft;
                     if (u + 4 <= RF) {
-                        *reinterpret_cast<float4*>(rowp + u) = make_float4(w0, w1, w2, w3);
+                        __stcs(reinterpret_cast<float4*>(rowp + u), make_float4(w0, w1, w2, w3));
                     } else if (u < RF) {
                         rowp[u] = w0;
                         if (u + 1 < RF) rowp[u + 1] = w1;
@@ -990,7 +991,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const floa
             for (int rr = r; rr < next; ++rr, o += RF) {
 #pragma unroll
                 for (int i = 0; i < V; ++i)
-                    if (vfull[i]) *reinterpret_cast<float4*>(o + 128 * i) = v[i];
+                    if (vfull[i]) __stcs(reinterpret_cast<float4*>(o + 128 * i), v[i]);
             }
         } else {
             // in row rr the tile's vectors start sft = (4 - rr * RF) mod 4 units later (then 16-byte aligned); the first sft units of a
@@ -1007,7 +1008,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const floa
                         const float* s = s_out + img0 + sft + 4 * f;
                         const float w0 = s[0], w1 = s[1], w2 = s[2], w3 = s[3];   // inside the 32-cell image (tile width rule above)
                         if (u + 4 <= RF) {
-                            *reinterpret_cast<float4*>(rowp + u) = make_float4(w0, w1, w2, w3);
+                            __stcs(reinterpret_cast<float4*>(rowp + u), make_float4(w0, w1, w2, w3));
                         } else {
                             rowp[u] = w0;
                             if (u + 1 < RF) rowp[u + 1] = w1;
@@ -1223,13 +1224,13 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         const BinGeom g = make_geom(false, v4 || phased ? 4 : 1, ps, d, n, rows, dw, row_offset, phased);
         // measured (profiles/r02_stitch.md): the segment kernel wins where the row-run kernel has to sum 7 floats per lane (rows not
         // 16-byte aligned: 0.61 vs 0.51 of the HBM peak at d = 4), the row-run kernel wins on aligned rows (0.71 vs 0.68)
-        // the cell-lane kernel (one cell per lane, issue-active 42 % where the row-run kernel has 72 %), measured on the 40 000^2 coverage
-        // list: aligned rows d = 16 / 4 / 2: 0.145 / 0.75 / 0.89 of the HBM copy peak vs 0.106 / 0.72 / 0.87 with the row-run kernel;
-        // d = 1 (footprints of 1120 floats) stays with the row-run kernel (0.96 vs 0.95). Unaligned rows: small footprints only
-        // (d = 16: 0.126 vs 0.089); the segment kernel keeps the wide ones (d = 4: 0.61 vs 0.56).
+        // the cell-lane kernel (one cell per lane, issue-active 46 % where the row-run kernel has 72 %), measured on the 40 000^2 coverage
+        // list with streaming stores in every kernel: aligned rows d = 16 / 4 / 2 / 1: 0.14 / 0.83 / 0.97 / 1.03 of the HBM copy peak vs
+        // 0.10 / 0.77 / 0.93 / 1.02 with the row-run kernel. Unaligned rows: small footprints only (d = 16: 0.13 vs 0.09); the segment
+        // kernel keeps the wide ones (d = 4: 0.68 vs 0.58).
         const bool cell_phased = shiftable;
         const bool cell_lane = staged && tile_rows_for(ps, d) <= 128 &&
-                               ((g_bin_variant >= 3 && (v4 || cell_phased)) || (g_bin_variant == 0 && ((v4 && (int64_t)(ps / d) * n < 1024) || (shiftable && ps / d < 24))));
+                               ((g_bin_variant >= 3 && (v4 || cell_phased)) || (g_bin_variant == 0 && ((v4 && (int64_t)(ps / d) * n < 2048) || (shiftable && ps / d < 24))));
         if (cell_lane) {
             const BinGeom gc = make_geom(false, 4, ps, d, n, rows, dw, row_offset, !v4, true);
 #define DH_CELL_CASE(NN)                                                                                                                            \
@@ -1268,7 +1269,9 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         const bool c4 = ps / d >= 96 && dw % 4 == 0 && reinterpret_cast<uintptr_t>(cell_argmax) % 4 == 0 &&
                         reinterpret_cast<uintptr_t>(count_map) % 16 == 0;
         const BinGeom g = make_geom(true, c4 ? 4 : 1, ps, d, cell_argmax ? n : 1, rows, dw, row_offset);   // count only: no logits staged
-        if (g_bin_variant == 2 && g.TH <= 128)
+        // class map / count outputs: the segment kernel for footprints of 24 cells and more (40 000^2 class map, d = 4 / 2 / 1: 0.33 / 0.43 /
+        // 0.67 ms vs 0.43 / 0.69 / 1.13 ms with the row-run kernel; d = 16: 0.25 vs 0.20 ms, the row-run kernel stays)
+        if ((g_bin_variant == 2 || (g_bin_variant == 0 && ps / d >= 24)) && g.TH <= 128)
             rc = c4 ? run_binned<4, 1, true, true, false, 4>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st)
                     : run_binned<1, 1, true, true, false, 3>(logits, coords, P, g, nullptr, count_map, cell_argmax, scratch, scratch_bytes, st);
         else

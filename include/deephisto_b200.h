@@ -187,7 +187,7 @@ DH_API int dh_stitch_binned_set_tile_rows(int rows);
 DH_API int dh_stitch_dense_set_variant(int variant);
 /* Tile-kernel formulation (same bits every way, tests/test_gpu_parity.py). 0 = auto: for sum maps of n <= 8 classes the cell-lane
  * kernel (a lane owns one cell and its n class sums; the run's row image goes through shared memory) on 16-byte aligned rows with
- * footprints under 1024 floats and on unaligned rows with footprints under 24 cells, the segment kernel (one lane per (row run,
+ * footprints under 2048 floats and on unaligned rows with footprints under 24 cells, the segment kernel (one lane per (row run,
  * column segment) region) on unaligned rows with wider footprints, the row-run kernels (every lane re-sums its own floats at each
  * footprint boundary) otherwise; 1 = row-run kernels only; 2 = segment kernel wherever it applies; 3 = cell-lane kernel wherever it
  * applies; 4 = profiling only: the cell-lane kernel without its stores. Measurements: profiles/r02_stitch.md. */
