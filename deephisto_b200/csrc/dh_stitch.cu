@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
             uint32_t* c0 = count_map + cell_row + tid;
             const bool h0 = tid < tj, h1 = tid + kStitchThreads < tj;
             for (int64_t r = 0; r < run; ++r) {
-                if (h0) c0[0] = creg[0];
-                if (h1) c0[kStitchThreads] = creg[1];
+                if (h0) __stcs(c0, creg[0]);
+                if (h1) __stcs(c0 + kStitchThreads, creg[1]);
                 c0 += g.dw;
             }
         }
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
             if (amax_vec) {
                 uint8_t* a0 = argmax_map + cell_row;
                 for (int64_t r = 0; r < run; ++r) {
-                    if (tid < (tj >> 2)) reinterpret_cast<uint32_t*>(a0)[tid] = areg[0];
+                    if (tid < (tj >> 2)) __stcs(reinterpret_cast<uint32_t*>(a0) + tid, areg[0]);
                     else if (tid == (tj >> 2) && (tj & 3)) {
                         for (int b = 0; b < (tj & 3); ++b) a0[(tj & ~3) + b] = (uint8_t)(areg[0] >> (8 * b));
                     }
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(kStitchThreads, PHASED ? 2 : DH_STITCH_MINB) s
                 uint8_t* a0 = argmax_map + cell_row + tid;
                 const bool h0 = tid < tj, h1 = tid + kStitchThreads < tj;
                 for (int64_t r = 0; r < run; ++r) {
-                    if (h0) a0[0] = (uint8_t)areg[0];
-                    if (h1) a0[kStitchThreads] = (uint8_t)areg[1];
+                    if (h0) __stcs(a0, (uint8_t)areg[0]);
+                    if (h1) __stcs(a0 + kStitchThreads, (uint8_t)areg[1]);
                     a0 += g.dw;
                 }
             }
