@@ -1292,8 +1292,9 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
             if (rc != DH_OK) return rc;
         }
         const bool seg = !cell_lane && staged && (g_bin_variant == 2 || (g_bin_variant == 0 && phased)) && g.TH <= 128 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
-        if (cell_lane) {}
-        else if (seg && phased) rc = run_binned<4, 1, false, true, true, 1>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
+        if (cell_lane) {
+            // done above
+        } else if (seg && phased) rc = run_binned<4, 1, false, true, true, 1>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4 && g.G == 2) rc = run_binned<4, 2, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg && v4) rc = run_binned<4, 1, false, true, false, 0>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         else if (seg) rc = run_binned<1, 1, false, true, false, 2>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
