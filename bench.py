@@ -386,8 +386,10 @@ def ours(args):
     launches = [0]
 
     # the coordinate launch of chunk i+1 runs on a second stream next to the gather of chunk i, as in AnnoRegionRndSampler.torch_generator
-    # (DH_BENCH_OVERLAP=0 puts both on one stream: A/B in profiles/r01_gather.md)
-    overlap = os.environ.get("DH_BENCH_OVERLAP", "1") == "1"
+    # (DH_BENCH_OVERLAP=0 puts both on one stream: A/B in profiles/r01_gather.md). A region of a single chunk (the driver's --steps 20)
+    # has nothing to overlap with: one stream then -- the cross-stream event hops only delay the gather (measured 7.20-7.22 M vs
+    # 6.97-7.14 M patches/s on one box, profiles/r02_e2e.md)
+    overlap = os.environ.get("DH_BENCH_OVERLAP", "1" if K > CHUNK else "0") == "1"
     side = torch.cuda.Stream(dev) if overlap else None
     drawn = [torch.cuda.Event(), torch.cuda.Event()]
     gathered = [torch.cuda.Event(), torch.cuda.Event()]
