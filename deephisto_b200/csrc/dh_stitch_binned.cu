@@ -36,6 +36,7 @@ constexpr int kBinCap = 128;    // patches per tile staged in shared memory; lon
 constexpr int kBinMaxN = 8;     // classes the cell kernel keeps in registers
 
 static int g_bin_tile_rows = 0;  // 0 = heuristic; profiling override (dh_stitch_binned_set_tile_rows)
+static int g_bin_sparse = -1;    // cell-lane kernel, per-lane patch sets: -1 = footprints under 24 cells, 0 / 1 = profiling override (DH_BIN_SPARSE)
 static int g_bin_variant = 0;    // 0 = auto (sum maps of n <= 8 classes: cell-lane kernel for footprints under 2048 floats on aligned rows and
                                  // under 24 cells on unaligned rows, segment kernel for wider footprints on unaligned rows; row-run kernels otherwise),
                                  // 1 = row-run kernels only, 2 = segment kernel whenever n <= 8, 3 = cell-lane kernel whenever n <= 8
@@ -49,6 +50,7 @@ struct BinGeom {
     int scale;              // units per cell: n (sum mode) or 1 (cell mode)
     int TH, TW;             // tile = TH rows x TW units (TW = 32 * VEC * G)
     int G;                  // groups of 32 * VEC units per tile: a lane owns VEC consecutive units in each group
+    int sparse;             // bin_cell_sum_kernel: footprints much narrower than the 32-cell tile -> per-lane patch sets (see the kernel)
     int phased;             // sum map rows not 16-byte aligned (dw * n % 4 != 0): in row r a tile covers units [t*TW + s_r, (t+1)*TW + s_r),
                             // s_r = (4 - r * dw * n) mod 4, so that every 4-unit vector is aligned; lists are binned 3 units wider
 };
@@ -956,6 +958,25 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const floa
     __syncwarp();   // also: every lane is done with s_raw before the row image (which aliases it) is written
 
     const uint32_t lanebit = 1u << lane;
+    // SPARSE (footprints much narrower than the tile, e.g. 14 of 32 cells at d = 16): a lane is covered by a third of the patches that
+    // cover its row. Each lane gets the set of patches that cover its COLUMN as bit words (a 32 x 32 bit transpose of the lane masks by
+    // ballots, once per tile); per run it walks `row set & column set` -- its own covering patches only, in ascending index -- instead
+    // of every patch of the row under a predicate. The trip count is the largest per-lane count of the warp (divergent loop).
+    const bool sparse = g.sparse != 0;
+    uint32_t colw[kCellCap / 32];
+#pragma unroll
+    for (int w = 0; w < kCellCap / 32; ++w) {
+        colw[w] = 0u;
+        if (sparse && w * 32 < L) {                          // warp-uniform
+            const int j = w * 32 + lane;
+            const uint32_t mk = j < L ? s_mask[j] : 0u;
+#pragma unroll
+            for (int l = 0; l < 32; ++l) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (mk >> l) & 1u);
+                if (lane == l) colw[w] = b;
+            }
+        }
+    }
     const int img0 = U0 - C0 * N;                            // the tile's first unit inside the row image (0 when aligned)
     bool vfull[V];                                           // aligned rows: the lane's vectors that exist (RF % 4 == 0: whole or not at all)
 #pragma unroll
@@ -968,6 +989,23 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const floa
         float acc[N];
 #pragma unroll
         for (int q = 0; q < N; ++q) acc[q] = 0.f;
+        if (sparse) {
+#pragma unroll
+            for (int w = 0; w < kCellCap / 32; ++w) {
+                if (w * 32 >= L) break;                      // warp-uniform
+                const int j = w * 32 + lane;
+                const int2 rw = j < L ? s_rows[j] : make_int2(0x7fff, 0);
+                unsigned mine = __ballot_sync(0xffffffffu, rw.x <= r && r < rw.y) & colw[w];
+                while (mine) {  // this lane's covering patches in ascending list index = the reference's order
+                    const int jj = w * 32 + __ffs(mine) - 1;
+                    mine &= mine - 1;
+                    const float4 lo = *reinterpret_cast<const float4*>(s_lg + jj * LS);
+                    float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (N > 4) hi = *reinterpret_cast<const float4*>(s_lg + jj * LS + 4);
+                    cell_add<N>(acc, true, lo, hi);
+                }
+            }
+        } else
         for (int j0 = 0; j0 < L; j0 += 32) {
             const int j = j0 + lane;
             const int2 rw = j < L ? s_rows[j] : make_int2(0x7fff, 0);
@@ -1058,6 +1096,7 @@ static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows,
                          bool cell_lane = false) {
     BinGeom g;
     g.phased = phased ? 1 : 0;
+    g.sparse = 0;
     g.rows = rows; g.row_offset = row_offset; g.dw = dw;
     g.ps = ps; g.d = d; g.n = n;
     g.scale = cell ? 1 : n;
@@ -1065,7 +1104,11 @@ static BinGeom make_geom(bool cell, int vec, int ps, int d, int n, int64_t rows,
     g.TH = tile_rows_for(ps, d);
     g.G = phased ? 1 : groups_for(cell, vec, ps, d, n);
     g.TW = 32 * vec * g.G;
-    if (cell_lane) { g.G = 1; g.TW = cell_tile_units(n, phased); }   // bin_cell_sum_kernel: 32 cells per tile
+    if (cell_lane) {                                                  // bin_cell_sum_kernel: 32 cells per tile
+        g.G = 1;
+        g.TW = cell_tile_units(n, phased);
+        g.sparse = (g_bin_sparse < 0 ? ps / d < 24 : g_bin_sparse) ? 1 : 0;
+    }
     g.nty = (rows + g.TH - 1) / g.TH;
     g.ntx = (g.units_per_row + g.TW - 1) / g.TW;
     return g;
@@ -1259,6 +1302,7 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         return e == cudaSuccess ? DH_OK : cuda_fail(e, "cudaMemsetAsync");
     }
     DH_REQUIRE(logits && coords && scratch, "dh_stitch_binned: null input");
+    if (const char* e = getenv("DH_BIN_SPARSE")) g_bin_sparse = e[0] == '0' ? 0 : (e[0] == '1' ? 1 : -1);   // profiling override
     int rc = DH_OK;
     const bool staged = n <= kBinMaxN;
     if (sum_map) {
