@@ -849,7 +849,10 @@ template <int N, bool PHASED, bool NOSTORE = false>
 __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const float* __restrict__ logits, const int32_t* __restrict__ coords, BinGeom g,
                                                                       const uint32_t* __restrict__ off, const uint32_t* __restrict__ len,
                                                                       const uint32_t* __restrict__ list, uint32_t* __restrict__ sorted,
-                                                                      float* __restrict__ sum_map) {
+                                                                      float* __restrict__ sum_map, uint32_t* __restrict__ count_map,
+                                                                      uint8_t* __restrict__ argmax_map) {
+    // outputs: the sum map (may be null), and / or the per-cell count and class (first arg max of the lane's own sums): a lane owns a
+    // cell, so these cost one compare chain and one byte / word store per row -- no second binning + tile pass for them
     constexpr int LS = 8;                                   // logits row stride in shared memory
     constexpr int TWU = PHASED ? (31 * N - 2) / 4 * 4 : 32 * N;
     constexpr int NV = TWU / 4;                             // 16-byte vectors per tile row
@@ -865,7 +868,12 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const floa
     const uint32_t beg = off[t];
     const int L = (int)len[t];
     if (L > kCellCap) {
-        bin_tile_slow<1, false>(logits, coords, g, beg, L, list, sorted, sum_map, nullptr, nullptr, ty, tx);
+        if (sum_map) bin_tile_slow<1, false>(logits, coords, g, beg, L, list, sorted, sum_map, nullptr, nullptr, ty, tx);
+        if (count_map || argmax_map) {     // the same tile in cell units: 32 cells per tile row (!PHASED: host check)
+            BinGeom gc = g;
+            gc.scale = 1; gc.units_per_row = g.dw; gc.TW = 32;
+            bin_tile_slow<1, true>(logits, coords, gc, beg, L, list, sorted, nullptr, count_map, argmax_map, ty, tx);
+        }
         return;
     }
     unsigned char* base = bin_smem + (size_t)w * cell_warp_smem_bytes();
@@ -989,6 +997,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const floa
         float acc[N];
 #pragma unroll
         for (int q = 0; q < N; ++q) acc[q] = 0.f;
+        uint32_t hits = 0;
         if (sparse) {
 #pragma unroll
             for (int w = 0; w < kCellCap / 32; ++w) {
@@ -1003,6 +1012,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const floa
                     float4 hi = make_float4(0.f, 0.f, 0.f, 0.f);
                     if constexpr (N > 4) hi = *reinterpret_cast<const float4*>(s_lg + jj * LS + 4);
                     cell_add<N>(acc, true, lo, hi);
+                    ++hits;
                 }
             }
         } else
@@ -1029,8 +1039,25 @@ __global__ void __launch_bounds__(kBinWarps * 32) bin_cell_sum_kernel(const floa
                 }
                 cell_add<N>(acc, cova, loa, hia);
                 cell_add<N>(acc, covb, lob, hib);
+                hits += (cova ? 1u : 0u) + (covb ? 1u : 0u);
             }
         }
+        if (count_map != nullptr || argmax_map != nullptr) {  // per-cell outputs straight from the lane's registers
+            int best_c = 0;
+            float best = acc[0];
+#pragma unroll
+            for (int c = 1; c < N; ++c)                       // np.argmax: first maximum; NaN counts as the maximum (first NaN wins)
+                if (acc[c] > best || (acc[c] != acc[c] && best == best)) { best = acc[c]; best_c = c; }
+            const int cell = C0 + lane;
+            if (cell < (int)g.dw) {
+                int64_t o = (int64_t)(R0 + r) * g.dw + cell;
+                for (int rr = r; rr < next; ++rr, o += g.dw) {
+                    if (argmax_map) __stcs(argmax_map + o, (uint8_t)best_c);
+                    if (count_map) __stcs(count_map + o, hits);
+                }
+            }
+        }
+        if (sum_map == nullptr) continue;                     // warp-uniform
         __syncwarp();                                        // the previous run's image has been read by every lane
 #pragma unroll
         for (int q = 0; q < N; ++q) s_out[lane * N + q] = acc[q];
@@ -1197,7 +1224,7 @@ static int run_binned(const float* logits, const int32_t* coords, int64_t P, con
             smem = kBinWarps * cell_warp_smem_bytes() + (g_bin_tile_rows / 100000) * 1024;
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_cell_sum_kernel)");
-            e = launch_dependent(pdl, kern, (unsigned)ctas, kBinWarps * 32, (size_t)smem, st, logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map);
+            e = launch_dependent(pdl, kern, (unsigned)ctas, kBinWarps * 32, (size_t)smem, st, logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map, (uint32_t*)nullptr, (uint8_t*)nullptr);
         if (e != cudaSuccess) return cuda_fail(e, "tile kernel");
             DH_CHECK_LAUNCH("bin_cell_sum_kernel<nostore>");
             return DH_OK;
@@ -1210,7 +1237,7 @@ static int run_binned(const float* logits, const int32_t* coords, int64_t P, con
         // concurrent writers (an all-zero map written by this kernel: 0.80-0.88 of the copy peak at 4 CTAs per SM, 0.87-0.90 at 3,
         // 0.90-0.94 at 2), the staging and summing want more warps to overlap with. Measured optimum (profiles/r02_stitch.md):
         // 3 CTAs for footprints under 512 floats on aligned rows, 2 for wider ones, 4 on unaligned rows.
-        if (!PHASED && g_bin_tile_rows / 100000 == 0) {
+        if (!PHASED && sum_map != nullptr && g_bin_tile_rows / 100000 == 0) {
             const int per_sm = (int64_t)(g.ps / g.d) * g.n < 512 ? 3 : 2;
             const int want = (227 * 1024 / per_sm - 1024) / 1024 * 1024;            // the largest request that still fits per_sm CTAs
             const int cap = 227 * 1024 / (per_sm + 1) - 1024;                        // anything above this excludes per_sm + 1 CTAs
@@ -1219,7 +1246,8 @@ static int run_binned(const float* logits, const int32_t* coords, int64_t P, con
         smem += (g_bin_tile_rows / 100000) * 1024;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bin_cell_sum_kernel)");
-        e = launch_dependent(pdl, kern, (unsigned)ctas, kBinWarps * 32, (size_t)smem, st, logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map);
+        e = launch_dependent(pdl, kern, (unsigned)ctas, kBinWarps * 32, (size_t)smem, st, logits, coords, g, s.off, s.len, s.list, s.sorted, sum_map,
+                             PHASED ? nullptr : count_map, PHASED ? nullptr : argmax_u8);
         if (e != cudaSuccess) return cuda_fail(e, "tile kernel");
     } else if constexpr (SEGK >= 0) {
         auto kern = bin_seg_kernel<SEGK, G>;
@@ -1305,6 +1333,19 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
     if (const char* e = getenv("DH_BIN_SPARSE")) g_bin_sparse = e[0] == '0' ? 0 : (e[0] == '1' ? 1 : -1);   // profiling override
     int rc = DH_OK;
     const bool staged = n <= kBinMaxN;
+    uint8_t* cell_argmax = argmax_u8 && staged ? argmax_u8 : nullptr;
+    bool cells_done = false;     // count / class map already written by the cell-lane launch
+#define DH_CELL_CASE(NN, PH, SUM, CNT, AMX)                                                                                                   \
+    case NN:                                                                                                                                  \
+        rc = PH ? run_binned<4, 1, false, true, true, -1, NN>(logits, coords, P, gc, SUM, nullptr, nullptr, scratch, scratch_bytes, st)        \
+                : run_binned<4, 1, false, true, false, -1, NN>(logits, coords, P, gc, SUM, CNT, AMX, scratch, scratch_bytes, st);              \
+        break;
+#define DH_CELL_SWITCH(PH, SUM, CNT, AMX)                                                                                                     \
+    switch (n) {                                                                                                                              \
+        DH_CELL_CASE(1, PH, SUM, CNT, AMX) DH_CELL_CASE(2, PH, SUM, CNT, AMX) DH_CELL_CASE(3, PH, SUM, CNT, AMX) DH_CELL_CASE(4, PH, SUM, CNT, AMX) \
+        DH_CELL_CASE(5, PH, SUM, CNT, AMX) DH_CELL_CASE(6, PH, SUM, CNT, AMX) DH_CELL_CASE(7, PH, SUM, CNT, AMX) DH_CELL_CASE(8, PH, SUM, CNT, AMX) \
+        default: rc = DH_ERR_INVALID; break;                                                                                                  \
+    }
     if (sum_map) {
         const bool v4 = sum_vec4(sum_map, dw, n);
         // rows not 16-byte aligned (dw * n % 4 != 0) but an aligned base: 16-byte stores at a per-row shift (bin_tile_phased_kernel)
@@ -1323,17 +1364,13 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
                                ((g_bin_variant >= 3 && (v4 || cell_phased)) || (g_bin_variant == 0 && ((v4 && (int64_t)(ps / d) * n < 2048) || (shiftable && ps / d < 24))));
         if (cell_lane) {
             const BinGeom gc = make_geom(false, 4, ps, d, n, rows, dw, row_offset, !v4, true);
-#define DH_CELL_CASE(NN)                                                                                                                            \
-    case NN:                                                                                                                                        \
-        rc = !v4 ? run_binned<4, 1, false, true, true, -1, NN>(logits, coords, P, gc, sum_map, nullptr, nullptr, scratch, scratch_bytes, st)        \
-                    : run_binned<4, 1, false, true, false, -1, NN>(logits, coords, P, gc, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);   \
-        break;
-            switch (n) {
-                DH_CELL_CASE(1) DH_CELL_CASE(2) DH_CELL_CASE(3) DH_CELL_CASE(4) DH_CELL_CASE(5) DH_CELL_CASE(6) DH_CELL_CASE(7) DH_CELL_CASE(8)
-                default: rc = DH_ERR_INVALID; break;
-            }
-#undef DH_CELL_CASE
+            // aligned rows: the count and the class map come out of the same launch (a lane owns a cell) instead of a second binning + tile pass
+            const bool fuse = v4 && (count_map || cell_argmax);
+            uint32_t* fc = fuse ? count_map : nullptr;
+            uint8_t* fa = fuse ? cell_argmax : nullptr;
+            DH_CELL_SWITCH(!v4, sum_map, fc, fa)
             if (rc != DH_OK) return rc;
+            cells_done = fuse;
         }
         const bool seg = !cell_lane && staged && (g_bin_variant == 2 || (g_bin_variant == 0 && phased)) && g.TH <= 128 && (int64_t)g.TW / n + 4 <= kSegCap - 2 && g.TW + 3 + 3 * n <= kSegVals;
         if (cell_lane) {
@@ -1352,8 +1389,18 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
                          : run_binned<1, 1, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         if (rc != DH_OK) return rc;
     }
-    uint8_t* cell_argmax = argmax_u8 && staged ? argmax_u8 : nullptr;
-    if (count_map || cell_argmax) {
+    if (!sum_map && cell_argmax && (g_bin_variant == 0 || g_bin_variant == 3) && tile_rows_for(ps, d) <= 128 && (int64_t)(ps / d) * n < 512) {
+        // class map (and count) without a sum map, footprints under 512 floats: the cell-lane kernel with its sums left in registers
+        // (40 000^2 list, class map only: d = 16 / 4 see profiles/r02_stitch.md); wider footprints keep the segment kernel below
+        const BinGeom gc = make_geom(false, 4, ps, d, n, rows, dw, row_offset, false, true);
+        float* const no_sum = nullptr;
+        DH_CELL_SWITCH(false, no_sum, count_map, cell_argmax)
+        if (rc != DH_OK) return rc;
+        cells_done = true;
+    }
+#undef DH_CELL_SWITCH
+#undef DH_CELL_CASE
+    if (!cells_done && (count_map || cell_argmax)) {
         // 4 cells per lane (uchar4 / uint4 stores) when the rows keep the vectors aligned
         // -- for footprints at least ~100 cells wide; narrower ones make a 128-cell tile mostly foreign patches (measured: d = 1 / 2 are
         // 1.9x / 1.3x faster with 4 cells per lane, d = 4 / 16 1.3x / 1.7x slower; profiles/r01_stitch.md)
