@@ -43,6 +43,30 @@ def test_host_only_entry_points():
     assert lib.dh_cover_scratch_words(2500, 2500) > 2500 * 2500 // 32
 
 
+def test_profiling_switches_validate_their_argument():
+    """The A/B switches between kernel formulations are host-only setters: every documented value is accepted, anything else comes
+    back as a negative status with a message naming the valid values; the scratch size is the same for every variant (the tile
+    geometries of all of them are covered by dh_stitch_binned_scratch_bytes)."""
+    lib = _lib.load()
+    try:
+        for name, valid in (("dh_stitch_binned_set_variant", range(0, 5)), ("dh_stitch_dense_set_variant", range(0, 2)), ("dh_cover_set_variant", range(0, 2))):
+            fn = getattr(lib, name)
+            for v in valid:
+                assert fn(v) == 0, (name, v)
+            for bad in (-1, max(valid) + 1, 99):
+                assert fn(bad) < 0, (name, bad)
+                assert "variant" in _lib.last_error()
+        sizes = set()
+        for v in range(0, 4):
+            assert lib.dh_stitch_binned_set_variant(v) == 0
+            sizes.add(lib.dh_stitch_binned_scratch_bytes(124928, 224, 4, 5, 10000, 10000))
+        assert len(sizes) == 1 and sizes.pop() > 124928 * 4
+    finally:
+        lib.dh_stitch_binned_set_variant(0)
+        lib.dh_stitch_dense_set_variant(0)
+        lib.dh_cover_set_variant(0)
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
 
