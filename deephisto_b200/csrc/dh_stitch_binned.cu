@@ -1365,7 +1365,9 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
         if (cell_lane) {
             const BinGeom gc = make_geom(false, 4, ps, d, n, rows, dw, row_offset, !v4, true);
             // aligned rows: the count and the class map come out of the same launch (a lane owns a cell) instead of a second binning + tile pass
-            const bool fuse = v4 && (count_map || cell_argmax);
+            // (footprints under 1024 floats: at d = 1 the per-lane byte / word stores of a 0.4 + 1.6 GB map pair cost as much as the
+            // segment kernel's separate pass with 4 cells per lane: 6.06 ms fused vs ~5.5 ms, profiles/r02_stitch.md)
+            const bool fuse = v4 && (count_map || cell_argmax) && (int64_t)(ps / d) * n < 1024;
             uint32_t* fc = fuse ? count_map : nullptr;
             uint8_t* fa = fuse ? cell_argmax : nullptr;
             DH_CELL_SWITCH(!v4, sum_map, fc, fa)
@@ -1389,7 +1391,9 @@ extern "C" DH_API int dh_stitch_binned(const float* logits, const int32_t* coord
                          : run_binned<1, 1, false, false>(logits, coords, P, g, sum_map, nullptr, nullptr, scratch, scratch_bytes, st);
         if (rc != DH_OK) return rc;
     }
-    if (!sum_map && cell_argmax && (g_bin_variant == 0 || g_bin_variant == 3) && tile_rows_for(ps, d) <= 128 && (int64_t)(ps / d) * n < 512) {
+    int64_t cellout_max = 512;                                      // floats; DH_BIN_CELLOUT_MAX: profiling override
+    if (const char* e = getenv("DH_BIN_CELLOUT_MAX")) cellout_max = atoll(e);
+    if (!sum_map && cell_argmax && (g_bin_variant == 0 || g_bin_variant == 3) && tile_rows_for(ps, d) <= 128 && (int64_t)(ps / d) * n < cellout_max) {
         // class map (and count) without a sum map, footprints under 512 floats: the cell-lane kernel with its sums left in registers
         // (40 000^2 list, class map only: d = 16 / 4 see profiles/r02_stitch.md); wider footprints keep the segment kernel below
         const BinGeom gc = make_geom(false, 4, ps, d, n, rows, dw, row_offset, false, true);

@@ -45,7 +45,7 @@ def cover_list(H, W, B=1024):
 hw = 40000
 coords = cover_list(hw, hw)
 logits = torch.randn((coords.shape[0], N), generator=torch.Generator(device="cuda").manual_seed(0), device="cuda")
-for d in (16, 8, 4):
+for d in ([int(x) for x in sys.argv[1].split(',')] if len(sys.argv) > 1 else (16, 8, 4)):
     dh = dw = hw // d
     for label, kw in (("class map", dict(want_sum=False, want_argmax=True)), ("class + count", dict(want_sum=False, want_argmax=True, want_count=True)),
                       ("sum + class + count", dict(want_sum=True, want_argmax=True, want_count=True))):
